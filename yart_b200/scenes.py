@@ -1,0 +1,316 @@
+"""Synthetic scene generators of the shapes BASELINE.json names, written as ".ysc" files
+(layout: yart_b200/host/scene_desc.hpp).  Pure data generation (numpy), no path arithmetic.
+
+The scene description mirrors the arguments of the reference's scene API
+(ParametricBSDF ctor: reference src/bsdf/parametric.hpp:15-36; Mesh: src/core/mesh.hpp:54-61;
+Node: src/core/scene.hpp:11-64; lights: src/core/light.hpp:76-171), so the same file feeds the
+reference (through oracle/ref_driver.cpp) and the CUDA path (through ys_scene_load).
+"""
+from __future__ import annotations
+
+import struct
+from dataclasses import dataclass, field
+
+import numpy as np
+
+LINEAR, SRGB, NONCOLOR = 0, 1, 2
+AREA, IMAGE_INF, UNIFORM_INF = 0, 1, 2
+IDENTITY = np.eye(4, dtype=np.float32)
+
+
+@dataclass
+class Texture:
+    data: np.ndarray  # (h, w, c) uint8, or (h, w, 3) float32
+    type: int = LINEAR
+
+
+@dataclass
+class Material:
+    base: tuple = (1.0, 1.0, 1.0)
+    base_tex: int = -1
+    mr_tex: int = -1
+    trans_tex: int = -1
+    normal_tex: int = -1
+    cc_tex: int = -1
+    emis_tex: int = -1
+    metallic: float = 0.0
+    roughness: float = 0.0
+    transmission: float = 0.0
+    ior: float = 1.5
+    anisotropic: float = 0.0
+    aniso_rotation: float = 0.0
+    clearcoat: float = 0.0
+    clearcoat_roughness: float = 0.0
+    emission: tuple = (0.0, 0.0, 0.0)
+    normal_scale: float = 1.0
+    thin: int = 0
+    volume_color: tuple = (1.0, 1.0, 1.0)
+    volume_density: float = 0.0
+
+    def pack(self) -> bytes:
+        return struct.pack(
+            "<3f6i8f3ff i3ff".replace(" ", ""),
+            *self.base, self.base_tex, self.mr_tex, self.trans_tex, self.normal_tex, self.cc_tex, self.emis_tex,
+            self.metallic, self.roughness, self.transmission, self.ior, self.anisotropic, self.aniso_rotation,
+            self.clearcoat, self.clearcoat_roughness, *self.emission, self.normal_scale, self.thin,
+            *self.volume_color, self.volume_density)
+
+
+@dataclass
+class Mesh:
+    positions: np.ndarray  # (n,3) f32
+    normals: np.ndarray  # (n,3)
+    tangents: np.ndarray  # (n,4)
+    uvs: np.ndarray  # (n,2)
+    faces: np.ndarray  # (m,4) u32: i0 i1 i2 material
+    light_idx: np.ndarray = None  # (m,) i32
+
+    def __post_init__(self):
+        self.positions = np.ascontiguousarray(self.positions, np.float32).reshape(-1, 3)
+        n = len(self.positions)
+        self.normals = np.ascontiguousarray(self.normals, np.float32).reshape(n, 3)
+        self.tangents = (np.zeros((n, 4), np.float32) if self.tangents is None
+                         else np.ascontiguousarray(self.tangents, np.float32).reshape(n, 4))
+        self.uvs = (np.zeros((n, 2), np.float32) if self.uvs is None
+                    else np.ascontiguousarray(self.uvs, np.float32).reshape(n, 2))
+        self.faces = np.ascontiguousarray(self.faces, np.uint32).reshape(-1, 4)
+        if self.light_idx is None:
+            self.light_idx = np.full(len(self.faces), -1, np.int32)
+        self.light_idx = np.ascontiguousarray(self.light_idx, np.int32)
+
+    def vertex_data(self) -> np.ndarray:
+        return np.ascontiguousarray(np.concatenate([self.normals, self.tangents, self.uvs], axis=1), np.float32)
+
+
+@dataclass
+class Node:
+    parent: int = -1
+    mesh: int = -1
+    transform: np.ndarray = None  # 4x4 row-major or None (default Transform)
+
+
+@dataclass
+class Light:
+    type: int = AREA
+    mesh: int = -1
+    tri: int = -1
+    emission: tuple = (0.0, 0.0, 0.0)
+    transform: np.ndarray = None
+    two_sided: int = 0
+    scene_radius: float = 100.0
+    hdr_tex: int = -1
+
+
+@dataclass
+class Scene:
+    textures: list = field(default_factory=list)
+    materials: list = field(default_factory=list)
+    meshes: list = field(default_factory=list)
+    nodes: list = field(default_factory=list)
+    lights: list = field(default_factory=list)
+    # suggested camera / settings (not part of the .ysc file)
+    camera: dict = field(default_factory=dict)
+
+    def n_tris(self) -> int:
+        return sum(len(m.faces) for m in self.meshes)
+
+    def add_area_lights(self, mesh_idx: int, node_transform=None):
+        """One AreaLight per emissive-material triangle of a mesh, light indices appended globally
+        (what reference src/gltf/gltf.cpp:299-314 does for a single emissive node)."""
+        m = self.meshes[mesh_idx]
+        for t, f in enumerate(m.faces):
+            em = self.materials[int(f[3])].emission
+            if em[0] * em[0] + em[1] * em[1] + em[2] * em[2] > 0:
+                m.light_idx[t] = len(self.lights)
+                self.lights.append(Light(AREA, mesh_idx, t, tuple(em), node_transform))
+
+    def write(self, path: str):
+        with open(path, "wb") as f:
+            f.write(b"YSC1")
+            f.write(struct.pack("<I", len(self.textures)))
+            for t in self.textures:
+                d = t.data
+                h, w, c = d.shape
+                is_float = 1 if d.dtype == np.float32 else 0
+                f.write(struct.pack("<5I", c, is_float, t.type, w, h))
+                f.write(np.ascontiguousarray(d).tobytes())
+            f.write(struct.pack("<I", len(self.materials)))
+            for m in self.materials:
+                f.write(m.pack())
+            f.write(struct.pack("<I", len(self.meshes)))
+            for m in self.meshes:
+                f.write(struct.pack("<II", len(m.positions), len(m.faces)))
+                f.write(m.positions.tobytes())
+                f.write(m.vertex_data().tobytes())
+                f.write(m.faces.tobytes())
+                f.write(m.light_idx.tobytes())
+            f.write(struct.pack("<I", len(self.nodes)))
+            for n in self.nodes:
+                has = 0 if n.transform is None else 1
+                mat = IDENTITY if n.transform is None else np.asarray(n.transform, np.float32)
+                f.write(struct.pack("<3i", n.parent, n.mesh, has))
+                f.write(np.ascontiguousarray(mat, np.float32).tobytes())
+            f.write(struct.pack("<I", len(self.lights)))
+            for l in self.lights:
+                has = 0 if l.transform is None else 1
+                mat = IDENTITY if l.transform is None else np.asarray(l.transform, np.float32)
+                f.write(struct.pack("<3i3fi", l.type, l.mesh, l.tri, *l.emission, has))
+                f.write(np.ascontiguousarray(mat, np.float32).tobytes())
+                f.write(struct.pack("<ifi", l.two_sided, l.scene_radius, l.hdr_tex))
+
+
+# ------------------------------------------------------------------------------------------
+# geometry helpers
+# ------------------------------------------------------------------------------------------
+def translation(x, y, z):
+    m = np.eye(4, dtype=np.float32)
+    m[:3, 3] = (x, y, z)
+    return m
+
+
+def rotation_y(deg):
+    a = np.float32(np.deg2rad(deg))
+    c, s = np.cos(a), np.sin(a)
+    m = np.eye(4, dtype=np.float32)
+    m[0, 0], m[0, 2], m[2, 0], m[2, 2] = c, s, -s, c
+    return m
+
+
+def scaling(s):
+    m = np.eye(4, dtype=np.float32)
+    m[0, 0] = m[1, 1] = m[2, 2] = s
+    return m
+
+
+class MeshBuilder:
+    """Accumulates flat-shaded quads/triangles with per-vertex normal, tangent, uv."""
+
+    def __init__(self):
+        self.p, self.n, self.t, self.uv, self.f = [], [], [], [], []
+
+    def tri(self, a, b, c, mat, uvs=((0, 0), (1, 0), (0, 1)), normal=None):
+        a, b, c = (np.asarray(v, np.float64) for v in (a, b, c))
+        nrm = np.cross(b - a, c - a)
+        ln = np.linalg.norm(nrm)
+        nrm = nrm / ln if ln > 0 else np.array([0.0, 1.0, 0.0])
+        if normal is not None:
+            nrm = np.asarray(normal, np.float64)
+        tg = b - a
+        lt = np.linalg.norm(tg)
+        tg = tg / lt if lt > 0 else np.array([1.0, 0.0, 0.0])
+        i = len(self.p)
+        for v, uv in zip((a, b, c), uvs):
+            self.p.append(v)
+            self.n.append(nrm)
+            self.t.append((*tg, 1.0))
+            self.uv.append(uv)
+        self.f.append((i, i + 1, i + 2, mat))
+
+    def quad(self, a, b, c, d, mat, uv_scale=1.0):
+        """a,b,c,d counter-clockwise seen from the front."""
+        s = uv_scale
+        self.tri(a, b, c, mat, ((0, 0), (s, 0), (s, s)))
+        self.tri(a, c, d, mat, ((0, 0), (s, s), (0, s)))
+
+    def box(self, lo, hi, mat, xf=None):
+        lo, hi = np.asarray(lo, np.float64), np.asarray(hi, np.float64)
+        c = np.array([[lo[0], lo[1], lo[2]], [hi[0], lo[1], lo[2]], [hi[0], hi[1], lo[2]], [lo[0], hi[1], lo[2]],
+                      [lo[0], lo[1], hi[2]], [hi[0], lo[1], hi[2]], [hi[0], hi[1], hi[2]], [lo[0], hi[1], hi[2]]])
+        if xf is not None:
+            c = (np.asarray(xf, np.float64)[:3, :3] @ c.T).T + np.asarray(xf, np.float64)[:3, 3]
+        for q in ((4, 5, 6, 7), (1, 0, 3, 2), (5, 1, 2, 6), (0, 4, 7, 3), (7, 6, 2, 3), (0, 1, 5, 4)):
+            self.quad(c[q[0]], c[q[1]], c[q[2]], c[q[3]], mat)
+
+    def build(self) -> Mesh:
+        return Mesh(np.array(self.p), np.array(self.n), np.array(self.t), np.array(self.uv),
+                    np.array(self.f, np.uint32))
+
+
+# ------------------------------------------------------------------------------------------
+# C1: procedural Cornell box (36 triangles, one quad area light, diffuse + glossy + metal)
+# ------------------------------------------------------------------------------------------
+def cornell(light_transform=True) -> Scene:
+    s = Scene()
+    s.materials = [
+        Material(base=(0.73, 0.73, 0.73), roughness=1.0),  # 0 white
+        Material(base=(0.65, 0.05, 0.05), roughness=1.0),  # 1 red
+        Material(base=(0.12, 0.45, 0.15), roughness=1.0),  # 2 green
+        Material(base=(0.8, 0.8, 0.8), roughness=0.2),  # 3 glossy dielectric-coated diffuse
+        Material(base=(0.9, 0.7, 0.3), roughness=0.3, metallic=1.0),  # 4 rough metal
+        Material(base=(1.0, 1.0, 1.0), roughness=1.0, emission=(17.0, 12.0, 4.0)),  # 5 light
+    ]
+    b = MeshBuilder()
+    b.quad((-5, 0, 5), (5, 0, 5), (5, 0, -5), (-5, 0, -5), 0)  # floor (normal +y)
+    b.quad((-5, 10, -5), (5, 10, -5), (5, 10, 5), (-5, 10, 5), 0)  # ceiling (normal -y)
+    b.quad((-5, 0, -5), (5, 0, -5), (5, 10, -5), (-5, 10, -5), 0)  # back (normal +z)
+    b.quad((-5, 0, 5), (-5, 0, -5), (-5, 10, -5), (-5, 10, 5), 1)  # left, red (normal +x)
+    b.quad((5, 0, -5), (5, 0, 5), (5, 10, 5), (5, 10, -5), 2)  # right, green (normal -x)
+    b.box((-1.5, 0, -1.5), (1.5, 3, 1.5), 3, translation(1.6, 0, 1.5) @ rotation_y(-18))  # short box, glossy
+    b.box((-1.5, 0, -1.5), (1.5, 6, 1.5), 4, translation(-1.7, 0, -1.6) @ rotation_y(20))  # tall box, metal
+    room = b.build()
+    lb = MeshBuilder()
+    lb.quad((-1.5, 0, -1.5), (1.5, 0, -1.5), (1.5, 0, 1.5), (-1.5, 0, 1.5), 5)  # faces down (normal -y)
+    light = lb.build()
+    s.meshes = [room, light]
+    lxf = translation(0.0, 9.99, 0.0) if light_transform else None
+    if not light_transform:
+        light.positions[:, 1] += np.float32(9.99)
+    s.nodes = [Node(-1, -1), Node(0, 0), Node(0, 1, lxf)]
+    s.add_area_lights(1, lxf)
+    s.camera = dict(pos=(0.0, 5.0, 15.0), target=(0.0, 5.0, 0.0), focal=35.0, fnum=0.0, exposure=0.0,
+                    w=512, h=512, spp=16)
+    return s
+
+
+# ------------------------------------------------------------------------------------------
+# C2: random triangle soup (traversal / intersection microbench), one big quad area light
+# ------------------------------------------------------------------------------------------
+def soup(n_tris=1_000_000, seed=1234, with_light=True) -> Scene:
+    rng = np.random.default_rng(seed)
+    s = Scene()
+    s.materials = [Material(base=(0.7, 0.7, 0.7), roughness=1.0),
+                   Material(base=(1.0, 1.0, 1.0), roughness=1.0, emission=(10.0, 10.0, 10.0))]
+    centres = rng.uniform(-10.0, 10.0, (n_tris, 1, 3))
+    ext = 5.0 * 2.0 / np.cbrt(n_tris)
+    verts = (centres + rng.uniform(-ext, ext, (n_tris, 3, 3))).astype(np.float32)
+    e1 = verts[:, 1] - verts[:, 0]
+    e2 = verts[:, 2] - verts[:, 0]
+    nrm = np.cross(e1, e2)
+    nrm /= np.maximum(np.linalg.norm(nrm, axis=1, keepdims=True), 1e-20)
+    normals = np.repeat(nrm[:, None, :], 3, axis=1).reshape(-1, 3)
+    faces = np.zeros((n_tris, 4), np.uint32)
+    faces[:, 0] = np.arange(n_tris) * 3
+    faces[:, 1] = faces[:, 0] + 1
+    faces[:, 2] = faces[:, 0] + 2
+    s.meshes = [Mesh(verts.reshape(-1, 3), normals, None, None, faces)]
+    s.nodes = [Node(-1, -1), Node(0, 0)]
+    if with_light:
+        lb = MeshBuilder()
+        lb.quad((-30, 25, -30), (30, 25, -30), (30, 25, 30), (-30, 25, 30), 1)  # faces down
+        s.meshes.append(lb.build())
+        s.nodes.append(Node(0, 1))
+        s.add_area_lights(1, None)
+    s.camera = dict(pos=(0.0, 0.0, 40.0), target=(0.0, 0.0, 0.0), focal=35.0, fnum=0.0, exposure=0.0,
+                    w=1920, h=1080, spp=1, maxdepth=1)
+    return s
+
+
+# ------------------------------------------------------------------------------------------
+# tiny two-quad scene (smoke tests / SURVEY Appendix C style)
+# ------------------------------------------------------------------------------------------
+def two_quads() -> Scene:
+    s = Scene()
+    s.materials = [Material(base=(0.8, 0.8, 0.8), roughness=1.0),
+                   Material(base=(0.8, 0.3, 0.2), roughness=0.4),
+                   Material(base=(1, 1, 1), roughness=1.0, emission=(8.0, 8.0, 8.0))]
+    b = MeshBuilder()
+    b.quad((-6, 0, 6), (6, 0, 6), (6, 0, -6), (-6, 0, -6), 0)
+    b.quad((-4, 0, -3), (4, 0, -3), (4, 8, -3), (-4, 8, -3), 1)
+    lb = MeshBuilder()
+    lb.quad((-2, 9, -2), (2, 9, -2), (2, 9, 2), (-2, 9, 2), 2)
+    s.meshes = [b.build(), lb.build()]
+    s.nodes = [Node(-1, -1), Node(0, 0), Node(0, 1)]
+    s.add_area_lights(1, None)
+    s.camera = dict(pos=(0.0, 5.0, 15.0), target=(0.0, 5.0, 0.0), focal=35.0, fnum=0.0, exposure=0.0,
+                    w=64, h=64, spp=16)
+    return s
