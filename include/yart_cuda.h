@@ -1,0 +1,350 @@
+/* yart_cuda.h — C ABI of the B200 wavefront path tracer that replaces yart's src/cpu
+ * tile renderer (render hot path only).  Plain pointers and sizes; no C++/torch types.
+ *
+ * The reference (teofum/yart) has no FFI: its path sits behind C++ virtuals/templates.
+ * Each entry point below names the reference interface it stands in for.  A maintainer's
+ * `yart::cuda::WavefrontRenderer : yart::Renderer` would bind exactly these.
+ *
+ * Two layers live in the same shared library (libyart_b200.so):
+ *   yc_*  device layer: flattened POD scene in, CUDA wavefront kernels, frames out.
+ *   ys_* / yr_*  host layer: C mirror of yart's Scene / Camera / Renderer API
+ *         (builds the SAH BVH exactly as src/core/bvh.hpp does and flattens it).
+ *
+ * All functions return YC_OK (0) or a negative YC_ERR_*; none throws across the ABI.
+ * The reference is `noexcept` everywhere and signals failure by nullptr / silent return
+ * (src/gltf/gltf.cpp:339, src/cpu/integrator.cpp:6); here the code is explicit.
+ */
+#ifndef YART_CUDA_H
+#define YART_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YC_OK 0
+#define YC_ERR_INVALID (-1)   /* bad argument / inconsistent scene description */
+#define YC_ERR_CUDA (-2)      /* CUDA runtime error (see yc_last_error) */
+#define YC_ERR_NO_SCENE (-3)  /* render/trace before yc_upload_scene (reference: `if (!scene) return;`) */
+#define YC_ERR_NO_DEVICE (-4) /* no usable CUDA device: there is NO CPU fallback */
+#define YC_ERR_STATE (-5)     /* call order violated (e.g. render_wave before begin_frame) */
+#define YC_ERR_IO (-6)
+
+#define YC_MAX_NODE_DEPTH 16
+
+/* ---------------------------------------------------------------------------------------
+ * Flattened scene (device layer input).  Host owns every pointer; yc_upload_scene copies.
+ * ------------------------------------------------------------------------------------- */
+
+/* Scene-graph node in DFS pre-order.  Replaces yart::Node (src/core/scene.hpp:11-64) as it is
+ * walked by RayIntegrator::testNode (src/cpu/ray-integrator.cpp:20-54). */
+typedef struct YcNode {
+  float inv[12];  /* rows 0..2 of Transform::m_inverseTransform (row-major 3x4) */
+  float fwd[12];  /* rows 0..2 of Transform::m_transform */
+  float nrm[9];   /* Transform::m_normalTransform = transpose(float3x3(inverse)) */
+  float bmin[3], bmax[3]; /* Node::boundingBox(), node object space */
+  int32_t mesh;   /* index into meshes, -1 = none */
+  int32_t parent; /* -1 for the root (node 0) */
+  int32_t skip;   /* index of the first node after this node's subtree */
+  int32_t depth;  /* root = 0; must be < YC_MAX_NODE_DEPTH */
+} YcNode;
+
+/* One inner BVH node with BOTH children's bounds inlined (64 B = 4 x 128-bit loads).
+ * Same tree, same child order and same boxes as yart::BVHNode (src/core/bvh.hpp:21-33):
+ * child 0 is `left`, child 1 is `left + 1`.
+ * ref: inner child → index of its YcBvhNode (relative to the mesh's first node);
+ *      leaf child  → 0x80000000 | index of its first YcBvhTri (relative to the mesh's first tri);
+ *      the leaf's triangles follow contiguously, the last one carries YC_TRI_LAST. */
+typedef struct YcBvhNode {
+  float c0min[3], c0max[3];
+  float c1min[3], c1max[3];
+  uint32_t ref0, ref1;
+  uint32_t pad0, pad1;
+} YcBvhNode;
+
+#define YC_REF_LEAF 0x80000000u
+#define YC_TRI_LAST 1u        /* last triangle of its leaf */
+#define YC_TRI_ALPHA 2u       /* material has alpha texels < 255 (parametric.cpp:57-61) */
+#define YC_TRI_TRANSPARENT 4u /* material.transparent() (parametric.cpp:80-82) */
+
+/* Leaf-ordered triangle record (48 B = 3 x 128-bit loads): positions pre-gathered in
+ * BVH::m_indices order so a leaf is one contiguous run. */
+typedef struct YcBvhTri {
+  float p0[3], p1[3], p2[3];
+  uint32_t prim;  /* original triangle index in the mesh (what Hit::idx holds) */
+  uint32_t flags; /* YC_TRI_* */
+  uint32_t pad;
+} YcBvhTri;
+
+typedef struct YcMesh {
+  float rootMin[3], rootMax[3]; /* BVH root bounds (tested first, ray-integrator.cpp:98) */
+  uint32_t rootRef;             /* like YcBvhNode::ref (root may itself be a leaf) */
+  uint32_t nodeOffset;          /* first YcBvhNode of this mesh in YcScene::bvhNodes */
+  uint32_t triOffset;           /* first YcBvhTri of this mesh in YcScene::bvhTris */
+  uint32_t vertOffset;          /* first vertex in the vertex arrays */
+  uint32_t primOffset;          /* first primitive in primIndices / primMaterial / primLight */
+  uint32_t nTris, nVerts, nInner;
+} YcMesh;
+
+/* ParametricBSDF parameters (src/bsdf/parametric.hpp:15-36 + derived members :48-76). */
+typedef struct YcMaterial {
+  float base[3];
+  float metallic, roughness, transmission, ior;
+  float anisotropic, clearcoat, clearcoatRoughness;
+  float emission[3];
+  float normalScale; /* stored, never applied — as in the reference (core/bsdf.cpp:46-56) */
+  float volumeColor[3];
+  float volumeDensity;
+  float localRotation[9]; /* float3x3(float4x4::rotation(-anisoRotation, z)) */
+  float invRotation[9];   /* float3x3(float4x4::rotation(+anisoRotation, z)) */
+  int32_t baseTex, mrTex, transTex, normalTex, ccTex, emisTex; /* -1 = none */
+  int32_t thinTransmission, hasAlpha, hasEmission;
+  int32_t pad;
+} YcMaterial;
+
+/* Texture<T,C> (src/core/texture.hpp:21-52).  u8 textures index texelsU8, float ones texelsF32. */
+typedef struct YcTexture {
+  uint64_t offset; /* element offset into texelsU8 / texelsF32 */
+  uint32_t width, height, channels;
+  uint32_t isFloat;
+  uint32_t type; /* 0 LinearRGB, 1 sRGB (gamma-2 storage), 2 NonColor */
+  uint32_t pad;
+} YcTexture;
+
+#define YC_LIGHT_AREA 0
+#define YC_LIGHT_IMAGE_INFINITE 1
+#define YC_LIGHT_UNIFORM_INFINITE 2
+
+/* Light (src/core/light.hpp).  Area lights carry their triangle (mesh space) so that
+ * AreaLight::sample (light.cpp:46-72) needs no mesh lookup. */
+typedef struct YcLight {
+  int32_t type;
+  int32_t twoSided;
+  float emission[3]; /* area / uniform */
+  float area;        /* AreaLight::m_area (transformed triangle) */
+  float power;       /* Light::power() */
+  float p0[3], p1[3], p2[3]; /* mesh-space vertices */
+  float n0[3], n1[3], n2[3]; /* mesh-space vertex normals */
+  float fwd[12], nrm[9];     /* Light::m_transform (area) */
+  /* infinite lights */
+  float sceneRadius, surfaceArea;
+  float Lavg[3];
+  float envFwd[12], envInv[12]; /* ImageInfiniteLight::transform (public member) */
+  int32_t hdrTex;
+  uint32_t distW, distH;        /* PiecewiseConstant2D resolution */
+  uint64_t distOffset;          /* float offset into YcScene::envDist of this light's block:
+                                   func[W*H] cdf[(W+1)*H] rowIntegral[H] mfunc[H] mcdf[H+1] mIntegral[1] */
+} YcLight;
+
+typedef struct YcScene {
+  const YcNode* nodes;       uint32_t nNodes;
+  const YcMesh* meshes;      uint32_t nMeshes;
+  const YcBvhNode* bvhNodes; uint64_t nBvhNodes;
+  const YcBvhTri* bvhTris;   uint64_t nBvhTris;
+  /* vertex attributes (all meshes concatenated) */
+  const float* positions;    /* 3 per vertex */
+  const float* normals;      /* 3 per vertex */
+  const float* tangents;     /* 4 per vertex */
+  const float* uvs;          /* 2 per vertex */
+  uint64_t nVerts;
+  /* primitives in original order (all meshes concatenated) */
+  const uint32_t* primIndices; /* 3 per primitive, mesh-local vertex indices */
+  const uint32_t* primMaterial;
+  const int32_t* primLight;    /* Mesh::lightIdx, -1 = none */
+  uint64_t nPrims;
+  const YcMaterial* materials; uint32_t nMaterials;
+  const YcTexture* textures;   uint32_t nTextures;
+  const uint8_t* texelsU8;     uint64_t nTexelsU8;
+  const float* texelsF32;      uint64_t nTexelsF32;
+  const YcLight* lights;       uint32_t nLights;
+  const float* envDist;        uint64_t nEnvDist;
+  /* PowerLightSampler (src/core/light-sampler.cpp:32-93) */
+  const uint32_t* infiniteLights; uint32_t nInfinite; /* scene light indices */
+  const uint32_t* areaLights;     uint32_t nArea;     /* scene light indices, m_lights order */
+  const float* lightPowerCdf;                         /* m_lightPowers (running sums), nArea */
+  float totalPower;
+  /* data tables (values dumped from the reference build, see yart_b200/data/README) */
+  const float* lutTables;   /* 14112 floats, order documented in csrc/luts.cuh */
+  int32_t hasAlpha;         /* any material with hasAlpha */
+} YcScene;
+
+/* Derived camera members (src/core/camera.hpp:17-22, computed by calcDerivedProperties :25-59). */
+typedef struct YcCamera {
+  float position[3];
+  float topLeftPixel[3];
+  float pixelDeltaU[3], pixelDeltaV[3];
+  float frameX[3], frameY[3], frameZ[3]; /* m_cameraFrame */
+  float apertureRadius;
+  uint32_t apertureSides;
+  float exposure;
+} YcCamera;
+
+typedef struct YcOptions {
+  uint32_t maxDepth;        /* RayIntegrator::m_maxDepth (default 30) */
+  uint32_t maxPathsInFlight; /* wavefront capacity; 0 = default (8 Mi paths) */
+  uint32_t reserved[6];
+} YcOptions;
+
+typedef struct YcRect { uint32_t x, y, w, h; } YcRect;
+
+#define YC_TONEMAP_NONE 0
+#define YC_TONEMAP_AGX 1
+#define YC_TONEMAP_AGX_GOLDEN 2
+#define YC_TONEMAP_AGX_PUNCHY 3
+
+#define YC_ESTIMATOR_GMON 0 /* what Integrator::render instantiates (integrator.cpp:17) */
+#define YC_ESTIMATOR_MON 1
+#define YC_ESTIMATOR_MEAN 2
+
+typedef struct YcFrameDesc {
+  uint32_t width, height;
+  uint32_t totalSamples; /* TileRenderer::samples: fixes the sampler's log2spp */
+  uint32_t tileSize;     /* TileRenderer::tileSize: fixes the sampler's nBase4Digits */
+  float background[3];   /* Renderer::backgroundColor */
+  uint32_t tonemap;      /* YC_TONEMAP_* */
+  uint32_t estimator;    /* YC_ESTIMATOR_* */
+  /* multi-GPU: this context renders only tiles whose row-major index % shardCount == shardIndex
+   * (tile list as in tile-renderer.hpp:127-144); other pixels stay 0 so frames sum across GPUs. */
+  uint32_t shardIndex, shardCount;
+} YcFrameDesc;
+
+typedef struct YcStats {
+  uint64_t raysReference;   /* reference definition: path segments + unoccluded non-zero-f NEE rays
+                               (mis-integrator.cpp:22,126) */
+  uint64_t raysExtend;      /* closest-hit rays traced */
+  uint64_t raysShadow;      /* any-hit rays traced */
+  uint64_t samples;         /* pixel samples taken */
+  uint64_t kernelLaunches;  /* CUDA kernels launched by this context since begin_frame */
+  double gpuMs;             /* CUDA-event time spent inside yc_render_wave since begin_frame */
+  uint64_t boxTests, triTests; /* only filled by counting traces (yc_trace with YC_TRACE_COUNT) */
+} YcStats;
+
+typedef struct YcRay { float o[3], tmin, d[3], tmax; } YcRay;
+
+/* What the reference's Hit holds after testNode (src/cpu/hit.hpp:8-17). */
+typedef struct YcHit {
+  float t;
+  uint32_t prim;     /* Hit::idx; 0xffffffff on miss */
+  int32_t material;  /* index of Hit::bsdf, -1 on miss */
+  int32_t lightIdx;
+  uint32_t backSide;
+  uint32_t didHit;
+  float p[3], n[3], tg[3], uv[2];
+  float attenuation[3];
+} YcHit;
+
+#define YC_TRACE_CLOSEST 0
+#define YC_TRACE_ANY 1     /* NEE ray: Ray::nee = true, hit.t preset to tmax */
+#define YC_TRACE_COUNT 16  /* OR-ed in: also count box / triangle tests into YcStats */
+
+typedef struct yc_ctx yc_ctx;
+
+/* --- device layer ------------------------------------------------------------------- */
+/* Replaces constructing a cpu::TileRenderer (src/cpu/tile-renderer.hpp:34-38). */
+int yc_create(int device, const YcOptions* opts, yc_ctx** out);
+void yc_destroy(yc_ctx* ctx);
+const char* yc_last_error(const yc_ctx* ctx);
+/* Replaces `renderer.scene = scene` (src/core/renderer.hpp:53). */
+int yc_upload_scene(yc_ctx* ctx, const YcScene* scene);
+/* Replaces the `const Camera&` the renderer holds (src/core/renderer.hpp:97). */
+int yc_set_camera(yc_ctx* ctx, const YcCamera* cam);
+/* Replaces TileRenderer::renderImpl's state reset (tile-renderer.hpp:118-124). */
+int yc_begin_frame(yc_ctx* ctx, const YcFrameDesc* frame);
+/* Replaces one wave of the worker loop + finishTile for every tile
+ * (tile-renderer.hpp:161-191, 205-239; Integrator::render, integrator.cpp:5-28):
+ * takes samples [sampleOffset, sampleOffset + waveSamples) of every pixel in `pixels`,
+ * runs the per-wave estimator, blends into the HDR frame with sample-count weights
+ * (takenBefore = samples already blended) and tonemaps. */
+int yc_render_wave(yc_ctx* ctx, YcRect pixels, uint32_t sampleOffset, uint32_t waveSamples,
+                   uint32_t takenBefore);
+/* Copies the frames to host (either pointer may be NULL).  width*height*4 floats each.
+ * Replaces reading Renderer::m_buffer (RenderData::buffer, renderer.hpp:22-28). */
+int yc_resolve(yc_ctx* ctx, float* hdrRGBA, float* ldrRGBA, YcStats* stats);
+/* Device pointers of the frames (for NCCL reductions by the caller). */
+int yc_frame_device_ptrs(yc_ctx* ctx, void** hdr, void** ldr, size_t* bytes);
+/* Re-run the tonemap over the whole HDR frame (after a cross-GPU sum). */
+int yc_retonemap(yc_ctx* ctx);
+/* Ray-level parity hook: RayIntegrator::testNode on caller rays (ray-integrator.cpp:20-54). */
+int yc_trace(yc_ctx* ctx, const YcRay* rays, size_t n, int mode, YcHit* hits, YcStats* stats);
+/* Same with rays/hits already resident on the device (`rays`/`hits` are device pointers);
+ * `repeat` back-to-back launches timed with CUDA events → *ms is the average per launch. */
+int yc_trace_device(yc_ctx* ctx, const void* raysDev, size_t n, int mode, void* hitsDev, int repeat,
+                    float* ms);
+int yc_device_alloc(yc_ctx* ctx, size_t bytes, void** out);
+int yc_device_free(yc_ctx* ctx, void* p);
+int yc_memcpy_h2d(yc_ctx* ctx, void* dst, const void* src, size_t bytes);
+int yc_memcpy_d2h(yc_ctx* ctx, void* dst, const void* src, size_t bytes);
+/* Primary rays exactly as RayIntegrator::sample generates them (ray-integrator.cpp:11-18),
+ * written to a device YcRay array of width*height*spp entries (sample-major). */
+int yc_generate_primary_rays(yc_ctx* ctx, uint32_t sampleOffset, uint32_t spp, void* raysDev);
+int yc_synchronize(yc_ctx* ctx);
+/* Function-level hooks used by the parity tests (device evaluations of the restated math). */
+int yc_kat(yc_ctx* ctx, const char* kind, const void* in, size_t inBytes, void* out, size_t outBytes);
+
+/* --- host layer: scene -------------------------------------------------------------- */
+typedef struct ys_scene ys_scene;
+
+/* Loads a ".ysc" scene description (yart_b200/host/scene_desc.hpp) and builds it through the
+ * same steps gltf::load performs on the reference API (materials, meshes + SAH BVH, node tree,
+ * lights).  Stands in for `gltf::load(path)` (src/gltf/gltf.cpp:319-358). */
+int ys_scene_load(const char* path, ys_scene** out);
+void ys_scene_destroy(ys_scene* s);
+const char* ys_last_error(void);
+/* Flattened view (valid until ys_scene_destroy). */
+const YcScene* ys_scene_flat(const ys_scene* s);
+double ys_scene_build_ms(const ys_scene* s);
+/* BVH of mesh `mesh` in the REFERENCE's node numbering/layout (for builder parity tests):
+ * nodes = nNodes × {min[3] max[3] leftFirst span} (32 B), indices = nTris × u32. */
+int ys_scene_bvh(const ys_scene* s, uint32_t mesh, const void** nodes, uint32_t* nNodes,
+                 const uint32_t** indices, uint32_t* nTris);
+
+/* Camera(imageSize, focalLength, fNumber) + moveAndLookAt(position, target, up)
+ * (src/core/camera.hpp:77-136); up = (0,0,0) keeps the default +Y. */
+int ys_camera_make(uint32_t width, uint32_t height, float focalLength, float fNumber,
+                   const float position[3], const float target[3], const float up[3],
+                   float exposure, uint32_t apertureSides, YcCamera* out);
+
+/* --- host layer: renderer ----------------------------------------------------------- */
+/* Mirror of cpu::TileRenderer's public knobs (tile-renderer.hpp:27-32) + Renderer fields. */
+typedef struct YrSettings {
+  uint32_t width, height;
+  uint32_t samples, firstWaveSamples, maxWaveSamples, tileSize;
+  uint32_t maxDepth;
+  float background[3];
+  uint32_t tonemap;   /* YC_TONEMAP_* (tonemapper == nullptr ↔ NONE) */
+  uint32_t estimator; /* YC_ESTIMATOR_* */
+  uint32_t shardIndex, shardCount;
+  int32_t device;
+} YrSettings;
+
+typedef struct YrRenderData {  /* Renderer::RenderData (renderer.hpp:22-28) */
+  uint64_t samplesTaken, totalSamples, totalRays;
+  double totalTimeMs;
+} YrRenderData;
+
+typedef struct YrWaveData {    /* Renderer::WaveData (renderer.hpp:33-38) */
+  uint64_t wave, waveSamples, rays;
+  double timeMs;
+} YrWaveData;
+
+typedef void (*yr_wave_callback)(const YrRenderData*, const YrWaveData*, void* user);
+
+typedef struct yr_renderer yr_renderer;
+int yr_create(const YrSettings* settings, const ys_scene* scene, const YcCamera* camera, yr_renderer** out);
+void yr_destroy(yr_renderer* r);
+int yr_set_wave_callback(yr_renderer* r, yr_wave_callback cb, void* user);
+int yr_render(yr_renderer* r);     /* Renderer::render(): asynchronous */
+int yr_abort(yr_renderer* r);      /* Renderer::abort() */
+int yr_wait(yr_renderer* r);       /* Renderer::wait() */
+int yr_render_sync(yr_renderer* r, YrRenderData* out); /* Renderer::renderSync() */
+/* Result buffers: LDR (what Renderer::m_buffer holds) and HDR accumulation. */
+int yr_read(yr_renderer* r, float* hdrRGBA, float* ldrRGBA, YcStats* stats);
+yc_ctx* yr_context(yr_renderer* r);
+const char* yr_last_error(const yr_renderer* r);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YART_CUDA_H */
