@@ -219,6 +219,8 @@ typedef struct YcStats {
   uint64_t kernelLaunches;  /* CUDA kernels launched by this context since begin_frame */
   double gpuMs;             /* CUDA-event time spent inside yc_render_wave since begin_frame */
   uint64_t boxTests, triTests; /* only filled by counting traces (yc_trace with YC_TRACE_COUNT) */
+  double extendMs;          /* CUDA-event time of the extend (closest-hit) launches, when yc_set_profiling(1) */
+  uint64_t extendLaunches;
 } YcStats;
 
 typedef struct YcRay { float o[3], tmin, d[3], tmax; } YcRay;
@@ -238,6 +240,7 @@ typedef struct YcHit {
 #define YC_TRACE_CLOSEST 0
 #define YC_TRACE_ANY 1     /* NEE ray: Ray::nee = true, hit.t preset to tmax */
 #define YC_TRACE_COUNT 16  /* OR-ed in: also count box / triangle tests into YcStats */
+#define YC_TRACE_USE_TMAX 32 /* OR-ed in (closest): preset hit.t = ray.tmax instead of infinity */
 
 typedef struct yc_ctx yc_ctx;
 
@@ -266,9 +269,12 @@ int yc_resolve(yc_ctx* ctx, float* hdrRGBA, float* ldrRGBA, YcStats* stats);
 int yc_frame_device_ptrs(yc_ctx* ctx, void** hdr, void** ldr, size_t* bytes);
 /* Re-run the tonemap over the whole HDR frame (after a cross-GPU sum). */
 int yc_retonemap(yc_ctx* ctx);
+/* Record per-launch CUDA-event time of the extend kernel into YcStats (bench roofline). */
+int yc_set_profiling(yc_ctx* ctx, int timeExtendKernel);
 /* Ray-level parity hook: RayIntegrator::testNode on caller rays (ray-integrator.cpp:20-54). */
 int yc_trace(yc_ctx* ctx, const YcRay* rays, size_t n, int mode, YcHit* hits, YcStats* stats);
-/* Same with rays/hits already resident on the device (`rays`/`hits` are device pointers);
+/* Same with rays already resident on the device; hitsDev receives n compact 20-byte records
+ * {f32 t, u, v; u32 prim; i32 node | backSide << 30 (-1 = miss)}.
  * `repeat` back-to-back launches timed with CUDA events → *ms is the average per launch. */
 int yc_trace_device(yc_ctx* ctx, const void* raysDev, size_t n, int mode, void* hitsDev, int repeat,
                     float* ms);

@@ -1,0 +1,274 @@
+"""yart_b200 — B200 wavefront path tracer behind yart's Scene / Camera / Renderer API.
+
+Python mirror of the host interface in include/yart_cuda.h (which itself mirrors reference
+src/core/renderer.hpp:17-104, src/cpu/tile-renderer.hpp:25-38, src/core/camera.hpp:77-136 and
+src/gltf/gltf.cpp:319-358).  All work happens in libyart_b200.so (CUDA, sm_100a); this module only
+marshals arguments.  Importing it never touches the GPU; creating a Renderer or Context does, and
+raises if there is no usable CUDA device — there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import (ESTIMATOR_GMON, ESTIMATOR_MEAN, ESTIMATOR_MON, TONEMAP_AGX, TONEMAP_AGX_GOLDEN, TONEMAP_AGX_PUNCHY,
+                   TONEMAP_NONE, TRACE_ANY, TRACE_CLOSEST, TRACE_COUNT, TRACE_USE_TMAX)
+
+_lib = None
+
+
+def lib():
+    """The product library (loaded on first use)."""
+    global _lib
+    if _lib is None:
+        _lib = capi.load()
+    return _lib
+
+
+def use_library(handle):
+    """Tests only: bind another build of the same C ABI (tests/hostsim)."""
+    global _lib
+    _lib = handle
+
+
+class YartError(RuntimeError):
+    pass
+
+
+def _check(rc, what, detail=b""):
+    if rc != 0:
+        names = {-1: "INVALID", -2: "CUDA", -3: "NO_SCENE", -4: "NO_DEVICE", -5: "STATE", -6: "IO"}
+        msg = detail.decode() if isinstance(detail, bytes) else str(detail)
+        raise YartError(f"{what} failed: YC_ERR_{names.get(rc, rc)} {msg}")
+
+
+def _f3(v):
+    return (C.c_float * 3)(*[float(x) for x in v])
+
+
+class Scene:
+    """yart::Scene built from a .ysc description (stands in for gltf::load)."""
+
+    def __init__(self, path: str):
+        self._h = C.c_void_p()
+        rc = lib().ys_scene_load(path.encode(), C.byref(self._h))
+        _check(rc, f"ys_scene_load({path})", lib().ys_last_error() or b"")
+        self.flat = lib().ys_scene_flat(self._h).contents
+        self.build_ms = lib().ys_scene_build_ms(self._h)
+
+    def close(self):
+        if self._h:
+            lib().ys_scene_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def n_tris(self) -> int:
+        return int(self.flat.nPrims)
+
+    def bvh(self, mesh: int = 0):
+        """(nodes, indices) in the reference's layout: nodes = structured array of 32-byte records."""
+        nodes, n_nodes, idx, n_tris = C.c_void_p(), C.c_uint32(), C.POINTER(C.c_uint32)(), C.c_uint32()
+        _check(lib().ys_scene_bvh(self._h, mesh, C.byref(nodes), C.byref(n_nodes), C.byref(idx), C.byref(n_tris)),
+               "ys_scene_bvh")
+        dt = np.dtype([("min", "<f4", 3), ("max", "<f4", 3), ("left", "<u4"), ("span", "<u4")])
+        buf = (C.c_char * (32 * n_nodes.value)).from_address(nodes.value)
+        return (np.frombuffer(buf, dt).copy(),
+                np.ctypeslib.as_array(idx, (n_tris.value,)).copy())
+
+
+def make_camera(width, height, focal=35.0, fnum=0.0, pos=(0, 0, 5), target=(0, 0, 0), up=(0, 0, 0), exposure=0.0,
+                sides=0) -> capi.YcCamera:
+    """Camera({w,h}, focal, fnum) + moveAndLookAt(pos, target, up) (camera.hpp:77-136)."""
+    cam = capi.YcCamera()
+    _check(lib().ys_camera_make(width, height, focal, fnum, _f3(pos), _f3(target), _f3(up), exposure, sides,
+                                C.byref(cam)), "ys_camera_make")
+    return cam
+
+
+class Context:
+    """Device layer (yc_*): one CUDA context + stream on one GPU."""
+
+    def __init__(self, device: int = 0, max_depth: int = 30, max_paths: int = 0):
+        self._h = C.c_void_p()
+        opts = capi.YcOptions(maxDepth=max_depth, maxPathsInFlight=max_paths)
+        _check(lib().yc_create(device, C.byref(opts), C.byref(self._h)), "yc_create",
+               b"(no usable CUDA device: yart_b200 has no CPU fallback)")
+        self.frame = None
+
+    def close(self):
+        if self._h:
+            lib().yc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        _check(rc, what, lib().yc_last_error(self._h) or b"")
+
+    def upload_scene(self, scene: Scene):
+        self._ck(lib().yc_upload_scene(self._h, C.byref(scene.flat)), "yc_upload_scene")
+
+    def set_camera(self, cam: capi.YcCamera):
+        self._ck(lib().yc_set_camera(self._h, C.byref(cam)), "yc_set_camera")
+
+    def begin_frame(self, width, height, total_samples, tile_size=64, background=(0, 0, 0), tonemap=TONEMAP_AGX,
+                    estimator=ESTIMATOR_GMON, shard_index=0, shard_count=1):
+        f = capi.YcFrameDesc(width, height, total_samples, tile_size, _f3(background), tonemap, estimator, shard_index,
+                             shard_count)
+        self._ck(lib().yc_begin_frame(self._h, C.byref(f)), "yc_begin_frame")
+        self.frame = f
+
+    def render_wave(self, sample_offset, wave_samples, taken_before, rect=None):
+        r = capi.YcRect(0, 0, self.frame.width, self.frame.height) if rect is None else capi.YcRect(*rect)
+        self._ck(lib().yc_render_wave(self._h, r, sample_offset, wave_samples, taken_before), "yc_render_wave")
+
+    def resolve(self, want_hdr=True, want_ldr=True):
+        h, w = self.frame.height, self.frame.width
+        hdr = np.empty((h, w, 4), np.float32) if want_hdr else None
+        ldr = np.empty((h, w, 4), np.float32) if want_ldr else None
+        st = capi.YcStats()
+        self._ck(lib().yc_resolve(self._h, hdr.ctypes.data if want_hdr else None, ldr.ctypes.data if want_ldr else None,
+                                  C.byref(st)), "yc_resolve")
+        return hdr, ldr, st
+
+    def stats(self) -> capi.YcStats:
+        st = capi.YcStats()
+        self._ck(lib().yc_resolve(self._h, None, None, C.byref(st)), "yc_resolve")
+        return st
+
+    def frame_device_ptrs(self):
+        hdr, ldr, n = C.c_void_p(), C.c_void_p(), C.c_size_t()
+        self._ck(lib().yc_frame_device_ptrs(self._h, C.byref(hdr), C.byref(ldr), C.byref(n)), "yc_frame_device_ptrs")
+        return hdr.value, ldr.value, n.value
+
+    def retonemap(self):
+        self._ck(lib().yc_retonemap(self._h), "yc_retonemap")
+
+    def set_profiling(self, on: bool):
+        self._ck(lib().yc_set_profiling(self._h, int(on)), "yc_set_profiling")
+
+    def trace(self, rays: np.ndarray, mode=TRACE_CLOSEST):
+        """rays: (n, 8) float32 rows {o[3], tmin, d[3], tmax} → (hits structured array, stats)."""
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
+        hits = np.zeros(len(rays), HIT_DTYPE)
+        st = capi.YcStats()
+        self._ck(lib().yc_trace(self._h, rays.ctypes.data, len(rays), mode, hits.ctypes.data, C.byref(st)), "yc_trace")
+        return hits, st
+
+    def device_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        self._ck(lib().yc_device_alloc(self._h, nbytes, C.byref(p)), "yc_device_alloc")
+        return p.value
+
+    def device_free(self, ptr: int):
+        self._ck(lib().yc_device_free(self._h, ptr), "yc_device_free")
+
+    def h2d(self, dst: int, src: np.ndarray):
+        src = np.ascontiguousarray(src)
+        self._ck(lib().yc_memcpy_h2d(self._h, dst, src.ctypes.data, src.nbytes), "yc_memcpy_h2d")
+
+    def d2h(self, dst: np.ndarray, src: int):
+        self._ck(lib().yc_memcpy_d2h(self._h, dst.ctypes.data, src, dst.nbytes), "yc_memcpy_d2h")
+
+    def generate_primary_rays(self, sample_offset: int, spp: int, rays_dev: int):
+        self._ck(lib().yc_generate_primary_rays(self._h, sample_offset, spp, rays_dev), "yc_generate_primary_rays")
+
+    def trace_device(self, rays_dev: int, n: int, hits_dev: int, mode=TRACE_CLOSEST, repeat=1) -> float:
+        ms = C.c_float()
+        self._ck(lib().yc_trace_device(self._h, rays_dev, n, mode, hits_dev, repeat, C.byref(ms)), "yc_trace_device")
+        return ms.value
+
+    def kat(self, kind: str, blob: bytes, out_words: int) -> np.ndarray:
+        out = np.zeros(out_words, np.float32)
+        buf = np.frombuffer(blob, np.uint8)
+        self._ck(lib().yc_kat(self._h, kind.encode(), buf.ctypes.data, len(blob), out.ctypes.data, out.nbytes),
+                 f"yc_kat({kind})")
+        return out
+
+
+HIT_DTYPE = np.dtype([("t", "<f4"), ("prim", "<u4"), ("material", "<i4"), ("lightIdx", "<i4"), ("backSide", "<u4"),
+                      ("didHit", "<u4"), ("p", "<f4", 3), ("n", "<f4", 3), ("tg", "<f4", 3), ("uv", "<f4", 2),
+                      ("attenuation", "<f4", 3)])
+COMPACT_HIT_DTYPE = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("prim", "<u4"), ("node", "<i4")])
+
+
+class Renderer:
+    """Mirror of cpu::TileRenderer's public surface (tile-renderer.hpp:27-38) + Renderer
+    (renderer.hpp:53-95): knobs as attributes, render()/abort()/wait()/render_sync()."""
+
+    def __init__(self, width, height, camera: capi.YcCamera, scene: Scene | None = None, samples=64,
+                 first_wave_samples=None, max_wave_samples=None, tile_size=64, max_depth=30, background=(0, 0, 0),
+                 tonemap=TONEMAP_AGX, estimator=ESTIMATOR_GMON, shard_index=0, shard_count=1, device=0):
+        # TileRenderer defaults: samples 64, firstWaveSamples 64, maxWaveSamples 128, tileSize 64 (:11-14)
+        s = capi.YrSettings(width, height, samples, 64 if first_wave_samples is None else first_wave_samples,
+                            128 if max_wave_samples is None else max_wave_samples, tile_size, max_depth,
+                            _f3(background), tonemap, estimator, shard_index, shard_count, device)
+        self.settings = s
+        self.scene = scene
+        self._h = C.c_void_p()
+        self._cb = None
+        _check(lib().yr_create(C.byref(s), scene._h if scene else None, C.byref(camera), C.byref(self._h)), "yr_create",
+               b"(no usable CUDA device: yart_b200 has no CPU fallback)")
+
+    def close(self):
+        if self._h:
+            lib().yr_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        _check(rc, what, lib().yr_last_error(self._h) or b"")
+
+    def on_wave_complete(self, fn):
+        """fn(render_data: dict, wave_data: dict) — Renderer::onRenderWaveComplete (renderer.hpp:60-75)."""
+        def tramp(rd, wd, _user):
+            r, w = rd.contents, wd.contents
+            fn(dict(samples_taken=r.samplesTaken, total_samples=r.totalSamples, total_rays=r.totalRays,
+                    total_time_ms=r.totalTimeMs),
+               dict(wave=w.wave, wave_samples=w.waveSamples, rays=w.rays, time_ms=w.timeMs))
+        self._cb = capi.WAVE_CALLBACK(tramp)
+        self._ck(lib().yr_set_wave_callback(self._h, self._cb, None), "yr_set_wave_callback")
+
+    def render(self):
+        self._ck(lib().yr_render(self._h), "yr_render")
+
+    def abort(self):
+        self._ck(lib().yr_abort(self._h), "yr_abort")
+
+    def wait(self):
+        self._ck(lib().yr_wait(self._h), "yr_wait")
+
+    def render_sync(self) -> dict:
+        d = capi.YrRenderData()
+        self._ck(lib().yr_render_sync(self._h, C.byref(d)), "yr_render_sync")
+        return dict(samples_taken=d.samplesTaken, total_samples=d.totalSamples, total_rays=d.totalRays,
+                    total_time_ms=d.totalTimeMs)
+
+    def read(self, want_hdr=True, want_ldr=True):
+        h, w = self.settings.height, self.settings.width
+        hdr = np.empty((h, w, 4), np.float32) if want_hdr else None
+        ldr = np.empty((h, w, 4), np.float32) if want_ldr else None
+        st = capi.YcStats()
+        self._ck(lib().yr_read(self._h, hdr.ctypes.data if want_hdr else None, ldr.ctypes.data if want_ldr else None,
+                               C.byref(st)), "yr_read")
+        return hdr, ldr, st
+
+    def context_handle(self):
+        return lib().yr_context(self._h)

@@ -5,11 +5,17 @@
 // without FMA contraction and its `fma()` is two roundings (vec.hpp:325-334), so the product must
 // not fuse either.  IEEE division / sqrt are nvcc defaults (-prec-div/-prec-sqrt).
 #pragma once
+#ifdef YB_HOSTSIM
+#include "hostshim.hpp"
+#define YB_DEV inline
+#define YB_CONST static const
+#else
 #include <cuda_runtime.h>
+#define YB_DEV __device__ __forceinline__
+#define YB_CONST __device__ __constant__
+#endif
 #include <math.h>
 #include <stdint.h>
-
-#define YB_DEV __device__ __forceinline__
 
 namespace yb {
 

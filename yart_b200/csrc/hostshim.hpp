@@ -1,0 +1,33 @@
+// hostshim.hpp — lets the device headers and the wavefront driver compile with plain g++
+// (-DYB_HOSTSIM) so that tests/hostsim can run the SAME code on the CPU, single-threaded, and
+// compare it bit for bit with oracle/_ref where no GPU is available.  Test infrastructure only:
+// the product library (libyart_b200.so) is always built by nvcc without this file.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+
+struct float4 {
+  float x, y, z, w;
+};
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+template <typename T>
+static inline T __ldg(const T* p) { return *p; }
+static inline uint32_t __brev(uint32_t v) {
+  v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
+  v = ((v >> 2) & 0x33333333u) | ((v & 0x33333333u) << 2);
+  v = ((v >> 4) & 0x0f0f0f0fu) | ((v & 0x0f0f0f0fu) << 4);
+  v = ((v >> 8) & 0x00ff00ffu) | ((v & 0x00ff00ffu) << 8);
+  return (v >> 16) | (v << 16);
+}
+static inline uint32_t __float_as_uint(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  return u;
+}
+static inline float __uint_as_float(uint32_t u) {
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}

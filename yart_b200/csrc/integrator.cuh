@@ -1,0 +1,302 @@
+// integrator.cuh — per-path stages of the wavefront MIS+NEE integrator.
+//
+// One camera path of the reference's MISIntegrator::Li (src/cpu/mis-integrator.cpp:13-106, with Ld
+// :111-133 and unoccluded :135-148) is cut into stages that run as separate kernels over queues of
+// path indices:
+//     raygen   RayIntegrator::sample            ray-integrator.cpp:11-18, integrator.cpp:20
+//     extend   testNode (closest hit)           mis-integrator.cpp:26
+//     shade    miss/env, BSDF sample, emission, NEE set-up, throughput, next ray, Russian roulette
+//                                                mis-integrator.cpp:27-102, 111-124, 128-132
+//     shadow   unoccluded() + the L += of Ld    mis-integrator.cpp:79-80, 124-126, 135-148
+// Every sampler draw happens in the reference's order.  Only when the scene
+// has alpha-tested materials can traversal consume draws (ray-integrator.cpp:211); then the
+// Russian-roulette draw, which follows the shadow ray's draws, is deferred to the head of the next
+// extend stage (DEFER_RR) and shadow writes the path's sampler dimension back.
+// Additions into L happen in the reference's order (shade(b) → shadow(b) → shade(b+1)), so a path's
+// radiance has the same rounding sequence as the oracle's.
+#pragma once
+#include "camera.cuh"
+#include "lights.cuh"
+#include "traverse.cuh"
+
+namespace yb {
+
+constexpr uint32_t kFlagDepthMask = 0xffu;
+constexpr uint32_t kFlagSpecular = 1u << 8;
+constexpr uint32_t kFlagRegularized = 1u << 9;
+constexpr uint32_t kFlagPendingRR = 1u << 10;
+constexpr int32_t kHitMiss = -1;
+constexpr int32_t kHitDead = -2;  // path ended by a deferred Russian roulette: shade must skip it
+constexpr uint32_t kBackSideBit = 1u << 30;
+
+// Path state in HBM, SoA over path slots (one slot per pixel-sample of the current chunk).
+struct PathState {
+  float4* rayO;     // origin.xyz, lastPdf
+  float4* rayD;     // dir.xyz, accRoughness
+  float4* L;        // radiance.rgb, unused
+  float4* att;      // throughput.rgb, unused
+  uint32_t* dim;    // sampler dimension
+  uint32_t* flags;  // depth | kFlag*
+  float4* hitA;     // t, u, v, prim (bits)
+  int32_t* hitB;    // node | backSide << 30, or kHitMiss / kHitDead
+};
+
+// NEE requests, compacted (one per shadow ray of the current bounce).
+struct ShadowQueue {
+  float4* o;    // origin.xyz, tMax
+  float4* d;    // dir.xyz, |wi . n|
+  float4* lif;  // (Li * f).rgb, pdfBSDF + pdfLight
+  float4* att;  // path throughput before this bounce's update .rgb, path index (bits)
+};
+
+struct Counters {
+  unsigned long long raysReference, raysExtend, raysShadow, boxTests, triTests;
+};
+
+// Everything a stage needs besides the scene.
+struct WaveParams {
+  YcCamera cam;
+  SamplerConfig smp;
+  float bg[3];
+  uint32_t maxDepth;
+  // chunk geometry: path i ↔ pixel pixelList[pixBase + i % nPix], sample s0 + i / nPix
+  const uint32_t* pixelList;  // x | y << 16
+  uint32_t pixBase, nPix, s0;
+};
+
+YB_DEV void pathPixelSample(const WaveParams& w, uint32_t i, uint32_t& px, uint32_t& py, uint32_t& sample) {
+  const uint32_t pix = w.pixelList[w.pixBase + i % w.nPix];
+  px = pix & 0xffffu;
+  py = pix >> 16;
+  sample = w.s0 + i / w.nPix;
+}
+
+YB_DEV Sampler pathSampler(const WaveParams& w, uint32_t i, uint32_t dim) {
+  uint32_t px, py, s;
+  pathPixelSample(w, i, px, py, s);
+  Sampler smp;
+  smp.start(w.smp, px, py, s);
+  smp.dim = dim;
+  return smp;
+}
+
+// ---- raygen ---------------------------------------------------------------------------
+YB_DEV void raygenStage(const WaveParams& w, const PathState& ps, uint32_t i) {
+  uint32_t px, py, s;
+  pathPixelSample(w, i, px, py, s);
+  Sampler smp;
+  smp.start(w.smp, px, py, s);  // Integrator::render, integrator.cpp:20
+  V3 o, d;
+  primaryRay(w.cam, smp, px, py, o, d);
+  ps.rayO[i] = make_float4(o.x, o.y, o.z, 0.0f);
+  ps.rayD[i] = make_float4(d.x, d.y, d.z, 0.0f);
+  ps.L[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  ps.att[i] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+  ps.dim[i] = smp.dim;
+  ps.flags[i] = 0u;
+}
+
+// Russian roulette, mis-integrator.cpp:97-102.  Returns false when the path dies.
+YB_DEV bool russianRoulette(Sampler& smp, uint32_t depth, V3& att) {
+  if (depth > 1 && maxComponent(att) < 1.0f) {
+    const float a = 1.0f - maxComponent(att);
+    const float q = 0.0f < a ? a : 0.0f;  // std::max(0.0f, a)
+    if (smp.get1D() < q) return false;
+    att /= 1.0f - q;
+  }
+  return true;
+}
+
+// ---- extend ---------------------------------------------------------------------------
+// ALPHA: scene has alpha-tested materials (traversal draws from the path's sampler).
+template <bool ALPHA, bool COUNT>
+YB_DEV void extendStage(const DScene& sc, const WaveParams& w, const PathState& ps, uint32_t i, TravStack& stack,
+                        TraceCounters& cnt) {
+  const float4 ro = ps.rayO[i], rd = ps.rayD[i];
+  Sampler smp;
+  if (ALPHA) {
+    smp = pathSampler(w, i, ps.dim[i]);
+    const uint32_t fl = ps.flags[i];
+    if (fl & kFlagPendingRR) {
+      const float4 a4 = ps.att[i];
+      V3 att(a4.x, a4.y, a4.z);
+      const uint32_t depth = fl & kFlagDepthMask;
+      const bool alive = russianRoulette(smp, depth, att) && depth < w.maxDepth;
+      ps.flags[i] = fl & ~kFlagPendingRR;
+      ps.dim[i] = smp.dim;
+      if (!alive) {
+        ps.hitB[i] = kHitDead;
+        return;
+      }
+      ps.att[i] = make_float4(att.x, att.y, att.z, 0.0f);
+    }
+  }
+  TraceState st;
+  st.hit.t = INFINITY;
+  st.hit.node = kHitMiss;
+  st.attenuation = V3(1.0f);
+  traceScene<false, ALPHA, COUNT, false>(sc, V3(ro.x, ro.y, ro.z), V3(rd.x, rd.y, rd.z), st, stack, &smp, cnt);
+  if (ALPHA) ps.dim[i] = smp.dim;
+  ps.hitA[i] = make_float4(st.hit.t, st.hit.u, st.hit.v, __uint_as_float(st.hit.prim));
+  ps.hitB[i] = st.hit.node < 0 ? kHitMiss : int32_t(uint32_t(st.hit.node) | (st.hit.backSide ? kBackSideBit : 0u));
+}
+
+// ---- shade ----------------------------------------------------------------------------
+struct ShadowRequest {
+  V3 o, d, lif, att;
+  float tMax, absDotN, denom;
+};
+
+enum : uint32_t { kShadeContinue = 1u, kShadeShadow = 2u };
+
+// Returns kShade* bits; `rq` is filled when kShadeShadow is set.  DEFER_RR ⇔ scene has alpha.
+template <bool DEFER_RR>
+YB_DEV uint32_t shadeStage(const DScene& sc, const WaveParams& w, const PathState& ps, uint32_t i, ShadowRequest& rq,
+                           uint32_t& raysReference) {
+  const int32_t hb = ps.hitB[i];
+  if (hb == kHitDead) return 0u;
+  raysReference += 1;  // mis-integrator.cpp:22
+  const float4 ro4 = ps.rayO[i], rd4 = ps.rayD[i], L4 = ps.L[i], a4 = ps.att[i];
+  const V3 rayO(ro4.x, ro4.y, ro4.z), rayD(rd4.x, rd4.y, rd4.z);
+  float lastPdf = ro4.w, accRoughness = rd4.w;
+  V3 L(L4.x, L4.y, L4.z), att(a4.x, a4.y, a4.z);
+  uint32_t fl = ps.flags[i];
+  uint32_t depth = fl & kFlagDepthMask;
+  const bool specularBounce = (fl & kFlagSpecular) != 0, regularized = (fl & kFlagRegularized) != 0;
+
+  if (hb == kHitMiss) {
+    // mis-integrator.cpp:27-43 — Le(octahedralUV(ray.dir)) ignores the light's transform
+    for (uint32_t k = 0; k < sc.nInf; k++) {
+      const YcLight& light = sc.lights[sc.infLights[k]];
+      const V3 Le = lightLe(sc, light, octahedralUV(rayD));
+      if (depth == 0 || specularBounce) {
+        L += att * Le;
+      } else {
+        const float pdfLight = lightPdf(sc, light, rayD);
+        const float wBSDF = lastPdf / (lastPdf + pdfLight);
+        L += att * wBSDF * Le;
+      }
+    }
+    L += att * V3(w.bg);
+    ps.L[i] = make_float4(L.x, L.y, L.z, 0.0f);
+    return 0u;
+  }
+
+  HitRec h;
+  const float4 ha = ps.hitA[i];
+  h.t = ha.x, h.u = ha.y, h.v = ha.z, h.prim = __float_as_uint(ha.w);
+  h.node = int32_t(uint32_t(hb) & ~kBackSideBit);
+  h.backSide = (uint32_t(hb) & kBackSideBit) ? 1u : 0u;
+  const SurfaceHit hit = resolveHit(sc, h, rayO, rayD);
+  const YcMaterial& mat = sc.materials[hit.material];
+  const Bsdf bsdf(sc, mat);
+  Sampler smp = pathSampler(w, i, ps.dim[i]);
+  const V3 wo = -rayD;
+
+  // mis-integrator.cpp:46-58
+  const V2 u = smp.get2D();
+  const float uc = smp.get1D();
+  const float uc2 = smp.get1D();
+  const BSDFSample res = bsdf.sample(wo, hit.n, hit.tg, hit.uv, u, uc, uc2, regularized);
+
+  // mis-integrator.cpp:61-73 (lastHit.p is this ray's origin: ray = Ray(hit.p, wi), lastHit = hit)
+  if (res.is(Emitted)) {
+    if (depth == 0 || specularBounce) {
+      L += att * res.Le;
+    } else if (hit.lightIdx != -1) {
+      const YcLight& light = sc.lights[hit.lightIdx];
+      const float pdfLight = lightPdf(sc, light, wo) * length2(rayO - hit.p) *
+                             lightPickProbability(sc, uint32_t(hit.lightIdx)) / absDot(wo, hit.n);
+      const float wBSDF = lastPdf / (lastPdf + pdfLight);
+      L += att * wBSDF * res.Le;
+    }
+  }
+
+  uint32_t result = 0u;
+  if (res.is(Reflected | Transmitted)) {
+    // mis-integrator.cpp:79-80 → Ld, :111-133
+    if (!res.is(Emitted | Specular) && sc.nLights != 0) {
+      const float ucl = smp.get1D();
+      const V2 ul = smp.get2D();
+      const PickedLight pick = pickLight(sc, ucl);
+      const YcLight& light = sc.lights[pick.index];
+      const LightSample ls = lightSample(sc, light, hit.p, ul);
+      const V3 f = bsdf.f(wo, ls.wi, hit.n, hit.tg, hit.uv);
+      if (length2(f) != 0.0f) {
+        // unoccluded(), :135-148
+        const V3 to = ls.p - hit.p;
+        rq.o = hit.p;
+        rq.d = normalized(to);
+        rq.tMax = length(to) - 0.001f;
+        const float pdfBSDF = bsdf.pdf(wo, ls.wi, hit.n, hit.tg, hit.uv);
+        float pdfLight = pick.p * ls.pdf / absDot(ls.n, ls.wi);
+        if (light.type == YC_LIGHT_AREA) pdfLight *= length2(hit.p - ls.p);
+        rq.lif = ls.Li * f;
+        rq.absDotN = absDot(ls.wi, hit.n);
+        rq.denom = pdfBSDF + pdfLight;
+        rq.att = att;
+        result |= kShadeShadow;
+      }
+    }
+    // mis-integrator.cpp:83-95
+    const V3 fcos = res.f * absDot(res.wi, hit.n);
+    att *= fcos / res.pdf;
+    if (h.backSide) att *= bsdf.attenuation(h.t);
+    fl = 0u;
+    if (res.is(Specular)) fl |= kFlagSpecular;
+    accRoughness += res.roughness;
+    if (accRoughness > 0.5f) fl |= kFlagRegularized;
+    lastPdf = res.pdf;
+    depth++;
+    bool alive = true;
+    if (DEFER_RR) {
+      fl |= kFlagPendingRR;
+      // a path at maxDepth still owes its roulette draw to nobody: the loop ends either way
+      alive = depth < w.maxDepth;
+    } else {
+      alive = russianRoulette(smp, depth, att) && depth < w.maxDepth;
+    }
+    if (alive) {
+      ps.rayO[i] = make_float4(hit.p.x, hit.p.y, hit.p.z, lastPdf);
+      ps.rayD[i] = make_float4(res.wi.x, res.wi.y, res.wi.z, accRoughness);
+      ps.att[i] = make_float4(att.x, att.y, att.z, 0.0f);
+      ps.flags[i] = fl | (depth & kFlagDepthMask);
+      result |= kShadeContinue;
+    }
+  }
+  ps.dim[i] = smp.dim;
+  ps.L[i] = make_float4(L.x, L.y, L.z, 0.0f);
+  return result;
+}
+
+// ---- shadow ---------------------------------------------------------------------------
+// Returns 1 if the NEE sample contributed (the ray the reference counts, mis-integrator.cpp:126).
+template <bool ALPHA, bool COUNT>
+YB_DEV uint32_t shadowStage(const DScene& sc, const WaveParams& w, const PathState& ps, const ShadowQueue& q,
+                            uint32_t j, TravStack& stack, TraceCounters& cnt) {
+  const float4 o4 = q.o[j], d4 = q.d[j], l4 = q.lif[j], a4 = q.att[j];
+  const uint32_t i = __float_as_uint(a4.w);
+  Sampler smp;
+  if (ALPHA) smp = pathSampler(w, i, ps.dim[i]);
+  TraceState st;
+  st.hit.t = o4.w;
+  st.hit.node = kHitMiss;
+  st.attenuation = V3(1.0f);
+  // Without alpha-tested materials nothing observable depends on what an occluded NEE ray finds
+  // after its first occluder, so the any-hit walk may stop there; with them the draws must match.
+  const bool occluded = ALPHA ? traceScene<true, true, COUNT, false>(sc, V3(o4.x, o4.y, o4.z), V3(d4.x, d4.y, d4.z), st,
+                                                                     stack, &smp, cnt)
+                              : traceScene<true, false, COUNT, true>(sc, V3(o4.x, o4.y, o4.z), V3(d4.x, d4.y, d4.z), st,
+                                                                     stack, &smp, cnt);
+  if (ALPHA) ps.dim[i] = smp.dim;
+  if (occluded) return 0u;
+  // Ld: ls.Li * f * att / ... (mis-integrator.cpp:132), then L += attenuation * Ld (:80)
+  const V3 Ld = V3(l4.x, l4.y, l4.z) * st.attenuation * d4.w / l4.w;
+  const float4 L4 = ps.L[i];
+  V3 L(L4.x, L4.y, L4.z);
+  L += V3(a4.x, a4.y, a4.z) * Ld;
+  ps.L[i] = make_float4(L.x, L.y, L.z, 0.0f);
+  return 1u;
+}
+
+}  // namespace yb

@@ -17,7 +17,7 @@ struct SamplerConfig {
 
 // permutations[24][4], sampler.hpp:116-141 (the 24 permutations of {0,1,2,3} in the order the
 // reference lists them), packed 2 bits per digit: entry p, digit d → (kPerm[p] >> (2*d)) & 3.
-__device__ __constant__ uint8_t kPerm[24] = {
+YB_CONST uint8_t kPerm[24] = {
   0xE4, 0xB4, 0xD8, 0x78, 0x6C, 0x9C, 0xE1, 0xB1, 0xC9, 0x39, 0x2D, 0x8D,
   0xC6, 0x36, 0xD2, 0x72, 0x4E, 0x1E, 0x27, 0x87, 0x1B, 0x4B, 0x63, 0x93};
 

@@ -1,0 +1,943 @@
+// wavefront.cu — the device layer of libyart_b200.so: yc_* entry points (include/yart_cuda.h) and
+// the wavefront kernels that replace yart's src/cpu tile renderer on sm_100a.
+//
+//   raygen → [ extend → shade → shadow ]* → accumulate   per chunk of pixel-samples
+//   finalize (estimator value, wave blend, tonemap)      per wave
+//
+// Reference mapping: TileRenderer worker loop + finishTile (src/cpu/tile-renderer.hpp:161-191,
+// 205-239), Integrator::render (src/cpu/integrator.cpp:5-28), MISIntegrator::Li/Ld
+// (src/cpu/mis-integrator.cpp:13-148), RayIntegrator::testNode (src/cpu/ray-integrator.cpp:20-54).
+// The per-path arithmetic lives in integrator.cuh / traverse.cuh / bsdf.cuh / lights.cuh; this file
+// owns memory, queues, launch geometry and the C ABI.  Compile with -fmad=false (dmath.cuh).
+//
+// extend and shadow are persistent kernels: one CTA set sized to the SM count, each warp pulling
+// 32 queue entries at a time with one atomic (lane 0) and keeping its traversal stack in shared
+// memory; node and triangle records are read as 128-bit loads (traverse.cuh).  shade compacts the
+// surviving paths and the NEE requests into the next queues with warp-aggregated appends.
+#include <algorithm>
+#include <cstdarg>
+#include <vector>
+
+#include "estimator.cuh"
+#include "integrator.cuh"
+#include "rt.cuh"
+
+using namespace yb;
+
+// ---------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------
+enum { kCtrExtendHead = 0, kCtrNextCount = 1, kCtrShadowCount = 2, kCtrShadowHead = 3, kCtrCount = 4 };
+
+struct yc_ctx {
+  rt::Stream st;
+  int device = 0, smCount = 1;
+  std::string err;
+  YcOptions opts{};
+  uint32_t capacity = 0;
+
+  std::vector<void*> sceneAllocs;
+  DScene ds{};
+  bool hasScene = false;
+  YcCamera cam{};
+  bool hasCamera = false;
+
+  // frame
+  bool inFrame = false;
+  YcFrameDesc frame{};
+  std::vector<uint32_t> pixels;  // this shard's pixels, tile-major: x | y << 16
+  uint32_t* dPixels = nullptr;
+  uint32_t* dPixelsScratch = nullptr;
+  float4 *dHdr = nullptr, *dLdr = nullptr, *dBuckets = nullptr;
+  size_t bucketCapacity = 0;  // pixels per bucket plane
+
+  // wavefront storage (capacity path slots)
+  PathState ps{};
+  ShadowQueue sq{};
+  uint32_t *dQueueA = nullptr, *dQueueB = nullptr, *dCtr = nullptr;
+  Counters* dCounters = nullptr;
+  std::vector<void*> waveAllocs;
+
+  rt::Event ev0, ev1, evK0, evK1;
+  uint64_t launches = 0;
+  double gpuMs = 0, extendMs = 0;
+  uint64_t extendLaunches = 0, raysExtend = 0;
+  bool timeExtend = false;
+};
+
+static int fail(yc_ctx* c, int code, const char* fmt, ...) {
+  if (c) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    c->err = buf;
+  }
+  return code;
+}
+#define YC_TRY(expr)                                                        \
+  do {                                                                      \
+    const char* e_ = (expr);                                                \
+    if (e_) return fail(ctx, YC_ERR_CUDA, "%s: %s", #expr, e_);             \
+  } while (0)
+
+template <typename T>
+static const char* devAlloc(std::vector<void*>& owner, T** p, size_t count) {
+  void* v = nullptr;
+  const char* e = rt::alloc(&v, count * sizeof(T));
+  if (e) return e;
+  owner.push_back(v);
+  *p = static_cast<T*>(v);
+  return nullptr;
+}
+
+template <typename T>
+static const char* devUpload(yc_ctx* ctx, const T* src, size_t count, const T** out) {
+  T* d = nullptr;
+  const char* e = devAlloc(ctx->sceneAllocs, &d, count);
+  if (e) return e;
+  if (count && (e = rt::h2d(ctx->st, d, src, count * sizeof(T)))) return e;
+  *out = d;
+  return nullptr;
+}
+
+static void freeAll(std::vector<void*>& v) {
+  for (void* p : v) rt::release(p);
+  v.clear();
+}
+
+// ---------------------------------------------------------------------------------------
+// stages as functors (run by rt::launchFor) and the two persistent traversal kernels
+// ---------------------------------------------------------------------------------------
+struct RaygenK {
+  WaveParams w;
+  PathState ps;
+  uint32_t* queue;
+  YB_DEV void operator()(uint32_t i) const {
+    raygenStage(w, ps, i);
+    queue[i] = i;
+  }
+};
+
+template <bool DEFER_RR>
+struct ShadeK {
+  DScene sc;
+  WaveParams w;
+  PathState ps;
+  ShadowQueue sq;
+  const uint32_t* queue;
+  uint32_t* nextQueue;
+  uint32_t* ctr;
+  Counters* counters;
+  YB_DEV void operator()(uint32_t j) const {
+    const uint32_t i = queue[j];
+    ShadowRequest rq;
+    uint32_t rays = 0;
+    const uint32_t r = shadeStage<DEFER_RR>(sc, w, ps, i, rq, rays);
+    aggregatedCount(&counters->raysReference, rays);
+    if (r & kShadeContinue) nextQueue[aggregatedAppend(ctr + kCtrNextCount)] = i;
+    if (r & kShadeShadow) {
+      const uint32_t k = aggregatedAppend(ctr + kCtrShadowCount);
+      sq.o[k] = make_float4(rq.o.x, rq.o.y, rq.o.z, rq.tMax);
+      sq.d[k] = make_float4(rq.d.x, rq.d.y, rq.d.z, rq.absDotN);
+      sq.lif[k] = make_float4(rq.lif.x, rq.lif.y, rq.lif.z, rq.denom);
+      sq.att[k] = make_float4(rq.att.x, rq.att.y, rq.att.z, __uint_as_float(i));
+    }
+  }
+};
+
+// Integrator::render's estimator.addSample loop for one chunk (integrator.cpp:19-24): pixel p adds
+// its K samples in sample order into bucket (sample index within the wave) % m.
+struct AccumulateK {
+  PathState ps;
+  float4* buckets;
+  size_t planeStride;
+  uint32_t pixBase, nPix, K, waveSampleBase, m, estimator;
+  float exposureScale;
+  YB_DEV void operator()(uint32_t p) const {
+    for (uint32_t k = 0; k < K; k++) {
+      const float4 L4 = ps.L[size_t(k) * nPix + p];
+      const V3 s = V3(L4.x, L4.y, L4.z) * exposureScale;
+      const uint32_t b = estimator == YC_ESTIMATOR_MEAN ? 0u : (waveSampleBase + k) % m;
+      if (estimatorAccepts(int(estimator), s)) {
+        float4* slot = buckets + size_t(b) * planeStride + (pixBase + p);
+        float4 v = *slot;
+        v.x += s.x, v.y += s.y, v.z += s.z;
+        v.w = __uint_as_float(__float_as_uint(v.w) + 1u);
+        *slot = v;
+      }
+    }
+  }
+};
+
+// Estimator::getValue + TileRenderer::finishTile's blend and tonemap (tile-renderer.hpp:220-239).
+struct FinalizeK {
+  const uint32_t* pixelList;
+  float4* buckets;
+  size_t planeStride;
+  float4 *hdr, *ldr;
+  uint32_t width, m, estimator, waveSamples, tonemap;
+  float wCurrent, wWave;
+  YB_DEV void operator()(uint32_t p) const {
+    V3 acc[kMaxBuckets];
+    uint32_t cnt[kMaxBuckets];
+    for (uint32_t b = 0; b < m; b++) {
+      float4* slot = buckets + size_t(b) * planeStride + p;
+      const float4 v = *slot;
+      acc[b] = V3(v.x, v.y, v.z);
+      cnt[b] = __float_as_uint(v.w);
+      *slot = make_float4(0.0f, 0.0f, 0.0f, 0.0f);  // ready for the next wave
+    }
+    const V3 wave = estimatorValue(int(estimator), acc, cnt, int(m), waveSamples);
+    const uint32_t pix = pixelList[p];
+    const size_t idx = size_t(pix >> 16) * width + (pix & 0xffffu);
+    const float4 cur = hdr[idx];
+    float4 h;
+    h.x = cur.x * wCurrent + wave.x * wWave;
+    h.y = cur.y * wCurrent + wave.y * wWave;
+    h.z = cur.z * wCurrent + wave.z * wWave;
+    h.w = cur.w * wCurrent + 1.0f * wWave;
+    hdr[idx] = h;
+    if (tonemap == YC_TONEMAP_NONE) {
+      ldr[idx] = h;
+    } else {
+      const V3 t = agx(V3(h.x, h.y, h.z), agxLook(tonemap));
+      ldr[idx] = make_float4(t.x, t.y, t.z, 1.0f);
+    }
+  }
+};
+
+struct RetonemapK {
+  float4 *hdr, *ldr;
+  uint32_t tonemap;
+  YB_DEV void operator()(uint32_t idx) const {
+    const float4 h = hdr[idx];
+    if (tonemap == YC_TONEMAP_NONE) {
+      ldr[idx] = h;
+    } else {
+      const V3 t = agx(V3(h.x, h.y, h.z), agxLook(tonemap));
+      ldr[idx] = make_float4(t.x, t.y, t.z, 1.0f);
+    }
+  }
+};
+
+#ifdef YB_HOSTSIM
+struct HostStack {
+  uint32_t ref[kShStack];
+  float d[kShStack];
+  TravStack ts;
+  HostStack() {
+    ts.shRef = ref;
+    ts.shD = d;
+    ts.stride = 1;
+  }
+};
+template <bool ALPHA, bool COUNT>
+static void runExtend(yc_ctx* ctx, const WaveParams& w, const uint32_t* queue, uint32_t n) {
+  HostStack hs;
+  TraceCounters cnt;
+  for (uint32_t j = 0; j < n; j++) extendStage<ALPHA, COUNT>(ctx->ds, w, ctx->ps, queue[j], hs.ts, cnt);
+  ctx->dCounters->boxTests += cnt.box;
+  ctx->dCounters->triTests += cnt.tri;
+}
+template <bool ALPHA, bool COUNT>
+static void runShadow(yc_ctx* ctx, const WaveParams& w) {
+  HostStack hs;
+  TraceCounters cnt;
+  const uint32_t n = ctx->dCtr[kCtrShadowCount];
+  uint32_t contributed = 0;
+  for (uint32_t j = 0; j < n; j++) contributed += shadowStage<ALPHA, COUNT>(ctx->ds, w, ctx->ps, ctx->sq, j, hs.ts, cnt);
+  ctx->dCounters->raysShadow += n;
+  ctx->dCounters->raysReference += contributed;
+  ctx->dCounters->boxTests += cnt.box;
+  ctx->dCounters->triTests += cnt.tri;
+}
+#else
+constexpr int kTraceBlock = 128;  // 4 warps per CTA
+
+// Persistent extend: each warp takes 32 queue entries per atomic; per-thread traversal stack in
+// shared memory ([entry][thread] so a warp's accesses hit 32 distinct banks).
+template <bool ALPHA, bool COUNT>
+__global__ void __launch_bounds__(kTraceBlock) extendKernel(DScene sc, WaveParams w, PathState ps, const uint32_t* queue,
+                                                            uint32_t n, uint32_t* ctr, Counters* counters) {
+  __shared__ uint32_t shRef[kShStack * kTraceBlock];
+  __shared__ float shD[kShStack * kTraceBlock];
+  TravStack stack;
+  stack.shRef = shRef + threadIdx.x;
+  stack.shD = shD + threadIdx.x;
+  stack.stride = kTraceBlock;
+  const int lane = threadIdx.x & 31;
+  TraceCounters cnt;
+  while (true) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(ctr + kCtrExtendHead, 32u);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= n) break;
+    const uint32_t j = base + lane;
+    if (j < n) extendStage<ALPHA, COUNT>(sc, w, ps, queue[j], stack, cnt);
+    __syncwarp();
+  }
+  if (COUNT) {
+    aggregatedCount(&counters->boxTests, cnt.box);
+    aggregatedCount(&counters->triTests, cnt.tri);
+  }
+}
+
+template <bool ALPHA, bool COUNT>
+__global__ void __launch_bounds__(kTraceBlock) shadowKernel(DScene sc, WaveParams w, PathState ps, ShadowQueue sq,
+                                                            uint32_t* ctr, Counters* counters) {
+  __shared__ uint32_t shRef[kShStack * kTraceBlock];
+  __shared__ float shD[kShStack * kTraceBlock];
+  TravStack stack;
+  stack.shRef = shRef + threadIdx.x;
+  stack.shD = shD + threadIdx.x;
+  stack.stride = kTraceBlock;
+  const int lane = threadIdx.x & 31;
+  const uint32_t n = ctr[kCtrShadowCount];
+  TraceCounters cnt;
+  uint32_t contributed = 0;
+  while (true) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(ctr + kCtrShadowHead, 32u);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= n) break;
+    const uint32_t j = base + lane;
+    if (j < n) contributed += shadowStage<ALPHA, COUNT>(sc, w, ps, sq, j, stack, cnt);
+    __syncwarp();
+  }
+  aggregatedCount(&counters->raysReference, contributed);
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counters->raysShadow, (unsigned long long)n);
+  if (COUNT) {
+    aggregatedCount(&counters->boxTests, cnt.box);
+    aggregatedCount(&counters->triTests, cnt.tri);
+  }
+}
+
+static int traceGrid(const yc_ctx* ctx, uint32_t n) {
+  // persistent: enough CTAs to fill every SM (registers cap residency well below this)
+  const int full = ctx->smCount * 8;
+  const int needed = int((n + kTraceBlock - 1) / kTraceBlock);
+  return std::max(1, std::min(full, needed));
+}
+
+template <bool ALPHA, bool COUNT>
+static void runExtend(yc_ctx* ctx, const WaveParams& w, const uint32_t* queue, uint32_t n) {
+  if (ctx->timeExtend) rt::eventRecord(ctx->st, ctx->evK0);
+  extendKernel<ALPHA, COUNT><<<traceGrid(ctx, n), kTraceBlock, 0, ctx->st.s>>>(ctx->ds, w, ctx->ps, queue, n, ctx->dCtr,
+                                                                               ctx->dCounters);
+  if (ctx->timeExtend) rt::eventRecord(ctx->st, ctx->evK1);
+}
+template <bool ALPHA, bool COUNT>
+static void runShadow(yc_ctx* ctx, const WaveParams& w, uint32_t upperBound) {
+  shadowKernel<ALPHA, COUNT><<<traceGrid(ctx, upperBound), kTraceBlock, 0, ctx->st.s>>>(ctx->ds, w, ctx->ps, ctx->sq,
+                                                                                        ctx->dCtr, ctx->dCounters);
+}
+#endif
+
+// ---------------------------------------------------------------------------------------
+// lifecycle
+// ---------------------------------------------------------------------------------------
+extern "C" int yc_create(int device, const YcOptions* opts, yc_ctx** out) {
+  if (!out) return YC_ERR_INVALID;
+  *out = nullptr;
+  yc_ctx* ctx = new (std::nothrow) yc_ctx();
+  if (!ctx) return YC_ERR_INVALID;
+  if (opts) ctx->opts = *opts;
+  if (ctx->opts.maxDepth == 0) ctx->opts.maxDepth = 30;  // RayIntegrator::m_maxDepth, ray-integrator.hpp:14
+  ctx->capacity = ctx->opts.maxPathsInFlight ? ctx->opts.maxPathsInFlight : (8u << 20);
+  ctx->device = device;
+  const char* e = rt::init(device, ctx->st, ctx->smCount);
+  if (e) {
+    // there is no CPU fallback: without a usable device the context does not exist
+    fprintf(stderr, "yart_b200: cannot create a CUDA context on device %d: %s\n", device, e);
+    delete ctx;
+    return YC_ERR_NO_DEVICE;
+  }
+  rt::eventCreate(ctx->ev0);
+  rt::eventCreate(ctx->ev1);
+  rt::eventCreate(ctx->evK0);
+  rt::eventCreate(ctx->evK1);
+  *out = ctx;
+  return YC_OK;
+}
+
+static void freeFrame(yc_ctx* ctx) {
+  rt::release(ctx->dPixels);
+  rt::release(ctx->dPixelsScratch);
+  rt::release(ctx->dHdr);
+  rt::release(ctx->dLdr);
+  rt::release(ctx->dBuckets);
+  ctx->dPixels = ctx->dPixelsScratch = nullptr;
+  ctx->dHdr = ctx->dLdr = ctx->dBuckets = nullptr;
+  ctx->inFrame = false;
+}
+
+extern "C" void yc_destroy(yc_ctx* ctx) {
+  if (!ctx) return;
+  rt::sync(ctx->st);
+  freeFrame(ctx);
+  freeAll(ctx->sceneAllocs);
+  freeAll(ctx->waveAllocs);
+  rt::eventDestroy(ctx->ev0);
+  rt::eventDestroy(ctx->ev1);
+  rt::eventDestroy(ctx->evK0);
+  rt::eventDestroy(ctx->evK1);
+  rt::destroy(ctx->st);
+  delete ctx;
+}
+
+extern "C" const char* yc_last_error(const yc_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int yc_synchronize(yc_ctx* ctx) {
+  if (!ctx) return YC_ERR_INVALID;
+  YC_TRY(rt::sync(ctx->st));
+  return YC_OK;
+}
+
+extern "C" int yc_upload_scene(yc_ctx* ctx, const YcScene* s) {
+  if (!ctx || !s) return YC_ERR_INVALID;
+  if (!s->nodes || s->nNodes == 0 || !s->lutTables) return fail(ctx, YC_ERR_INVALID, "scene has no nodes or no LUT tables");
+  for (uint32_t i = 0; i < s->nNodes; i++) {
+    const YcNode& n = s->nodes[i];
+    if (n.depth < 0 || n.depth >= YC_MAX_NODE_DEPTH || n.skip <= int32_t(i) || n.skip > int32_t(s->nNodes) ||
+        n.mesh >= int32_t(s->nMeshes) || n.parent >= int32_t(i))
+      return fail(ctx, YC_ERR_INVALID, "node %u is inconsistent (depth/skip/mesh/parent)", i);
+  }
+  for (uint64_t i = 0; i < s->nPrims; i++)
+    if (s->primMaterial[i] >= s->nMaterials) return fail(ctx, YC_ERR_INVALID, "primitive %llu: bad material", (unsigned long long)i);
+  YC_TRY(rt::sync(ctx->st));
+  freeAll(ctx->sceneAllocs);
+  ctx->hasScene = false;
+  DScene d{};
+  const YcBvhNode* bn = nullptr;
+  const YcBvhTri* bt = nullptr;
+  YC_TRY(devUpload(ctx, s->nodes, s->nNodes, &d.nodes));
+  YC_TRY(devUpload(ctx, s->meshes, s->nMeshes, &d.meshes));
+  YC_TRY(devUpload(ctx, s->bvhNodes, size_t(s->nBvhNodes), &bn));
+  YC_TRY(devUpload(ctx, s->bvhTris, size_t(s->nBvhTris), &bt));
+  d.bvhNodes = reinterpret_cast<const float4*>(bn);
+  d.bvhTris = reinterpret_cast<const float4*>(bt);
+  YC_TRY(devUpload(ctx, s->positions, size_t(s->nVerts) * 3, &d.positions));
+  YC_TRY(devUpload(ctx, s->normals, size_t(s->nVerts) * 3, &d.normals));
+  YC_TRY(devUpload(ctx, s->tangents, size_t(s->nVerts) * 4, &d.tangents));
+  YC_TRY(devUpload(ctx, s->uvs, size_t(s->nVerts) * 2, &d.uvs));
+  YC_TRY(devUpload(ctx, s->primIndices, size_t(s->nPrims) * 3, &d.primIndices));
+  YC_TRY(devUpload(ctx, s->primMaterial, size_t(s->nPrims), &d.primMaterial));
+  YC_TRY(devUpload(ctx, s->primLight, size_t(s->nPrims), &d.primLight));
+  YC_TRY(devUpload(ctx, s->materials, s->nMaterials, &d.materials));
+  YC_TRY(devUpload(ctx, s->textures, s->nTextures, &d.textures));
+  YC_TRY(devUpload(ctx, s->texelsU8, size_t(s->nTexelsU8), &d.texU8));
+  YC_TRY(devUpload(ctx, s->texelsF32, size_t(s->nTexelsF32), &d.texF32));
+  YC_TRY(devUpload(ctx, s->lights, s->nLights, &d.lights));
+  YC_TRY(devUpload(ctx, s->envDist, size_t(s->nEnvDist), &d.envDist));
+  YC_TRY(devUpload(ctx, s->infiniteLights, s->nInfinite, &d.infLights));
+  YC_TRY(devUpload(ctx, s->areaLights, s->nArea, &d.areaLights));
+  YC_TRY(devUpload(ctx, s->lightPowerCdf, s->nArea, &d.powerCdf));
+  YC_TRY(devUpload(ctx, s->lutTables, 14112, &d.lut));
+  d.nNodes = s->nNodes, d.nMeshes = s->nMeshes, d.nLights = s->nLights;
+  d.nInf = s->nInfinite, d.nArea = s->nArea, d.totalPower = s->totalPower, d.hasAlpha = s->hasAlpha;
+  ctx->ds = d;
+  ctx->hasScene = true;
+  return YC_OK;
+}
+
+extern "C" int yc_set_camera(yc_ctx* ctx, const YcCamera* cam) {
+  if (!ctx || !cam) return YC_ERR_INVALID;
+  ctx->cam = *cam;
+  ctx->hasCamera = true;
+  return YC_OK;
+}
+
+static int ensureWaveStorage(yc_ctx* ctx) {
+  if (!ctx->waveAllocs.empty()) return YC_OK;
+  const size_t P = ctx->capacity;
+  auto& own = ctx->waveAllocs;
+  YC_TRY(devAlloc(own, &ctx->ps.rayO, P));
+  YC_TRY(devAlloc(own, &ctx->ps.rayD, P));
+  YC_TRY(devAlloc(own, &ctx->ps.L, P));
+  YC_TRY(devAlloc(own, &ctx->ps.att, P));
+  YC_TRY(devAlloc(own, &ctx->ps.dim, P));
+  YC_TRY(devAlloc(own, &ctx->ps.flags, P));
+  YC_TRY(devAlloc(own, &ctx->ps.hitA, P));
+  YC_TRY(devAlloc(own, &ctx->ps.hitB, P));
+  YC_TRY(devAlloc(own, &ctx->sq.o, P));
+  YC_TRY(devAlloc(own, &ctx->sq.d, P));
+  YC_TRY(devAlloc(own, &ctx->sq.lif, P));
+  YC_TRY(devAlloc(own, &ctx->sq.att, P));
+  YC_TRY(devAlloc(own, &ctx->dQueueA, P));
+  YC_TRY(devAlloc(own, &ctx->dQueueB, P));
+  YC_TRY(devAlloc(own, &ctx->dCtr, size_t(kCtrCount)));
+  YC_TRY(devAlloc(own, &ctx->dCounters, size_t(1)));
+  YC_TRY(rt::zero(ctx->st, ctx->dCounters, sizeof(Counters)));
+  YC_TRY(rt::zero(ctx->st, ctx->dCtr, kCtrCount * sizeof(uint32_t)));
+  return YC_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// frame + waves
+// ---------------------------------------------------------------------------------------
+static uint32_t log2IntU(uint32_t v) {  // math_base.hpp:156-162 on integers (floor log2)
+  uint32_t r = 0;
+  while (v >>= 1) r++;
+  return r;
+}
+static uint32_t roundUpPow2(uint32_t v) {  // math_base.hpp:164-170
+  uint32_t p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+extern "C" int yc_begin_frame(yc_ctx* ctx, const YcFrameDesc* f) {
+  if (!ctx || !f) return YC_ERR_INVALID;
+  if (!ctx->hasScene) return fail(ctx, YC_ERR_NO_SCENE, "yc_begin_frame before yc_upload_scene");
+  if (!ctx->hasCamera) return fail(ctx, YC_ERR_STATE, "yc_begin_frame before yc_set_camera");
+  if (f->width == 0 || f->height == 0 || f->width > 65535 || f->height > 65535 || f->tileSize == 0 ||
+      f->totalSamples == 0 || f->estimator > YC_ESTIMATOR_MEAN || f->tonemap > YC_TONEMAP_AGX_PUNCHY)
+    return fail(ctx, YC_ERR_INVALID, "bad frame description");
+  const uint32_t shardCount = f->shardCount ? f->shardCount : 1;
+  if (f->shardIndex >= shardCount) return fail(ctx, YC_ERR_INVALID, "shardIndex >= shardCount");
+  YC_TRY(rt::sync(ctx->st));
+  freeFrame(ctx);
+  int rc = ensureWaveStorage(ctx);
+  if (rc != YC_OK) return rc;
+  ctx->frame = *f;
+  ctx->frame.shardCount = shardCount;
+  // tile list as TileRenderer::renderImpl builds it (tile-renderer.hpp:127-144), sharded by index
+  ctx->pixels.clear();
+  const uint32_t ts = f->tileSize;
+  const uint32_t tilesX = (f->width + ts - 1) / ts, tilesY = (f->height + ts - 1) / ts;
+  for (uint32_t ty = 0; ty < tilesY; ty++)
+    for (uint32_t tx = 0; tx < tilesX; tx++) {
+      const uint32_t index = ty * tilesX + tx;
+      if (index % shardCount != f->shardIndex) continue;
+      const uint32_t x0 = tx * ts, y0 = ty * ts;
+      const uint32_t tw = std::min(ts, f->width - x0), th = std::min(ts, f->height - y0);
+      for (uint32_t y = 0; y < th; y++)
+        for (uint32_t x = 0; x < tw; x++) ctx->pixels.push_back((x0 + x) | ((y0 + y) << 16));
+    }
+  const size_t nPix = ctx->pixels.size(), frameTexels = size_t(f->width) * f->height;
+  void* p = nullptr;
+  YC_TRY(rt::alloc(&p, std::max<size_t>(nPix, 1) * 4));
+  ctx->dPixels = static_cast<uint32_t*>(p);
+  YC_TRY(rt::alloc(&p, std::max<size_t>(nPix, 1) * 4));
+  ctx->dPixelsScratch = static_cast<uint32_t*>(p);
+  YC_TRY(rt::alloc(&p, frameTexels * sizeof(float4)));
+  ctx->dHdr = static_cast<float4*>(p);
+  YC_TRY(rt::alloc(&p, frameTexels * sizeof(float4)));
+  ctx->dLdr = static_cast<float4*>(p);
+  ctx->bucketCapacity = std::max<size_t>(nPix, 1);
+  YC_TRY(rt::alloc(&p, ctx->bucketCapacity * kMaxBuckets * sizeof(float4)));
+  ctx->dBuckets = static_cast<float4*>(p);
+  YC_TRY(rt::h2d(ctx->st, ctx->dPixels, ctx->pixels.data(), nPix * 4));
+  YC_TRY(rt::zero(ctx->st, ctx->dHdr, frameTexels * sizeof(float4)));
+  YC_TRY(rt::zero(ctx->st, ctx->dLdr, frameTexels * sizeof(float4)));
+  YC_TRY(rt::zero(ctx->st, ctx->dBuckets, ctx->bucketCapacity * kMaxBuckets * sizeof(float4)));
+  YC_TRY(rt::zero(ctx->st, ctx->dCounters, sizeof(Counters)));
+  YC_TRY(rt::sync(ctx->st));
+  ctx->launches = 0;
+  ctx->gpuMs = ctx->extendMs = 0;
+  ctx->extendLaunches = 0;
+  ctx->raysExtend = 0;
+  ctx->inFrame = true;
+  return YC_OK;
+}
+
+template <bool ALPHA>
+static int renderChunks(yc_ctx* ctx, const uint32_t* dList, uint32_t nPixCall, uint32_t sampleOffset, uint32_t waveSamples,
+                        uint32_t m) {
+  const YcFrameDesc& f = ctx->frame;
+  WaveParams w{};
+  w.cam = ctx->cam;
+  // SobolSampler ctor (sampler.hpp:74-82) as TileRenderer calls it: (totalSamples, {tileSize, tileSize})
+  w.smp.log2spp = log2IntU(f.totalSamples);
+  w.smp.nBase4Digits = log2IntU(roundUpPow2(f.tileSize)) + (w.smp.log2spp + 1) / 2;
+  memcpy(w.bg, f.background, sizeof w.bg);
+  w.maxDepth = ctx->opts.maxDepth;
+  w.pixelList = dList;
+  const float exposureScale = std::exp2(ctx->cam.exposure);  // integrator.cpp:23
+  const uint32_t B = std::min<uint32_t>(nPixCall, ctx->capacity);
+  const uint32_t Kmax = std::max<uint32_t>(1u, ctx->capacity / B);
+  for (uint32_t pixBase = 0; pixBase < nPixCall; pixBase += B) {
+    const uint32_t nPix = std::min(B, nPixCall - pixBase);
+    for (uint32_t sDone = 0; sDone < waveSamples;) {
+      const uint32_t K = std::min(Kmax, waveSamples - sDone);
+      const uint32_t nPaths = K * nPix;
+      w.pixBase = pixBase, w.nPix = nPix, w.s0 = sampleOffset + sDone;
+      uint32_t *qCur = ctx->dQueueA, *qNext = ctx->dQueueB;
+      rt::launchFor(ctx->st, nPaths, RaygenK{w, ctx->ps, qCur});
+      ctx->launches++;
+      uint32_t n = nPaths;
+      for (uint32_t bounce = 0; bounce < ctx->opts.maxDepth && n > 0; bounce++) {
+        YC_TRY(rt::zero(ctx->st, ctx->dCtr, kCtrCount * sizeof(uint32_t)));
+        runExtend<ALPHA, false>(ctx, w, qCur, n);
+        rt::launchFor(ctx->st, n, ShadeK<ALPHA>{ctx->ds, w, ctx->ps, ctx->sq, qCur, qNext, ctx->dCtr, ctx->dCounters});
+#ifdef YB_HOSTSIM
+        runShadow<ALPHA, false>(ctx, w);
+#else
+        runShadow<ALPHA, false>(ctx, w, n);
+#endif
+        ctx->launches += 3;
+        uint32_t ctr[kCtrCount];
+        YC_TRY(rt::d2h(ctx->st, ctr, ctx->dCtr, sizeof ctr));
+        if (ctx->timeExtend) {
+          ctx->extendMs += rt::eventElapsedMs(ctx->evK0, ctx->evK1);
+          ctx->extendLaunches++;
+        }
+        ctx->raysExtend += n;  // every queue entry is one closest-hit ray
+        n = ctr[kCtrNextCount];
+        std::swap(qCur, qNext);
+      }
+      rt::launchFor(ctx->st, nPix,
+                    AccumulateK{ctx->ps, ctx->dBuckets, ctx->bucketCapacity, pixBase, nPix, K, sDone, m, f.estimator,
+                                exposureScale});
+      ctx->launches++;
+      sDone += K;
+    }
+  }
+  YC_TRY(rt::lastError());
+  return YC_OK;
+}
+
+extern "C" int yc_render_wave(yc_ctx* ctx, YcRect px, uint32_t sampleOffset, uint32_t waveSamples, uint32_t takenBefore) {
+  if (!ctx) return YC_ERR_INVALID;
+  if (!ctx->inFrame) return fail(ctx, YC_ERR_STATE, "yc_render_wave before yc_begin_frame");
+  const YcFrameDesc& f = ctx->frame;
+  if (waveSamples == 0 || px.w == 0 || px.h == 0) return YC_OK;
+  if (uint64_t(px.x) + px.w > f.width || uint64_t(px.y) + px.h > f.height)
+    return fail(ctx, YC_ERR_INVALID, "pixel rectangle outside the frame");
+  const uint32_t* dList = ctx->dPixels;
+  uint32_t nPixCall = uint32_t(ctx->pixels.size());
+  if (!(px.x == 0 && px.y == 0 && px.w == f.width && px.h == f.height)) {
+    std::vector<uint32_t> sub;
+    for (uint32_t v : ctx->pixels) {
+      const uint32_t x = v & 0xffffu, y = v >> 16;
+      if (x >= px.x && x < px.x + px.w && y >= px.y && y < px.y + px.h) sub.push_back(v);
+    }
+    nPixCall = uint32_t(sub.size());
+    YC_TRY(rt::h2d(ctx->st, ctx->dPixelsScratch, sub.data(), sub.size() * 4));
+    dList = ctx->dPixelsScratch;
+  }
+  if (nPixCall == 0) return YC_OK;
+  rt::eventRecord(ctx->st, ctx->ev0);
+  const uint32_t m = f.estimator == YC_ESTIMATOR_MEAN ? 1u : uint32_t(estimatorBuckets(int(waveSamples), kMaxBuckets));
+  const int rc = ctx->ds.hasAlpha ? renderChunks<true>(ctx, dList, nPixCall, sampleOffset, waveSamples, m)
+                                  : renderChunks<false>(ctx, dList, nPixCall, sampleOffset, waveSamples, m);
+  if (rc != YC_OK) return rc;
+  // finishTile's weights, tile-renderer.hpp:220-223
+  const uint32_t takenAfter = takenBefore + waveSamples;
+  const float wCurrent = float(takenBefore) / float(takenAfter), wWave = float(waveSamples) / float(takenAfter);
+  rt::launchFor(ctx->st, nPixCall,
+                FinalizeK{dList, ctx->dBuckets, ctx->bucketCapacity, ctx->dHdr, ctx->dLdr, f.width, m, f.estimator,
+                          waveSamples, f.tonemap, wCurrent, wWave});
+  ctx->launches++;
+  rt::eventRecord(ctx->st, ctx->ev1);
+  YC_TRY(rt::sync(ctx->st));
+  YC_TRY(rt::lastError());
+  ctx->gpuMs += rt::eventElapsedMs(ctx->ev0, ctx->ev1);
+  return YC_OK;
+}
+
+static int readStats(yc_ctx* ctx, YcStats* stats) {
+  if (!stats) return YC_OK;
+  Counters c{};
+  if (ctx->dCounters) YC_TRY(rt::d2h(ctx->st, &c, ctx->dCounters, sizeof c));
+  memset(stats, 0, sizeof *stats);
+  stats->raysReference = c.raysReference;
+  stats->raysExtend = ctx->raysExtend;
+  stats->raysShadow = c.raysShadow;
+  stats->boxTests = c.boxTests;
+  stats->triTests = c.triTests;
+  stats->kernelLaunches = ctx->launches;
+  stats->gpuMs = ctx->gpuMs;
+  stats->extendMs = ctx->extendMs;
+  stats->extendLaunches = ctx->extendLaunches;
+  return YC_OK;
+}
+
+extern "C" int yc_resolve(yc_ctx* ctx, float* hdrRGBA, float* ldrRGBA, YcStats* stats) {
+  if (!ctx) return YC_ERR_INVALID;
+  if (!ctx->inFrame) return fail(ctx, YC_ERR_STATE, "yc_resolve before yc_begin_frame");
+  const size_t bytes = size_t(ctx->frame.width) * ctx->frame.height * sizeof(float4);
+  if (hdrRGBA) YC_TRY(rt::d2h(ctx->st, hdrRGBA, ctx->dHdr, bytes));
+  if (ldrRGBA) YC_TRY(rt::d2h(ctx->st, ldrRGBA, ctx->dLdr, bytes));
+  return readStats(ctx, stats);
+}
+
+extern "C" int yc_frame_device_ptrs(yc_ctx* ctx, void** hdr, void** ldr, size_t* bytes) {
+  if (!ctx) return YC_ERR_INVALID;
+  if (!ctx->inFrame) return fail(ctx, YC_ERR_STATE, "no frame");
+  if (hdr) *hdr = ctx->dHdr;
+  if (ldr) *ldr = ctx->dLdr;
+  if (bytes) *bytes = size_t(ctx->frame.width) * ctx->frame.height * sizeof(float4);
+  return YC_OK;
+}
+
+extern "C" int yc_retonemap(yc_ctx* ctx) {
+  if (!ctx) return YC_ERR_INVALID;
+  if (!ctx->inFrame) return fail(ctx, YC_ERR_STATE, "no frame");
+  rt::launchFor(ctx->st, ctx->frame.width * ctx->frame.height, RetonemapK{ctx->dHdr, ctx->dLdr, ctx->frame.tonemap});
+  ctx->launches++;
+  YC_TRY(rt::sync(ctx->st));
+  YC_TRY(rt::lastError());
+  return YC_OK;
+}
+
+extern "C" int yc_set_profiling(yc_ctx* ctx, int timeExtendKernel) {
+  if (!ctx) return YC_ERR_INVALID;
+  ctx->timeExtend = timeExtendKernel != 0;
+  return YC_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// ray-level hooks (parity tests + traversal microbench)
+// ---------------------------------------------------------------------------------------
+// The oracle's trace harness (oracle/ref_driver.cpp cmdTrace) restarts its sampler at pixel (0,0),
+// sample 0 of a (16 spp, 64x64) SobolSampler before every ray; alpha-test draws use the same stream.
+YB_DEV Sampler traceHookSampler() {
+  SamplerConfig c;
+  c.log2spp = 4;
+  c.nBase4Digits = 6 + 2;
+  Sampler s;
+  s.start(c, 0, 0, 0);
+  return s;
+}
+
+template <bool NEE, bool ALPHA, bool COUNT>
+YB_DEV void traceOne(const DScene& sc, const YcRay& ray, bool useTMax, YcHit& out, TravStack& stack, TraceCounters& cnt) {
+  Sampler smp = traceHookSampler();
+  TraceState st;
+  st.hit.t = (NEE || useTMax) ? ray.tmax : INFINITY;
+  st.hit.node = kHitMiss;
+  st.hit.u = st.hit.v = 0.0f;
+  st.hit.prim = 0xffffffffu;
+  st.hit.backSide = 0;
+  st.attenuation = V3(1.0f);
+  const V3 o(ray.o), d(ray.d);
+  const bool did = traceScene<NEE, ALPHA, COUNT, false>(sc, o, d, st, stack, &smp, cnt);
+  out.t = st.hit.t;
+  out.didHit = did ? 1u : 0u;
+  out.prim = did ? st.hit.prim : 0xffffffffu;
+  out.material = -1, out.lightIdx = -1, out.backSide = 0;
+  for (int k = 0; k < 3; k++) out.p[k] = out.n[k] = out.tg[k] = 0.0f;
+  out.uv[0] = out.uv[1] = 0.0f;
+  out.attenuation[0] = st.attenuation.x, out.attenuation[1] = st.attenuation.y, out.attenuation[2] = st.attenuation.z;
+  if (did) {
+    const SurfaceHit s = resolveHit(sc, st.hit, o, d);
+    out.material = s.material, out.lightIdx = s.lightIdx, out.backSide = st.hit.backSide;
+    out.p[0] = s.p.x, out.p[1] = s.p.y, out.p[2] = s.p.z;
+    out.n[0] = s.n.x, out.n[1] = s.n.y, out.n[2] = s.n.z;
+    out.tg[0] = s.tg.x, out.tg[1] = s.tg.y, out.tg[2] = s.tg.z;
+    out.uv[0] = s.uv.x, out.uv[1] = s.uv.y;
+  }
+}
+
+// compact record of the device-resident variant: 20 bytes per hit (t, u, v, prim, node|backSide)
+struct CompactHit {
+  float t, u, v;
+  uint32_t prim;
+  int32_t node;
+};
+
+#ifdef YB_HOSTSIM
+template <bool NEE, bool ALPHA, bool COUNT>
+static void runTrace(yc_ctx* ctx, const YcRay* rays, uint32_t n, bool useTMax, YcHit* hits, CompactHit* compact) {
+  HostStack hs;
+  TraceCounters cnt;
+  for (uint32_t i = 0; i < n; i++) {
+    YcHit h;
+    traceOne<NEE, ALPHA, COUNT>(ctx->ds, rays[i], useTMax, h, hs.ts, cnt);
+    if (hits) hits[i] = h;
+  }
+  (void)compact;
+  ctx->dCounters->boxTests += cnt.box;
+  ctx->dCounters->triTests += cnt.tri;
+}
+#else
+template <bool NEE, bool ALPHA, bool COUNT, bool COMPACT>
+__global__ void __launch_bounds__(kTraceBlock) traceKernel(DScene sc, const YcRay* rays, uint32_t n, int useTMax, YcHit* hits,
+                                                           CompactHit* compact, uint32_t* head, Counters* counters) {
+  __shared__ uint32_t shRef[kShStack * kTraceBlock];
+  __shared__ float shD[kShStack * kTraceBlock];
+  TravStack stack;
+  stack.shRef = shRef + threadIdx.x;
+  stack.shD = shD + threadIdx.x;
+  stack.stride = kTraceBlock;
+  const int lane = threadIdx.x & 31;
+  TraceCounters cnt;
+  while (true) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(head, 32u);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= n) break;
+    const uint32_t i = base + lane;
+    if (i < n) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(rays) + 2 * size_t(i));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(rays) + 2 * size_t(i) + 1);
+      if (COMPACT) {
+        Sampler smp = traceHookSampler();
+        TraceState st;
+        st.hit.t = (NEE || useTMax) ? b.w : INFINITY;
+        st.hit.node = kHitMiss;
+        st.hit.u = st.hit.v = 0.0f;
+        st.hit.prim = 0xffffffffu;
+        st.hit.backSide = 0;
+        st.attenuation = V3(1.0f);
+        traceScene<NEE, ALPHA, COUNT, false>(sc, V3(a.x, a.y, a.z), V3(b.x, b.y, b.z), st, stack, &smp, cnt);
+        CompactHit c;
+        c.t = st.hit.t, c.u = st.hit.u, c.v = st.hit.v, c.prim = st.hit.prim;
+        c.node = st.hit.node < 0 ? kHitMiss : int32_t(uint32_t(st.hit.node) | (st.hit.backSide ? kBackSideBit : 0u));
+        compact[i] = c;
+      } else {
+        YcRay r;
+        r.o[0] = a.x, r.o[1] = a.y, r.o[2] = a.z, r.tmin = a.w;
+        r.d[0] = b.x, r.d[1] = b.y, r.d[2] = b.z, r.tmax = b.w;
+        YcHit h;
+        traceOne<NEE, ALPHA, COUNT>(sc, r, useTMax != 0, h, stack, cnt);
+        hits[i] = h;
+      }
+    }
+    __syncwarp();
+  }
+  if (COUNT) {
+    aggregatedCount(&counters->boxTests, cnt.box);
+    aggregatedCount(&counters->triTests, cnt.tri);
+  }
+}
+
+template <bool NEE, bool ALPHA, bool COUNT>
+static void runTrace(yc_ctx* ctx, const YcRay* rays, uint32_t n, bool useTMax, YcHit* hits, CompactHit* compact) {
+  const int grid = traceGrid(ctx, n);
+  if (compact)
+    traceKernel<NEE, ALPHA, COUNT, true><<<grid, kTraceBlock, 0, ctx->st.s>>>(ctx->ds, rays, n, useTMax, hits, compact,
+                                                                              ctx->dCtr, ctx->dCounters);
+  else
+    traceKernel<NEE, ALPHA, COUNT, false><<<grid, kTraceBlock, 0, ctx->st.s>>>(ctx->ds, rays, n, useTMax, hits, compact,
+                                                                               ctx->dCtr, ctx->dCounters);
+}
+#endif
+
+static void dispatchTrace(yc_ctx* ctx, int mode, const YcRay* rays, uint32_t n, YcHit* hits, CompactHit* compact) {
+  const bool nee = (mode & 0xf) == YC_TRACE_ANY, count = (mode & YC_TRACE_COUNT) != 0, alpha = ctx->ds.hasAlpha != 0;
+  const bool useTMax = (mode & YC_TRACE_USE_TMAX) != 0;
+#define YB_TR(N, A, C) runTrace<N, A, C>(ctx, rays, n, useTMax, hits, compact)
+  if (nee) {
+    if (alpha) count ? YB_TR(true, true, true) : YB_TR(true, true, false);
+    else count ? YB_TR(true, false, true) : YB_TR(true, false, false);
+  } else {
+    if (alpha) count ? YB_TR(false, true, true) : YB_TR(false, true, false);
+    else count ? YB_TR(false, false, true) : YB_TR(false, false, false);
+  }
+#undef YB_TR
+}
+
+extern "C" int yc_trace_device(yc_ctx* ctx, const void* raysDev, size_t n, int mode, void* hitsDev, int repeat, float* ms) {
+  if (!ctx || !raysDev || !hitsDev || n > 0xffffffffull) return YC_ERR_INVALID;
+  if (!ctx->hasScene) return fail(ctx, YC_ERR_NO_SCENE, "yc_trace_device before yc_upload_scene");
+  int rc = ensureWaveStorage(ctx);
+  if (rc != YC_OK) return rc;
+  if (repeat < 1) repeat = 1;
+  float total = 0.0f;
+  for (int r = 0; r < repeat; r++) {
+    YC_TRY(rt::zero(ctx->st, ctx->dCtr, kCtrCount * sizeof(uint32_t)));
+    rt::eventRecord(ctx->st, ctx->ev0);
+    dispatchTrace(ctx, mode, static_cast<const YcRay*>(raysDev), uint32_t(n), nullptr, static_cast<CompactHit*>(hitsDev));
+    rt::eventRecord(ctx->st, ctx->ev1);
+    ctx->launches++;
+    YC_TRY(rt::sync(ctx->st));
+    YC_TRY(rt::lastError());
+    total += rt::eventElapsedMs(ctx->ev0, ctx->ev1);
+  }
+  if (ms) *ms = total / float(repeat);
+  return YC_OK;
+}
+
+extern "C" int yc_trace(yc_ctx* ctx, const YcRay* rays, size_t n, int mode, YcHit* hits, YcStats* stats) {
+  if (!ctx || (n && (!rays || !hits)) || n > 0xffffffffull) return YC_ERR_INVALID;
+  if (!ctx->hasScene) return fail(ctx, YC_ERR_NO_SCENE, "yc_trace before yc_upload_scene");
+  int rc = ensureWaveStorage(ctx);
+  if (rc != YC_OK) return rc;
+  if (mode & YC_TRACE_COUNT) YC_TRY(rt::zero(ctx->st, ctx->dCounters, sizeof(Counters)));
+  if (n) {
+    void *dr = nullptr, *dh = nullptr;
+    YC_TRY(rt::alloc(&dr, n * sizeof(YcRay)));
+    const char* e = rt::alloc(&dh, n * sizeof(YcHit));
+    if (e) {
+      rt::release(dr);
+      return fail(ctx, YC_ERR_CUDA, "alloc hits: %s", e);
+    }
+    e = rt::h2d(ctx->st, dr, rays, n * sizeof(YcRay));
+    if (!e) e = rt::zero(ctx->st, ctx->dCtr, kCtrCount * sizeof(uint32_t));
+    if (!e) {
+      dispatchTrace(ctx, mode, static_cast<const YcRay*>(dr), uint32_t(n), static_cast<YcHit*>(dh), nullptr);
+      ctx->launches++;
+      e = rt::d2h(ctx->st, hits, dh, n * sizeof(YcHit));
+    }
+    if (!e) e = rt::lastError();
+    rt::release(dr);
+    rt::release(dh);
+    if (e) return fail(ctx, YC_ERR_CUDA, "yc_trace: %s", e);
+  }
+  return readStats(ctx, stats);
+}
+
+extern "C" int yc_device_alloc(yc_ctx* ctx, size_t bytes, void** out) {
+  if (!ctx || !out) return YC_ERR_INVALID;
+  YC_TRY(rt::alloc(out, bytes));
+  return YC_OK;
+}
+extern "C" int yc_device_free(yc_ctx* ctx, void* p) {
+  if (!ctx) return YC_ERR_INVALID;
+  rt::sync(ctx->st);
+  rt::release(p);
+  return YC_OK;
+}
+extern "C" int yc_memcpy_h2d(yc_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  if (!ctx || !dst || !src) return YC_ERR_INVALID;
+  YC_TRY(rt::h2d(ctx->st, dst, src, bytes));
+  return YC_OK;
+}
+extern "C" int yc_memcpy_d2h(yc_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  if (!ctx || !dst || !src) return YC_ERR_INVALID;
+  YC_TRY(rt::d2h(ctx->st, dst, src, bytes));
+  return YC_OK;
+}
+
+// RayIntegrator::sample's rays (ray-integrator.cpp:11-18) for the current frame, sample-major.
+struct PrimaryRayK {
+  WaveParams w;
+  YcRay* rays;
+  YB_DEV void operator()(uint32_t i) const {
+    uint32_t px, py, s;
+    pathPixelSample(w, i, px, py, s);
+    Sampler smp;
+    smp.start(w.smp, px, py, s);
+    V3 o, d;
+    primaryRay(w.cam, smp, px, py, o, d);
+    YcRay r;
+    r.o[0] = o.x, r.o[1] = o.y, r.o[2] = o.z, r.tmin = kTMin;
+    r.d[0] = d.x, r.d[1] = d.y, r.d[2] = d.z, r.tmax = INFINITY;
+    rays[i] = r;
+  }
+};
+
+extern "C" int yc_generate_primary_rays(yc_ctx* ctx, uint32_t sampleOffset, uint32_t spp, void* raysDev) {
+  if (!ctx || !raysDev) return YC_ERR_INVALID;
+  if (!ctx->inFrame) return fail(ctx, YC_ERR_STATE, "yc_generate_primary_rays before yc_begin_frame");
+  const YcFrameDesc& f = ctx->frame;
+  WaveParams w{};
+  w.cam = ctx->cam;
+  w.smp.log2spp = log2IntU(f.totalSamples);
+  w.smp.nBase4Digits = log2IntU(roundUpPow2(f.tileSize)) + (w.smp.log2spp + 1) / 2;
+  w.pixelList = ctx->dPixels;
+  w.pixBase = 0, w.nPix = uint32_t(ctx->pixels.size()), w.s0 = sampleOffset;
+  const uint64_t n = uint64_t(w.nPix) * spp;
+  if (n > 0xffffffffull) return fail(ctx, YC_ERR_INVALID, "too many rays");
+  rt::launchFor(ctx->st, uint32_t(n), PrimaryRayK{w, static_cast<YcRay*>(raysDev)});
+  ctx->launches++;
+  YC_TRY(rt::sync(ctx->st));
+  YC_TRY(rt::lastError());
+  return YC_OK;
+}
+
+#include "kat.cuh"

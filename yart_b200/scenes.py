@@ -314,3 +314,98 @@ def two_quads() -> Scene:
     s.camera = dict(pos=(0.0, 5.0, 15.0), target=(0.0, 5.0, 0.0), focal=35.0, fnum=0.0, exposure=0.0,
                     w=64, h=64, spp=16)
     return s
+
+
+# ------------------------------------------------------------------------------------------
+# procedural textures
+# ------------------------------------------------------------------------------------------
+def _noise_tex(rng, w, h, c, lo=0, hi=255):
+    """Smooth-ish random 8-bit texture (low-res noise upsampled + detail)."""
+    cw, ch = max(2, w // 8), max(2, h // 8)
+    coarse = rng.uniform(lo, hi, (ch, cw, c))
+    ys = (np.arange(h) * ch // h)[:, None]
+    xs = (np.arange(w) * cw // w)[None, :]
+    img = coarse[ys, xs] + rng.uniform(-12, 12, (h, w, c))
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+def sky_hdr(w=64, h=64, seed=5, sun=4000.0) -> np.ndarray:
+    """Octahedral-layout HDR sky: vertical gradient + a small hot sun patch (float32, (h,w,3))."""
+    rng = np.random.default_rng(seed)
+    v = np.linspace(0, 1, h, dtype=np.float32)[:, None, None]
+    img = (0.2 + 0.8 * v) * np.array([0.5, 0.7, 1.0], np.float32)[None, None, :]
+    img = img * (1.0 + 0.1 * rng.uniform(-1, 1, (h, w, 1)).astype(np.float32))
+    cy, cx, r = int(h * 0.62), int(w * 0.33), max(1, w // 32)
+    img[cy - r:cy + r, cx - r:cx + r] = np.array([sun, sun * 0.9, sun * 0.7], np.float32)
+    return np.ascontiguousarray(img, np.float32)
+
+
+# ------------------------------------------------------------------------------------------
+# material zoo: every ParametricBSDF feature + every light type (function-level KATs, small renders)
+# ------------------------------------------------------------------------------------------
+def material_zoo(env=True) -> Scene:
+    rng = np.random.default_rng(11)
+    s = Scene()
+    base_rgba = _noise_tex(rng, 32, 16, 4, 40, 255)
+    base_rgba[::3, ::2, 3] = 90  # alpha cut-outs
+    base_opaque = _noise_tex(rng, 16, 16, 4, 60, 255)
+    base_opaque[..., 3] = 255
+    s.textures = [
+        Texture(base_rgba, SRGB),  # 0 base + alpha
+        Texture(base_opaque, SRGB),  # 1 base, opaque
+        Texture(_noise_tex(rng, 16, 32, 2, 20, 255), NONCOLOR),  # 2 roughness/metallic
+        Texture(_noise_tex(rng, 16, 16, 1, 0, 255), NONCOLOR),  # 3 transmission
+        Texture(np.clip(_noise_tex(rng, 32, 32, 3, 90, 165).astype(np.int32) + np.array([0, 0, 80]), 0, 255).astype(np.uint8), NONCOLOR),  # 4 normal
+        Texture(_noise_tex(rng, 8, 8, 1, 100, 255), NONCOLOR),  # 5 clearcoat
+        Texture(_noise_tex(rng, 8, 16, 3, 0, 255), SRGB),  # 6 emission
+        Texture(sky_hdr(32, 32, 5, 300.0), LINEAR),  # 7 env
+    ]
+    s.materials = [
+        Material(base=(0.8, 0.7, 0.6), roughness=1.0),  # 0 diffuse
+        Material(base=(0.8, 0.6, 0.4), metallic=0.3, roughness=0.4, clearcoat=0.5, clearcoat_roughness=0.1),  # 1 SURVEY App. C
+        Material(base=(0.95, 0.8, 0.4), metallic=1.0, roughness=0.25),  # 2 metal
+        Material(base=(0.9, 0.9, 0.9), metallic=1.0, roughness=0.01),  # 3 mirror (smooth → specular)
+        Material(base=(0.9, 0.95, 1.0), transmission=1.0, roughness=0.0, ior=1.5, thin=0,
+                 volume_color=(0.6, 0.8, 0.9), volume_density=0.7),  # 4 solid smooth glass + volume
+        Material(base=(0.9, 0.95, 1.0), transmission=1.0, roughness=0.35, ior=1.33, thin=0),  # 5 rough solid glass
+        Material(base=(1.0, 0.9, 0.8), transmission=0.8, roughness=0.2, ior=1.5, thin=1),  # 6 thin rough glass
+        Material(base=(1.0, 1.0, 1.0), transmission=1.0, roughness=0.0, ior=1.5, thin=1),  # 7 thin smooth (transparent to NEE)
+        Material(base=(0.7, 0.2, 0.2), metallic=0.8, roughness=0.3, anisotropic=0.8, aniso_rotation=0.6),  # 8 aniso
+        Material(base=(1, 1, 1), base_tex=0, roughness=0.6),  # 9 alpha-tested textured
+        Material(base=(1, 1, 1), base_tex=1, mr_tex=2, normal_tex=4, roughness=1.0, metallic=1.0),  # 10 full PBR textured
+        Material(base=(0.6, 0.6, 0.9), trans_tex=3, transmission=1.0, roughness=0.15, thin=1),  # 11 transmission tex
+        Material(base=(0.1, 0.3, 0.8), roughness=0.5, clearcoat=1.0, clearcoat_roughness=0.03, cc_tex=5),  # 12 car paint
+        Material(base=(1, 1, 1), roughness=1.0, emission=(6.0, 5.0, 3.0), emis_tex=6),  # 13 textured emitter
+        Material(base=(1, 1, 1), roughness=1.0, emission=(12.0, 12.0, 12.0)),  # 14 emitter
+        Material(base=(0.5, 0.5, 0.5), roughness=0.05, clearcoat=0.7, clearcoat_roughness=0.0),  # 15 smooth coat
+        Material(base=(0.3, 0.8, 0.3), roughness=0.0),  # 16 smooth glossy (specular branch)
+    ]
+    # geometry: a floor, a back wall split in material patches, a few boxes, two emissive quads
+    b = MeshBuilder()
+    b.quad((-8, 0, 8), (8, 0, 8), (8, 0, -8), (-8, 0, -8), 10, uv_scale=3.0)
+    mats = [0, 1, 2, 3, 8, 9, 12, 15, 16, 11, 6, 7]
+    for i, m in enumerate(mats):
+        x0 = -8 + i * (16 / len(mats))
+        x1 = x0 + 16 / len(mats)
+        b.quad((x0, 0, -6), (x1, 0, -6), (x1, 7, -6), (x0, 7, -6), m, uv_scale=2.0)
+    b.box((-1.2, 0, -1.2), (1.2, 2.4, 1.2), 4, translation(-3.5, 0.01, 0.5) @ rotation_y(25))
+    b.box((-1.0, 0, -1.0), (1.0, 2.0, 1.0), 5, translation(0.0, 0.01, 1.5) @ rotation_y(-15))
+    b.box((-1.0, 0, -1.0), (1.0, 3.0, 1.0), 9, translation(3.5, 0.01, 0.0) @ rotation_y(40))
+    b.quad((-2.5, 0.5, 3.0), (2.5, 0.5, 3.0), (2.5, 3.0, 3.0), (-2.5, 3.0, 3.0), 7)  # thin pane in front
+    room = b.build()
+    lb = MeshBuilder()
+    lb.quad((-2, 0, -1), (2, 0, -1), (2, 0, 1), (-2, 0, 1), 14)
+    lb.quad((-1, -0.5, 2), (1, -0.5, 2), (1, -0.5, 3), (-1, -0.5, 3), 13, uv_scale=1.0)
+    lights = lb.build()
+    s.meshes = [room, lights]
+    lxf = translation(0.5, 8.0, -1.0) @ rotation_y(30)
+    inner = translation(0.2, 0.0, -0.3) @ scaling(1.1)
+    # two-level graph: root → group(transform) → room ; root → lights(transform)
+    s.nodes = [Node(-1, -1), Node(0, -1, inner), Node(1, 0, rotation_y(5)), Node(0, 1, lxf)]
+    s.add_area_lights(1, lxf)
+    if env:
+        s.lights.append(Light(IMAGE_INF, hdr_tex=7, scene_radius=60.0, transform=rotation_y(40)))
+    s.lights.append(Light(UNIFORM_INF, emission=(0.05, 0.05, 0.08), scene_radius=60.0))
+    s.camera = dict(pos=(0.5, 4.0, 13.0), target=(0.0, 2.5, 0.0), focal=35.0, fnum=4.0, exposure=1.0,
+                    w=96, h=64, spp=16)
+    return s
