@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py — Mrays/s of the render hot path on BASELINE.json configs[1]:
+synthetic 1M-triangle random-soup scene, 1920x1080, primary + shadow rays only (maxDepth = 1).
+
+A step = one pass of the hot path over one batch: one wave of SPP samples of every pixel of the
+1080p frame (raygen → extend → shade → shadow → accumulate → finalize).
+
+  value      whole-job Mrays/s (reference ray definition, mis-integrator.cpp:22,126) with the scene,
+             BVH and camera resident in HBM; timed with CUDA events on the launching stream
+  e2e        same metric through the public Renderer API (yr_render_sync + yr_read): per step the
+             frame set-up H2D copies and the HDR+LDR frame D2H copies are inside the timed region
+  roofline   extend (closest-hit) kernel: algorithmic bytes per launch / its CUDA-event duration
+  cpu_baseline  the reference's own tile-threaded CPU renderer (oracle/_ref/oracle_ref_perf) on the
+             box's host cores, bounded to 1 spp of the same frame
+
+N > 1 (torchrun, one rank per GPU): scene replicated, rank r renders sample wave r of the frame
+(weak scaling: SPP samples per GPU), the per-GPU HDR frames are combined with an NCCL all-reduce
+over NVLink and re-tonemapped; value = rays of all ranks / max-over-ranks time.
+
+--impl reference times the reference CPU renderer alone (all host threads), same metric/config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H = 1920, 1080
+METRIC = "Mrays/s at 1080p (primary + shadow rays, reference ray count)"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def scene_path(n_tris: int) -> str:
+    import tempfile
+    from yart_b200 import scenes
+    d = os.environ.get("YART_BENCH_CACHE", os.path.join(tempfile.gettempdir(), "yart_b200_bench"))
+    os.makedirs(d, exist_ok=True)
+    p = os.path.join(d, f"soup_{n_tris}.ysc")
+    if not os.path.exists(p):
+        t0 = time.time()
+        tmp = p + f".tmp{os.getpid()}"
+        scenes.soup(n_tris).write(tmp)
+        os.replace(tmp, p)
+        log(f"[bench] generated {p} in {time.time() - t0:.1f}s")
+    return p
+
+
+CAM = dict(pos=(0.0, 0.0, 40.0), target=(0.0, 0.0, 0.0), focal=35.0, fnum=0.0, exposure=0.0)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.lines, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
+                                          "100", "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [l.split(", ") for t, l in self.lines if t0 - 0.05 <= t <= t1 + 0.15] or [l.split(", ") for _, l in self.lines]
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks() -> tuple[float, str]:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_reference(path: str, steps: int, warmup: int, spp: int = 1) -> dict:
+    """The reference's TileRenderer on all host threads: `steps` timed renderSync() calls of
+    `spp` samples of the 1080p frame, after `warmup` untimed ones (one process, one BVH build)."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "oracle_ref_perf")
+    if not os.path.exists(exe):
+        exe = os.path.join(ROOT, "oracle", "_ref", "oracle_ref")
+    out = "/tmp/yart_bench_ref.bin"
+    cmd = [exe, "render", path, out, f"w={W}", f"h={H}", f"spp={spp}", "maxdepth=1", "tonemap=agx",
+           "pos=%g,%g,%g" % CAM["pos"], "target=%g,%g,%g" % CAM["target"], f"repeat={steps + warmup}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"reference CPU renderer failed: {r.stderr[-2000:]}")
+    j = json.loads(r.stdout.strip().splitlines()[-1])
+    rays, prev = [], 0
+    for tot, ms in j["steps"]:  # m_totalRays accumulates over renderSync calls
+        rays.append((tot - prev, ms))
+        prev = tot
+    timed = rays[warmup:]
+    tot_rays, tot_ms = sum(r for r, _ in timed), sum(m for _, m in timed)
+    return dict(mrays=tot_rays / tot_ms / 1e3, ms_per_step=tot_ms / len(timed), rays_per_step=tot_rays / len(timed),
+                threads=j["threads"], build_ms=j["build_ms"], spp=spp, exe=os.path.basename(exe))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    path = scene_path(args.tris)
+    res = cpu_reference(path, args.steps, max(args.warmup, 1), spp=1)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["mrays"], "unit": "Mrays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"soup {args.tris} tris, {W}x{H}, primary+shadow (maxDepth 1)", "step": "1 spp of the frame",
+                   "bvh_build_ms_excluded": res["build_ms"]},
+        "cpu_baseline": {"value": res["mrays"], "unit": "Mrays/s", "cores": res["threads"], "kind": "reference",
+                         "sample": f"{args.steps} x 1 spp of the 1080p frame, {res['exe']} (unmodified reference, -O3 -march=x86-64-v3)"},
+        "e2e": {"value": res["mrays"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "samples_per_s": W * H * 1 / (res["ms_per_step"] / 1e3),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import numpy as np
+    import yart_b200 as Y
+    from yart_b200 import capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if rank == 0:
+        path = scene_path(args.tris)
+    if dist:
+        dist.barrier()
+    path = scene_path(args.tris)
+
+    Y.use_library(capi.load())  # raises if libyart_b200.so is missing: no fallback
+    t0 = time.time()
+    scene = Y.Scene(path)
+    log(f"[bench r{rank}] scene {scene.n_tris} tris, host SAH build {scene.build_ms:.0f} ms (load {time.time() - t0:.1f}s)")
+    cam = Y.make_camera(W, H, CAM["focal"], CAM["fnum"], CAM["pos"], CAM["target"], (0, 0, 0), CAM["exposure"])
+    spp = args.spp
+
+    # ---- device-resident arm ---------------------------------------------------------------
+    ctx = Y.Context(device=local, max_depth=1)
+    ctx.upload_scene(scene)
+    ctx.set_camera(cam)
+    ctx.set_profiling(True)
+    total_spp = spp * world
+    ctx.begin_frame(W, H, total_spp, 64, (0, 0, 0), Y.TONEMAP_AGX)
+
+    frame_t = None
+    if dist:
+        import torch
+        hdr_ptr, _, nbytes = ctx.frame_device_ptrs()
+
+        class _Alias:  # zero-copy view of the context's HDR frame for NCCL
+            __cuda_array_interface__ = {"shape": (nbytes // 4,), "typestr": "<f4", "data": (hdr_ptr, False), "version": 3}
+        frame_t = torch.as_tensor(_Alias(), device=f"cuda:{local}")
+
+    def sync_all():
+        if dist:
+            import torch
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step():
+        """One pass: this rank's wave of `spp` samples; N > 1: combine the HDR frames over NCCL."""
+        ctx.render_wave(rank * spp, spp, 0)
+        ar_ms = 0.0
+        if dist:
+            import torch
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            frame_t.mul_(1.0 / world)  # equal sample counts per wave: finishTile's weights collapse to 1/N
+            dist.all_reduce(frame_t)
+            e1.record()
+            torch.cuda.synchronize()
+            ar_ms = e0.elapsed_time(e1)
+            ctx.retonemap()
+        return ar_ms
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sync_all()
+    s0 = ctx.stats()
+    clocks = ClockSampler(local)
+    w0 = time.time()
+    ar_total = 0.0
+    for _ in range(args.steps):
+        ar_total += step()
+    sync_all()
+    w1 = time.time()
+    clk = clocks.stop(w0, w1)
+    s1 = ctx.stats()
+    dev_ms = (s1.gpuMs - s0.gpuMs) + ar_total
+    rays = s1.raysReference - s0.raysReference
+    traced = (s1.raysExtend - s0.raysExtend) + (s1.raysShadow - s0.raysShadow)
+    ext_ms = (s1.extendMs - s0.extendMs) / max(1, s1.extendLaunches - s0.extendLaunches)
+    launches = s1.kernelLaunches - s0.kernelLaunches
+
+    # ---- extend-kernel roofline: algorithmic bytes of the reference traversal on these rays ------
+    n_rays = W * H * spp
+    rays_dev, hits_dev = ctx.device_alloc(n_rays * 32), ctx.device_alloc(n_rays * 20)
+    ctx.begin_frame(W, H, total_spp, 64, (0, 0, 0), Y.TONEMAP_AGX)
+    ctx.generate_primary_rays(rank * spp, spp, rays_dev)
+    one = np.zeros((1, 8), np.float32)
+    one[0, 4:7] = (0, 0, -1)
+    ctx.trace(one, Y.TRACE_CLOSEST | Y.TRACE_COUNT)  # zeroes the work counters
+    c0 = ctx.stats()
+    lib, h = Y.lib(), ctx._h
+    import ctypes as C
+    ms_c = C.c_float()
+    rc = lib.yc_trace_device(h, rays_dev, n_rays, Y.TRACE_CLOSEST | Y.TRACE_COUNT, hits_dev, 1, C.byref(ms_c))
+    assert rc == 0
+    c1 = ctx.stats()
+    box, tri = c1.boxTests - c0.boxTests, c1.triTests - c0.triTests
+    trace_ms = ctx.trace_device(rays_dev, n_rays, hits_dev, Y.TRACE_CLOSEST, repeat=3)
+    ctx.device_free(rays_dev)
+    ctx.device_free(hits_dev)
+    algo_bytes = n_rays * (32 + 20) + 32 * box + 52 * tri
+    peak, peak_src = peaks()
+    achieved = algo_bytes / (ext_ms / 1e3) / 1e9 if ext_ms > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "extend_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+
+    # ---- end-to-end arm: public Renderer API, host buffers ------------------------------------
+    r = Y.Renderer(W, H, cam, scene, samples=spp, first_wave_samples=spp, max_wave_samples=spp, max_depth=1,
+                   tonemap=Y.TONEMAP_AGX, device=local)
+    e2e_rays = 0
+
+    def e2e_step():
+        nonlocal e2e_rays
+        d = r.render_sync()
+        hdr, ldr, _ = r.read()
+        e2e_rays = d["total_rays"]
+        return hdr
+
+    for _ in range(2):
+        e2e_step()
+    sync_all()
+    e0 = time.time()
+    n_e2e = max(2, min(args.steps, 10))
+    for _ in range(n_e2e):
+        e2e_step()
+    sync_all()
+    e2e_s = (time.time() - e0)
+    r.close()
+
+    # ---- max over ranks, aggregate ------------------------------------------------------------
+    if dist:
+        import torch
+        t = torch.tensor([dev_ms, (w1 - w0) * 1e3, e2e_s], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, wall_ms, e2e_s = t.tolist()
+        c = torch.tensor([rays, traced, e2e_rays * n_e2e, launches], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(c)
+        rays, traced, e2e_total, launches = c.tolist()
+    else:
+        wall_ms, e2e_total = (w1 - w0) * 1e3, e2e_rays * n_e2e
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            try:
+                cr = cpu_reference(path, 2, 1, spp=1)
+                cpu = {"value": cr["mrays"], "unit": "Mrays/s", "cores": cr["threads"], "kind": "reference",
+                       "sample": f"2 x 1 spp of the same 1080p frame through the unmodified reference's TileRenderer "
+                                 f"({cr['exe']}); BVH build {cr['build_ms']:.0f} ms excluded"}
+            except Exception as ex:  # noqa: BLE001
+                cpu = {"value": None, "unit": "Mrays/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {ex}"}
+        line = {
+            "metric": METRIC, "value": rays / dev_ms / 1e3, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"soup {args.tris} tris, {W}x{H}, primary+shadow (maxDepth 1)",
+                       "step": f"one wave of {spp} spp per GPU ({W * H * spp} primary rays + their NEE shadow rays)",
+                       "parallelism": f"sample-wave sharding x{world}, scene replicated, NCCL all-reduce of HDR frames",
+                       "l2": "working set (112 MB BVH + 0.8 GB path state per step) exceeds the 126 MB L2; no flush"},
+            "wall_ms_per_step": wall_ms / args.steps,
+            "traced_mrays_per_s": traced / dev_ms / 1e3,
+            "samples_per_s": W * H * spp * world / (dev_ms / args.steps / 1e3),
+            "gpu_launches": int(launches),
+            "clocks": clk,
+            "e2e": {"value": e2e_total / e2e_s / 1e6, "unit": "Mrays/s",
+                    "h2d_bytes_per_step": 4 * W * H + 256, "d2h_bytes_per_step": 2 * W * H * 16,
+                    "call": "Renderer.render_sync() + Renderer.read() (yr_render_sync + yr_read), host frames"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "extendKernel<false,false>", "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": ext_ms,
+                         "box_tests_per_ray": box / n_rays, "tri_tests_per_ray": tri / n_rays,
+                         "standalone_trace_ms": trace_ms},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--tris", type=int, default=1_000_000)
+    ap.add_argument("--spp", type=int, default=4)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

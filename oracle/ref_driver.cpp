@@ -257,10 +257,22 @@ static int cmdRender(int argc, char** argv) {
   r.backgroundColor = a.vec3("bg", {0, 0, 0});
   r.tonemapper = nullptr;  // m_buffer then carries the HDR accumulation (tile-renderer.hpp:238)
 
+  // repeat=N: time N back-to-back renderSync() calls of the same frame (bench.py's reference arm);
+  // the last one is written out.  Each line of "steps" is one call: rays and wall milliseconds.
+  int repeat = int(a.num("repeat", 1));
+  std::vector<std::pair<uint64_t, double>> steps;
   auto t0 = std::chrono::high_resolution_clock::now();
   auto res = r.renderSync();
   auto t1 = std::chrono::high_resolution_clock::now();
   double ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+  steps.push_back({uint64_t(res.totalRays), ms});
+  for (int it = 1; it < repeat; it++) {
+    t0 = std::chrono::high_resolution_clock::now();
+    auto again = r.renderSync();
+    t1 = std::chrono::high_resolution_clock::now();
+    ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    steps.push_back({uint64_t(again.totalRays), ms});
+  }
 
   tonemap::AgX agx;
   std::string tm = a.str("tonemap", "agx");
@@ -285,8 +297,11 @@ static int cmdRender(int argc, char** argv) {
       float4 p = tm == "none" ? res.buffer(x, y) : float4(agx(hdr), 1.0f);
       out.putn(p.data(), 4);
     }
-  printf("{\"rays\": %llu, \"ms\": %.3f, \"threads\": %u, \"build_ms\": %.3f, \"w\": %u, \"h\": %u, \"spp\": %u}\n",
+  printf("{\"rays\": %llu, \"ms\": %.3f, \"threads\": %u, \"build_ms\": %.3f, \"w\": %u, \"h\": %u, \"spp\": %u, \"steps\": [",
          (unsigned long long) res.totalRays, ms, r.threadCount, rs.buildMs, w, h, r.samples);
+  for (size_t i = 0; i < steps.size(); i++)
+    printf("%s[%llu, %.3f]", i ? ", " : "", (unsigned long long) steps[i].first, steps[i].second);
+  printf("]}\n");
   return 0;
 }
 

@@ -1,0 +1,105 @@
+"""Regenerates tests/golden/*.npz by running the UNMODIFIED reference (oracle/_ref/oracle_ref,
+built by oracle/Makefile from /root/reference) on seeded inputs.
+
+    python tests/golden/generate.py
+
+Each file stores the exact input (KAT blob / rays / render settings) next to the reference's
+output, so tests can replay the input through the CUDA path (or the hostsim build) and compare.
+The scenes are produced by yart_b200/scenes.py (deterministic, seeded).
+"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import harness as H  # noqa: E402
+
+OUT = H.GOLDEN
+
+KATS = [  # (file tag, kind, n, kwargs, scene)
+    ("sampler16", "sampler", 512, dict(spp=16), None),
+    ("sampler128", "sampler", 512, dict(spp=128), None),
+    ("sampler1024", "sampler", 512, dict(spp=1024), None),
+    ("sampler4096", "sampler", 512, dict(spp=4096), None),
+    ("ggx", "ggx", 1024, {}, None),
+    ("gmon16", "gmon", 256, dict(samples=16), None),
+    ("gmon64", "gmon", 256, dict(samples=64), None),
+    ("gmon128", "gmon", 128, dict(samples=128), None),
+    ("gmon3", "gmon", 64, dict(samples=3), None),
+    ("agx0", "agx", 1024, dict(look=0), None),
+    ("agx1", "agx", 512, dict(look=1), None),
+    ("agx2", "agx", 512, dict(look=2), None),
+    ("camera", "camera", 512, dict(), None),
+    ("camera_poly", "camera", 512, dict(sides=6, fnum=1.4), None),
+    ("camera_pinhole", "camera", 512, dict(fnum=0.0, w=1920, h=1080, pos=(0, 0, 40), target=(0, 0, 0)), None),
+    ("lut", "lut", 2048, {}, "material_zoo"),
+    ("texture", "texture", 2048, dict(n_textures=8), "material_zoo"),
+    ("bsdf", "bsdf", 4096, dict(n_materials=17), "material_zoo"),
+    ("light", "light", 2048, dict(n_lights=6), "material_zoo"),
+]
+
+TRACE_SCENES = [("cornell", {}), ("material_zoo", {}), ("soup", dict(n_tris=20000)), ("two_quads", {})]
+
+RENDERS = [  # (tag, scene, scene kwargs, w, h, spp, first, max, maxdepth, tonemap)
+    ("two_quads", "two_quads", {}, 64, 64, 16, 16, 16, 30, "agx"),
+    ("cornell", "cornell", {}, 64, 64, 16, 16, 16, 30, "agx"),
+    ("cornell_waves", "cornell", {}, 48, 40, 8, 1, 4, 30, "agx"),
+    ("zoo", "material_zoo", {}, 96, 64, 16, 16, 16, 30, "agx"),
+    ("zoo_waves", "material_zoo", {}, 48, 32, 64, 4, 32, 30, "golden"),
+    ("soup_d1", "soup", dict(n_tris=20000), 96, 54, 4, 4, 4, 1, "agx"),
+]
+
+
+def trace_rays(cam, n, seed=3, spread=12.0):
+    rng = np.random.default_rng(seed)
+    o = np.tile(np.asarray(cam["pos"], np.float32), (n, 1)) + rng.normal(0, 0.5, (n, 3)).astype(np.float32)
+    tgt = np.asarray(cam["target"], np.float32) + rng.uniform(-spread, spread, (n, 3)).astype(np.float32)
+    d = tgt - o
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    r = np.zeros((n, 8), np.float32)
+    r[:, 0:3], r[:, 3], r[:, 4:7], r[:, 7] = o, 0.001, d, rng.uniform(5, 40, n)
+    k = n // 3  # rays born inside the scene, any direction
+    r[:k, 0:3] = rng.uniform(-4, 4, (k, 3))
+    r[:k, 1] = np.abs(r[:k, 1]) + 0.1
+    dd = rng.normal(size=(k, 3))
+    r[:k, 4:7] = dd / np.linalg.norm(dd, axis=1, keepdims=True)
+    r[-8:, 4:7] = np.eye(3, dtype=np.float32)[np.arange(8) % 3]  # axis-aligned: zero components → inf idir
+    return r
+
+
+def main():
+    assert H.have_oracle(), "build oracle/_ref first: make -C oracle ref"
+    for tag, kind, n, kw, scene in KATS:
+        blob = H.kat_input(kind, n, **kw)
+        sp = H.scene_file(scene) if scene else None
+        out = H.oracle_kat(kind, blob, sp)
+        np.savez_compressed(os.path.join(OUT, f"kat_{tag}.npz"), kind=kind, scene=scene or "",
+                            blob=np.frombuffer(blob, np.uint8), out=out)
+        print("kat", tag, out.size)
+    for name, kw in TRACE_SCENES:
+        sp, cam = H.scene_file(name, **kw), H.scene_camera(name, **kw)
+        rays = trace_rays(cam, 3000)
+        closest = H.oracle_trace(sp, rays, "closest")
+        anyhit = H.oracle_trace(sp, rays, "any")
+        np.savez_compressed(os.path.join(OUT, f"trace_{name}.npz"), scene=name, kwargs=repr(kw), rays=rays,
+                            closest=closest, anyhit=anyhit)
+        print("trace", name, int(closest["didHit"].sum()), int(anyhit["didHit"].sum()))
+    for tag, name, kw, w, h, spp, first, mx, depth, tm in RENDERS:
+        sp, cam = H.scene_file(name, **kw), H.scene_camera(name, **kw)
+        r = H.oracle_render(sp, w, h, spp, cam, first=first, max=mx, maxdepth=depth, tonemap=tm, threads=4)
+        np.savez_compressed(os.path.join(OUT, f"render_{tag}.npz"), scene=name, kwargs=repr(kw),
+                            settings=np.array([w, h, spp, first, mx, depth]), tonemap=tm, hdr=r["hdr"], ldr=r["ldr"],
+                            rays=r["rays"])
+        print("render", tag, r["rays"])
+    for name, kw in [("cornell", {}), ("material_zoo", {}), ("soup", dict(n_tris=3000))]:
+        sp = H.scene_file(name, **kw)
+        meshes = H.oracle_bvh(sp)
+        np.savez_compressed(os.path.join(OUT, f"bvh_{name}.npz"), scene=name, kwargs=repr(kw),
+                            **{f"nodes{i}": m[0] for i, m in enumerate(meshes)},
+                            **{f"idx{i}": m[1] for i, m in enumerate(meshes)})
+        print("bvh", name, [len(m[0]) for m in meshes])
+
+
+if __name__ == "__main__":
+    main()
