@@ -252,5 +252,6 @@ def rel_mse(img: np.ndarray, ref: np.ndarray, eps: float = 1e-2) -> float:
 
 
 def bits_equal(a: np.ndarray, b: np.ndarray) -> np.ndarray:
-    """Bitwise float equality (NaN == NaN when same payload)."""
-    return np.ascontiguousarray(a, np.float32).view(np.uint32) == np.ascontiguousarray(b, np.float32).view(np.uint32)
+    """Bitwise float equality; any NaN equals any NaN (payloads are not part of the contract)."""
+    a, b = np.ascontiguousarray(a, np.float32), np.ascontiguousarray(b, np.float32)
+    return (a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))

@@ -9,6 +9,7 @@
 // only returned by the diffuse branch of sampleGlossy; clearcoat Fresnel uses IOR 1.5 except in
 // the smooth-coat branch.
 #pragma once
+#include "libm_exact.cuh"
 #include "scene_dev.cuh"
 #include "texture.cuh"
 
@@ -110,8 +111,8 @@ YB_DEV float FavgFit(float ior) { return (ior - 1.0f) / (4.08567f + 1.00071f * i
 YB_DEV V3 sampleCosineHemisphere(V2 u) {
   const float phi = u.x * 2.0f * kPi;
   const float sqrtr2 = sqrtf(u.y);
-  const float x = cosf(phi) * sqrtr2;
-  const float y = sinf(phi) * sqrtr2;
+  const float x = cosfExact(phi) * sqrtr2;
+  const float y = sinfExact(phi) * sqrtr2;
   const float z = sqrtf(1.0f - u.y);
   return V3(x, y, z);
 }
@@ -119,7 +120,7 @@ YB_DEV V3 sampleCosineHemisphere(V2 u) {
 YB_DEV V2 sampleDiskUniform(V2 u) {
   const float r = sqrtf(u.x);
   const float theta = 2.0f * kPi * u.y;
-  return V2(r * cosf(theta), r * sinf(theta));
+  return V2(r * cosfExact(theta), r * sinfExact(theta));
 }
 // sampling.hpp:54-64
 YB_DEV V3 sampleTriUniform(V2 u) {
@@ -583,7 +584,7 @@ struct Bsdf {
   YB_DEV V3 attenuation(float d) const {
     if (mat.thinTransmission) return V3(1.0f);
     V3 e = (V3(mat.volumeColor) - 1.0f) * d * mat.volumeDensity;
-    return V3(expf(e.x), expf(e.y), expf(e.z));
+    return V3(expfExact(e.x), expfExact(e.y), expfExact(e.z));
   }
 };
 

@@ -14,9 +14,9 @@ namespace yb {
 
 // sampling.hpp:20-28
 YB_DEV V2 pixelJitterGaussian(V2 u, float stdDev) {
-  float a = sqrtf(-2.0f * logf(u.x)) * stdDev;
+  float a = sqrtf(-2.0f * logfExact(u.x)) * stdDev;
   float b = 2.0f * kPi * u.y;
-  return V2(a * cosf(b), a * sinf(b));
+  return V2(a * cosfExact(b), a * sinfExact(b));
 }
 
 // sampling.hpp:72-89
@@ -29,8 +29,8 @@ YB_DEV V2 samplePolyUniform(V2 u, uint32_t sides) {
   V3 b = sampleTriUniform(u);
   float theta1 = float(side) / float(sides) * 2.0f * kPi;
   float theta2 = float(side + 1) / float(sides) * 2.0f * kPi;
-  float c1 = cosf(theta1), s1 = sinf(theta1);
-  float c2 = cosf(theta2), s2 = sinf(theta2);
+  float c1 = cosfExact(theta1), s1 = sinfExact(theta1);
+  float c2 = cosfExact(theta2), s2 = sinfExact(theta2);
   // float2(0,0)*b0 + float2(-s1,c1)*b1 + float2(-s2,c2)*b2, left to right
   V2 r = V2(0.0f, 0.0f) * b.x + V2(-s1, c1) * b.y;
   return r + V2(-s2, c2) * b.z;
