@@ -269,7 +269,7 @@ def run_ours(args):
     def e2e_step():
         nonlocal e2e_rays
         d = r.render_sync()
-        hdr, ldr, _ = r.read()
+        hdr, ldr, _ = r.read(pinned=True)
         e2e_rays = d["total_rays"]
         return hdr
 
@@ -320,8 +320,8 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clk,
             "e2e": {"value": e2e_total / e2e_s / 1e6, "unit": "Mrays/s",
-                    "h2d_bytes_per_step": 4 * W * H + 256, "d2h_bytes_per_step": 2 * W * H * 16,
-                    "call": "Renderer.render_sync() + Renderer.read() (yr_render_sync + yr_read), host frames"},
+                    "h2d_bytes_per_step": 256, "d2h_bytes_per_step": 2 * W * H * 16,
+                    "call": "Renderer.render_sync() + Renderer.read(pinned=True) (yr_render_sync + yr_read): camera/frame description in, HDR + LDR frames out to page-locked host memory"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "extendKernel<false,false>", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": ext_ms,

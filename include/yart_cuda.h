@@ -49,6 +49,7 @@ typedef struct YcNode {
   int32_t parent; /* -1 for the root (node 0) */
   int32_t skip;   /* index of the first node after this node's subtree */
   int32_t depth;  /* root = 0; must be < YC_MAX_NODE_DEPTH */
+  int32_t identityChain; /* 1 iff this node's and all its ancestors' transforms are exactly the identity */
 } YcNode;
 
 /* One inner BVH node with BOTH children's bounds inlined (64 B = 4 x 128-bit loads).
@@ -184,6 +185,9 @@ typedef struct YcCamera {
 typedef struct YcOptions {
   uint32_t maxDepth;        /* RayIntegrator::m_maxDepth (default 30) */
   uint32_t maxPathsInFlight; /* wavefront capacity; 0 = default (8 Mi paths) */
+  /* reserved[0], reserved[1]: warp-scheduling knobs of the traversal kernels (0 = default):
+   * refill threshold (idle lanes) and inner-step threshold (lanes on inner nodes).  They never
+   * change results. */
   uint32_t reserved[6];
 } YcOptions;
 
@@ -280,6 +284,10 @@ int yc_trace_device(yc_ctx* ctx, const void* raysDev, size_t n, int mode, void* 
                     float* ms);
 int yc_device_alloc(yc_ctx* ctx, size_t bytes, void** out);
 int yc_device_free(yc_ctx* ctx, void* p);
+/* Page-locked host memory for frame read-back / ray upload at full PCIe rate (optional: every entry
+ * point also accepts ordinary pageable memory). */
+int yc_host_alloc(yc_ctx* ctx, size_t bytes, void** out);
+int yc_host_free(yc_ctx* ctx, void* p);
 int yc_memcpy_h2d(yc_ctx* ctx, void* dst, const void* src, size_t bytes);
 int yc_memcpy_d2h(yc_ctx* ctx, void* dst, const void* src, size_t bytes);
 /* Primary rays exactly as RayIntegrator::sample generates them (ray-integrator.cpp:11-18),

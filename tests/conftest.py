@@ -13,7 +13,7 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
-@pytest.fixture(scope="session")
+@pytest.fixture
 def hostsim_lib():
     """The product sources compiled for the CPU (tests/hostsim) bound as the active library."""
     import harness
@@ -23,7 +23,7 @@ def hostsim_lib():
     yield lib
 
 
-@pytest.fixture(scope="session")
+@pytest.fixture
 def cuda_lib():
     """The product library (CUDA).  Fails loudly if it is missing — GPU tests never fall back."""
     import yart_b200

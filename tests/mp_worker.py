@@ -1,0 +1,62 @@
+"""Worker for the world_size-2 CPU tests of the multi-GPU host logic (gloo backend).
+Each rank plays one GPU: it renders its share with the hostsim build and the frames are combined
+with torch.distributed exactly as bench.py / a multi-GPU caller would with NCCL."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def run(rank: int, world: int, port: int, mode: str, out_dir: str):
+    import torch
+    import torch.distributed as dist
+    import harness as H
+    import yart_b200 as Y
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    Y.use_library(H.hostsim())
+    cam = H.scene_camera("cornell")
+    sc = Y.Scene(H.scene_file("cornell"))
+    w = h = 48
+    c = Y.make_camera(w, h, cam["focal"], cam["fnum"], cam["pos"], cam["target"])
+    ctx = Y.Context()
+    ctx.upload_scene(sc)
+    ctx.set_camera(c)
+    spp = 8
+    if mode == "tiles":
+        # interleaved tile sharding (SURVEY §8e primary): disjoint pixels, sum = full frame, bit-exact
+        ctx.begin_frame(w, h, spp, 16, (0, 0, 0), Y.TONEMAP_AGX, shard_index=rank, shard_count=world)
+        ctx.render_wave(0, spp, 0)
+        hdr, ldr, st = ctx.resolve()
+        t_hdr, t_ldr = torch.from_numpy(hdr), torch.from_numpy(ldr)
+        dist.all_reduce(t_hdr)
+        dist.all_reduce(t_ldr)
+    else:
+        # sample-wave sharding (bench.py's N > 1 path): rank r renders wave r of spp samples of the
+        # whole frame; equal wave sizes → finishTile's weights collapse to 1 / world
+        ctx.begin_frame(w, h, spp * world, 16, (0, 0, 0), Y.TONEMAP_AGX)
+        ctx.render_wave(rank * spp, spp, 0)
+        hdr, _, st = ctx.resolve()
+        t_hdr = torch.from_numpy(hdr)
+        t_hdr.mul_(1.0 / world)
+        dist.all_reduce(t_hdr)
+        t_ldr = None
+    rays = torch.tensor([st.raysReference], dtype=torch.int64)
+    dist.all_reduce(rays)
+    if rank == 0:
+        np.save(os.path.join(out_dir, f"{mode}_hdr.npy"), t_hdr.numpy())
+        if t_ldr is not None:
+            np.save(os.path.join(out_dir, f"{mode}_ldr.npy"), t_ldr.numpy())
+        np.save(os.path.join(out_dir, f"{mode}_rays.npy"), rays.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    run(int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), sys.argv[4], sys.argv[5])

@@ -96,9 +96,10 @@ def make_camera(width, height, focal=35.0, fnum=0.0, pos=(0, 0, 5), target=(0, 0
 class Context:
     """Device layer (yc_*): one CUDA context + stream on one GPU."""
 
-    def __init__(self, device: int = 0, max_depth: int = 30, max_paths: int = 0):
+    def __init__(self, device: int = 0, max_depth: int = 30, max_paths: int = 0, refill_min: int = 0, inner_min: int = 0):
         self._h = C.c_void_p()
         opts = capi.YcOptions(maxDepth=max_depth, maxPathsInFlight=max_paths)
+        opts.reserved[0], opts.reserved[1] = refill_min, inner_min  # traversal scheduling knobs (0 = default)
         _check(lib().yc_create(device, C.byref(opts), C.byref(self._h)), "yc_create",
                b"(no usable CUDA device: yart_b200 has no CPU fallback)")
         self.frame = None
@@ -224,6 +225,9 @@ class Renderer:
 
     def close(self):
         if self._h:
+            for p, _ in getattr(self, "_pinned", {}).values():
+                lib().yc_host_free(self.context_handle(), p)
+            self._pinned = {}
             lib().yr_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -261,10 +265,26 @@ class Renderer:
         return dict(samples_taken=d.samplesTaken, total_samples=d.totalSamples, total_rays=d.totalRays,
                     total_time_ms=d.totalTimeMs)
 
-    def read(self, want_hdr=True, want_ldr=True):
+    def _pinned_frame(self, key):
+        """A page-locked (h, w, 4) float32 array owned by this renderer (allocated once)."""
+        if not hasattr(self, "_pinned"):
+            self._pinned = {}
+        if key not in self._pinned:
+            h, w = self.settings.height, self.settings.width
+            p = C.c_void_p()
+            _check(lib().yc_host_alloc(self.context_handle(), h * w * 16, C.byref(p)), "yc_host_alloc")
+            buf = (C.c_float * (h * w * 4)).from_address(p.value)
+            self._pinned[key] = (p, np.frombuffer(buf, np.float32).reshape(h, w, 4))
+        return self._pinned[key][1]
+
+    def read(self, want_hdr=True, want_ldr=True, pinned=False):
         h, w = self.settings.height, self.settings.width
-        hdr = np.empty((h, w, 4), np.float32) if want_hdr else None
-        ldr = np.empty((h, w, 4), np.float32) if want_ldr else None
+        if pinned:
+            hdr = self._pinned_frame("hdr") if want_hdr else None
+            ldr = self._pinned_frame("ldr") if want_ldr else None
+        else:
+            hdr = np.empty((h, w, 4), np.float32) if want_hdr else None
+            ldr = np.empty((h, w, 4), np.float32) if want_ldr else None
         st = capi.YcStats()
         self._ck(lib().yr_read(self._h, hdr.ctypes.data if want_hdr else None, ldr.ctypes.data if want_ldr else None,
                                C.byref(st)), "yr_read")

@@ -108,6 +108,8 @@ PROTOTYPES = {
     "yc_trace_device": (C.c_int, [P, P, C.c_size_t, C.c_int, P, C.c_int, C.POINTER(f32)]),
     "yc_device_alloc": (C.c_int, [P, C.c_size_t, C.POINTER(P)]),
     "yc_device_free": (C.c_int, [P, P]),
+    "yc_host_alloc": (C.c_int, [P, C.c_size_t, C.POINTER(P)]),
+    "yc_host_free": (C.c_int, [P, P]),
     "yc_memcpy_h2d": (C.c_int, [P, P, P, C.c_size_t]),
     "yc_memcpy_d2h": (C.c_int, [P, P, P, C.c_size_t]),
     "yc_generate_primary_rays": (C.c_int, [P, u32, u32, P]),

@@ -109,11 +109,13 @@ YB_DEV bool russianRoulette(Sampler& smp, uint32_t depth, V3& att) {
 
 // ---- extend ---------------------------------------------------------------------------
 // ALPHA: scene has alpha-tested materials (traversal draws from the path's sampler).
-template <bool ALPHA, bool COUNT>
-YB_DEV void extendStage(const DScene& sc, const WaveParams& w, const PathState& ps, uint32_t i, TravStack& stack,
-                        TraceCounters& cnt) {
+// extendLoad / extendStore bracket the closest-hit traversal of one path, so the sequential driver
+// below and the persistent warp kernel (trace_kernels.cuh) share every bit of arithmetic.
+template <bool ALPHA>
+YB_DEV bool extendLoad(const WaveParams& w, const PathState& ps, uint32_t i, V3& o, V3& d, Sampler& smp) {
   const float4 ro = ps.rayO[i], rd = ps.rayD[i];
-  Sampler smp;
+  o = V3(ro.x, ro.y, ro.z);
+  d = V3(rd.x, rd.y, rd.z);
   if (ALPHA) {
     smp = pathSampler(w, i, ps.dim[i]);
     const uint32_t fl = ps.flags[i];
@@ -126,19 +128,40 @@ YB_DEV void extendStage(const DScene& sc, const WaveParams& w, const PathState& 
       ps.dim[i] = smp.dim;
       if (!alive) {
         ps.hitB[i] = kHitDead;
-        return;
+        return false;
       }
       ps.att[i] = make_float4(att.x, att.y, att.z, 0.0f);
     }
   }
-  TraceState st;
-  st.hit.t = INFINITY;
-  st.hit.node = kHitMiss;
-  st.attenuation = V3(1.0f);
-  traceScene<false, ALPHA, COUNT, false>(sc, V3(ro.x, ro.y, ro.z), V3(rd.x, rd.y, rd.z), st, stack, &smp, cnt);
+  return true;
+}
+
+template <bool ALPHA>
+YB_DEV void extendStore(const PathState& ps, uint32_t i, const TraceState& st, const Sampler& smp) {
   if (ALPHA) ps.dim[i] = smp.dim;
   ps.hitA[i] = make_float4(st.hit.t, st.hit.u, st.hit.v, __uint_as_float(st.hit.prim));
   ps.hitB[i] = st.hit.node < 0 ? kHitMiss : int32_t(uint32_t(st.hit.node) | (st.hit.backSide ? kBackSideBit : 0u));
+}
+
+YB_DEV void initTraceState(TraceState& st, float tMax) {
+  st.hit.t = tMax;
+  st.hit.u = st.hit.v = 0.0f;
+  st.hit.prim = 0xffffffffu;
+  st.hit.node = kHitMiss;
+  st.hit.backSide = 0;
+  st.attenuation = V3(1.0f);
+}
+
+template <bool ALPHA, bool COUNT>
+YB_DEV void extendStage(const DScene& sc, const WaveParams& w, const PathState& ps, uint32_t i, TravStack& stack,
+                        TraceCounters& cnt) {
+  V3 o, d;
+  Sampler smp;
+  if (!extendLoad<ALPHA>(w, ps, i, o, d, smp)) return;
+  TraceState st;
+  initTraceState(st, INFINITY);
+  traceScene<false, ALPHA, COUNT, false>(sc, o, d, st, stack, &smp, cnt);
+  extendStore<ALPHA>(ps, i, st, smp);
 }
 
 // ---- shade ----------------------------------------------------------------------------
@@ -270,33 +293,48 @@ YB_DEV uint32_t shadeStage(const DScene& sc, const WaveParams& w, const PathStat
 }
 
 // ---- shadow ---------------------------------------------------------------------------
-// Returns 1 if the NEE sample contributed (the ray the reference counts, mis-integrator.cpp:126).
-template <bool ALPHA, bool COUNT>
-YB_DEV uint32_t shadowStage(const DScene& sc, const WaveParams& w, const PathState& ps, const ShadowQueue& q,
-                            uint32_t j, TravStack& stack, TraceCounters& cnt) {
-  const float4 o4 = q.o[j], d4 = q.d[j], l4 = q.lif[j], a4 = q.att[j];
-  const uint32_t i = __float_as_uint(a4.w);
-  Sampler smp;
+template <bool ALPHA>
+YB_DEV uint32_t shadowLoad(const WaveParams& w, const PathState& ps, const ShadowQueue& q, uint32_t j, V3& o, V3& d,
+                           float& tMax, Sampler& smp) {
+  const float4 o4 = q.o[j], d4 = q.d[j];
+  const uint32_t i = __float_as_uint(q.att[j].w);
+  o = V3(o4.x, o4.y, o4.z);
+  d = V3(d4.x, d4.y, d4.z);
+  tMax = o4.w;
   if (ALPHA) smp = pathSampler(w, i, ps.dim[i]);
-  TraceState st;
-  st.hit.t = o4.w;
-  st.hit.node = kHitMiss;
-  st.attenuation = V3(1.0f);
-  // Without alpha-tested materials nothing observable depends on what an occluded NEE ray finds
-  // after its first occluder, so the any-hit walk may stop there; with them the draws must match.
-  const bool occluded = ALPHA ? traceScene<true, true, COUNT, false>(sc, V3(o4.x, o4.y, o4.z), V3(d4.x, d4.y, d4.z), st,
-                                                                     stack, &smp, cnt)
-                              : traceScene<true, false, COUNT, true>(sc, V3(o4.x, o4.y, o4.z), V3(d4.x, d4.y, d4.z), st,
-                                                                     stack, &smp, cnt);
+  return i;
+}
+
+// Returns 1 if the NEE sample contributed (the ray the reference counts, mis-integrator.cpp:126).
+template <bool ALPHA>
+YB_DEV uint32_t shadowFinish(const PathState& ps, const ShadowQueue& q, uint32_t j, uint32_t i, const TraceState& st,
+                             bool occluded, const Sampler& smp) {
   if (ALPHA) ps.dim[i] = smp.dim;
   if (occluded) return 0u;
-  // Ld: ls.Li * f * att / ... (mis-integrator.cpp:132), then L += attenuation * Ld (:80)
-  const V3 Ld = V3(l4.x, l4.y, l4.z) * st.attenuation * d4.w / l4.w;
+  const float4 l4 = q.lif[j], a4 = q.att[j];
+  // Ld: ls.Li * f * att * |wi.n| / (pdfBSDF + pdfLight) (mis-integrator.cpp:132), then L += attenuation * Ld (:80)
+  const V3 Ld = V3(l4.x, l4.y, l4.z) * st.attenuation * q.d[j].w / l4.w;
   const float4 L4 = ps.L[i];
   V3 L(L4.x, L4.y, L4.z);
   L += V3(a4.x, a4.y, a4.z) * Ld;
   ps.L[i] = make_float4(L.x, L.y, L.z, 0.0f);
   return 1u;
+}
+
+// Without alpha-tested materials nothing observable depends on what an occluded NEE ray finds
+// after its first occluder, so the any-hit walk may stop there (EARLY_OUT = !ALPHA); with them the
+// sampler draws must match the reference's, which keeps walking (ray-integrator.cpp:121).
+template <bool ALPHA, bool COUNT>
+YB_DEV uint32_t shadowStage(const DScene& sc, const WaveParams& w, const PathState& ps, const ShadowQueue& q,
+                            uint32_t j, TravStack& stack, TraceCounters& cnt) {
+  V3 o, d;
+  float tMax;
+  Sampler smp;
+  const uint32_t i = shadowLoad<ALPHA>(w, ps, q, j, o, d, tMax, smp);
+  TraceState st;
+  initTraceState(st, tMax);
+  const bool occluded = traceScene<true, ALPHA, COUNT, !ALPHA>(sc, o, d, st, stack, &smp, cnt);
+  return shadowFinish<ALPHA>(ps, q, j, i, st, occluded, smp);
 }
 
 }  // namespace yb

@@ -27,6 +27,8 @@ inline const char* alloc(void** p, size_t bytes) {
   return *p ? nullptr : "out of host memory (hostsim)";
 }
 inline void release(void* p) { free(p); }
+inline const char* hostAlloc(void** p, size_t bytes) { return alloc(p, bytes); }
+inline void hostRelease(void* p) { free(p); }
 inline const char* h2d(Stream&, void* d, const void* s, size_t n) {
   memcpy(d, s, n);
   return nullptr;
@@ -77,6 +79,10 @@ inline void destroy(Stream& st) {
 inline const char* alloc(void** p, size_t bytes) { return errstr(cudaMalloc(p, bytes ? bytes : 1)); }
 inline void release(void* p) {
   if (p) cudaFree(p);
+}
+inline const char* hostAlloc(void** p, size_t bytes) { return errstr(cudaMallocHost(p, bytes ? bytes : 1)); }
+inline void hostRelease(void* p) {
+  if (p) cudaFreeHost(p);
 }
 inline const char* h2d(Stream& st, void* d, const void* s, size_t n) {
   if (n == 0) return nullptr;

@@ -57,6 +57,25 @@ YB_DEV bool slab(const LocalRay& r, V3 lo, V3 hi, float tmn, float tmx, float& d
   return t1 >= t0;
 }
 
+// The same test for BVH child boxes inside a live traversal step (hit.t is not NaN there, because a
+// step only runs when `d < hit.t` held): with a non-NaN second operand `m > n ? m : n` equals
+// fmaxf(m, n) and `m < n ? m : n` equals fminf(m, n) for every m including NaN (both return n), up to
+// the sign of a zero that can never be selected (t0 >= tMin > 0) or never matters (t1 = ±0 < t0).
+// One FMNMX instead of FSETP + FSEL per fold.
+template <bool COUNT>
+YB_DEV bool slabLive(const LocalRay& r, V3 lo, V3 hi, float tmn, float tmx, float& d, TraceCounters& cnt) {
+  if (COUNT) cnt.box++;
+  const bool sx = r.d.x < 0.0f, sy = r.d.y < 0.0f, sz = r.d.z < 0.0f;
+  V3 bmin(sx ? hi.x : lo.x, sy ? hi.y : lo.y, sz ? hi.z : lo.z);
+  V3 bmax(sx ? lo.x : hi.x, sy ? lo.y : hi.y, sz ? lo.z : hi.z);
+  V3 tmin = bmin * r.idir + r.odir;
+  V3 tmax = bmax * r.idir + r.odir;
+  const float t0 = fmaxf(tmin.z, fmaxf(tmin.y, fmaxf(tmin.x, tmn)));
+  const float t1 = fminf(tmax.z, fminf(tmax.y, fminf(tmax.x, tmx)));
+  d = t0;
+  return t1 >= t0;
+}
+
 // Per-thread traversal stack: column `tid` of two shared arrays + local spill.
 struct TravStack {
   uint32_t* shRef;

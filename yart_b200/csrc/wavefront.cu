@@ -21,6 +21,9 @@
 #include "estimator.cuh"
 #include "integrator.cuh"
 #include "rt.cuh"
+#ifndef YB_HOSTSIM
+#include "trace_kernels.cuh"
+#endif
 
 using namespace yb;
 
@@ -55,6 +58,7 @@ struct yc_ctx {
   PathState ps{};
   ShadowQueue sq{};
   uint32_t *dQueueA = nullptr, *dQueueB = nullptr, *dCtr = nullptr;
+  void* dSpill = nullptr;  // traversal-stack spill area of the persistent kernels
   Counters* dCounters = nullptr;
   std::vector<void*> waveAllocs;
 
@@ -254,59 +258,59 @@ static void runShadow(yc_ctx* ctx, const WaveParams& w) {
   ctx->dCounters->triTests += cnt.tri;
 }
 #else
-constexpr int kTraceBlock = 128;  // 4 warps per CTA
+// Persistent extend / shadow kernels: IO adapters around tracePersistent (trace_kernels.cuh).
+template <bool ALPHA>
+struct ExtendIO {
+  WaveParams w;
+  PathState ps;
+  const uint32_t* queue;
+  __device__ __forceinline__ bool load(uint32_t j, V3& o, V3& d, float& tMax, Sampler& smp) const {
+    tMax = INFINITY;
+    return extendLoad<ALPHA>(w, ps, queue[j], o, d, smp);
+  }
+  __device__ __forceinline__ void store(uint32_t j, const TraceState& st, bool, const Sampler& smp) const {
+    extendStore<ALPHA>(ps, queue[j], st, smp);
+  }
+};
 
-// Persistent extend: each warp takes 32 queue entries per atomic; per-thread traversal stack in
-// shared memory ([entry][thread] so a warp's accesses hit 32 distinct banks).
 template <bool ALPHA, bool COUNT>
 __global__ void __launch_bounds__(kTraceBlock) extendKernel(DScene sc, WaveParams w, PathState ps, const uint32_t* queue,
-                                                            uint32_t n, uint32_t* ctr, Counters* counters) {
-  __shared__ uint32_t shRef[kShStack * kTraceBlock];
-  __shared__ float shD[kShStack * kTraceBlock];
-  TravStack stack;
-  stack.shRef = shRef + threadIdx.x;
-  stack.shD = shD + threadIdx.x;
-  stack.stride = kTraceBlock;
-  const int lane = threadIdx.x & 31;
+                                                            uint32_t n, uint32_t* ctr, Counters* counters, uint2* spill,
+                                                            TraceTuning tune) {
+  ExtendIO<ALPHA> io{w, ps, queue};
   TraceCounters cnt;
-  while (true) {
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(ctr + kCtrExtendHead, 32u);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (base >= n) break;
-    const uint32_t j = base + lane;
-    if (j < n) extendStage<ALPHA, COUNT>(sc, w, ps, queue[j], stack, cnt);
-    __syncwarp();
-  }
+  tracePersistent<false, ALPHA, COUNT, false>(sc, io, n, ctr + kCtrExtendHead, spill, tune, cnt);
   if (COUNT) {
     aggregatedCount(&counters->boxTests, cnt.box);
     aggregatedCount(&counters->triTests, cnt.tri);
   }
 }
 
+template <bool ALPHA>
+struct ShadowIO {
+  WaveParams w;
+  PathState ps;
+  ShadowQueue sq;
+  uint32_t contributed = 0;
+  uint32_t pathOf[1];  // unused
+  __device__ __forceinline__ bool load(uint32_t j, V3& o, V3& d, float& tMax, Sampler& smp) const {
+    shadowLoad<ALPHA>(w, ps, sq, j, o, d, tMax, smp);
+    return true;
+  }
+  __device__ __forceinline__ void store(uint32_t j, const TraceState& st, bool occluded, const Sampler& smp) {
+    contributed += shadowFinish<ALPHA>(ps, sq, j, __float_as_uint(sq.att[j].w), st, occluded, smp);
+  }
+};
+
 template <bool ALPHA, bool COUNT>
 __global__ void __launch_bounds__(kTraceBlock) shadowKernel(DScene sc, WaveParams w, PathState ps, ShadowQueue sq,
-                                                            uint32_t* ctr, Counters* counters) {
-  __shared__ uint32_t shRef[kShStack * kTraceBlock];
-  __shared__ float shD[kShStack * kTraceBlock];
-  TravStack stack;
-  stack.shRef = shRef + threadIdx.x;
-  stack.shD = shD + threadIdx.x;
-  stack.stride = kTraceBlock;
-  const int lane = threadIdx.x & 31;
+                                                            uint32_t* ctr, Counters* counters, uint2* spill, TraceTuning tune) {
   const uint32_t n = ctr[kCtrShadowCount];
+  ShadowIO<ALPHA> io{w, ps, sq};
   TraceCounters cnt;
-  uint32_t contributed = 0;
-  while (true) {
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(ctr + kCtrShadowHead, 32u);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (base >= n) break;
-    const uint32_t j = base + lane;
-    if (j < n) contributed += shadowStage<ALPHA, COUNT>(sc, w, ps, sq, j, stack, cnt);
-    __syncwarp();
-  }
-  aggregatedCount(&counters->raysReference, contributed);
+  // EARLY_OUT = !ALPHA: see shadowStage (integrator.cuh)
+  tracePersistent<true, ALPHA, COUNT, !ALPHA>(sc, io, n, ctr + kCtrShadowHead, spill, tune, cnt);
+  aggregatedCount(&counters->raysReference, io.contributed);
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counters->raysShadow, (unsigned long long)n);
   if (COUNT) {
     aggregatedCount(&counters->boxTests, cnt.box);
@@ -314,24 +318,30 @@ __global__ void __launch_bounds__(kTraceBlock) shadowKernel(DScene sc, WaveParam
   }
 }
 
+static int traceGridMax(const yc_ctx* ctx) { return ctx->smCount * 8; }
+static TraceTuning tuning(const yc_ctx* ctx) {
+  TraceTuning t;
+  t.refillMin = ctx->opts.reserved[0] ? int(ctx->opts.reserved[0]) : 8;
+  t.innerMin = ctx->opts.reserved[1] ? int(ctx->opts.reserved[1]) : 12;
+  return t;
+}
 static int traceGrid(const yc_ctx* ctx, uint32_t n) {
-  // persistent: enough CTAs to fill every SM (registers cap residency well below this)
-  const int full = ctx->smCount * 8;
+  // persistent: enough CTAs to fill every SM (registers / shared memory cap residency below this)
   const int needed = int((n + kTraceBlock - 1) / kTraceBlock);
-  return std::max(1, std::min(full, needed));
+  return std::max(1, std::min(traceGridMax(ctx), needed));
 }
 
 template <bool ALPHA, bool COUNT>
 static void runExtend(yc_ctx* ctx, const WaveParams& w, const uint32_t* queue, uint32_t n) {
   if (ctx->timeExtend) rt::eventRecord(ctx->st, ctx->evK0);
-  extendKernel<ALPHA, COUNT><<<traceGrid(ctx, n), kTraceBlock, 0, ctx->st.s>>>(ctx->ds, w, ctx->ps, queue, n, ctx->dCtr,
-                                                                               ctx->dCounters);
+  extendKernel<ALPHA, COUNT><<<traceGrid(ctx, n), kTraceBlock, 0, ctx->st.s>>>(
+    ctx->ds, w, ctx->ps, queue, n, ctx->dCtr, ctx->dCounters, static_cast<uint2*>(ctx->dSpill), tuning(ctx));
   if (ctx->timeExtend) rt::eventRecord(ctx->st, ctx->evK1);
 }
 template <bool ALPHA, bool COUNT>
 static void runShadow(yc_ctx* ctx, const WaveParams& w, uint32_t upperBound) {
-  shadowKernel<ALPHA, COUNT><<<traceGrid(ctx, upperBound), kTraceBlock, 0, ctx->st.s>>>(ctx->ds, w, ctx->ps, ctx->sq,
-                                                                                        ctx->dCtr, ctx->dCounters);
+  shadowKernel<ALPHA, COUNT><<<traceGrid(ctx, upperBound), kTraceBlock, 0, ctx->st.s>>>(
+    ctx->ds, w, ctx->ps, ctx->sq, ctx->dCtr, ctx->dCounters, static_cast<uint2*>(ctx->dSpill), tuning(ctx));
 }
 #endif
 
@@ -469,6 +479,13 @@ static int ensureWaveStorage(yc_ctx* ctx) {
   YC_TRY(devAlloc(own, &ctx->dQueueB, P));
   YC_TRY(devAlloc(own, &ctx->dCtr, size_t(kCtrCount)));
   YC_TRY(devAlloc(own, &ctx->dCounters, size_t(1)));
+#ifndef YB_HOSTSIM
+  {
+    uint2* sp = nullptr;
+    YC_TRY(devAlloc(own, &sp, size_t(traceGridMax(ctx)) * kTraceBlock * (kMaxStack - kShStack)));
+    ctx->dSpill = sp;
+  }
+#endif
   YC_TRY(rt::zero(ctx->st, ctx->dCounters, sizeof(Counters)));
   YC_TRY(rt::zero(ctx->st, ctx->dCtr, kCtrCount * sizeof(uint32_t)));
   return YC_OK;
@@ -498,41 +515,50 @@ extern "C" int yc_begin_frame(yc_ctx* ctx, const YcFrameDesc* f) {
   const uint32_t shardCount = f->shardCount ? f->shardCount : 1;
   if (f->shardIndex >= shardCount) return fail(ctx, YC_ERR_INVALID, "shardIndex >= shardCount");
   YC_TRY(rt::sync(ctx->st));
-  freeFrame(ctx);
   int rc = ensureWaveStorage(ctx);
   if (rc != YC_OK) return rc;
+  // same geometry as the previous frame: keep the allocations and the pixel list, just clear
+  const bool sameLayout = ctx->dHdr && ctx->frame.width == f->width && ctx->frame.height == f->height &&
+                          ctx->frame.tileSize == f->tileSize && ctx->frame.shardIndex == f->shardIndex &&
+                          ctx->frame.shardCount == shardCount;
+  ctx->inFrame = false;
   ctx->frame = *f;
   ctx->frame.shardCount = shardCount;
-  // tile list as TileRenderer::renderImpl builds it (tile-renderer.hpp:127-144), sharded by index
-  ctx->pixels.clear();
-  const uint32_t ts = f->tileSize;
-  const uint32_t tilesX = (f->width + ts - 1) / ts, tilesY = (f->height + ts - 1) / ts;
-  for (uint32_t ty = 0; ty < tilesY; ty++)
-    for (uint32_t tx = 0; tx < tilesX; tx++) {
-      const uint32_t index = ty * tilesX + tx;
-      if (index % shardCount != f->shardIndex) continue;
-      const uint32_t x0 = tx * ts, y0 = ty * ts;
-      const uint32_t tw = std::min(ts, f->width - x0), th = std::min(ts, f->height - y0);
-      for (uint32_t y = 0; y < th; y++)
-        for (uint32_t x = 0; x < tw; x++) ctx->pixels.push_back((x0 + x) | ((y0 + y) << 16));
-    }
-  const size_t nPix = ctx->pixels.size(), frameTexels = size_t(f->width) * f->height;
-  void* p = nullptr;
-  YC_TRY(rt::alloc(&p, std::max<size_t>(nPix, 1) * 4));
-  ctx->dPixels = static_cast<uint32_t*>(p);
-  YC_TRY(rt::alloc(&p, std::max<size_t>(nPix, 1) * 4));
-  ctx->dPixelsScratch = static_cast<uint32_t*>(p);
-  YC_TRY(rt::alloc(&p, frameTexels * sizeof(float4)));
-  ctx->dHdr = static_cast<float4*>(p);
-  YC_TRY(rt::alloc(&p, frameTexels * sizeof(float4)));
-  ctx->dLdr = static_cast<float4*>(p);
-  ctx->bucketCapacity = std::max<size_t>(nPix, 1);
-  YC_TRY(rt::alloc(&p, ctx->bucketCapacity * kMaxBuckets * sizeof(float4)));
-  ctx->dBuckets = static_cast<float4*>(p);
-  YC_TRY(rt::h2d(ctx->st, ctx->dPixels, ctx->pixels.data(), nPix * 4));
+  const size_t frameTexels = size_t(f->width) * f->height;
+  if (!sameLayout) {
+    freeFrame(ctx);
+    // tile list as TileRenderer::renderImpl builds it (tile-renderer.hpp:127-144), sharded by index
+    ctx->pixels.clear();
+    const uint32_t ts = f->tileSize;
+    const uint32_t tilesX = (f->width + ts - 1) / ts, tilesY = (f->height + ts - 1) / ts;
+    for (uint32_t ty = 0; ty < tilesY; ty++)
+      for (uint32_t tx = 0; tx < tilesX; tx++) {
+        const uint32_t index = ty * tilesX + tx;
+        if (index % shardCount != f->shardIndex) continue;
+        const uint32_t x0 = tx * ts, y0 = ty * ts;
+        const uint32_t tw = std::min(ts, f->width - x0), th = std::min(ts, f->height - y0);
+        for (uint32_t y = 0; y < th; y++)
+          for (uint32_t x = 0; x < tw; x++) ctx->pixels.push_back((x0 + x) | ((y0 + y) << 16));
+      }
+    const size_t nPixNew = ctx->pixels.size();
+    void* p = nullptr;
+    YC_TRY(rt::alloc(&p, std::max<size_t>(nPixNew, 1) * 4));
+    ctx->dPixels = static_cast<uint32_t*>(p);
+    YC_TRY(rt::alloc(&p, std::max<size_t>(nPixNew, 1) * 4));
+    ctx->dPixelsScratch = static_cast<uint32_t*>(p);
+    YC_TRY(rt::alloc(&p, frameTexels * sizeof(float4)));
+    ctx->dHdr = static_cast<float4*>(p);
+    YC_TRY(rt::alloc(&p, frameTexels * sizeof(float4)));
+    ctx->dLdr = static_cast<float4*>(p);
+    ctx->bucketCapacity = std::max<size_t>(nPixNew, 1);
+    YC_TRY(rt::alloc(&p, ctx->bucketCapacity * kMaxBuckets * sizeof(float4)));
+    ctx->dBuckets = static_cast<float4*>(p);
+    YC_TRY(rt::h2d(ctx->st, ctx->dPixels, ctx->pixels.data(), nPixNew * 4));
+    // finalize leaves every bucket it reads zeroed, so the planes only need clearing once
+    YC_TRY(rt::zero(ctx->st, ctx->dBuckets, ctx->bucketCapacity * kMaxBuckets * sizeof(float4)));
+  }
   YC_TRY(rt::zero(ctx->st, ctx->dHdr, frameTexels * sizeof(float4)));
   YC_TRY(rt::zero(ctx->st, ctx->dLdr, frameTexels * sizeof(float4)));
-  YC_TRY(rt::zero(ctx->st, ctx->dBuckets, ctx->bucketCapacity * kMaxBuckets * sizeof(float4)));
   YC_TRY(rt::zero(ctx->st, ctx->dCounters, sizeof(Counters)));
   YC_TRY(rt::sync(ctx->st));
   ctx->launches = 0;
@@ -754,51 +780,59 @@ static void runTrace(yc_ctx* ctx, const YcRay* rays, uint32_t n, bool useTMax, Y
   ctx->dCounters->triTests += cnt.tri;
 }
 #else
-template <bool NEE, bool ALPHA, bool COUNT, bool COMPACT>
-__global__ void __launch_bounds__(kTraceBlock) traceKernel(DScene sc, const YcRay* rays, uint32_t n, int useTMax, YcHit* hits,
-                                                           CompactHit* compact, uint32_t* head, Counters* counters) {
-  __shared__ uint32_t shRef[kShStack * kTraceBlock];
-  __shared__ float shD[kShStack * kTraceBlock];
-  TravStack stack;
-  stack.shRef = shRef + threadIdx.x;
-  stack.shD = shD + threadIdx.x;
-  stack.stride = kTraceBlock;
-  const int lane = threadIdx.x & 31;
-  TraceCounters cnt;
-  while (true) {
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(head, 32u);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (base >= n) break;
-    const uint32_t i = base + lane;
-    if (i < n) {
+template <bool NEE, bool ALPHA, bool COMPACT>
+struct TraceIO {
+  DScene sc;
+  const YcRay* rays;
+  YcHit* hits;
+  CompactHit* compact;
+  int useTMax;
+  __device__ __forceinline__ bool load(uint32_t i, V3& o, V3& d, float& tMax, Sampler& smp) const {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(rays) + 2 * size_t(i));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(rays) + 2 * size_t(i) + 1);
+    o = V3(a.x, a.y, a.z);
+    d = V3(b.x, b.y, b.z);
+    tMax = (NEE || useTMax) ? b.w : INFINITY;
+    smp = traceHookSampler();
+    return true;
+  }
+  __device__ __forceinline__ void store(uint32_t i, const TraceState& st, bool did, const Sampler&) const {
+    if (COMPACT) {
+      CompactHit c;
+      c.t = st.hit.t, c.u = st.hit.u, c.v = st.hit.v, c.prim = st.hit.prim;
+      c.node = st.hit.node < 0 ? kHitMiss : int32_t(uint32_t(st.hit.node) | (st.hit.backSide ? kBackSideBit : 0u));
+      compact[i] = c;
+      return;
+    }
+    YcHit out;
+    out.t = st.hit.t;
+    out.didHit = did ? 1u : 0u;
+    out.prim = did ? st.hit.prim : 0xffffffffu;
+    out.material = -1, out.lightIdx = -1, out.backSide = 0;
+    for (int k = 0; k < 3; k++) out.p[k] = out.n[k] = out.tg[k] = 0.0f;
+    out.uv[0] = out.uv[1] = 0.0f;
+    out.attenuation[0] = st.attenuation.x, out.attenuation[1] = st.attenuation.y, out.attenuation[2] = st.attenuation.z;
+    if (did) {
       const float4 a = __ldg(reinterpret_cast<const float4*>(rays) + 2 * size_t(i));
       const float4 b = __ldg(reinterpret_cast<const float4*>(rays) + 2 * size_t(i) + 1);
-      if (COMPACT) {
-        Sampler smp = traceHookSampler();
-        TraceState st;
-        st.hit.t = (NEE || useTMax) ? b.w : INFINITY;
-        st.hit.node = kHitMiss;
-        st.hit.u = st.hit.v = 0.0f;
-        st.hit.prim = 0xffffffffu;
-        st.hit.backSide = 0;
-        st.attenuation = V3(1.0f);
-        traceScene<NEE, ALPHA, COUNT, false>(sc, V3(a.x, a.y, a.z), V3(b.x, b.y, b.z), st, stack, &smp, cnt);
-        CompactHit c;
-        c.t = st.hit.t, c.u = st.hit.u, c.v = st.hit.v, c.prim = st.hit.prim;
-        c.node = st.hit.node < 0 ? kHitMiss : int32_t(uint32_t(st.hit.node) | (st.hit.backSide ? kBackSideBit : 0u));
-        compact[i] = c;
-      } else {
-        YcRay r;
-        r.o[0] = a.x, r.o[1] = a.y, r.o[2] = a.z, r.tmin = a.w;
-        r.d[0] = b.x, r.d[1] = b.y, r.d[2] = b.z, r.tmax = b.w;
-        YcHit h;
-        traceOne<NEE, ALPHA, COUNT>(sc, r, useTMax != 0, h, stack, cnt);
-        hits[i] = h;
-      }
+      const SurfaceHit s = resolveHit(sc, st.hit, V3(a.x, a.y, a.z), V3(b.x, b.y, b.z));
+      out.material = s.material, out.lightIdx = s.lightIdx, out.backSide = st.hit.backSide;
+      out.p[0] = s.p.x, out.p[1] = s.p.y, out.p[2] = s.p.z;
+      out.n[0] = s.n.x, out.n[1] = s.n.y, out.n[2] = s.n.z;
+      out.tg[0] = s.tg.x, out.tg[1] = s.tg.y, out.tg[2] = s.tg.z;
+      out.uv[0] = s.uv.x, out.uv[1] = s.uv.y;
     }
-    __syncwarp();
+    hits[i] = out;
   }
+};
+
+template <bool NEE, bool ALPHA, bool COUNT, bool COMPACT>
+__global__ void __launch_bounds__(kTraceBlock) traceKernel(DScene sc, const YcRay* rays, uint32_t n, int useTMax, YcHit* hits,
+                                                           CompactHit* compact, uint32_t* head, Counters* counters,
+                                                           uint2* spill, TraceTuning tune) {
+  TraceIO<NEE, ALPHA, COMPACT> io{sc, rays, hits, compact, useTMax};
+  TraceCounters cnt;
+  tracePersistent<NEE, ALPHA, COUNT, false>(sc, io, n, head, spill, tune, cnt);
   if (COUNT) {
     aggregatedCount(&counters->boxTests, cnt.box);
     aggregatedCount(&counters->triTests, cnt.tri);
@@ -808,12 +842,13 @@ __global__ void __launch_bounds__(kTraceBlock) traceKernel(DScene sc, const YcRa
 template <bool NEE, bool ALPHA, bool COUNT>
 static void runTrace(yc_ctx* ctx, const YcRay* rays, uint32_t n, bool useTMax, YcHit* hits, CompactHit* compact) {
   const int grid = traceGrid(ctx, n);
+  uint2* spill = static_cast<uint2*>(ctx->dSpill);
   if (compact)
     traceKernel<NEE, ALPHA, COUNT, true><<<grid, kTraceBlock, 0, ctx->st.s>>>(ctx->ds, rays, n, useTMax, hits, compact,
-                                                                              ctx->dCtr, ctx->dCounters);
+                                                                              ctx->dCtr, ctx->dCounters, spill, tuning(ctx));
   else
     traceKernel<NEE, ALPHA, COUNT, false><<<grid, kTraceBlock, 0, ctx->st.s>>>(ctx->ds, rays, n, useTMax, hits, compact,
-                                                                               ctx->dCtr, ctx->dCounters);
+                                                                               ctx->dCtr, ctx->dCounters, spill, tuning(ctx));
 }
 #endif
 
@@ -890,6 +925,16 @@ extern "C" int yc_device_free(yc_ctx* ctx, void* p) {
   if (!ctx) return YC_ERR_INVALID;
   rt::sync(ctx->st);
   rt::release(p);
+  return YC_OK;
+}
+extern "C" int yc_host_alloc(yc_ctx* ctx, size_t bytes, void** out) {
+  if (!ctx || !out) return YC_ERR_INVALID;
+  YC_TRY(rt::hostAlloc(out, bytes));
+  return YC_OK;
+}
+extern "C" int yc_host_free(yc_ctx* ctx, void* p) {
+  if (!ctx) return YC_ERR_INVALID;
+  rt::hostRelease(p);
   return YC_OK;
 }
 extern "C" int yc_memcpy_h2d(yc_ctx* ctx, void* dst, const void* src, size_t bytes) {

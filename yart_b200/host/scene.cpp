@@ -229,6 +229,10 @@ bool HostScene::build(const ysc::SceneDesc& d, std::string* err) {
     put3(y.bmin, b.bounds.mn);
     put3(y.bmax, b.bounds.mx);
     y.mesh = nd.mesh, y.parent = parentFlat, y.skip = int(nodes.size()), y.depth = depth;
+    static const float kIdentityRows[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    const bool selfIdentity = memcmp(y.inv, kIdentityRows, sizeof kIdentityRows) == 0 &&
+                              memcmp(y.fwd, kIdentityRows, sizeof kIdentityRows) == 0;
+    y.identityChain = selfIdentity && (parentFlat < 0 || nodes[parentFlat].identityChain);
     return b;
   };
   visit(0, -1, 0);
