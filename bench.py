@@ -34,6 +34,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 W, H = 1920, 1080
+_REAL_STDOUT = sys.stdout
 METRIC = "Mrays/s at 1080p (primary + shadow rays, reference ray count)"
 
 
@@ -145,7 +146,7 @@ def run_reference(args):
         "e2e": {"value": res["mrays"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "samples_per_s": W * H * 1 / (res["ms_per_step"] / 1e3),
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_REAL_STDOUT, flush=True)
 
 
 def run_ours(args):
@@ -329,7 +330,7 @@ def run_ours(args):
                          "standalone_trace_ms": trace_ms},
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_REAL_STDOUT, flush=True)
     ctx.close()
     if dist:
         dist.barrier()
@@ -337,6 +338,12 @@ def run_ours(args):
 
 
 def main():
+    # Only the JSON line may reach stdout: libraries (NCCL prints its version there) write to fd 1 too,
+    # so fd 1 is pointed at stderr for the run and the line goes to the saved descriptor.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

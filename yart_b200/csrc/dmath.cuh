@@ -8,10 +8,12 @@
 #ifdef YB_HOSTSIM
 #include "hostshim.hpp"
 #define YB_DEV inline
+#define YB_DEV_NI inline
 #define YB_CONST static const
 #else
 #include <cuda_runtime.h>
 #define YB_DEV __device__ __forceinline__
+#define YB_DEV_NI __device__ __noinline__
 #define YB_CONST __device__ __constant__
 #endif
 #include <math.h>

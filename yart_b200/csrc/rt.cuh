@@ -48,7 +48,7 @@ inline void eventRecord(Stream&, Event& e) { e.t = std::chrono::high_resolution_
 inline float eventElapsedMs(Event& a, Event& b) { return std::chrono::duration<float, std::milli>(b.t - a.t).count(); }
 inline const char* lastError() { return nullptr; }
 
-template <class F>
+template <int MIN_BLOCKS = 1, class F>
 inline void launchFor(Stream&, uint32_t n, const F& f) {
   for (uint32_t i = 0; i < n; i++) f(i);
 }
@@ -111,15 +111,16 @@ inline float eventElapsedMs(Event& a, Event& b) {
 }
 inline const char* lastError() { return errstr(cudaGetLastError()); }
 
-template <class F>
-__global__ void __launch_bounds__(256) forKernel(uint32_t n, F f) {
+// MIN_BLOCKS: resident CTAs per SM the register allocation must allow (occupancy vs registers)
+template <class F, int MIN_BLOCKS>
+__global__ void __launch_bounds__(256, MIN_BLOCKS) forKernel(uint32_t n, F f) {
   const uint32_t i = blockIdx.x * 256u + threadIdx.x;
   if (i < n) f(i);
 }
-template <class F>
+template <int MIN_BLOCKS = 1, class F>
 inline void launchFor(Stream& st, uint32_t n, const F& f) {
   if (n == 0) return;
-  forKernel<F><<<(n + 255u) / 256u, 256, 0, st.s>>>(n, f);
+  forKernel<F, MIN_BLOCKS><<<(n + 255u) / 256u, 256, 0, st.s>>>(n, f);
 }
 #endif
 

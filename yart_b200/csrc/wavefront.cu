@@ -27,6 +27,10 @@
 
 using namespace yb;
 
+#ifndef YB_SHADE_MIN_BLOCKS
+#define YB_SHADE_MIN_BLOCKS 1
+#endif
+
 // ---------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------
@@ -597,7 +601,7 @@ static int renderChunks(yc_ctx* ctx, const uint32_t* dList, uint32_t nPixCall, u
       for (uint32_t bounce = 0; bounce < ctx->opts.maxDepth && n > 0; bounce++) {
         YC_TRY(rt::zero(ctx->st, ctx->dCtr, kCtrCount * sizeof(uint32_t)));
         runExtend<ALPHA, false>(ctx, w, qCur, n);
-        rt::launchFor(ctx->st, n, ShadeK<ALPHA>{ctx->ds, w, ctx->ps, ctx->sq, qCur, qNext, ctx->dCtr, ctx->dCounters});
+        rt::launchFor<YB_SHADE_MIN_BLOCKS>(ctx->st, n, ShadeK<ALPHA>{ctx->ds, w, ctx->ps, ctx->sq, qCur, qNext, ctx->dCtr, ctx->dCounters});
 #ifdef YB_HOSTSIM
         runShadow<ALPHA, false>(ctx, w);
 #else
