@@ -39,7 +39,10 @@ KATS = [  # (file tag, kind, n, kwargs, scene)
     ("light", "light", 2048, dict(n_lights=6), "material_zoo"),
 ]
 
-TRACE_SCENES = [("cornell", {}), ("material_zoo", {}), ("soup", dict(n_tris=20000)), ("two_quads", {})]
+SPONZA_S = dict(n_tris=6000, tex_res=32, env_res=32, n_materials=9)
+MCLAREN_S = dict(n_tris=6000, env_res=32)
+TRACE_SCENES = [("cornell", {}), ("material_zoo", {}), ("soup", dict(n_tris=20000)), ("two_quads", {}),
+                ("sponza", SPONZA_S), ("mclaren", MCLAREN_S)]
 
 RENDERS = [  # (tag, scene, scene kwargs, w, h, spp, first, max, maxdepth, tonemap)
     ("two_quads", "two_quads", {}, 64, 64, 16, 16, 16, 30, "agx"),
@@ -48,6 +51,8 @@ RENDERS = [  # (tag, scene, scene kwargs, w, h, spp, first, max, maxdepth, tonem
     ("zoo", "material_zoo", {}, 96, 64, 16, 16, 16, 30, "agx"),
     ("zoo_waves", "material_zoo", {}, 48, 32, 64, 4, 32, 30, "golden"),
     ("soup_d1", "soup", dict(n_tris=20000), 96, 54, 4, 4, 4, 1, "agx"),
+    ("sponza_small", "sponza", SPONZA_S, 96, 54, 16, 16, 16, 30, "agx"),   # C3 shape: textured PBR + env only
+    ("mclaren_small", "mclaren", MCLAREN_S, 96, 54, 16, 4, 8, 30, "punchy"),  # C4 shape: coat / glass / volume
 ]
 
 

@@ -55,6 +55,8 @@ def scene_camera(name: str, **kw) -> dict:
     from yart_b200 import scenes
     if name == "soup":
         kw = dict(kw, n_tris=8)  # camera does not depend on the triangle count
+    if name in ("sponza", "mclaren"):
+        kw = dict(kw, n_tris=100, env_res=4, **({"tex_res": 4} if name == "sponza" else {}))
     return getattr(scenes, name)(**kw).camera
 
 

@@ -153,3 +153,84 @@ def test_empty_and_degenerate_inputs():
     bad[:, 7] = np.inf
     hits, _ = ctx.trace(bad)
     assert hits["didHit"].tolist() == [0, 1, 0]  # what the reference does too: a NaN t passes `t <= tMin || hit.t <= t`
+
+
+# ------------------------------------------------------------------------------------------
+# BASELINE.json configs at (or near) full size
+# ------------------------------------------------------------------------------------------
+def _render_ctx(sc, cam, w, h, spp, waves, max_depth=30, tonemap=Y.TONEMAP_AGX, **frame_kw):
+    c = Y.make_camera(w, h, cam["focal"], cam["fnum"], cam["pos"], cam["target"], (0, 0, 0), cam["exposure"])
+    ctx = Y.Context(max_depth=max_depth)
+    ctx.upload_scene(sc)
+    ctx.set_camera(c)
+    ctx.begin_frame(w, h, spp, 64, (0, 0, 0), tonemap, **frame_kw)
+    taken = 0
+    for wv in waves:
+        ctx.render_wave(taken, wv, taken)
+        taken += wv
+    hdr, ldr, st = ctx.resolve()
+    ctx.close()
+    return hdr, ldr, st
+
+
+needs_oracle = pytest.mark.skipif(not H.have_oracle(), reason="oracle/_ref/oracle_ref not present on this box")
+
+
+@needs_oracle
+def test_c1_cornell_512_16spp_matches_reference_run_here():
+    """configs[0] exactly: Cornell box, 512x512, 16 spp MIS+NEE, against the reference run on this box."""
+    sp, cam = H.scene_file("cornell"), H.scene_camera("cornell")
+    ref = H.oracle_render(sp, 512, 512, 16, cam, first=16, max=16, tonemap="agx")
+    hdr, ldr, st = _render_ctx(Y.Scene(sp), cam, 512, 512, 16, [16])
+    assert H.rel_mse(hdr, ref["hdr"]) < 1e-3 and H.rel_mse(ldr, ref["ldr"]) < 1e-3  # the north-star bar
+    assert st.raysReference == ref["rays"]
+    assert H.bits_equal(hdr, ref["hdr"]).all()
+    assert np.allclose(ldr, ref["ldr"], rtol=2e-5, atol=1e-6)
+
+
+@needs_oracle
+def test_c3_sponza_shape_1080p_matches_reference_run_here():
+    """configs[2] shape at full resolution and triangle count (260 K tris, textured PBR + normal maps +
+    alpha cut-outs, env light only), 1 spp so the CPU reference finishes in seconds."""
+    kw = dict(n_tris=260_000, tex_res=256, env_res=512)
+    from yart_b200 import scenes
+    sp, cam = H.scene_file("sponza", **kw), scenes.sponza(n_tris=100, tex_res=4, env_res=4).camera
+    ref = H.oracle_render(sp, 1920, 1080, 1, cam, first=1, max=1, tonemap="agx")
+    sc = Y.Scene(sp)
+    assert 200_000 < sc.n_tris < 300_000
+    hdr, ldr, st = _render_ctx(sc, cam, 1920, 1080, 1, [1])
+    assert H.rel_mse(hdr, ref["hdr"]) < 1e-3 and H.rel_mse(ldr, ref["ldr"]) < 1e-3
+    assert st.raysReference == ref["rays"]
+    assert H.bits_equal(hdr, ref["hdr"]).mean() > 0.999999  # identical up to a libm last-bit event per ~1e8 calls
+
+
+def test_c4_mclaren_shape_2m_tris_properties():
+    """configs[3] shape at full size (≈2 M tris, clearcoat / chrome / thin + solid glass with volume,
+    emissive lamps + env): determinism, finite output, tile shards sum to the full frame."""
+    from yart_b200 import scenes
+    kw = dict(n_tris=2_000_000, env_res=512)
+    sp, cam = H.scene_file("mclaren", **kw), scenes.mclaren(n_tris=100, env_res=4).camera
+    sc = Y.Scene(sp)
+    assert sc.n_tris > 1_800_000
+    w, h = 960, 540
+    a = _render_ctx(sc, cam, w, h, 4, [4])
+    b = _render_ctx(sc, cam, w, h, 4, [4])
+    assert H.bits_equal(a[0], b[0]).all() and a[2].raysReference == b[2].raysReference
+    assert np.isfinite(a[0]).all() and a[0][..., :3].mean() > 0.01
+    parts = [_render_ctx(sc, cam, w, h, 4, [4], shard_index=k, shard_count=2) for k in range(2)]
+    assert H.bits_equal(parts[0][0] + parts[1][0], a[0]).all()
+    assert parts[0][2].raysReference + parts[1][2].raysReference == a[2].raysReference
+
+
+def test_c5_4k_progressive_gmon_sharded_equals_unsharded():
+    """configs[4] shape: 3840x2160, progressive waves (8, 16) with GMoN, tile-sharded over 2 contexts;
+    the summed frames must be bit-identical to the unsharded render."""
+    sp, cam = H.scene_file("cornell"), H.scene_camera("cornell")
+    sc = Y.Scene(sp)
+    w, h = 3840, 2160
+    full = _render_ctx(sc, cam, w, h, 24, [8, 16])
+    parts = [_render_ctx(sc, cam, w, h, 24, [8, 16], shard_index=k, shard_count=2) for k in range(2)]
+    assert H.bits_equal(parts[0][0] + parts[1][0], full[0]).all()
+    assert H.bits_equal(parts[0][1] + parts[1][1], full[1]).all()
+    assert parts[0][2].raysReference + parts[1][2].raysReference == full[2].raysReference
+    assert np.isfinite(full[0]).all()

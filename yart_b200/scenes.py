@@ -409,3 +409,222 @@ def material_zoo(env=True) -> Scene:
     s.camera = dict(pos=(0.5, 4.0, 13.0), target=(0.0, 2.5, 0.0), focal=35.0, fnum=4.0, exposure=1.0,
                     w=96, h=64, spp=16)
     return s
+
+
+# ------------------------------------------------------------------------------------------
+# parametric surfaces (vectorised) for the large synthetic scenes
+# ------------------------------------------------------------------------------------------
+def surface_mesh(fn, nu: int, nv: int, mat: int, uv_scale=(1.0, 1.0), flip=False):
+    """Tessellates p = fn(u, v), u,v in [0,1], into nu x nv quads (2 triangles each).
+    Returns (positions, normals, tangents(4), uvs, faces) with smooth normals from finite differences."""
+    u = np.linspace(0.0, 1.0, nu + 1)
+    v = np.linspace(0.0, 1.0, nv + 1)
+    U, V = np.meshgrid(u, v, indexing="xy")  # (nv+1, nu+1)
+    P = fn(U, V)  # (nv+1, nu+1, 3)
+    e = 1e-4
+    dU = (fn(np.clip(U + e, 0, 1), V) - fn(np.clip(U - e, 0, 1), V))
+    dV = (fn(U, np.clip(V + e, 0, 1)) - fn(U, np.clip(V - e, 0, 1)))
+    N = np.cross(dU, dV)
+    ln = np.linalg.norm(N, axis=-1, keepdims=True)
+    N = np.where(ln > 1e-20, N / np.maximum(ln, 1e-20), np.array([0.0, 1.0, 0.0]))
+    T = dU / np.maximum(np.linalg.norm(dU, axis=-1, keepdims=True), 1e-20)
+    if flip:
+        N = -N
+    idx = (np.arange(nv + 1)[:, None] * (nu + 1) + np.arange(nu + 1)[None, :])
+    a, b, c, d = idx[:-1, :-1], idx[:-1, 1:], idx[1:, 1:], idx[1:, :-1]
+    if flip:
+        f1 = np.stack([a, c, b], -1)
+        f2 = np.stack([a, d, c], -1)
+    else:
+        f1 = np.stack([a, b, c], -1)
+        f2 = np.stack([a, c, d], -1)
+    faces = np.concatenate([f1.reshape(-1, 3), f2.reshape(-1, 3)], 0)
+    faces = np.concatenate([faces, np.full((len(faces), 1), mat)], 1).astype(np.uint32)
+    uv = np.stack([U * uv_scale[0], V * uv_scale[1]], -1)
+    tg = np.concatenate([T, np.ones(T.shape[:-1] + (1,))], -1)
+    return (P.reshape(-1, 3).astype(np.float32), N.reshape(-1, 3).astype(np.float32),
+            tg.reshape(-1, 4).astype(np.float32), uv.reshape(-1, 2).astype(np.float32), faces)
+
+
+class BigMesh:
+    """Concatenates surface patches into one Mesh (one BVH, like a merged glTF mesh, gltf.cpp:178-270)."""
+
+    def __init__(self):
+        self.parts = []
+        self.nv = 0
+
+    def add(self, part):
+        p, n, t, uv, f = part
+        f = f.copy()
+        f[:, :3] += self.nv
+        self.nv += len(p)
+        self.parts.append((p, n, t, uv, f))
+
+    def n_tris(self):
+        return sum(len(x[4]) for x in self.parts)
+
+    def build(self) -> Mesh:
+        cat = lambda k: np.concatenate([x[k] for x in self.parts], 0)
+        return Mesh(cat(0), cat(1), cat(2), cat(3), cat(4))
+
+
+def _plane(origin, du, dv):
+    o, du, dv = (np.asarray(x, np.float64) for x in (origin, du, dv))
+    return lambda U, V: o + U[..., None] * du + V[..., None] * dv
+
+
+def _cylinder(cx, cz, r, y0, y1, flute=0.0, nfl=16):
+    def fn(U, V):
+        ang = 2 * np.pi * U
+        rr = r * (1.0 + flute * np.cos(nfl * ang)) * (1.0 + 0.08 * np.cos(np.pi * V) ** 8)
+        return np.stack([cx + rr * np.cos(ang), y0 + (y1 - y0) * V, cz - rr * np.sin(ang)], -1)
+    return fn
+
+
+def _arch(x0, x1, z, y, r_tube):
+    """Half torus spanning x0..x1 at height y (an arch between two columns)."""
+    R = 0.5 * (x1 - x0)
+    cx = 0.5 * (x0 + x1)
+
+    def fn(U, V):
+        a = np.pi * U  # along the arch
+        b = 2 * np.pi * V  # around the tube
+        rr = R + r_tube * np.cos(b)
+        return np.stack([cx - rr * np.cos(a), y + rr * np.sin(a), z + r_tube * np.sin(b)], -1)
+    return fn
+
+
+def _pbr_material_set(rng, tex_res, n_sets, textures, alpha_every=0):
+    """n_sets textured PBR materials (base sRGB RGBA, MR, normal); returns material list."""
+    mats = []
+    for k in range(n_sets):
+        base = _noise_tex(rng, tex_res, tex_res, 4, 50, 240)
+        base[..., :3] = (base[..., :3] * rng.uniform(0.6, 1.0, 3)).astype(np.uint8)
+        base[..., 3] = 255
+        if alpha_every and k % alpha_every == alpha_every - 1:
+            yy, xx = np.mgrid[0:tex_res, 0:tex_res]
+            holes = ((xx // max(1, tex_res // 8) + yy // max(1, tex_res // 8)) % 3 == 0)
+            base[holes, 3] = 0
+        mr = _noise_tex(rng, tex_res, tex_res, 2, 60, 255)
+        mr[..., 1] = (mr[..., 1] * 0.15).astype(np.uint8)  # mostly dielectric
+        nrm = _noise_tex(rng, tex_res, tex_res, 3, 100, 155)
+        nrm[..., 2] = 235
+        i0 = len(textures)
+        textures += [Texture(base, SRGB), Texture(mr, NONCOLOR), Texture(nrm, NONCOLOR)]
+        mats.append(Material(base=(1, 1, 1), base_tex=i0, mr_tex=i0 + 1, normal_tex=i0 + 2, roughness=1.0, metallic=1.0))
+    return mats
+
+
+# ------------------------------------------------------------------------------------------
+# C3: Sponza-shaped atrium, textured PBR + normal maps, lit only by an HDR environment map
+# ------------------------------------------------------------------------------------------
+def sponza(n_tris=260_000, tex_res=1024, env_res=2048, n_materials=24, seed=21) -> Scene:
+    rng = np.random.default_rng(seed)
+    s = Scene()
+    s.materials = _pbr_material_set(rng, tex_res, n_materials, s.textures, alpha_every=8)
+    # tessellation budget: d scales every patch; triangles grow ~ d^2
+    d = max(1, int(round(np.sqrt(n_tris / 1716.0))))
+    bm = BigMesh()
+    L, Wd, Hh = 30.0, 12.0, 14.0  # atrium length (x), width (z), height
+    m = lambda k: k % n_materials
+    bm.add(surface_mesh(lambda U, V: _plane((-L / 2, 0, Wd / 2), (L, 0, 0), (0, 0, -Wd))(U, V) +
+                        np.stack([0 * U, 0.02 * np.sin(40 * U) * np.sin(30 * V), 0 * U], -1), 12 * d, 6 * d, m(0), (8, 4)))
+    bm.add(surface_mesh(_plane((-L / 2, 0, -Wd / 2), (L, 0, 0), (0, Hh, 0)), 10 * d, 5 * d, m(1), (6, 3)))  # back wall
+    bm.add(surface_mesh(_plane((L / 2, 0, Wd / 2), (-L, 0, 0), (0, Hh, 0)), 10 * d, 5 * d, m(2), (6, 3)))  # front wall
+    bm.add(surface_mesh(_plane((-L / 2, 0, Wd / 2), (0, 0, -Wd), (0, Hh, 0)), 5 * d, 5 * d, m(3), (3, 3)))  # left
+    bm.add(surface_mesh(_plane((L / 2, 0, -Wd / 2), (0, 0, Wd), (0, Hh, 0)), 5 * d, 5 * d, m(4), (3, 3)))  # right
+    ncol = 8
+    xs = np.linspace(-L / 2 + 3, L / 2 - 3, ncol)
+    for row, z in enumerate((-Wd / 2 + 2.5, Wd / 2 - 2.5)):
+        for i, x in enumerate(xs):
+            bm.add(surface_mesh(_cylinder(x, z, 0.45, 0.0, 6.0, 0.04), 6 * d, 3 * d, m(5 + (i + row) % 6), (2, 4)))
+            bm.add(surface_mesh(_cylinder(x, z, 0.38, 7.0, 11.5, 0.0), 4 * d, 2 * d, m(11 + (i + row) % 4), (2, 3)))
+            if i + 1 < ncol:
+                bm.add(surface_mesh(_arch(x, xs[i + 1], z, 6.0, 0.3), 5 * d, 2 * d, m(15 + i % 3), (3, 1)))
+        # gallery floor slab along the row
+        zz = z + (1.2 if row == 0 else -1.2)
+        bm.add(surface_mesh(_plane((-L / 2, 7.0, zz - 1.4), (L, 0, 0), (0, 0, 2.8)), 8 * d, 2 * d, m(18 + row), (8, 1),
+                            flip=True))
+    # hanging drapes with alpha cut-outs (material k % 8 == 7 carries the holes)
+    for i, x in enumerate(xs[1::2]):
+        def drape(U, V, x=x, i=i):
+            return np.stack([x + 0.15 * np.sin(6 * np.pi * V + i), 10.5 - 5.0 * V, -1.5 + 3.0 * U + 0 * V], -1)
+        bm.add(surface_mesh(drape, 3 * d, 4 * d, 7 if n_materials > 7 else 0, (2, 3)))
+    s.meshes = [bm.build()]
+    s.nodes = [Node(-1, -1), Node(0, 0)]
+    s.textures.append(Texture(sky_hdr(env_res, env_res, 5, 6000.0), LINEAR))
+    s.lights = [Light(IMAGE_INF, hdr_tex=len(s.textures) - 1, scene_radius=100.0)]
+    # src/main.cpp:32-34, 69-72 style: f/4, exposure set for the env brightness
+    s.camera = dict(pos=(-12.0, 2.0, 0.5), target=(8.0, 5.0, -0.5), focal=24.0, fnum=4.0, exposure=0.0,
+                    w=1920, h=1080, spp=1024)
+    return s
+
+
+# ------------------------------------------------------------------------------------------
+# C4: McLaren-shaped scene: metallic paint + clearcoat, chrome, thin and solid glass (+ volume),
+#     emissive headlights, ground, HDR environment
+# ------------------------------------------------------------------------------------------
+def mclaren(n_tris=2_000_000, env_res=2048, seed=33) -> Scene:
+    rng = np.random.default_rng(seed)
+    s = Scene()
+    s.materials = [
+        Material(base=(0.85, 0.25, 0.02), metallic=0.9, roughness=0.35, clearcoat=1.0, clearcoat_roughness=0.03),  # 0 paint
+        Material(base=(0.95, 0.95, 0.95), metallic=1.0, roughness=0.05),  # 1 chrome
+        Material(base=(0.03, 0.03, 0.03), roughness=0.8),  # 2 tyre
+        Material(base=(0.9, 0.95, 1.0), transmission=1.0, roughness=0.0, ior=1.5, thin=1),  # 3 window (thin glass)
+        Material(base=(1.0, 1.0, 1.0), transmission=1.0, roughness=0.05, ior=1.5, thin=0,
+                 volume_color=(0.9, 0.6, 0.3), volume_density=1.5),  # 4 solid lens with Beer-Lambert volume
+        Material(base=(1, 1, 1), roughness=1.0, emission=(40.0, 38.0, 30.0)),  # 5 headlight emitter
+        Material(base=(0.35, 0.35, 0.36), roughness=0.6),  # 6 asphalt
+        Material(base=(0.05, 0.05, 0.06), metallic=1.0, roughness=0.3, anisotropic=0.7, aniso_rotation=0.3),  # 7 brushed trim
+    ]
+    d = max(1, int(round(np.sqrt(n_tris / 2905.0))))
+    bm = BigMesh()
+
+    def body(U, V):
+        th, ph = np.pi * V, 2 * np.pi * U
+        bump = 1.0 + 0.03 * np.sin(9 * ph) * np.sin(7 * th) + 0.15 * np.exp(-((V - 0.35) / 0.12) ** 2) * (np.cos(ph) > 0)
+        x = 2.3 * np.sin(th) * np.cos(ph) * bump
+        y = 0.62 + 0.55 * np.cos(th) * bump
+        z = 1.0 * np.sin(th) * np.sin(ph) * bump
+        return np.stack([x, np.maximum(y, 0.18), z], -1)
+    bm.add(surface_mesh(body, 40 * d, 20 * d, 0))
+
+    def canopy(U, V):
+        th, ph = 0.5 * np.pi * V, 2 * np.pi * U
+        return np.stack([-0.2 + 0.9 * np.sin(th) * np.cos(ph), 1.0 + 0.42 * np.cos(th), 0.62 * np.sin(th) * np.sin(ph)], -1)
+    bm.add(surface_mesh(canopy, 16 * d, 8 * d, 3))
+
+    for sx in (-1.45, 1.45):
+        for sz in (-1.02, 1.02):
+            def tyre(U, V, sx=sx, sz=sz):
+                a, b = 2 * np.pi * U, 2 * np.pi * V
+                rr = 0.36 + 0.12 * np.cos(b)
+                return np.stack([sx + rr * np.cos(a), 0.48 + rr * np.sin(a), sz + 0.13 * np.sin(b)], -1)
+            bm.add(surface_mesh(tyre, 12 * d, 6 * d, 2))
+
+            def rim(U, V, sx=sx, sz=sz):
+                a = 2 * np.pi * U
+                rr = 0.26 * V * (1.0 + 0.12 * np.cos(5 * a))
+                return np.stack([sx + rr * np.cos(a), 0.48 + rr * np.sin(a), sz + np.sign(sz) * (0.14 - 0.05 * V) + 0 * a], -1)
+            bm.add(surface_mesh(rim, 10 * d, 3 * d, 1, flip=sz < 0))
+    for sz in (-0.55, 0.55):
+        def lens(U, V, sz=sz):
+            th, ph = np.pi * V, 2 * np.pi * U
+            return np.stack([2.05 + 0.16 * np.sin(th) * np.cos(ph), 0.62 + 0.1 * np.cos(th), sz + 0.2 * np.sin(th) * np.sin(ph)], -1)
+        bm.add(surface_mesh(lens, 8 * d, 4 * d, 4))
+    bm.add(surface_mesh(_plane((-2.2, 0.75, -0.9), (0.0, 0, 1.8), (0.5, 0.05, 0.0)), 4 * d, 1 * d, 7))  # rear trim
+    bm.add(surface_mesh(_plane((-12, 0, 8), (24, 0, 0), (0, 0, -16)), 8 * d, 6 * d, 6, (12, 8)))  # ground
+    car = bm.build()
+    lb = MeshBuilder()
+    for sz in (-0.55, 0.55):  # emitters inside the lenses, facing +x
+        lb.quad((2.0, 0.56, sz - 0.08), (2.0, 0.56, sz + 0.08), (2.0, 0.68, sz + 0.08), (2.0, 0.68, sz - 0.08), 5)
+    lamps = lb.build()
+    s.meshes = [car, lamps]
+    s.nodes = [Node(-1, -1), Node(0, 0), Node(0, 1)]
+    s.add_area_lights(1, None)
+    s.textures.append(Texture(sky_hdr(env_res, env_res, 9, 3000.0), LINEAR))
+    s.lights.append(Light(IMAGE_INF, hdr_tex=len(s.textures) - 1, scene_radius=100.0))
+    s.camera = dict(pos=(5.5, 1.6, 4.2), target=(0.0, 0.6, 0.0), focal=35.0, fnum=4.0, exposure=0.0,
+                    w=1920, h=1080, spp=1024)
+    return s
