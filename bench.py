@@ -216,19 +216,30 @@ def run_ours(args):
             ctx.retonemap()
         return ar_ms
 
+    clocks = ClockSampler(local)  # started before the warm-up: nvidia-smi needs ~0.3 s to print its first sample
     for _ in range(max(args.warmup, 3)):
         step()
     sync_all()
     s0 = ctx.stats()
-    clocks = ClockSampler(local)
     w0 = time.time()
     ar_total = 0.0
     for _ in range(args.steps):
         ar_total += step()
     sync_all()
     w1 = time.time()
-    clk = clocks.stop(w0, w1)
     s1 = ctx.stats()
+    # keep the GPU under the same load until a few clock samples exist (not timed); the number of
+    # extra steps is agreed across ranks so the collectives stay matched
+    n_extra = int((0.5 - (w1 - w0)) / max((w1 - w0) / args.steps, 1e-4)) + 1 if w1 - w0 < 0.5 else 0
+    if dist:
+        import torch
+        t = torch.tensor([n_extra], device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        n_extra = int(t.item())
+    for _ in range(min(n_extra, 200)):
+        step()
+    sync_all()
+    clk = clocks.stop(w0, time.time())
     dev_ms = (s1.gpuMs - s0.gpuMs) + ar_total
     rays = s1.raysReference - s0.raysReference
     traced = (s1.raysExtend - s0.raysExtend) + (s1.raysShadow - s0.raysShadow)

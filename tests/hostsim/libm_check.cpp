@@ -1,6 +1,6 @@
 // libm_check — TEST INFRASTRUCTURE.  Compares csrc/libm_exact.cuh (compiled for the host) with this
 // machine's glibc over EVERY float of the argument ranges the render path uses:
-//   sinf, cosf on [0, 8)   logf on (0, 1]   expf on [-87, 4]
+//   sinf, cosf on [0, 8)   logf on (0, 1]   expf on [-87, 4]   log2f on (0, 1e30]   powf(x, {1, 0.8, 1.35, 2.2}) on [-16, 16]
 // Prints one line per function: values tested, mismatches.   g++ -O2 -ffp-contract=off -DYB_HOSTSIM
 #include <cmath>
 #include <cstdio>
@@ -59,5 +59,13 @@ int main(int argc, char** argv) {
   sweep("logf", 1, bitsOf(1.0f), false, yb::logfExact, [](float x) { return logf(x); }, stride);
   sweep("expf", 0, bitsOf(4.0f), false, yb::expfExact, [](float x) { return expf(x); }, stride);
   sweep("expf", 0, bitsOf(87.0f), true, yb::expfExact, [](float x) { return expf(x); }, stride);
+  sweep("log2f", 1, bitsOf(1e30f), false, yb::log2fExact, [](float x) { return log2f(x); }, stride);
+  const float ys[4] = {1.0f, 0.8f, 1.35f, 2.2f};  // AgX look powers and the final 2.2
+  for (float y : ys) {
+    char name[32];
+    snprintf(name, sizeof name, "powf(x,%g)", y);
+    sweep(name, 0, bitsOf(16.0f), false, [y](float x) { return yb::powfExact(x, y); }, [y](float x) { return powf(x, y); }, stride);
+    sweep(name, 1, bitsOf(16.0f), true, [y](float x) { return yb::powfExact(x, y); }, [y](float x) { return powf(x, y); }, stride);
+  }
   return 0;
 }

@@ -12,11 +12,9 @@ import numpy as np
 import harness as H
 import yart_b200 as Y
 
-# KAT output columns whose path goes through log2f / powf (AgX only): the one place where the CUDA
-# build still uses the platform libm, so the last ulp may differ from glibc.  Everything else is
-# +,-,*,/,sqrt in IEEE fp32 without FMA contraction plus the glibc-exact sinf/cosf/logf/expf of
-# csrc/libm_exact.cuh, and must be bit-exact on the GPU too.
-TRANSCENDENTAL_COLUMNS = {"agx": [0, 1, 2]}
+# Every KAT is +,-,*,/,sqrt in IEEE fp32 without FMA contraction plus the glibc-exact
+# sinf/cosf/logf/expf/log2f/powf of csrc/libm_exact.cuh: bit-exact on the GPU too.
+TRANSCENDENTAL_COLUMNS = {}
 
 
 def golden_files(prefix: str):
@@ -120,12 +118,11 @@ def check_render(path, exact: bool):
     else:
         # GPU.  north_star tolerance: per-pixel relative MSE < 1e-3 at equal spp with the reference's
         # sampler seeds, HDR and after AgX.  The path arithmetic is bit-compatible (see above), so the
-        # HDR frame and the ray count are in fact identical; only the tonemap's log2f/powf may move the
-        # LDR frame by an ulp.
+        # HDR frame, the LDR frame and the ray count are in fact identical.
         assert H.rel_mse(hdr, g["hdr"]) < 1e-3, f"{tag}: HDR relMSE {H.rel_mse(hdr, g['hdr'])}"
         assert H.rel_mse(ldr, g["ldr"]) < 1e-3, f"{tag}: LDR relMSE {H.rel_mse(ldr, g['ldr'])}"
         assert data["total_rays"] == int(g["rays"]), f"{tag}: ray count {data['total_rays']} vs {int(g['rays'])}"
         assert H.bits_equal(hdr, g["hdr"]).all(), f"{tag}: HDR differs in {(~H.bits_equal(hdr, g['hdr'])).sum()} words"
-        assert np.allclose(ldr, g["ldr"], rtol=2e-5, atol=1e-6, equal_nan=True), f"{tag}: LDR beyond ulp-level tolerance"
+        assert H.bits_equal(ldr, g["ldr"]).all(), f"{tag}: LDR differs in {(~H.bits_equal(ldr, g['ldr'])).sum()} words"
     assert st.raysExtend >= data["total_rays"] - st.raysShadow
     return hdr, ldr

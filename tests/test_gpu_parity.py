@@ -184,8 +184,7 @@ def test_c1_cornell_512_16spp_matches_reference_run_here():
     hdr, ldr, st = _render_ctx(Y.Scene(sp), cam, 512, 512, 16, [16])
     assert H.rel_mse(hdr, ref["hdr"]) < 1e-3 and H.rel_mse(ldr, ref["ldr"]) < 1e-3  # the north-star bar
     assert st.raysReference == ref["rays"]
-    assert H.bits_equal(hdr, ref["hdr"]).all()
-    assert np.allclose(ldr, ref["ldr"], rtol=2e-5, atol=1e-6)
+    assert H.bits_equal(hdr, ref["hdr"]).all() and H.bits_equal(ldr, ref["ldr"]).all()
 
 
 @needs_oracle
@@ -201,7 +200,8 @@ def test_c3_sponza_shape_1080p_matches_reference_run_here():
     hdr, ldr, st = _render_ctx(sc, cam, 1920, 1080, 1, [1])
     assert H.rel_mse(hdr, ref["hdr"]) < 1e-3 and H.rel_mse(ldr, ref["ldr"]) < 1e-3
     assert st.raysReference == ref["rays"]
-    assert H.bits_equal(hdr, ref["hdr"]).mean() > 0.999999  # identical up to a libm last-bit event per ~1e8 calls
+    # identical up to a libm last-bit event per ~1e9 calls (glibc's FMA ifunc variants, see libm_exact.cuh)
+    assert H.bits_equal(hdr, ref["hdr"]).mean() > 0.999999 and H.bits_equal(ldr, ref["ldr"]).mean() > 0.999999
 
 
 def test_c4_mclaren_shape_2m_tris_properties():

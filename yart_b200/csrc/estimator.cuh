@@ -7,6 +7,7 @@
 #pragma once
 #include "../../include/yart_cuda.h"
 #include "dmath.cuh"
+#include "libm_exact.cuh"
 
 namespace yb {
 
@@ -127,7 +128,7 @@ YB_DEV V3 agx(V3 val, const AgxLook& look) {
                        float(-0.0529716355144438), float(-0.0980434501171241), float(1.15107367264116)};
   const float minEv = -12.47393f, maxEv = 4.026069f;
   val = mul3x3(A, val);
-  V3 lg(log2f(val.x), log2f(val.y), log2f(val.z));
+  V3 lg(log2fExact(val.x), log2fExact(val.y), log2fExact(val.z));
   // clamp(v, lo, hi) = min(hi, max(lo, v)) with math::min/max semantics (vec.hpp:437-446)
   val = V3(rmin(maxEv, rmax(minEv, lg.x)), rmin(maxEv, rmax(minEv, lg.y)), rmin(maxEv, rmax(minEv, lg.z)));
   val = (val - V3(minEv)) / (V3(maxEv) - V3(minEv));
@@ -135,12 +136,12 @@ YB_DEV V3 agx(V3 val, const AgxLook& look) {
   // applyLook
   float l = luma(val);
   V3 b = val * look.slope + look.offset;
-  val = V3(powf(b.x, look.power.x), powf(b.y, look.power.y), powf(b.z, look.power.z));
+  val = V3(powfExact(b.x, look.power.x), powfExact(b.y, look.power.y), powfExact(b.z, look.power.z));
   val = V3(l) + look.sat * (val - l);
   // end
   val = mul3x3(AI, val);
   val = V3(rmin(1.0f, rmax(0.0f, val.x)), rmin(1.0f, rmax(0.0f, val.y)), rmin(1.0f, rmax(0.0f, val.z)));
-  return V3(powf(val.x, 2.2f), powf(val.y, 2.2f), powf(val.z, 2.2f));
+  return V3(powfExact(val.x, 2.2f), powfExact(val.y, 2.2f), powfExact(val.z, 2.2f));
 }
 
 }  // namespace yb

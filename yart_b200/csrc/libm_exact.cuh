@@ -194,4 +194,121 @@ YB_DEV float expfExact(float x) {
   return float(y);
 }
 
+namespace libm {
+// __log2f_data (e_log2f_data.c): 16 x {invc, log2(c)}; __powf_log2_data.tab holds the same pairs
+YB_CONST double kLog2Tab[32] = {
+  0x1.661ec79f8f3bep+0, -0x1.efec65b963019p-2, 0x1.571ed4aaf883dp+0, -0x1.b0b6832d4fca4p-2,
+  0x1.49539f0f010bp+0,  -0x1.7418b0a1fb77bp-2, 0x1.3c995b0b80385p+0, -0x1.39de91a6dcf7bp-2,
+  0x1.30d190c8864a5p+0, -0x1.01d9bf3f2b631p-2, 0x1.25e227b0b8eap+0,  -0x1.97c1d1b3b7afp-3,
+  0x1.1bb4a4a1a343fp+0, -0x1.2f9e393af3c9fp-3, 0x1.12358f08ae5bap+0, -0x1.960cbbf788d5cp-4,
+  0x1.0953f419900a7p+0, -0x1.a6f9db6475fcep-5, 0x1p+0,               0x0p+0,
+  0x1.e608cfd9a47acp-1, 0x1.338ca9f24f53dp-4,  0x1.ca4b31f026aap-1,  0x1.476a9543891bap-3,
+  0x1.b2036576afce6p-1, 0x1.e840b4ac4e4d2p-3,  0x1.9c2d163a1aa2dp-1, 0x1.40645f0c6651cp-2,
+  0x1.886e6037841edp-1, 0x1.88e9c2c1b9ff8p-2,  0x1.767dcf5534862p-1, 0x1.ce0a44eb17bccp-2};
+constexpr double kLog2A0 = -0x1.712b6f70a7e4dp-2, kLog2A1 = 0x1.ecabf496832ep-2, kLog2A2 = -0x1.715479ffae3dep-1,
+                 kLog2A3 = 0x1.715475f35c8b8p0;
+// __powf_log2_data.poly (POWF_SCALE = 1)
+constexpr double kPowA0 = 0x1.27616c9496e0bp-2, kPowA1 = -0x1.71969a075c67ap-2, kPowA2 = 0x1.ec70a6ca7baddp-2,
+                 kPowA3 = -0x1.7154748bef6c8p-1, kPowA4 = 0x1.71547652ab82bp0;
+// __exp2f_data.poly and shift_scaled (= 0x1.8p+52 / 32)
+constexpr double kExp2C0 = 0x1.c6af84b912394p-5, kExp2C1 = 0x1.ebfce50fac4f3p-3, kExp2C2 = 0x1.62e42ff0c52d6p-1;
+constexpr double kExp2ShiftScaled = 0x1.8p+52 / 32.0;
+}  // namespace libm
+
+// e_log2f.c.  x <= 0, inf, NaN: platform log2f (same IEEE special values).
+YB_DEV float log2fExact(float x) {
+  using namespace libm;
+  uint32_t ix = __float_as_uint(x);
+  if (ix == 0x3f800000u) return 0.0f;
+  if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u) {
+    if (ix * 2 == 0 || ix == 0x7f800000u || (ix & 0x80000000u) || ix * 2 >= 0xff000000u) return log2f(x);
+    ix = __float_as_uint(x * 0x1p23f);
+    ix -= 23u << 23;
+  }
+  const uint32_t tmp = ix - 0x3f330000u;
+  const int i = int((tmp >> (23 - 4)) % 16u);
+  const uint32_t top = tmp & 0xff800000u;
+  const uint32_t iz = ix - top;
+  const int k = int32_t(tmp) >> 23;
+  const double invc = kLog2Tab[2 * i], logc = kLog2Tab[2 * i + 1];
+  const double z = double(__uint_as_float(iz));
+  const double r = dadd(dmul(z, invc), -1.0);
+  const double y0 = dadd(logc, double(k));
+  const double r2 = dmul(r, r);
+  double y = dadd(dmul(kLog2A1, r), kLog2A2);
+  y = dadd(dmul(kLog2A0, r2), y);
+  const double p = dadd(dmul(kLog2A3, r), y0);
+  y = dadd(dmul(y, r2), p);
+  return float(y);
+}
+
+// e_powf.c for finite non-zero x and finite non-zero y; zeros, infinities and NaNs take the platform
+// powf (IEEE 754 special values, identical in both libraries).
+YB_DEV float powfExact(float x, float y) {
+  using namespace libm;
+  uint32_t ix = __float_as_uint(x);
+  const uint32_t iy = __float_as_uint(y);
+  uint64_t signBias = 0;
+  const bool yZeroInfNan = 2u * iy - 1u >= 2u * 0x7f800000u - 1u;
+  if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u || yZeroInfNan) {
+    const bool xZeroInfNan = 2u * ix - 1u >= 2u * 0x7f800000u - 1u;
+    if (yZeroInfNan || xZeroInfNan) return powf(x, y);
+    if (ix & 0x80000000u) {
+      // finite x < 0: checkint(iy)
+      const int e = int(iy >> 23) & 0xff;
+      int yint;
+      if (e < 0x7f) yint = 0;
+      else if (e > 0x7f + 23) yint = 2;
+      else if (iy & ((1u << (0x7f + 23 - e)) - 1u)) yint = 0;
+      else if (iy & (1u << (0x7f + 23 - e))) yint = 1;
+      else yint = 2;
+      if (yint == 0) return powf(x, y);  // NaN (invalid)
+      if (yint == 1) signBias = 1ull << (5 + 11);
+      ix &= 0x7fffffffu;
+    }
+    if (ix < 0x00800000u) {
+      ix = __float_as_uint(x * 0x1p23f);
+      ix &= 0x7fffffffu;
+      ix -= 23u << 23;
+    }
+  }
+  // log2_inline
+  const uint32_t tmp = ix - 0x3f330000u;
+  const int i = int((tmp >> (23 - 4)) % 16u);
+  const uint32_t top = tmp & 0xff800000u;
+  const uint32_t iz = ix - top;
+  const int k = int32_t(top) >> 23;
+  const double invc = kLog2Tab[2 * i], logc = kLog2Tab[2 * i + 1];
+  const double z = double(__uint_as_float(iz));
+  const double r = dadd(dmul(z, invc), -1.0);
+  const double y0 = dadd(logc, double(k));
+  const double r2 = dmul(r, r);
+  double yy = dadd(dmul(kPowA0, r), kPowA1);
+  const double p = dadd(dmul(kPowA2, r), kPowA3);
+  const double r4 = dmul(r2, r2);
+  double q = dadd(dmul(kPowA4, r), y0);
+  q = dadd(dmul(p, r2), q);
+  yy = dadd(dmul(yy, r4), q);
+  const double ylogx = dmul(double(y), yy);
+  if (((asU64(ylogx) >> 47) & 0xffff) >= (asU64(126.0) >> 47)) {
+    if (ylogx > 0x1.fffffffd1d571p+6) return signBias ? -INFINITY : INFINITY;
+    if (ylogx <= -150.0) return signBias ? -0.0f : 0.0f;
+  }
+  // exp2_inline
+  double kd = dadd(ylogx, kExp2ShiftScaled);
+  const uint64_t ki = asU64(kd);
+  kd = dadd(kd, -kExp2ShiftScaled);
+  const double rr = dadd(ylogx, -kd);
+  uint64_t t = kExp2Tab[ki % 32u];
+  const uint64_t ski = ki + signBias;
+  t += ski << (52 - 5);
+  const double s = asDouble(t);
+  const double zz = dadd(dmul(kExp2C0, rr), kExp2C1);
+  const double rr2 = dmul(rr, rr);
+  double res = dadd(dmul(kExp2C2, rr), 1.0);
+  res = dadd(dmul(zz, rr2), res);
+  res = dmul(res, s);
+  return float(res);
+}
+
 }  // namespace yb

@@ -28,7 +28,7 @@
 using namespace yb;
 
 #ifndef YB_SHADE_MIN_BLOCKS
-#define YB_SHADE_MIN_BLOCKS 1
+#define YB_SHADE_MIN_BLOCKS 2
 #endif
 
 // ---------------------------------------------------------------------------------------
