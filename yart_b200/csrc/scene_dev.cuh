@@ -17,6 +17,7 @@ namespace yb {
 struct DScene {
   const YcNode* nodes;
   uint32_t nNodes;
+  const int32_t* nodePath;  // [nNodes][YC_MAX_NODE_DEPTH]: ancestors of node i from the root (level 0) down to i
   const YcMesh* meshes;
   uint32_t nMeshes;
   const float4* bvhNodes;

@@ -52,12 +52,12 @@ struct WarpStack {
 };
 
 // Ray in the object space of scene node `node`: the chain of inverse transforms root → node, applied
-// in the recursion's order (ray-integrator.cpp:26-30).  Ancestors are found by walking parent links.
+// in the recursion's order (ray-integrator.cpp:26-30).  The ancestor chain is a host-built table.
 __device__ __forceinline__ void nodeLocalRay(const DScene& sc, uint32_t node, int depth, V3& o, V3& d) {
+  const int32_t* __restrict__ path = sc.nodePath + size_t(node) * YC_MAX_NODE_DEPTH;
+#pragma unroll 1
   for (int level = 0; level <= depth; level++) {
-    uint32_t a = node;
-    for (int up = depth - level; up > 0; up--) a = uint32_t(sc.nodes[a].parent);
-    const YcNode& nd = sc.nodes[a];
+    const YcNode& nd = sc.nodes[path[level]];
     const V3 no = xformRows(nd.inv, o, 1.0f), ndir = xformRows(nd.inv, d, 0.0f);
     o = no;
     d = ndir;
@@ -109,6 +109,10 @@ __device__ __forceinline__ void tracePersistent(const DScene& sc, IO& io, uint32
   const float4* __restrict__ nodes = nullptr;
   const float4* __restrict__ tris = nullptr;
   uint32_t meshIdx = 0;
+  constexpr bool SPEC = !COUNT;           // counting builds reproduce the reference's box-test counts
+  constexpr uint32_t kNoRef = 0xffffffffu;  // "no current node" (has the leaf bit: never stepped as inner)
+  uint32_t pend = 0u;                     // parked leaf (0 = none; leaf refs carry bit 31)
+  float pendD = 0.0f;
 
   for (;;) {
     // ---- refill idle lanes -------------------------------------------------------------------
@@ -176,6 +180,7 @@ __device__ __forceinline__ void tracePersistent(const DScene& sc, IO& io, uint32
         cur = mesh.rootRef;
         dcur = dd;
         sp = 0;
+        pend = 0u;
         meshHit = false;
         entered = true;
         break;
@@ -189,7 +194,17 @@ __device__ __forceinline__ void tracePersistent(const DScene& sc, IO& io, uint32
     }
 
     // ---- inner-node steps ------------------------------------------------------------------------
+    // SPEC (all non-counting builds): a lane that reaches a leaf parks it in `pend` and keeps walking;
+    // it only blocks when it reaches a second leaf (or runs out of stack) with one still parked.
+    // Parked leaves are tested in the order they were reached, before any later leaf, so the sequence
+    // of triangle tests — and with it the accepted hit, exact ties and alpha-test draws — is the
+    // reference's.  Only box culling sees a slightly older hit.t, i.e. a few extra box tests.
     for (;;) {
+      if (SPEC && state == kLaneTrav && (cur & YC_REF_LEAF) && cur != kNoRef && pend == 0u) {
+        pend = cur, pendD = dcur;
+        if (sp == 0) cur = kNoRef;
+        else stack.pop(--sp, cur, dcur);
+      }
       const bool inner = state == kLaneTrav && !(cur & YC_REF_LEAF);
       const unsigned im = __ballot_sync(FULL, inner);
       if (im == 0) break;
@@ -216,7 +231,8 @@ __device__ __forceinline__ void tracePersistent(const DScene& sc, IO& io, uint32
         if (hit1 || hit2) {
           cur = nearRef, dcur = nearD;
         } else if (sp == 0) {
-          state = kLaneNode;  // this mesh is done: on to the next scene node
+          if (SPEC && pend != 0u) cur = kNoRef;  // mesh walked, one leaf still parked
+          else state = kLaneNode;                // this mesh is done: on to the next scene node
         } else {
           stack.pop(--sp, cur, dcur);
         }
@@ -224,10 +240,25 @@ __device__ __forceinline__ void tracePersistent(const DScene& sc, IO& io, uint32
     }
 
     // ---- leaf step -------------------------------------------------------------------------------
-    if (state == kLaneTrav && (cur & YC_REF_LEAF)) {
-      if (dcur < st.hit.t) {
+    // kNoRef carries the leaf bit, so "cur is a leaf" also covers "nothing left but a parked leaf".
+    if (state == kLaneTrav && ((cur & YC_REF_LEAF) || (SPEC && pend != 0u))) {
+      uint32_t leaf = cur;
+      float leafD = dcur;
+      if (SPEC) {
+        if (pend != 0u) {
+          leaf = pend, leafD = pendD;
+          pend = 0u;
+        } else {
+          // only reachable for cur == kNoRef with nothing parked (cannot happen) or a fresh leaf
+          if (cur != kNoRef) {
+            if (sp == 0) cur = kNoRef;
+            else stack.pop(--sp, cur, dcur);
+          }
+        }
+      }
+      if (leaf != kNoRef && leafD < st.hit.t) {
         const YcMesh& mesh = sc.meshes[meshIdx];
-        uint32_t ti = cur & ~YC_REF_LEAF;
+        uint32_t ti = leaf & ~YC_REF_LEAF;
         while (true) {
           const float4 a = __ldg(tris + 3 * size_t(ti)), b = __ldg(tris + 3 * size_t(ti) + 1),
                        c = __ldg(tris + 3 * size_t(ti) + 2);
@@ -241,6 +272,9 @@ __device__ __forceinline__ void tracePersistent(const DScene& sc, IO& io, uint32
       if (NEE && EARLY_OUT && didHit) {
         io.store(item, st, true, smp);
         state = kLaneIdle;
+        pend = 0u;
+      } else if (SPEC) {
+        if (cur == kNoRef) state = kLaneNode;  // stack empty and nothing parked any more
       } else if (sp == 0) {
         state = kLaneNode;
       } else {

@@ -326,7 +326,7 @@ static int traceGridMax(const yc_ctx* ctx) { return ctx->smCount * 8; }
 static TraceTuning tuning(const yc_ctx* ctx) {
   TraceTuning t;
   t.refillMin = ctx->opts.reserved[0] ? int(ctx->opts.reserved[0]) : 8;
-  t.innerMin = ctx->opts.reserved[1] ? int(ctx->opts.reserved[1]) : 12;
+  t.innerMin = ctx->opts.reserved[1] ? int(ctx->opts.reserved[1]) : 20;
   return t;
 }
 static int traceGrid(const yc_ctx* ctx, uint32_t n) {
@@ -415,7 +415,8 @@ extern "C" int yc_upload_scene(yc_ctx* ctx, const YcScene* s) {
   for (uint32_t i = 0; i < s->nNodes; i++) {
     const YcNode& n = s->nodes[i];
     if (n.depth < 0 || n.depth >= YC_MAX_NODE_DEPTH || n.skip <= int32_t(i) || n.skip > int32_t(s->nNodes) ||
-        n.mesh >= int32_t(s->nMeshes) || n.parent >= int32_t(i))
+        n.mesh >= int32_t(s->nMeshes) || n.parent >= int32_t(i) || (i == 0) != (n.parent < 0) ||
+        (n.parent >= 0 && n.depth != s->nodes[n.parent].depth + 1) || (n.parent < 0 && n.depth != 0))
       return fail(ctx, YC_ERR_INVALID, "node %u is inconsistent (depth/skip/mesh/parent)", i);
   }
   for (uint64_t i = 0; i < s->nPrims; i++)
@@ -427,6 +428,17 @@ extern "C" int yc_upload_scene(yc_ctx* ctx, const YcScene* s) {
   const YcBvhNode* bn = nullptr;
   const YcBvhTri* bt = nullptr;
   YC_TRY(devUpload(ctx, s->nodes, s->nNodes, &d.nodes));
+  {
+    std::vector<int32_t> path(size_t(s->nNodes) * YC_MAX_NODE_DEPTH, 0);
+    for (uint32_t i = 0; i < s->nNodes; i++) {
+      int32_t a = int32_t(i);
+      for (int level = s->nodes[i].depth; level >= 0 && a >= 0; level--) {
+        path[size_t(i) * YC_MAX_NODE_DEPTH + level] = a;
+        a = s->nodes[a].parent;
+      }
+    }
+    YC_TRY(devUpload(ctx, path.data(), path.size(), &d.nodePath));
+  }
   YC_TRY(devUpload(ctx, s->meshes, s->nMeshes, &d.meshes));
   YC_TRY(devUpload(ctx, s->bvhNodes, size_t(s->nBvhNodes), &bn));
   YC_TRY(devUpload(ctx, s->bvhTris, size_t(s->nBvhTris), &bt));

@@ -218,6 +218,13 @@ bool HostScene::build(const ysc::SceneDesc& d, std::string* err) {
     if (depth >= YC_MAX_NODE_DEPTH) nodeErr = "scene graph deeper than YC_MAX_NODE_DEPTH";
     int self = int(nodes.size());
     nodes.push_back(YcNode{});
+    {
+      // known before the children are visited: they look at their parent's flag
+      static const float kIdentityRows[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+      const bool selfIdentity = memcmp(b.xf.inv.m, kIdentityRows, sizeof kIdentityRows) == 0 &&
+                                memcmp(b.xf.fwd.m, kIdentityRows, sizeof kIdentityRows) == 0;
+      nodes[self].identityChain = selfIdentity && (parentFlat < 0 || nodes[parentFlat].identityChain);
+    }
     for (int c : children[idx]) {
       Built cb = visit(c, self, depth + 1);
       b.bounds = Bounds3::join(b.bounds, cb.xf.bounds(cb.bounds));  // Node::appendChild, scene.hpp:54-58
@@ -229,10 +236,7 @@ bool HostScene::build(const ysc::SceneDesc& d, std::string* err) {
     put3(y.bmin, b.bounds.mn);
     put3(y.bmax, b.bounds.mx);
     y.mesh = nd.mesh, y.parent = parentFlat, y.skip = int(nodes.size()), y.depth = depth;
-    static const float kIdentityRows[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
-    const bool selfIdentity = memcmp(y.inv, kIdentityRows, sizeof kIdentityRows) == 0 &&
-                              memcmp(y.fwd, kIdentityRows, sizeof kIdentityRows) == 0;
-    y.identityChain = selfIdentity && (parentFlat < 0 || nodes[parentFlat].identityChain);
+
     return b;
   };
   visit(0, -1, 0);
