@@ -251,8 +251,7 @@ def run_ours(args):
     rays_dev, hits_dev = ctx.device_alloc(n_rays * 32), ctx.device_alloc(n_rays * 20)
     ctx.begin_frame(W, H, total_spp, 64, (0, 0, 0), Y.TONEMAP_AGX)
     ctx.generate_primary_rays(rank * spp, spp, rays_dev)
-    one = np.zeros((1, 8), np.float32)
-    one[0, 4:7] = (0, 0, -1)
+    one = np.array([[0, 0, 40, 0.001, 0.01, 0.02, -0.99975, np.inf]], np.float32)  # any ordinary ray
     ctx.trace(one, Y.TRACE_CLOSEST | Y.TRACE_COUNT)  # zeroes the work counters
     c0 = ctx.stats()
     lib, h = Y.lib(), ctx._h

@@ -304,6 +304,27 @@ typedef struct ys_scene ys_scene;
  * same steps gltf::load performs on the reference API (materials, meshes + SAH BVH, node tree,
  * lights).  Stands in for `gltf::load(path)` (src/gltf/gltf.cpp:319-358). */
 int ys_scene_load(const char* path, ys_scene** out);
+/* Environment map handed to the GLB entry points: main.cpp:81-84 adds an ImageInfiniteLight(sceneRadius,
+ * &hdri) after gltf::load.  rgb = width*height*3 floats in octahedral layout; transform row-major 4x4. */
+typedef struct YsEnvLight {
+  uint32_t width, height;
+  const float* rgb;
+  float sceneRadius;
+  int32_t hasTransform;
+  float transform[16];
+} YsEnvLight;
+/* gltf::load(path) for binary glTF (src/gltf/gltf.cpp:319-358), from scratch (fastgltf is not vendored in the
+ * reference): materials with the KHR extensions the reference enables, merged meshes, TRS node tree, one
+ * AreaLight per emissive triangle.  env may be NULL. */
+int ys_scene_load_glb(const char* path, const YsEnvLight* env, ys_scene** out);
+/* Same, written out as a .ysc description (so the identical scene can be fed to the oracle driver). */
+int ys_glb_convert(const char* glbPath, const char* yscPath, const YsEnvLight* env);
+/* loadTexture<C> (src/core/texture.hpp:62-90) on an in-memory PNG: decode to RGBA8, pick `channels`, sRGB →
+ * gamma-2 8-bit.  out may be NULL to query the size. */
+int ys_decode_texture(const void* png, size_t len, uint32_t type, uint32_t nChannels, const int32_t* channels,
+                      uint8_t* out, size_t outBytes, uint32_t* width, uint32_t* height);
+/* output::writePPM (src/output/ppm.cpp:6-21) on an RGBA float frame. */
+int ys_write_ppm(const char* path, const float* rgba, uint32_t width, uint32_t height);
 void ys_scene_destroy(ys_scene* s);
 const char* ys_last_error(void);
 /* Flattened view (valid until ys_scene_destroy). */
@@ -355,6 +376,8 @@ int yr_wait(yr_renderer* r);       /* Renderer::wait() */
 int yr_render_sync(yr_renderer* r, YrRenderData* out); /* Renderer::renderSync() */
 /* Result buffers: LDR (what Renderer::m_buffer holds) and HDR accumulation. */
 int yr_read(yr_renderer* r, float* hdrRGBA, float* ldrRGBA, YcStats* stats);
+/* writePPM(out, renderer buffer): the tonemapped frame as a binary PPM (frontend main.cpp writes out.ppm). */
+int yr_write_ppm(yr_renderer* r, const char* path);
 yc_ctx* yr_context(yr_renderer* r);
 const char* yr_last_error(const yr_renderer* r);
 

@@ -18,6 +18,8 @@
 #include <bsdf/luts.hpp>
 #include <cpu/mis-integrator.hpp>
 #include <cpu/tile-renderer.hpp>
+#include <output/ppm.hpp>
+#include <fstream>
 
 #include "../yart_b200/host/scene_desc.hpp"
 
@@ -297,6 +299,17 @@ static int cmdRender(int argc, char** argv) {
       float4 p = tm == "none" ? res.buffer(x, y) : float4(agx(hdr), 1.0f);
       out.putn(p.data(), 4);
     }
+  if (a.has("ppm")) {
+    // the reference's own writer (src/output/ppm.cpp:6-21) on the tonemapped frame
+    Buffer ldr(w, h);
+    for (uint32_t y = 0; y < h; y++)
+      for (uint32_t x = 0; x < w; x++) {
+        float3 hdr = float3(res.buffer(x, y));
+        ldr(x, y) = tm == "none" ? res.buffer(x, y) : float4(agx(hdr), 1.0f);
+      }
+    std::ofstream os(a.str("ppm", "out.ppm"), std::ios::binary);
+    output::writePPM(os, ldr);
+  }
   printf("{\"rays\": %llu, \"ms\": %.3f, \"threads\": %u, \"build_ms\": %.3f, \"w\": %u, \"h\": %u, \"spp\": %u, \"steps\": [",
          (unsigned long long) res.totalRays, ms, r.threadCount, rs.buildMs, w, h, r.samples);
   for (size_t i = 0; i < steps.size(); i++)
@@ -648,6 +661,39 @@ static int cmdKat(int argc, char** argv) {
   return 0;
 }
 
+// texload in.png type(0 linear,1 sRGB,2 noncolor) C ch0,ch1,... out.bin
+// out: u32 w, h, C then w*h*C bytes — the reference's loadTexture<C> (core/texture.hpp:62-90, stb_image decode)
+template <size_t C>
+static int texloadImpl(const std::vector<uint8_t>& png, int type, const std::vector<uint32_t>& ch, const char* outPath) {
+  std::array<uint32_t, C> channels{};
+  for (size_t i = 0; i < C; i++) channels[i] = ch[i];
+  SDRTexture<C> t = loadTexture<C>(png.data(), int32_t(png.size()), TextureType(type), channels);
+  Writer out(outPath);
+  out.put(uint32_t(t.width()));
+  out.put(uint32_t(t.height()));
+  out.put(uint32_t(C));
+  out.putn(t.data.data(), t.data.size());
+  return 0;
+}
+static int cmdTexload(int argc, char** argv) {
+  if (argc < 7) return 1;
+  auto png = readFile(argv[2]);
+  int type = atoi(argv[3]), C = atoi(argv[4]);
+  std::vector<uint32_t> ch;
+  for (const char* p = argv[5]; *p;) {
+    ch.push_back(uint32_t(strtoul(p, const_cast<char**>(&p), 10)));
+    if (*p == ',') p++;
+  }
+  if (int(ch.size()) < C) return 1;
+  switch (C) {
+    case 1: return texloadImpl<1>(png, type, ch, argv[6]);
+    case 2: return texloadImpl<2>(png, type, ch, argv[6]);
+    case 3: return texloadImpl<3>(png, type, ch, argv[6]);
+    case 4: return texloadImpl<4>(png, type, ch, argv[6]);
+  }
+  return 1;
+}
+
 int main(int argc, char** argv) {
   if (argc < 2) {
     fprintf(stderr,
@@ -655,7 +701,8 @@ int main(int argc, char** argv) {
             "       oracle_ref trace scene.ysc rays.bin hits.bin [mode=closest|any]\n"
             "       oracle_ref bvh scene.ysc out.bin\n"
             "       oracle_ref tables out.bin\n"
-            "       oracle_ref kat <kind> in.bin out.bin [scene.ysc]\n");
+            "       oracle_ref kat <kind> in.bin out.bin [scene.ysc]\n"
+            "       oracle_ref texload in.png type C ch0,ch1,.. out.bin\n");
     return 1;
   }
   std::string cmd = argv[1];
@@ -664,6 +711,7 @@ int main(int argc, char** argv) {
   if (cmd == "bvh") return cmdBvh(argc, argv);
   if (cmd == "tables") return cmdTables(argc, argv);
   if (cmd == "kat") return cmdKat(argc, argv);
+  if (cmd == "texload") return cmdTexload(argc, argv);
   fprintf(stderr, "unknown command %s\n", cmd.c_str());
   return 1;
 }

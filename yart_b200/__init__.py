@@ -48,13 +48,55 @@ def _f3(v):
     return (C.c_float * 3)(*[float(x) for x in v])
 
 
-class Scene:
-    """yart::Scene built from a .ysc description (stands in for gltf::load)."""
+def _env_struct(env, radius, transform):
+    if env is None:
+        return None, None
+    rgb = np.ascontiguousarray(env, np.float32)
+    e = capi.YsEnvLight(rgb.shape[1], rgb.shape[0], rgb.ctypes.data_as(C.POINTER(C.c_float)), radius,
+                        0 if transform is None else 1)
+    if transform is not None:
+        e.transform = (C.c_float * 16)(*np.asarray(transform, np.float32).reshape(-1))
+    return e, rgb  # keep rgb alive
 
-    def __init__(self, path: str):
+
+def glb_to_ysc(glb_path: str, ysc_path: str, env=None, env_radius=100.0, env_transform=None):
+    """ys_glb_convert: the GLB loader's result as a .ysc scene description."""
+    e, keep = _env_struct(env, env_radius, env_transform)
+    rc = lib().ys_glb_convert(glb_path.encode(), ysc_path.encode(), C.byref(e) if e is not None else None)
+    _check(rc, f"ys_glb_convert({glb_path})", lib().ys_last_error() or b"")
+
+
+def decode_texture(png: bytes, tex_type: int, channels) -> np.ndarray:
+    """ys_decode_texture: loadTexture<C> (core/texture.hpp:62-90) on an in-memory PNG → (h, w, C) uint8."""
+    ch = (C.c_int32 * len(channels))(*channels)
+    w, h = C.c_uint32(), C.c_uint32()
+    buf = np.frombuffer(png, np.uint8)
+    rc = lib().ys_decode_texture(buf.ctypes.data, len(png), tex_type, len(channels), ch, None, 0, C.byref(w), C.byref(h))
+    _check(rc, "ys_decode_texture", lib().ys_last_error() or b"")
+    out = np.empty((h.value, w.value, len(channels)), np.uint8)
+    rc = lib().ys_decode_texture(buf.ctypes.data, len(png), tex_type, len(channels), ch, out.ctypes.data, out.nbytes,
+                                 C.byref(w), C.byref(h))
+    _check(rc, "ys_decode_texture", lib().ys_last_error() or b"")
+    return out
+
+
+def write_ppm(path: str, rgba: np.ndarray):
+    rgba = np.ascontiguousarray(rgba, np.float32)
+    _check(lib().ys_write_ppm(path.encode(), rgba.ctypes.data, rgba.shape[1], rgba.shape[0]), "ys_write_ppm")
+
+
+class Scene:
+    """yart::Scene built from a .ysc description or a binary glTF file (stands in for gltf::load)."""
+
+    def __init__(self, path: str, env=None, env_radius=100.0, env_transform=None):
         self._h = C.c_void_p()
-        rc = lib().ys_scene_load(path.encode(), C.byref(self._h))
-        _check(rc, f"ys_scene_load({path})", lib().ys_last_error() or b"")
+        if path.lower().endswith(".glb"):
+            e, keep = _env_struct(env, env_radius, env_transform)
+            rc = lib().ys_scene_load_glb(path.encode(), C.byref(e) if e is not None else None, C.byref(self._h))
+            _check(rc, f"ys_scene_load_glb({path})", lib().ys_last_error() or b"")
+        else:
+            rc = lib().ys_scene_load(path.encode(), C.byref(self._h))
+            _check(rc, f"ys_scene_load({path})", lib().ys_last_error() or b"")
         self.flat = lib().ys_scene_flat(self._h).contents
         self.build_ms = lib().ys_scene_build_ms(self._h)
 
@@ -289,6 +331,9 @@ class Renderer:
         self._ck(lib().yr_read(self._h, hdr.ctypes.data if want_hdr else None, ldr.ctypes.data if want_ldr else None,
                                C.byref(st)), "yr_read")
         return hdr, ldr, st
+
+    def write_ppm(self, path: str):
+        self._ck(lib().yr_write_ppm(self._h, path.encode()), "yr_write_ppm")
 
     def context_handle(self):
         return lib().yr_context(self._h)

@@ -88,6 +88,11 @@ class YrWaveData(C.Structure):
     _fields_ = [("wave", u64), ("waveSamples", u64), ("rays", u64), ("timeMs", C.c_double)]
 
 
+class YsEnvLight(C.Structure):
+    _fields_ = [("width", u32), ("height", u32), ("rgb", C.POINTER(f32)), ("sceneRadius", f32), ("hasTransform", i32),
+                ("transform", f32 * 16)]
+
+
 WAVE_CALLBACK = C.CFUNCTYPE(None, C.POINTER(YrRenderData), C.POINTER(YrWaveData), C.c_void_p)
 
 P = C.c_void_p
@@ -116,6 +121,10 @@ PROTOTYPES = {
     "yc_synchronize": (C.c_int, [P]),
     "yc_kat": (C.c_int, [P, C.c_char_p, P, C.c_size_t, P, C.c_size_t]),
     "ys_scene_load": (C.c_int, [C.c_char_p, C.POINTER(P)]),
+    "ys_scene_load_glb": (C.c_int, [C.c_char_p, C.POINTER(YsEnvLight), C.POINTER(P)]),
+    "ys_glb_convert": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(YsEnvLight)]),
+    "ys_decode_texture": (C.c_int, [P, C.c_size_t, u32, u32, C.POINTER(i32), P, C.c_size_t, C.POINTER(u32), C.POINTER(u32)]),
+    "ys_write_ppm": (C.c_int, [C.c_char_p, P, u32, u32]),
     "ys_scene_destroy": (None, [P]),
     "ys_last_error": (C.c_char_p, []),
     "ys_scene_flat": (C.POINTER(YcScene), [P]),
@@ -130,6 +139,7 @@ PROTOTYPES = {
     "yr_wait": (C.c_int, [P]),
     "yr_render_sync": (C.c_int, [P, C.POINTER(YrRenderData)]),
     "yr_read": (C.c_int, [P, P, P, C.POINTER(YcStats)]),
+    "yr_write_ppm": (C.c_int, [P, C.c_char_p]),
     "yr_context": (P, [P]),
     "yr_last_error": (C.c_char_p, [P]),
 }

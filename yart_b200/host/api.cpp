@@ -12,10 +12,19 @@
 #include <mutex>
 #include <new>
 #include <thread>
+#include <cstring>
+#include <vector>
 
 #include "scene.hpp"
 
 using namespace yartb;
+
+namespace yartb {
+bool loadGlb(const std::string& path, ysc::SceneDesc& out, std::string* err);
+bool writePpm(const std::string& path, const float* rgba, uint32_t w, uint32_t h);
+bool decodeTextureForTest(const uint8_t* png, size_t len, uint32_t type, int C, const int* channels, ysc::TextureDesc& out,
+                          std::string& err);
+}  // namespace yartb
 
 struct ys_scene {
   HostScene host;
@@ -43,6 +52,84 @@ extern "C" int ys_scene_load(const char* path, ys_scene** out) {
   }
   *out = s;
   return YC_OK;
+}
+
+// main.cpp:81-84: `ImageInfiniteLight(radius, &hdri); scene->addLight(...)` after gltf::load
+static void appendEnv(ysc::SceneDesc& d, const YsEnvLight* env) {
+  if (!env || !env->rgb || env->width < 2 || env->height < 2) return;
+  ysc::TextureDesc t;
+  t.channels = 3, t.isFloat = 1, t.type = ysc::LinearRGB, t.width = env->width, t.height = env->height;
+  t.f32.assign(env->rgb, env->rgb + size_t(env->width) * env->height * 3);
+  d.textures.push_back(std::move(t));
+  ysc::LightDesc l;
+  l.type = ysc::ImageInfiniteT;
+  l.hdrTex = int32_t(d.textures.size()) - 1;
+  l.sceneRadius = env->sceneRadius;
+  l.hasTransform = env->hasTransform;
+  if (env->hasTransform) memcpy(l.m, env->transform, sizeof l.m);
+  d.lights.push_back(l);
+}
+
+extern "C" int ys_glb_convert(const char* glbPath, const char* yscPath, const YsEnvLight* env) {
+  if (!glbPath || !yscPath) return YC_ERR_INVALID;
+  ysc::SceneDesc d;
+  std::string err;
+  if (!loadGlb(glbPath, d, &err)) {
+    g_ysError = err;
+    return YC_ERR_IO;
+  }
+  appendEnv(d, env);
+  if (!ysc::save(yscPath, d)) {
+    g_ysError = std::string("cannot write ") + yscPath;
+    return YC_ERR_IO;
+  }
+  return YC_OK;
+}
+
+extern "C" int ys_scene_load_glb(const char* path, const YsEnvLight* env, ys_scene** out) {
+  if (!path || !out) return YC_ERR_INVALID;
+  *out = nullptr;
+  ysc::SceneDesc d;
+  std::string err;
+  if (!loadGlb(path, d, &err)) {
+    g_ysError = err;
+    return YC_ERR_IO;
+  }
+  appendEnv(d, env);
+  ys_scene* s = new (std::nothrow) ys_scene();
+  if (!s) return YC_ERR_INVALID;
+  if (!s->host.build(d, &err)) {
+    g_ysError = err;
+    delete s;
+    return YC_ERR_INVALID;
+  }
+  *out = s;
+  return YC_OK;
+}
+
+extern "C" int ys_decode_texture(const void* png, size_t len, uint32_t type, uint32_t nChannels, const int32_t* channels,
+                                 uint8_t* out, size_t outBytes, uint32_t* width, uint32_t* height) {
+  if (!png || !channels || nChannels < 1 || nChannels > 4) return YC_ERR_INVALID;
+  ysc::TextureDesc t;
+  std::string err;
+  int ch[4] = {0, 1, 2, 3};
+  for (uint32_t i = 0; i < nChannels; i++) ch[i] = channels[i];
+  if (!decodeTextureForTest(static_cast<const uint8_t*>(png), len, type, int(nChannels), ch, t, err)) {
+    g_ysError = err;
+    return YC_ERR_IO;
+  }
+  if (width) *width = t.width;
+  if (height) *height = t.height;
+  if (out) {
+    if (outBytes < t.u8.size()) return YC_ERR_INVALID;
+    memcpy(out, t.u8.data(), t.u8.size());
+  }
+  return YC_OK;
+}
+
+extern "C" int ys_write_ppm(const char* path, const float* rgba, uint32_t width, uint32_t height) {
+  if (!path || !rgba || !width || !height) return YC_ERR_INVALID;
+  return writePpm(path, rgba, width, height) ? YC_OK : YC_ERR_IO;
 }
 
 extern "C" void ys_scene_destroy(ys_scene* s) { delete s; }
@@ -247,6 +334,14 @@ extern "C" int yr_wait(yr_renderer* r) {
   if (!r) return YC_ERR_INVALID;
   if (r->worker.joinable()) r->worker.join();
   return r->lastRc;
+}
+
+extern "C" int yr_write_ppm(yr_renderer* r, const char* path) {
+  if (!r || !path) return YC_ERR_INVALID;
+  std::vector<float> ldr(size_t(r->s.width) * r->s.height * 4);
+  int rc = yc_resolve(r->ctx, nullptr, ldr.data(), nullptr);
+  if (rc != YC_OK) return rfail(r, rc, yc_last_error(r->ctx));
+  return writePpm(path, ldr.data(), r->s.width, r->s.height) ? YC_OK : rfail(r, YC_ERR_IO, std::string("cannot write ") + path);
 }
 
 extern "C" int yr_read(yr_renderer* r, float* hdrRGBA, float* ldrRGBA, YcStats* stats) {
