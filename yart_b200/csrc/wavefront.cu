@@ -27,6 +27,9 @@
 
 using namespace yb;
 
+#ifndef YB_TRACE_MIN_BLOCKS
+#define YB_TRACE_MIN_BLOCKS 8  // 8 CTAs x 4 warps per SM: caps the traversal kernels at 64 registers
+#endif
 #ifndef YB_SHADE_MIN_BLOCKS
 #define YB_SHADE_MIN_BLOCKS 2
 #endif
@@ -278,7 +281,7 @@ struct ExtendIO {
 };
 
 template <bool ALPHA, bool COUNT>
-__global__ void __launch_bounds__(kTraceBlock) extendKernel(DScene sc, WaveParams w, PathState ps, const uint32_t* queue,
+__global__ void __launch_bounds__(kTraceBlock, YB_TRACE_MIN_BLOCKS) extendKernel(DScene sc, WaveParams w, PathState ps, const uint32_t* queue,
                                                             uint32_t n, uint32_t* ctr, Counters* counters, uint2* spill,
                                                             TraceTuning tune) {
   ExtendIO<ALPHA> io{w, ps, queue};
@@ -843,7 +846,7 @@ struct TraceIO {
 };
 
 template <bool NEE, bool ALPHA, bool COUNT, bool COMPACT>
-__global__ void __launch_bounds__(kTraceBlock) traceKernel(DScene sc, const YcRay* rays, uint32_t n, int useTMax, YcHit* hits,
+__global__ void __launch_bounds__(kTraceBlock, YB_TRACE_MIN_BLOCKS) traceKernel(DScene sc, const YcRay* rays, uint32_t n, int useTMax, YcHit* hits,
                                                            CompactHit* compact, uint32_t* head, Counters* counters,
                                                            uint2* spill, TraceTuning tune) {
   TraceIO<NEE, ALPHA, COMPACT> io{sc, rays, hits, compact, useTMax};
