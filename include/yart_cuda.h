@@ -187,7 +187,8 @@ typedef struct YcOptions {
   uint32_t maxPathsInFlight; /* wavefront capacity; 0 = default (8 Mi paths) */
   /* reserved[0], reserved[1]: warp-scheduling knobs of the traversal kernels (0 = default):
    * refill threshold (idle lanes) and inner-step threshold (lanes on inner nodes).  They never
-   * change results. */
+   * change results.  reserved[2]: number of surviving paths at which a chunk's remaining bounces are
+   * handed to the per-path tail kernel (0 = default 16384, 0xffffffff = never). */
   uint32_t reserved[6];
 } YcOptions;
 

@@ -138,10 +138,12 @@ def make_camera(width, height, focal=35.0, fnum=0.0, pos=(0, 0, 5), target=(0, 0
 class Context:
     """Device layer (yc_*): one CUDA context + stream on one GPU."""
 
-    def __init__(self, device: int = 0, max_depth: int = 30, max_paths: int = 0, refill_min: int = 0, inner_min: int = 0):
+    def __init__(self, device: int = 0, max_depth: int = 30, max_paths: int = 0, refill_min: int = 0, inner_min: int = 0,
+                 tail_threshold: int = 0):
         self._h = C.c_void_p()
         opts = capi.YcOptions(maxDepth=max_depth, maxPathsInFlight=max_paths)
         opts.reserved[0], opts.reserved[1] = refill_min, inner_min  # traversal scheduling knobs (0 = default)
+        opts.reserved[2] = 0xffffffff if tail_threshold < 0 else tail_threshold  # tail kernel hand-over (-1 = never)
         _check(lib().yc_create(device, C.byref(opts), C.byref(self._h)), "yc_create",
                b"(no usable CUDA device: yart_b200 has no CPU fallback)")
         self.frame = None

@@ -50,7 +50,7 @@ struct ShadowQueue {
 };
 
 struct Counters {
-  unsigned long long raysReference, raysExtend, raysShadow, boxTests, triTests;
+  unsigned long long raysReference, raysExtend, raysShadow, boxTests, triTests;  // raysExtend: tail kernel only
 };
 
 // Everything a stage needs besides the scene.
@@ -173,11 +173,42 @@ struct ShadowRequest {
 enum : uint32_t { kShadeContinue = 1u, kShadeShadow = 2u };
 
 // Returns kShade* bits; `rq` is filled when kShadeShadow is set.  DEFER_RR ⇔ scene has alpha.
+// Miss shading (mis-integrator.cpp:27-43) as its own stage: extend sorts queue entries into a "hit" and a
+// "miss" queue, so the heavy surface-shading code runs in warps where every lane has work.
+YB_DEV void shadeMissStage(const DScene& sc, const WaveParams& w, const PathState& ps, uint32_t i, uint32_t& raysReference) {
+  raysReference += 1;  // mis-integrator.cpp:22
+  const float4 ro4 = ps.rayO[i], rd4 = ps.rayD[i], L4 = ps.L[i], a4 = ps.att[i];
+  const V3 rayD(rd4.x, rd4.y, rd4.z);
+  const float lastPdf = ro4.w;
+  V3 L(L4.x, L4.y, L4.z), att(a4.x, a4.y, a4.z);
+  const uint32_t fl = ps.flags[i];
+  const uint32_t depth = fl & kFlagDepthMask;
+  const bool specularBounce = (fl & kFlagSpecular) != 0;
+  // Le(octahedralUV(ray.dir)) ignores the light's transform
+  for (uint32_t k = 0; k < sc.nInf; k++) {
+    const YcLight& light = sc.lights[sc.infLights[k]];
+    const V3 Le = lightLe(sc, light, octahedralUV(rayD));
+    if (depth == 0 || specularBounce) {
+      L += att * Le;
+    } else {
+      const float pdfLight = lightPdf(sc, light, rayD);
+      const float wBSDF = lastPdf / (lastPdf + pdfLight);
+      L += att * wBSDF * Le;
+    }
+  }
+  L += att * V3(w.bg);
+  ps.L[i] = make_float4(L.x, L.y, L.z, 0.0f);
+}
+
 template <bool DEFER_RR>
 YB_DEV uint32_t shadeStage(const DScene& sc, const WaveParams& w, const PathState& ps, uint32_t i, ShadowRequest& rq,
                            uint32_t& raysReference) {
   const int32_t hb = ps.hitB[i];
   if (hb == kHitDead) return 0u;
+  if (hb == kHitMiss) {
+    shadeMissStage(sc, w, ps, i, raysReference);
+    return 0u;
+  }
   raysReference += 1;  // mis-integrator.cpp:22
   const float4 ro4 = ps.rayO[i], rd4 = ps.rayD[i], L4 = ps.L[i], a4 = ps.att[i];
   const V3 rayO(ro4.x, ro4.y, ro4.z), rayD(rd4.x, rd4.y, rd4.z);
@@ -186,24 +217,6 @@ YB_DEV uint32_t shadeStage(const DScene& sc, const WaveParams& w, const PathStat
   uint32_t fl = ps.flags[i];
   uint32_t depth = fl & kFlagDepthMask;
   const bool specularBounce = (fl & kFlagSpecular) != 0, regularized = (fl & kFlagRegularized) != 0;
-
-  if (hb == kHitMiss) {
-    // mis-integrator.cpp:27-43 — Le(octahedralUV(ray.dir)) ignores the light's transform
-    for (uint32_t k = 0; k < sc.nInf; k++) {
-      const YcLight& light = sc.lights[sc.infLights[k]];
-      const V3 Le = lightLe(sc, light, octahedralUV(rayD));
-      if (depth == 0 || specularBounce) {
-        L += att * Le;
-      } else {
-        const float pdfLight = lightPdf(sc, light, rayD);
-        const float wBSDF = lastPdf / (lastPdf + pdfLight);
-        L += att * wBSDF * Le;
-      }
-    }
-    L += att * V3(w.bg);
-    ps.L[i] = make_float4(L.x, L.y, L.z, 0.0f);
-    return 0u;
-  }
 
   HitRec h;
   const float4 ha = ps.hitA[i];

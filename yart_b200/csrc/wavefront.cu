@@ -37,7 +37,8 @@ using namespace yb;
 // ---------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------
-enum { kCtrExtendHead = 0, kCtrNextCount = 1, kCtrShadowCount = 2, kCtrShadowHead = 3, kCtrCount = 4 };
+enum { kCtrExtendHead = 0, kCtrNextCount = 1, kCtrShadowCount = 2, kCtrShadowHead = 3, kCtrHitCount = 4, kCtrMissCount = 5,
+       kCtrCount = 8 };
 
 struct yc_ctx {
   rt::Stream st;
@@ -64,7 +65,7 @@ struct yc_ctx {
   // wavefront storage (capacity path slots)
   PathState ps{};
   ShadowQueue sq{};
-  uint32_t *dQueueA = nullptr, *dQueueB = nullptr, *dCtr = nullptr;
+  uint32_t *dQueueA = nullptr, *dQueueH = nullptr, *dQueueM = nullptr, *dCtr = nullptr;  // cur/next, hit, miss
   void* dSpill = nullptr;  // traversal-stack spill area of the persistent kernels
   Counters* dCounters = nullptr;
   std::vector<void*> waveAllocs;
@@ -74,6 +75,7 @@ struct yc_ctx {
   double gpuMs = 0, extendMs = 0;
   uint64_t extendLaunches = 0, raysExtend = 0;
   bool timeExtend = false;
+  uint32_t tailThreshold = 16384;  // paths left in a chunk at which the tail kernel takes over (0 = never)
 };
 
 static int fail(yc_ctx* c, int code, const char* fmt, ...) {
@@ -131,6 +133,8 @@ struct RaygenK {
   }
 };
 
+// Surface shading over the HIT queue extend produced (count on the device: the launch is sized for the
+// upper bound and surplus threads leave at once).
 template <bool DEFER_RR>
 struct ShadeK {
   DScene sc;
@@ -142,6 +146,7 @@ struct ShadeK {
   uint32_t* ctr;
   Counters* counters;
   YB_DEV void operator()(uint32_t j) const {
+    if (j >= ctr[kCtrHitCount]) return;
     const uint32_t i = queue[j];
     ShadowRequest rq;
     uint32_t rays = 0;
@@ -155,6 +160,22 @@ struct ShadeK {
       sq.lif[k] = make_float4(rq.lif.x, rq.lif.y, rq.lif.z, rq.denom);
       sq.att[k] = make_float4(rq.att.x, rq.att.y, rq.att.z, __uint_as_float(i));
     }
+  }
+};
+
+// Miss shading over the MISS queue (environment lights with MIS, background).
+struct ShadeMissK {
+  DScene sc;
+  WaveParams w;
+  PathState ps;
+  const uint32_t* queue;
+  uint32_t* ctr;
+  Counters* counters;
+  YB_DEV void operator()(uint32_t j) const {
+    if (j >= ctr[kCtrMissCount]) return;
+    uint32_t rays = 0;
+    shadeMissStage(sc, w, ps, queue[j], rays);
+    aggregatedCount(&counters->raysReference, rays);
   }
 };
 
@@ -248,7 +269,14 @@ template <bool ALPHA, bool COUNT>
 static void runExtend(yc_ctx* ctx, const WaveParams& w, const uint32_t* queue, uint32_t n) {
   HostStack hs;
   TraceCounters cnt;
-  for (uint32_t j = 0; j < n; j++) extendStage<ALPHA, COUNT>(ctx->ds, w, ctx->ps, queue[j], hs.ts, cnt);
+  for (uint32_t j = 0; j < n; j++) {
+    const uint32_t i = queue[j];
+    extendStage<ALPHA, COUNT>(ctx->ds, w, ctx->ps, i, hs.ts, cnt);
+    const int32_t hb = ctx->ps.hitB[i];
+    if (hb == kHitDead) continue;
+    if (hb == kHitMiss) ctx->dQueueM[ctx->dCtr[kCtrMissCount]++] = i;
+    else ctx->dQueueH[ctx->dCtr[kCtrHitCount]++] = i;
+  }
   ctx->dCounters->boxTests += cnt.box;
   ctx->dCounters->triTests += cnt.tri;
 }
@@ -271,20 +299,25 @@ struct ExtendIO {
   WaveParams w;
   PathState ps;
   const uint32_t* queue;
+  uint32_t *hitQueue, *missQueue, *ctr;
   __device__ __forceinline__ bool load(uint32_t j, V3& o, V3& d, float& tMax, Sampler& smp) const {
     tMax = INFINITY;
     return extendLoad<ALPHA>(w, ps, queue[j], o, d, smp);
   }
   __device__ __forceinline__ void store(uint32_t j, const TraceState& st, bool, const Sampler& smp) const {
-    extendStore<ALPHA>(ps, queue[j], st, smp);
+    const uint32_t i = queue[j];
+    extendStore<ALPHA>(ps, i, st, smp);
+    // sort into the hit / miss queues (paths killed by a deferred roulette never get here)
+    if (st.hit.node >= 0) hitQueue[aggregatedAppend(ctr + kCtrHitCount)] = i;
+    else missQueue[aggregatedAppend(ctr + kCtrMissCount)] = i;
   }
 };
 
 template <bool ALPHA, bool COUNT>
 __global__ void __launch_bounds__(kTraceBlock, YB_TRACE_MIN_BLOCKS) extendKernel(DScene sc, WaveParams w, PathState ps, const uint32_t* queue,
-                                                            uint32_t n, uint32_t* ctr, Counters* counters, uint2* spill,
-                                                            TraceTuning tune) {
-  ExtendIO<ALPHA> io{w, ps, queue};
+                                                            uint32_t n, uint32_t* hitQueue, uint32_t* missQueue, uint32_t* ctr,
+                                                            Counters* counters, uint2* spill, TraceTuning tune) {
+  ExtendIO<ALPHA> io{w, ps, queue, hitQueue, missQueue, ctr};
   TraceCounters cnt;
   tracePersistent<false, ALPHA, COUNT, false>(sc, io, n, ctr + kCtrExtendHead, spill, tune, cnt);
   if (COUNT) {
@@ -325,6 +358,50 @@ __global__ void __launch_bounds__(kTraceBlock) shadowKernel(DScene sc, WaveParam
   }
 }
 
+// Tail of a chunk: once only a few thousand paths survive, every further bounce of the wavefront is
+// bound by the latency of its slowest ray (launch after launch).  The tail kernel gives each surviving
+// path one thread that runs its remaining bounces to the end — extend → shade → shadow in the same
+// order and with the same stage functions as the wavefront, so results are unchanged — and all the
+// slow rays overlap instead of adding up.
+constexpr int kTailBlock = 128;
+template <bool ALPHA>
+__global__ void __launch_bounds__(kTailBlock) tailKernel(DScene sc, WaveParams w, PathState ps, ShadowQueue sq,
+                                                         const uint32_t* queue, uint32_t n, uint32_t firstBounce,
+                                                         Counters* counters) {
+  __shared__ uint32_t shRef[kShStack * kTailBlock];
+  __shared__ float shD[kShStack * kTailBlock];
+  TravStack stack;
+  stack.shRef = shRef + threadIdx.x;
+  stack.shD = shD + threadIdx.x;
+  stack.stride = kTailBlock;
+  const uint32_t j = blockIdx.x * kTailBlock + threadIdx.x;
+  uint32_t raysRef = 0, nExtend = 0, nShadow = 0;
+  if (j < n) {
+    const uint32_t i = queue[j];
+    TraceCounters cnt;
+    for (uint32_t bounce = firstBounce; bounce < w.maxDepth; bounce++) {
+      extendStage<ALPHA, false>(sc, w, ps, i, stack, cnt);
+      nExtend++;
+      ShadowRequest rq;
+      const uint32_t r = shadeStage<ALPHA>(sc, w, ps, i, rq, raysRef);
+      if (r & kShadeShadow) {
+        // slot j of the NEE queue is this thread's own
+        sq.o[j] = make_float4(rq.o.x, rq.o.y, rq.o.z, rq.tMax);
+        sq.d[j] = make_float4(rq.d.x, rq.d.y, rq.d.z, rq.absDotN);
+        sq.lif[j] = make_float4(rq.lif.x, rq.lif.y, rq.lif.z, rq.denom);
+        sq.att[j] = make_float4(rq.att.x, rq.att.y, rq.att.z, __uint_as_float(i));
+        raysRef += shadowStage<ALPHA, false>(sc, w, ps, sq, j, stack, cnt);
+        nShadow++;
+      }
+      if (!(r & kShadeContinue)) break;
+    }
+  }
+  __syncwarp();
+  aggregatedCount(&counters->raysReference, raysRef);
+  aggregatedCount(&counters->raysExtend, nExtend);
+  aggregatedCount(&counters->raysShadow, nShadow);
+}
+
 static int traceGridMax(const yc_ctx* ctx) { return ctx->smCount * 8; }
 static TraceTuning tuning(const yc_ctx* ctx) {
   TraceTuning t;
@@ -342,7 +419,8 @@ template <bool ALPHA, bool COUNT>
 static void runExtend(yc_ctx* ctx, const WaveParams& w, const uint32_t* queue, uint32_t n) {
   if (ctx->timeExtend) rt::eventRecord(ctx->st, ctx->evK0);
   extendKernel<ALPHA, COUNT><<<traceGrid(ctx, n), kTraceBlock, 0, ctx->st.s>>>(
-    ctx->ds, w, ctx->ps, queue, n, ctx->dCtr, ctx->dCounters, static_cast<uint2*>(ctx->dSpill), tuning(ctx));
+    ctx->ds, w, ctx->ps, queue, n, ctx->dQueueH, ctx->dQueueM, ctx->dCtr, ctx->dCounters, static_cast<uint2*>(ctx->dSpill),
+    tuning(ctx));
   if (ctx->timeExtend) rt::eventRecord(ctx->st, ctx->evK1);
 }
 template <bool ALPHA, bool COUNT>
@@ -363,6 +441,7 @@ extern "C" int yc_create(int device, const YcOptions* opts, yc_ctx** out) {
   if (opts) ctx->opts = *opts;
   if (ctx->opts.maxDepth == 0) ctx->opts.maxDepth = 30;  // RayIntegrator::m_maxDepth, ray-integrator.hpp:14
   ctx->capacity = ctx->opts.maxPathsInFlight ? ctx->opts.maxPathsInFlight : (8u << 20);
+  if (ctx->opts.reserved[2]) ctx->tailThreshold = ctx->opts.reserved[2] == 0xffffffffu ? 0u : ctx->opts.reserved[2];
   ctx->device = device;
   const char* e = rt::init(device, ctx->st, ctx->smCount);
   if (e) {
@@ -495,7 +574,8 @@ static int ensureWaveStorage(yc_ctx* ctx) {
   YC_TRY(devAlloc(own, &ctx->sq.lif, P));
   YC_TRY(devAlloc(own, &ctx->sq.att, P));
   YC_TRY(devAlloc(own, &ctx->dQueueA, P));
-  YC_TRY(devAlloc(own, &ctx->dQueueB, P));
+  YC_TRY(devAlloc(own, &ctx->dQueueH, P));
+  YC_TRY(devAlloc(own, &ctx->dQueueM, P));
   YC_TRY(devAlloc(own, &ctx->dCtr, size_t(kCtrCount)));
   YC_TRY(devAlloc(own, &ctx->dCounters, size_t(1)));
 #ifndef YB_HOSTSIM
@@ -609,20 +689,23 @@ static int renderChunks(yc_ctx* ctx, const uint32_t* dList, uint32_t nPixCall, u
       const uint32_t K = std::min(Kmax, waveSamples - sDone);
       const uint32_t nPaths = K * nPix;
       w.pixBase = pixBase, w.nPix = nPix, w.s0 = sampleOffset + sDone;
-      uint32_t *qCur = ctx->dQueueA, *qNext = ctx->dQueueB;
+      // queues: A = this bounce's paths (rewritten by shade as the next bounce's), H / M = extend's hit / miss sort
+      uint32_t* qCur = ctx->dQueueA;
       rt::launchFor(ctx->st, nPaths, RaygenK{w, ctx->ps, qCur});
       ctx->launches++;
       uint32_t n = nPaths;
       for (uint32_t bounce = 0; bounce < ctx->opts.maxDepth && n > 0; bounce++) {
         YC_TRY(rt::zero(ctx->st, ctx->dCtr, kCtrCount * sizeof(uint32_t)));
         runExtend<ALPHA, false>(ctx, w, qCur, n);
-        rt::launchFor<YB_SHADE_MIN_BLOCKS>(ctx->st, n, ShadeK<ALPHA>{ctx->ds, w, ctx->ps, ctx->sq, qCur, qNext, ctx->dCtr, ctx->dCounters});
+        rt::launchFor(ctx->st, n, ShadeMissK{ctx->ds, w, ctx->ps, ctx->dQueueM, ctx->dCtr, ctx->dCounters});
+        rt::launchFor<YB_SHADE_MIN_BLOCKS>(ctx->st, n, ShadeK<ALPHA>{ctx->ds, w, ctx->ps, ctx->sq, ctx->dQueueH, qCur, ctx->dCtr,
+                                                                      ctx->dCounters});
 #ifdef YB_HOSTSIM
         runShadow<ALPHA, false>(ctx, w);
 #else
         runShadow<ALPHA, false>(ctx, w, n);
 #endif
-        ctx->launches += 3;
+        ctx->launches += 4;
         uint32_t ctr[kCtrCount];
         YC_TRY(rt::d2h(ctx->st, ctr, ctx->dCtr, sizeof ctr));
         if (ctx->timeExtend) {
@@ -631,7 +714,14 @@ static int renderChunks(yc_ctx* ctx, const uint32_t* dList, uint32_t nPixCall, u
         }
         ctx->raysExtend += n;  // every queue entry is one closest-hit ray
         n = ctr[kCtrNextCount];
-        std::swap(qCur, qNext);
+#ifndef YB_HOSTSIM
+        if (n > 0 && n <= ctx->tailThreshold && bounce + 1 < ctx->opts.maxDepth) {
+          tailKernel<ALPHA><<<(n + kTailBlock - 1) / kTailBlock, kTailBlock, 0, ctx->st.s>>>(
+            ctx->ds, w, ctx->ps, ctx->sq, qCur, n, bounce + 1, ctx->dCounters);
+          ctx->launches++;
+          n = 0;
+        }
+#endif
       }
       rt::launchFor(ctx->st, nPix,
                     AccumulateK{ctx->ps, ctx->dBuckets, ctx->bucketCapacity, pixBase, nPix, K, sDone, m, f.estimator,
@@ -689,7 +779,7 @@ static int readStats(yc_ctx* ctx, YcStats* stats) {
   if (ctx->dCounters) YC_TRY(rt::d2h(ctx->st, &c, ctx->dCounters, sizeof c));
   memset(stats, 0, sizeof *stats);
   stats->raysReference = c.raysReference;
-  stats->raysExtend = ctx->raysExtend;
+  stats->raysExtend = ctx->raysExtend + c.raysExtend;
   stats->raysShadow = c.raysShadow;
   stats->boxTests = c.boxTests;
   stats->triTests = c.triTests;
