@@ -490,8 +490,16 @@ struct Bsdf {
   }
 
   // ---- fImpl / pdfImpl / sampleImpl, parametric.cpp:84-258 -------------------------------------
-  YB_DEV V3 fImpl(V3 _wo, V3 _wi, V2 uv) const {
-    MatEval e = evalMaterialTextures(sc, mat, uv);
+  // The uv-taking entry points evaluate the material's textures and forward to the MatEval ones; shade
+  // evaluates them (and the local frame) once per hit and shares them between sample / f / pdf — the
+  // reference recomputes identical values in each call (core/bsdf.cpp:5-41).
+  YB_DEV V3 fImpl(V3 _wo, V3 _wi, V2 uv) const { return fImpl(_wo, _wi, evalMaterialTextures(sc, mat, uv)); }
+  YB_DEV float pdfImpl(V3 wo, V3 wi, V2 uv) const { return pdfImpl(wo, wi, evalMaterialTextures(sc, mat, uv)); }
+  YB_DEV BSDFSample sampleImpl(V3 _wo, V2 uv, V2 u, float uc, float uc2, bool regularized) const {
+    return sampleImpl(_wo, uv, evalMaterialTextures(sc, mat, uv), u, uc, uc2, regularized);
+  }
+
+  YB_DEV V3 fImpl(V3 _wo, V3 _wi, const MatEval& e) const {
     GGX mf(e.r, mat.anisotropic);
     const float cMetallic = e.m;
     const float cDielectric = (1.0f - e.m) * e.t;
@@ -509,8 +517,7 @@ struct Bsdf {
     }
     return val;
   }
-  YB_DEV float pdfImpl(V3 wo, V3 wi, V2 uv) const {
-    MatEval e = evalMaterialTextures(sc, mat, uv);  // base fetch is unused here; same taps otherwise
+  YB_DEV float pdfImpl(V3 wo, V3 wi, const MatEval& e) const {
     GGX mf(e.r, mat.anisotropic);
     const float pMetallic = e.m;
     const float pDielectric = (1.0f - e.m) * e.t;
@@ -527,8 +534,7 @@ struct Bsdf {
     }
     return pdf;
   }
-  YB_DEV BSDFSample sampleImpl(V3 _wo, V2 uv, V2 u, float uc, float uc2, bool regularized) const {
-    MatEval e = evalMaterialTextures(sc, mat, uv);
+  YB_DEV BSDFSample sampleImpl(V3 _wo, V2 uv, const MatEval& e, V2 u, float uc, float uc2, bool regularized) const {
     float r = e.r, cr = e.cr;
     if (regularized) {
       r = roughen(r);

@@ -233,7 +233,13 @@ YB_DEV uint32_t shadeStage(const DScene& sc, const WaveParams& w, const PathStat
   const V2 u = smp.get2D();
   const float uc = smp.get1D();
   const float uc2 = smp.get1D();
-  const BSDFSample res = bsdf.sample(wo, hit.n, hit.tg, hit.uv, u, uc, uc2, regularized);
+  // BSDF::sample / f / pdf (core/bsdf.cpp:5-41) each rebuild the same local frame and re-read the same
+  // texels; here they are evaluated once per hit and shared (identical values, see bsdf.cuh).
+  const Frame fr = Bsdf::localFrame(hit.n, hit.tg);
+  const MatEval me = evalMaterialTextures(sc, mat, hit.uv);
+  const V3 woLocal = fr.wtl(wo);
+  BSDFSample res = bsdf.sampleImpl(woLocal, hit.uv, me, u, uc, uc2, regularized);
+  res.wi = fr.ltw(res.wi);
 
   // mis-integrator.cpp:61-73 (lastHit.p is this ray's origin: ray = Ray(hit.p, wi), lastHit = hit)
   if (res.is(Emitted)) {
@@ -257,14 +263,15 @@ YB_DEV uint32_t shadeStage(const DScene& sc, const WaveParams& w, const PathStat
       const PickedLight pick = pickLight(sc, ucl);
       const YcLight& light = sc.lights[pick.index];
       const LightSample ls = lightSample(sc, light, hit.p, ul);
-      const V3 f = bsdf.f(wo, ls.wi, hit.n, hit.tg, hit.uv);
+      const V3 wiLocal = fr.wtl(ls.wi);
+      const V3 f = bsdf.fImpl(woLocal, wiLocal, me);
       if (length2(f) != 0.0f) {
         // unoccluded(), :135-148
         const V3 to = ls.p - hit.p;
         rq.o = hit.p;
         rq.d = normalized(to);
         rq.tMax = length(to) - 0.001f;
-        const float pdfBSDF = bsdf.pdf(wo, ls.wi, hit.n, hit.tg, hit.uv);
+        const float pdfBSDF = bsdf.pdfImpl(woLocal, wiLocal, me);
         float pdfLight = pick.p * ls.pdf / absDot(ls.n, ls.wi);
         if (light.type == YC_LIGHT_AREA) pdfLight *= length2(hit.p - ls.p);
         rq.lif = ls.Li * f;
