@@ -94,9 +94,11 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.lines, self.proc = [], None
+        if index < 0:
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
-                                          "100", "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "200", "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
         except OSError:
@@ -244,7 +246,9 @@ def run_ours(args):
             ctx.retonemap()
         return ar_ms
 
-    clocks = ClockSampler(local)  # started before the warm-up: nvidia-smi needs ~0.3 s to print its first sample
+    # started before the warm-up: nvidia-smi needs ~0.3 s to print its first sample.  Rank 0 samples its own
+    # GPU only: eight concurrent nvidia-smi pollers contend for the driver lock and perturb the step time.
+    clocks = ClockSampler(local if rank == 0 else -1)
     for _ in range(max(args.warmup, 3)):
         step()
     sync_all()
