@@ -211,7 +211,9 @@ def run_ours(args):
     ctx.upload_scene(scene)
     ctx.set_camera(cam)
     ctx.set_profiling(True)
-    total_spp = spp * world
+    n_warm = max(args.warmup, 3)
+    waves_per_rank = n_warm + args.steps
+    total_spp = spp * world * waves_per_rank  # the job: every rank renders `waves_per_rank` waves of `spp` samples
     ctx.begin_frame(W, H, total_spp, 64, (0, 0, 0), Y.TONEMAP_AGX)
 
     frame_t = None
@@ -230,38 +232,48 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    def step():
-        """One pass: this rank's wave of `spp` samples; N > 1: combine the HDR frames over NCCL."""
-        ctx.render_wave(rank * spp, spp, 0)
-        ar_ms = 0.0
-        if dist:
-            import torch
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            frame_t.mul_(1.0 / world)  # equal sample counts per wave: finishTile's weights collapse to 1/N
-            dist.all_reduce(frame_t)
-            e1.record()
-            torch.cuda.synchronize()
-            ar_ms = e0.elapsed_time(e1)
+    def step(k):
+        """One pass: wave (k * world + rank) of the job — `spp` samples of every pixel — blended into this
+        rank's HDR frame with finishTile's sample-count weights."""
+        k = min(k, waves_per_rank - 1)
+        ctx.render_wave((k * world + rank) * spp, spp, k * spp)
+
+    def combine(scratch=False):
+        """N > 1: the per-GPU HDR frames (equal sample counts) are averaged with one NCCL all-reduce over
+        NVLink and re-tonemapped — once per job, inside the timed region.  scratch=True (warm-up) runs the
+        same collective on a copy so the frames being accumulated are left alone."""
+        if not dist:
+            return 0.0
+        import torch
+        t = frame_t.clone() if scratch else frame_t
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        t.mul_(1.0 / world)
+        dist.all_reduce(t)
+        e1.record()
+        torch.cuda.synchronize()
+        if not scratch:
             ctx.retonemap()
-        return ar_ms
+        return e0.elapsed_time(e1)
 
     # started before the warm-up: nvidia-smi needs ~0.3 s to print its first sample.  Rank 0 samples its own
     # GPU only: eight concurrent nvidia-smi pollers contend for the driver lock and perturb the step time.
     clocks = ClockSampler(local if rank == 0 else -1)
-    for _ in range(max(args.warmup, 3)):
-        step()
+    for k in range(n_warm):
+        step(k)
+    if dist:
+        combine(scratch=True)  # warms NCCL up (parity of this path: tests/test_multi_gpu_cpu.py)
     sync_all()
     s0 = ctx.stats()
     w0 = time.time()
-    ar_total = 0.0
-    for _ in range(args.steps):
-        ar_total += step()
+    for k in range(args.steps):
+        step(n_warm + k)
+    ar_total = combine()
     sync_all()
     w1 = time.time()
     s1 = ctx.stats()
     # keep the GPU under the same load until a few clock samples exist (not timed); the number of
-    # extra steps is agreed across ranks so the collectives stay matched
+    # extra steps is agreed across ranks so nothing can hang
     n_extra = int((0.5 - (w1 - w0)) / max((w1 - w0) / args.steps, 1e-4)) + 1 if w1 - w0 < 0.5 else 0
     if dist:
         import torch
@@ -269,7 +281,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         n_extra = int(t.item())
     for _ in range(min(n_extra, 200)):
-        step()
+        step(waves_per_rank - 1)
     sync_all()
     clk = clocks.stop(w0, time.time())
     dev_ms = (s1.gpuMs - s0.gpuMs) + ar_total
@@ -282,7 +294,7 @@ def run_ours(args):
     n_rays = W * H * spp
     rays_dev, hits_dev = ctx.device_alloc(n_rays * 32), ctx.device_alloc(n_rays * 20)
     ctx.begin_frame(W, H, total_spp, 64, (0, 0, 0), Y.TONEMAP_AGX)
-    ctx.generate_primary_rays(rank * spp, spp, rays_dev)
+    ctx.generate_primary_rays((n_warm * world + rank) * spp, spp, rays_dev)  # the first timed wave's rays
     one = np.array([[0, 0, 40, 0.001, 0.01, 0.02, -0.99975, np.inf]], np.float32)  # any ordinary ray
     ctx.trace(one, Y.TRACE_CLOSEST | Y.TRACE_COUNT)  # zeroes the work counters
     c0 = ctx.stats()
@@ -359,7 +371,8 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD_TEXT,
                        "step": f"one wave of {spp} spp per GPU ({W * H * spp} camera paths)",
-                       "parallelism": f"sample-wave sharding x{world}, scene replicated, NCCL all-reduce of HDR frames",
+                       "parallelism": f"sample-wave sharding x{world}: rank r renders waves r, r+N, ... of the job; scene replicated; "
+                                      "one NCCL all-reduce of the HDR frames per job (inside the timed region)",
                        "l2": "inputs larger than L2: BVH + 0.8 GB of path state streamed per step exceed the 126 MB L2; no flush"},
             "wall_ms_per_step": wall_ms / args.steps,
             "traced_mrays_per_s": traced / dev_ms / 1e3,
