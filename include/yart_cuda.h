@@ -274,8 +274,10 @@ int yc_resolve(yc_ctx* ctx, float* hdrRGBA, float* ldrRGBA, YcStats* stats);
 int yc_frame_device_ptrs(yc_ctx* ctx, void** hdr, void** ldr, size_t* bytes);
 /* Re-run the tonemap over the whole HDR frame (after a cross-GPU sum). */
 int yc_retonemap(yc_ctx* ctx);
-/* Record per-launch CUDA-event time of the extend kernel into YcStats (bench roofline). */
-int yc_set_profiling(yc_ctx* ctx, int timeExtendKernel);
+/* Bit 0: record per-launch CUDA-event time of the extend kernel into YcStats (bench roofline).
+ * Bit 1: run the counting builds of extend / shadow so YcStats.boxTests / triTests accumulate
+ * (reference-traversal work; the counting builds do not park leaves speculatively). */
+int yc_set_profiling(yc_ctx* ctx, int flags);
 /* Ray-level parity hook: RayIntegrator::testNode on caller rays (ray-integrator.cpp:20-54). */
 int yc_trace(yc_ctx* ctx, const YcRay* rays, size_t n, int mode, YcHit* hits, YcStats* stats);
 /* Same with rays already resident on the device; hitsDev receives n compact 20-byte records

@@ -74,7 +74,7 @@ struct yc_ctx {
   uint64_t launches = 0;
   double gpuMs = 0, extendMs = 0;
   uint64_t extendLaunches = 0, raysExtend = 0;
-  bool timeExtend = false;
+  bool timeExtend = false, countTraversal = false;
   uint32_t tailThreshold = 16384;  // paths left in a chunk at which the tail kernel takes over (0 = never)
 };
 
@@ -696,14 +696,16 @@ static int renderChunks(yc_ctx* ctx, const uint32_t* dList, uint32_t nPixCall, u
       uint32_t n = nPaths;
       for (uint32_t bounce = 0; bounce < ctx->opts.maxDepth && n > 0; bounce++) {
         YC_TRY(rt::zero(ctx->st, ctx->dCtr, kCtrCount * sizeof(uint32_t)));
-        runExtend<ALPHA, false>(ctx, w, qCur, n);
+        if (ctx->countTraversal) runExtend<ALPHA, true>(ctx, w, qCur, n);
+        else runExtend<ALPHA, false>(ctx, w, qCur, n);
         rt::launchFor(ctx->st, n, ShadeMissK{ctx->ds, w, ctx->ps, ctx->dQueueM, ctx->dCtr, ctx->dCounters});
         rt::launchFor<YB_SHADE_MIN_BLOCKS>(ctx->st, n, ShadeK<ALPHA>{ctx->ds, w, ctx->ps, ctx->sq, ctx->dQueueH, qCur, ctx->dCtr,
                                                                       ctx->dCounters});
 #ifdef YB_HOSTSIM
         runShadow<ALPHA, false>(ctx, w);
 #else
-        runShadow<ALPHA, false>(ctx, w, n);
+        if (ctx->countTraversal) runShadow<ALPHA, true>(ctx, w, n);
+        else runShadow<ALPHA, false>(ctx, w, n);
 #endif
         ctx->launches += 4;
         uint32_t ctr[kCtrCount];
@@ -820,7 +822,8 @@ extern "C" int yc_retonemap(yc_ctx* ctx) {
 
 extern "C" int yc_set_profiling(yc_ctx* ctx, int timeExtendKernel) {
   if (!ctx) return YC_ERR_INVALID;
-  ctx->timeExtend = timeExtendKernel != 0;
+  ctx->timeExtend = (timeExtendKernel & 1) != 0;
+  ctx->countTraversal = (timeExtendKernel & 2) != 0;  // counting builds of extend / shadow (box / triangle tests)
   return YC_OK;
 }
 
