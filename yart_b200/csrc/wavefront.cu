@@ -163,6 +163,21 @@ struct ShadeK {
   }
 };
 
+// After extend: sorts the bounce's paths into a hit queue and a miss queue (paths killed by a deferred
+// roulette drop out), one warp-aggregated append per category and warp, so that the heavy surface shading
+// runs in full warps.  (Appending from inside the persistent extend kernel costs one atomic per ray.)
+struct SortK {
+  PathState ps;
+  const uint32_t* queue;
+  uint32_t *hitQueue, *missQueue, *ctr;
+  YB_DEV void operator()(uint32_t j) const {
+    const uint32_t i = queue[j];
+    const int32_t hb = ps.hitB[i];
+    if (hb >= 0) hitQueue[aggregatedAppend(ctr + kCtrHitCount)] = i;
+    else if (hb == kHitMiss) missQueue[aggregatedAppend(ctr + kCtrMissCount)] = i;
+  }
+};
+
 // Miss shading over the MISS queue (environment lights with MIS, background).
 struct ShadeMissK {
   DScene sc;
@@ -269,14 +284,7 @@ template <bool ALPHA, bool COUNT>
 static void runExtend(yc_ctx* ctx, const WaveParams& w, const uint32_t* queue, uint32_t n) {
   HostStack hs;
   TraceCounters cnt;
-  for (uint32_t j = 0; j < n; j++) {
-    const uint32_t i = queue[j];
-    extendStage<ALPHA, COUNT>(ctx->ds, w, ctx->ps, i, hs.ts, cnt);
-    const int32_t hb = ctx->ps.hitB[i];
-    if (hb == kHitDead) continue;
-    if (hb == kHitMiss) ctx->dQueueM[ctx->dCtr[kCtrMissCount]++] = i;
-    else ctx->dQueueH[ctx->dCtr[kCtrHitCount]++] = i;
-  }
+  for (uint32_t j = 0; j < n; j++) extendStage<ALPHA, COUNT>(ctx->ds, w, ctx->ps, queue[j], hs.ts, cnt);
   ctx->dCounters->boxTests += cnt.box;
   ctx->dCounters->triTests += cnt.tri;
 }
@@ -299,25 +307,20 @@ struct ExtendIO {
   WaveParams w;
   PathState ps;
   const uint32_t* queue;
-  uint32_t *hitQueue, *missQueue, *ctr;
   __device__ __forceinline__ bool load(uint32_t j, V3& o, V3& d, float& tMax, Sampler& smp) const {
     tMax = INFINITY;
     return extendLoad<ALPHA>(w, ps, queue[j], o, d, smp);
   }
   __device__ __forceinline__ void store(uint32_t j, const TraceState& st, bool, const Sampler& smp) const {
-    const uint32_t i = queue[j];
-    extendStore<ALPHA>(ps, i, st, smp);
-    // sort into the hit / miss queues (paths killed by a deferred roulette never get here)
-    if (st.hit.node >= 0) hitQueue[aggregatedAppend(ctr + kCtrHitCount)] = i;
-    else missQueue[aggregatedAppend(ctr + kCtrMissCount)] = i;
+    extendStore<ALPHA>(ps, queue[j], st, smp);
   }
 };
 
 template <bool ALPHA, bool COUNT>
 __global__ void __launch_bounds__(kTraceBlock, YB_TRACE_MIN_BLOCKS) extendKernel(DScene sc, WaveParams w, PathState ps, const uint32_t* queue,
-                                                            uint32_t n, uint32_t* hitQueue, uint32_t* missQueue, uint32_t* ctr,
-                                                            Counters* counters, uint2* spill, TraceTuning tune) {
-  ExtendIO<ALPHA> io{w, ps, queue, hitQueue, missQueue, ctr};
+                                                            uint32_t n, uint32_t* ctr, Counters* counters, uint2* spill,
+                                                            TraceTuning tune) {
+  ExtendIO<ALPHA> io{w, ps, queue};
   TraceCounters cnt;
   tracePersistent<false, ALPHA, COUNT, false>(sc, io, n, ctr + kCtrExtendHead, spill, tune, cnt);
   if (COUNT) {
@@ -419,8 +422,7 @@ template <bool ALPHA, bool COUNT>
 static void runExtend(yc_ctx* ctx, const WaveParams& w, const uint32_t* queue, uint32_t n) {
   if (ctx->timeExtend) rt::eventRecord(ctx->st, ctx->evK0);
   extendKernel<ALPHA, COUNT><<<traceGrid(ctx, n), kTraceBlock, 0, ctx->st.s>>>(
-    ctx->ds, w, ctx->ps, queue, n, ctx->dQueueH, ctx->dQueueM, ctx->dCtr, ctx->dCounters, static_cast<uint2*>(ctx->dSpill),
-    tuning(ctx));
+    ctx->ds, w, ctx->ps, queue, n, ctx->dCtr, ctx->dCounters, static_cast<uint2*>(ctx->dSpill), tuning(ctx));
   if (ctx->timeExtend) rt::eventRecord(ctx->st, ctx->evK1);
 }
 template <bool ALPHA, bool COUNT>
@@ -698,6 +700,7 @@ static int renderChunks(yc_ctx* ctx, const uint32_t* dList, uint32_t nPixCall, u
         YC_TRY(rt::zero(ctx->st, ctx->dCtr, kCtrCount * sizeof(uint32_t)));
         if (ctx->countTraversal) runExtend<ALPHA, true>(ctx, w, qCur, n);
         else runExtend<ALPHA, false>(ctx, w, qCur, n);
+        rt::launchFor(ctx->st, n, SortK{ctx->ps, qCur, ctx->dQueueH, ctx->dQueueM, ctx->dCtr});
         rt::launchFor(ctx->st, n, ShadeMissK{ctx->ds, w, ctx->ps, ctx->dQueueM, ctx->dCtr, ctx->dCounters});
         rt::launchFor<YB_SHADE_MIN_BLOCKS>(ctx->st, n, ShadeK<ALPHA>{ctx->ds, w, ctx->ps, ctx->sq, ctx->dQueueH, qCur, ctx->dCtr,
                                                                       ctx->dCounters});
@@ -707,7 +710,7 @@ static int renderChunks(yc_ctx* ctx, const uint32_t* dList, uint32_t nPixCall, u
         if (ctx->countTraversal) runShadow<ALPHA, true>(ctx, w, n);
         else runShadow<ALPHA, false>(ctx, w, n);
 #endif
-        ctx->launches += 4;
+        ctx->launches += 5;
         uint32_t ctr[kCtrCount];
         YC_TRY(rt::d2h(ctx->st, ctr, ctx->dCtr, sizeof ctr));
         if (ctx->timeExtend) {
