@@ -22,6 +22,9 @@ KATS = [  # (file tag, kind, n, kwargs, scene)
     ("sampler128", "sampler", 512, dict(spp=128), None),
     ("sampler1024", "sampler", 512, dict(spp=1024), None),
     ("sampler4096", "sampler", 512, dict(spp=4096), None),
+    ("sampler3", "sampler", 256, dict(spp=3), None),      # log2Int rounds in log space: 3 → 2
+    ("sampler12", "sampler", 256, dict(spp=12), None),    # 12 → 4
+    ("sampler100", "sampler", 256, dict(spp=100), None),  # 100 → 7
     ("ggx", "ggx", 1024, {}, None),
     ("gmon16", "gmon", 256, dict(samples=16), None),
     ("gmon64", "gmon", 256, dict(samples=64), None),

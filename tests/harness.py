@@ -28,11 +28,20 @@ def have_oracle() -> bool:
     return os.path.exists(ORACLE)
 
 
-def run_oracle(*args, binary=ORACLE) -> str:
-    r = subprocess.run([binary, *map(str, args)], capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError(f"oracle_ref {' '.join(map(str, args))} failed: {r.stderr}")
-    return r.stdout
+def run_oracle(*args, binary=ORACLE, timeout=600) -> str:
+    """Runs the oracle binary.  The reference's wave barrier reads `m_currentWave` / `m_waveSamples` outside its
+    locks and can deadlock with several threads on tiny frames, hence the timeout + one retry."""
+    cmd = [binary, *map(str, args)]
+    for attempt in range(2):
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+        except subprocess.TimeoutExpired:
+            if attempt == 0:
+                continue
+            raise RuntimeError(f"oracle_ref {' '.join(map(str, args))} timed out twice")
+        if r.returncode != 0:
+            raise RuntimeError(f"oracle_ref {' '.join(map(str, args))} failed: {r.stderr}")
+        return r.stdout
 
 
 # ------------------------------------------------------------------------------------------
@@ -90,11 +99,15 @@ def oracle_render(scene: str, w: int, h: int, spp: int, cam: dict, binary=ORACLE
     with tempfile.TemporaryDirectory() as d:
         fout = os.path.join(d, "img.bin")
         args = ["render", scene, fout, f"w={w}", f"h={h}", f"spp={spp}",
-                "pos=%g,%g,%g" % tuple(cam["pos"]), "target=%g,%g,%g" % tuple(cam["target"]),
+                "pos=%.17g,%.17g,%.17g" % tuple(cam["pos"]), "target=%.17g,%.17g,%.17g" % tuple(cam["target"]),
                 f"focal={cam.get('focal', 35.0)}", f"fnum={cam.get('fnum', 0.0)}", f"exposure={cam.get('exposure', 0.0)}",
                 f"sides={cam.get('sides', 0)}"]
+        # small frames: one worker thread (the output does not depend on the thread count, and a single thread
+        # cannot trip the reference's wave-barrier race); large frames keep the reference's default
+        if "threads" not in kw and w * h <= 256 * 256:
+            kw = dict(kw, threads=1)
         args += [f"{k}={v}" for k, v in kw.items()]
-        run_oracle(*args, binary=binary)
+        run_oracle(*args, binary=binary, timeout=120 if w * h <= 256 * 256 else 900)
         raw = open(fout, "rb").read()
     ww, hh, rays, ms, threads, build_ms = struct.unpack_from("<IIQdId", raw, 0)
     off = struct.calcsize("<IIQdId")

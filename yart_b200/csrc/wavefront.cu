@@ -595,10 +595,16 @@ static int ensureWaveStorage(yc_ctx* ctx) {
 // ---------------------------------------------------------------------------------------
 // frame + waves
 // ---------------------------------------------------------------------------------------
-static uint32_t log2IntU(uint32_t v) {  // math_base.hpp:156-162 on integers (floor log2)
-  uint32_t r = 0;
-  while (v >>= 1) r++;
-  return r;
+// log2Int(float), math_base.hpp:156-160: the exponent, plus one when the significand is at least sqrt(2)'s
+// (pbrt's rounding Log2Int) — e.g. 3 → 2, 5 → 2, 12 → 4, 100 → 7; exact for powers of two.
+static uint32_t log2IntU(uint32_t value) {
+  const float v = float(value);
+  if (v < 1.0f) return 0;
+  uint32_t bits;
+  memcpy(&bits, &v, 4);
+  const int32_t exponent = int32_t(bits >> 23) - 127;
+  const uint32_t significand = bits & ((1u << 23) - 1u);
+  return uint32_t(exponent + (significand >= 0x3504f3u ? 1 : 0));
 }
 static uint32_t roundUpPow2(uint32_t v) {  // math_base.hpp:164-170
   uint32_t p = 1;

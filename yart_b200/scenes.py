@@ -628,3 +628,90 @@ def mclaren(n_tris=2_000_000, env_res=2048, seed=33) -> Scene:
     s.camera = dict(pos=(5.5, 1.6, 4.2), target=(0.0, 0.6, 0.0), focal=35.0, fnum=4.0, exposure=0.0,
                     w=1920, h=1080, spp=1024)
     return s
+
+
+# ------------------------------------------------------------------------------------------
+# randomised small scenes (parity fuzzing): every material feature, nested transforms, all light types
+# ------------------------------------------------------------------------------------------
+def random_scene(seed: int) -> Scene:
+    rng = np.random.default_rng(1000 + seed)
+    s = Scene()
+    n_tex = 6
+    for k in range(n_tex):
+        w, h = int(rng.integers(2, 24)), int(rng.integers(2, 24))
+        s.textures.append(Texture(_noise_tex(rng, w, h, 4, 0, 255), SRGB))  # 4k+0 base (with alpha)
+        s.textures[-1].data[rng.uniform(size=(h, w)) < 0.3, 3] = int(rng.integers(0, 255))
+        s.textures.append(Texture(_noise_tex(rng, w, h, 2, 0, 255), NONCOLOR))  # mr
+        s.textures.append(Texture(_noise_tex(rng, w, h, 1, 0, 255), NONCOLOR))  # mono (transmission / clearcoat)
+        s.textures.append(Texture(_noise_tex(rng, w, h, 3, 60, 200), NONCOLOR))  # normal / emission rgb
+    def pick(kind, p=0.4):
+        return int(rng.integers(0, n_tex)) * 4 + kind if rng.uniform() < p else -1
+    n_mat = int(rng.integers(3, 9))
+    for k in range(n_mat):
+        emissive = rng.uniform() < 0.25
+        s.materials.append(Material(
+            base=tuple(rng.uniform(0.05, 1.0, 3)), base_tex=pick(0), mr_tex=pick(1), trans_tex=pick(2, 0.2), normal_tex=pick(3, 0.3),
+            cc_tex=pick(2, 0.2), emis_tex=pick(3, 0.5) if emissive else -1,
+            metallic=float(rng.choice([0.0, 1.0, rng.uniform()])), roughness=float(rng.choice([0.0, 1.0, rng.uniform(0.02, 1.0)])),
+            transmission=float(rng.choice([0.0, 0.0, 1.0, rng.uniform()])), ior=float(rng.uniform(1.05, 2.2)),
+            anisotropic=float(rng.choice([0.0, rng.uniform()])), aniso_rotation=float(rng.uniform(0, 3.0)),
+            clearcoat=float(rng.choice([0.0, 0.0, 1.0, rng.uniform()])), clearcoat_roughness=float(rng.choice([0.0, rng.uniform(0, 0.5)])),
+            emission=tuple(rng.uniform(0.5, 20.0, 3)) if emissive else (0.0, 0.0, 0.0), thin=int(rng.integers(0, 2)),
+            volume_color=tuple(rng.uniform(0.2, 1.0, 3)), volume_density=float(rng.uniform(0, 2.0))))
+    if not any(m.emission[0] > 0 for m in s.materials):
+        s.materials[-1].emission = (9.0, 8.0, 7.0)
+    n_mesh = int(rng.integers(2, 5))
+    for mi in range(n_mesh):
+        b = MeshBuilder()
+        for _ in range(int(rng.integers(1, 5))):
+            c = rng.uniform(-3, 3, 3)
+            e = rng.uniform(0.3, 2.5, 3)
+            mat = int(rng.integers(0, n_mat))
+            if rng.uniform() < 0.5:
+                b.box(c - e / 2, c + e / 2, mat, rotation_y(float(rng.uniform(0, 90))))
+            else:
+                b.quad(c + (-e[0], 0, e[2]), c + (e[0], 0, e[2]), c + (e[0], e[1] * 0.2, -e[2]), c + (-e[0], 0, -e[2]), mat,
+                       uv_scale=float(rng.uniform(0.5, 3.0)))
+        if rng.uniform() < 0.3:  # a degenerate (zero-area) triangle and a sliver
+            b.tri((0, 0, 0), (1, 1, 1), (2, 2, 2), int(rng.integers(0, n_mat)))
+            b.tri((0, 0, 0), (1, 0, 0), (2, 1e-7, 0), int(rng.integers(0, n_mat)))
+        s.meshes.append(b.build())
+    b = MeshBuilder()  # a big floor so most paths keep bouncing
+    b.quad((-9, -3.2, 9), (9, -3.2, 9), (9, -3.2, -9), (-9, -3.2, -9), 0, uv_scale=4.0)
+    s.meshes.append(b.build())
+
+    def xf():
+        m = translation(*rng.uniform(-1.5, 1.5, 3)) @ rotation_y(float(rng.uniform(0, 360)))
+        if rng.uniform() < 0.5:
+            m = m @ scaling(float(rng.uniform(0.6, 1.6)))
+        if rng.uniform() < 0.3:  # non-uniform scale + shear-free x rotation
+            sc = np.eye(4, dtype=np.float32)
+            sc[0, 0], sc[1, 1] = rng.uniform(0.5, 1.5), rng.uniform(0.5, 1.5)
+            m = m @ sc
+        return m.astype(np.float32)
+    s.nodes = [Node(-1, -1, xf() if rng.uniform() < 0.3 else None)]
+    emissive_mesh_nodes = {}
+    for mi in range(len(s.meshes)):
+        parent = int(rng.integers(0, len(s.nodes)))
+        if rng.uniform() < 0.4:  # an intermediate group node
+            s.nodes.append(Node(parent, -1, xf()))
+            parent = len(s.nodes) - 1
+        t = xf() if rng.uniform() < 0.7 else None
+        s.nodes.append(Node(parent, mi, t))
+        emissive_mesh_nodes[mi] = len(s.nodes) - 1
+    # area lights: only for meshes whose node chain is a single transform under an identity root, the subset in
+    # which the reference's light placement is well defined; others stay non-light emitters
+    for mi, ni in emissive_mesh_nodes.items():
+        n = s.nodes[ni]
+        if n.parent == 0 and s.nodes[0].transform is None:
+            s.add_area_lights(mi, n.transform)
+    if rng.uniform() < 0.6:
+        s.textures.append(Texture(sky_hdr(int(rng.integers(4, 40)), int(rng.integers(4, 40)), seed, float(rng.uniform(5, 500))), LINEAR))
+        s.lights.append(Light(IMAGE_INF, hdr_tex=len(s.textures) - 1, scene_radius=float(rng.uniform(20, 200)),
+                              transform=rotation_y(float(rng.uniform(0, 360))) if rng.uniform() < 0.5 else None))
+    if rng.uniform() < 0.4 or not s.lights:
+        s.lights.append(Light(UNIFORM_INF, emission=tuple(rng.uniform(0.05, 1.0, 3)), scene_radius=50.0))
+    s.camera = dict(pos=tuple(rng.uniform(-1, 1, 3) + (0, 1.5, 11)), target=tuple(rng.uniform(-1, 1, 3)), focal=float(rng.uniform(20, 50)),
+                    fnum=float(rng.choice([0.0, 1.4, 4.0])), exposure=float(rng.uniform(-1, 1)), sides=int(rng.choice([0, 0, 5, 8])),
+                    w=40, h=24, spp=int(rng.choice([3, 4, 5, 8, 12, 16])))
+    return s
