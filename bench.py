@@ -210,7 +210,7 @@ def run_ours(args):
     ctx = Y.Context(device=local, max_depth=MAX_DEPTH)
     ctx.upload_scene(scene)
     ctx.set_camera(cam)
-    ctx.set_profiling(True)
+    ctx.set_profiling(os.environ.get('YART_BENCH_NO_PROFILE') is None)
     n_warm = max(args.warmup, 3)
     waves_per_rank = n_warm + args.steps
     total_spp = spp * world * waves_per_rank  # the job: every rank renders `waves_per_rank` waves of `spp` samples

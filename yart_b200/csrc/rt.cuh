@@ -45,6 +45,7 @@ inline const char* sync(Stream&) { return nullptr; }
 inline void eventCreate(Event&) {}
 inline void eventDestroy(Event&) {}
 inline void eventRecord(Stream&, Event& e) { e.t = std::chrono::high_resolution_clock::now(); }
+inline void eventSync(Event&) {}
 inline float eventElapsedMs(Event& a, Event& b) { return std::chrono::duration<float, std::milli>(b.t - a.t).count(); }
 inline const char* lastError() { return nullptr; }
 
@@ -104,6 +105,7 @@ inline void eventDestroy(Event& e) {
   e.e = nullptr;
 }
 inline void eventRecord(Stream& st, Event& e) { cudaEventRecord(e.e, st.s); }
+inline void eventSync(Event& e) { cudaEventSynchronize(e.e); }
 inline float eventElapsedMs(Event& a, Event& b) {
   float ms = 0.0f;
   cudaEventElapsedTime(&ms, a.e, b.e);

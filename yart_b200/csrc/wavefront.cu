@@ -717,9 +717,13 @@ static int renderChunks(yc_ctx* ctx, const uint32_t* dList, uint32_t nPixCall, u
         else runShadow<ALPHA, false>(ctx, w, n);
 #endif
         ctx->launches += 5;
-        uint32_t ctr[kCtrCount];
-        YC_TRY(rt::d2h(ctx->st, ctr, ctx->dCtr, sizeof ctr));
+        uint32_t ctr[kCtrCount] = {0};
+        // the counts are only needed to size the next bounce: none after the last one (no host round trip
+        // inside a maxDepth-1 chunk at all)
+        static const bool forceSync = getenv("YART_SYNC_LAST_BOUNCE") != nullptr;  // A/B switch (measurement only)
+        if (bounce + 1 < ctx->opts.maxDepth || forceSync) YC_TRY(rt::d2h(ctx->st, ctr, ctx->dCtr, sizeof ctr));
         if (ctx->timeExtend) {
+          rt::eventSync(ctx->evK1);  // waits for the extend launch only; the kernels behind it are already queued
           ctx->extendMs += rt::eventElapsedMs(ctx->evK0, ctx->evK1);
           ctx->extendLaunches++;
         }
