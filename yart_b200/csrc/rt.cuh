@@ -46,6 +46,13 @@ inline void eventCreate(Event&) {}
 inline void eventDestroy(Event&) {}
 inline void eventRecord(Stream&, Event& e) { e.t = std::chrono::high_resolution_clock::now(); }
 inline void eventSync(Event&) {}
+inline bool eventReady(Event&) { return true; }
+inline const char* streamCreate(Stream&) { return nullptr; }
+inline void streamWaitEvent(Stream&, Event&) {}
+inline const char* d2hAsync(Stream&, void* d, const void* s, size_t n) {
+  memcpy(d, s, n);
+  return nullptr;
+}
 inline float eventElapsedMs(Event& a, Event& b) { return std::chrono::duration<float, std::milli>(b.t - a.t).count(); }
 inline const char* lastError() { return nullptr; }
 
@@ -106,6 +113,13 @@ inline void eventDestroy(Event& e) {
 }
 inline void eventRecord(Stream& st, Event& e) { cudaEventRecord(e.e, st.s); }
 inline void eventSync(Event& e) { cudaEventSynchronize(e.e); }
+inline bool eventReady(Event& e) { return cudaEventQuery(e.e) == cudaSuccess; }
+inline const char* streamCreate(Stream& st) { return errstr(cudaStreamCreateWithFlags(&st.s, cudaStreamNonBlocking)); }
+inline void streamWaitEvent(Stream& st, Event& e) { cudaStreamWaitEvent(st.s, e.e, 0); }
+// dst must be page-locked (hostAlloc) for the copy to be asynchronous
+inline const char* d2hAsync(Stream& st, void* d, const void* s, size_t n) {
+  return errstr(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, st.s));
+}
 inline float eventElapsedMs(Event& a, Event& b) {
   float ms = 0.0f;
   cudaEventElapsedTime(&ms, a.e, b.e);

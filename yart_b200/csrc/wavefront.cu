@@ -40,8 +40,29 @@ using namespace yb;
 enum { kCtrExtendHead = 0, kCtrNextCount = 1, kCtrShadowCount = 2, kCtrShadowHead = 3, kCtrHitCount = 4, kCtrMissCount = 5,
        kCtrCount = 8 };
 
+// Two chunks of a wave are in flight at a time, each on its own stream with its own path state: while one
+// chunk waits for the slowest ray of a traversal launch (a single ray with a zero direction component can walk
+// 14 K boxes alone, see profiles/README.md) or for its bounce-count read-back, the other keeps the GPU busy.
+constexpr int kLanes = 2;
+struct Lane {
+  rt::Stream st;       // lane 0 shares the context's main stream
+  PathState ps{};
+  ShadowQueue sq{};
+  uint32_t *qA = nullptr, *qH = nullptr, *qM = nullptr, *ctr = nullptr;  // cur/next, hit, miss queues; counters
+  uint32_t* hCtr = nullptr;  // page-locked copy of the counters
+  void* spill = nullptr;     // traversal-stack spill area of the persistent kernels
+  rt::Event evCtr, evAcc;
+  uint32_t capacity = 0;
+  // chunk in flight
+  bool active = false, waiting = false, done = false;
+  uint32_t chunk = 0, n = 0, bounce = 0;
+  WaveParams w{};
+  uint32_t K = 0, sDone = 0;
+};
+
 struct yc_ctx {
   rt::Stream st;
+  Lane lanes[kLanes];
   int device = 0, smCount = 1;
   std::string err;
   YcOptions opts{};
@@ -62,15 +83,15 @@ struct yc_ctx {
   float4 *dHdr = nullptr, *dLdr = nullptr, *dBuckets = nullptr;
   size_t bucketCapacity = 0;  // pixels per bucket plane
 
-  // wavefront storage (capacity path slots)
-  PathState ps{};
-  ShadowQueue sq{};
-  uint32_t *dQueueA = nullptr, *dQueueH = nullptr, *dQueueM = nullptr, *dCtr = nullptr;  // cur/next, hit, miss
-  void* dSpill = nullptr;  // traversal-stack spill area of the persistent kernels
+  // wavefront storage lives in the lanes; the ray hooks (yc_trace*) use lane 0's counters and spill area
+  uint32_t* dCtr = nullptr;
+  void* dSpill = nullptr;
   Counters* dCounters = nullptr;
   std::vector<void*> waveAllocs;
 
-  rt::Event ev0, ev1, evK0, evK1;
+  rt::Event ev0, ev1;
+  std::vector<std::pair<rt::Event, rt::Event>> extendEvents;  // one pair per timed extend launch of the wave
+  size_t extendEventsUsed = 0;
   uint64_t launches = 0;
   double gpuMs = 0, extendMs = 0;
   uint64_t extendLaunches = 0, raysExtend = 0;
@@ -281,20 +302,20 @@ struct HostStack {
   }
 };
 template <bool ALPHA, bool COUNT>
-static void runExtend(yc_ctx* ctx, const WaveParams& w, const uint32_t* queue, uint32_t n) {
+static void runExtend(yc_ctx* ctx, Lane& L, uint32_t n) {
   HostStack hs;
   TraceCounters cnt;
-  for (uint32_t j = 0; j < n; j++) extendStage<ALPHA, COUNT>(ctx->ds, w, ctx->ps, queue[j], hs.ts, cnt);
+  for (uint32_t j = 0; j < n; j++) extendStage<ALPHA, COUNT>(ctx->ds, L.w, L.ps, L.qA[j], hs.ts, cnt);
   ctx->dCounters->boxTests += cnt.box;
   ctx->dCounters->triTests += cnt.tri;
 }
 template <bool ALPHA, bool COUNT>
-static void runShadow(yc_ctx* ctx, const WaveParams& w) {
+static void runShadow(yc_ctx* ctx, Lane& L, uint32_t) {
   HostStack hs;
   TraceCounters cnt;
-  const uint32_t n = ctx->dCtr[kCtrShadowCount];
+  const uint32_t n = L.ctr[kCtrShadowCount];
   uint32_t contributed = 0;
-  for (uint32_t j = 0; j < n; j++) contributed += shadowStage<ALPHA, COUNT>(ctx->ds, w, ctx->ps, ctx->sq, j, hs.ts, cnt);
+  for (uint32_t j = 0; j < n; j++) contributed += shadowStage<ALPHA, COUNT>(ctx->ds, L.w, L.ps, L.sq, j, hs.ts, cnt);
   ctx->dCounters->raysShadow += n;
   ctx->dCounters->raysReference += contributed;
   ctx->dCounters->boxTests += cnt.box;
@@ -419,16 +440,25 @@ static int traceGrid(const yc_ctx* ctx, uint32_t n) {
 }
 
 template <bool ALPHA, bool COUNT>
-static void runExtend(yc_ctx* ctx, const WaveParams& w, const uint32_t* queue, uint32_t n) {
-  if (ctx->timeExtend) rt::eventRecord(ctx->st, ctx->evK0);
-  extendKernel<ALPHA, COUNT><<<traceGrid(ctx, n), kTraceBlock, 0, ctx->st.s>>>(
-    ctx->ds, w, ctx->ps, queue, n, ctx->dCtr, ctx->dCounters, static_cast<uint2*>(ctx->dSpill), tuning(ctx));
-  if (ctx->timeExtend) rt::eventRecord(ctx->st, ctx->evK1);
+static void runExtend(yc_ctx* ctx, Lane& L, uint32_t n) {
+  std::pair<rt::Event, rt::Event>* ev = nullptr;
+  if (ctx->timeExtend) {
+    if (ctx->extendEventsUsed == ctx->extendEvents.size()) {
+      ctx->extendEvents.emplace_back();
+      rt::eventCreate(ctx->extendEvents.back().first);
+      rt::eventCreate(ctx->extendEvents.back().second);
+    }
+    ev = &ctx->extendEvents[ctx->extendEventsUsed++];
+    rt::eventRecord(L.st, ev->first);
+  }
+  extendKernel<ALPHA, COUNT><<<traceGrid(ctx, n), kTraceBlock, 0, L.st.s>>>(ctx->ds, L.w, L.ps, L.qA, n, L.ctr, ctx->dCounters,
+                                                                            static_cast<uint2*>(L.spill), tuning(ctx));
+  if (ev) rt::eventRecord(L.st, ev->second);
 }
 template <bool ALPHA, bool COUNT>
-static void runShadow(yc_ctx* ctx, const WaveParams& w, uint32_t upperBound) {
-  shadowKernel<ALPHA, COUNT><<<traceGrid(ctx, upperBound), kTraceBlock, 0, ctx->st.s>>>(
-    ctx->ds, w, ctx->ps, ctx->sq, ctx->dCtr, ctx->dCounters, static_cast<uint2*>(ctx->dSpill), tuning(ctx));
+static void runShadow(yc_ctx* ctx, Lane& L, uint32_t upperBound) {
+  shadowKernel<ALPHA, COUNT><<<traceGrid(ctx, upperBound), kTraceBlock, 0, L.st.s>>>(
+    ctx->ds, L.w, L.ps, L.sq, L.ctr, ctx->dCounters, static_cast<uint2*>(L.spill), tuning(ctx));
 }
 #endif
 
@@ -454,8 +484,17 @@ extern "C" int yc_create(int device, const YcOptions* opts, yc_ctx** out) {
   }
   rt::eventCreate(ctx->ev0);
   rt::eventCreate(ctx->ev1);
-  rt::eventCreate(ctx->evK0);
-  rt::eventCreate(ctx->evK1);
+  for (int l = 0; l < kLanes; l++) {
+    Lane& L = ctx->lanes[l];
+    if (l == 0) L.st = ctx->st;
+    else if (const char* le = rt::streamCreate(L.st)) {
+      fprintf(stderr, "yart_b200: cannot create a stream: %s\n", le);
+      delete ctx;
+      return YC_ERR_CUDA;
+    }
+    rt::eventCreate(L.evCtr);
+    rt::eventCreate(L.evAcc);
+  }
   *out = ctx;
   return YC_OK;
 }
@@ -479,8 +518,18 @@ extern "C" void yc_destroy(yc_ctx* ctx) {
   freeAll(ctx->waveAllocs);
   rt::eventDestroy(ctx->ev0);
   rt::eventDestroy(ctx->ev1);
-  rt::eventDestroy(ctx->evK0);
-  rt::eventDestroy(ctx->evK1);
+  for (auto& ev : ctx->extendEvents) {
+    rt::eventDestroy(ev.first);
+    rt::eventDestroy(ev.second);
+  }
+  for (int l = 0; l < kLanes; l++) {
+    Lane& L = ctx->lanes[l];
+    rt::sync(L.st);
+    rt::hostRelease(L.hCtr);
+    rt::eventDestroy(L.evCtr);
+    rt::eventDestroy(L.evAcc);
+    if (l > 0) rt::destroy(L.st);
+  }
   rt::destroy(ctx->st);
   delete ctx;
 }
@@ -561,34 +610,42 @@ extern "C" int yc_set_camera(yc_ctx* ctx, const YcCamera* cam) {
 
 static int ensureWaveStorage(yc_ctx* ctx) {
   if (!ctx->waveAllocs.empty()) return YC_OK;
-  const size_t P = ctx->capacity;
   auto& own = ctx->waveAllocs;
-  YC_TRY(devAlloc(own, &ctx->ps.rayO, P));
-  YC_TRY(devAlloc(own, &ctx->ps.rayD, P));
-  YC_TRY(devAlloc(own, &ctx->ps.L, P));
-  YC_TRY(devAlloc(own, &ctx->ps.att, P));
-  YC_TRY(devAlloc(own, &ctx->ps.dim, P));
-  YC_TRY(devAlloc(own, &ctx->ps.flags, P));
-  YC_TRY(devAlloc(own, &ctx->ps.hitA, P));
-  YC_TRY(devAlloc(own, &ctx->ps.hitB, P));
-  YC_TRY(devAlloc(own, &ctx->sq.o, P));
-  YC_TRY(devAlloc(own, &ctx->sq.d, P));
-  YC_TRY(devAlloc(own, &ctx->sq.lif, P));
-  YC_TRY(devAlloc(own, &ctx->sq.att, P));
-  YC_TRY(devAlloc(own, &ctx->dQueueA, P));
-  YC_TRY(devAlloc(own, &ctx->dQueueH, P));
-  YC_TRY(devAlloc(own, &ctx->dQueueM, P));
-  YC_TRY(devAlloc(own, &ctx->dCtr, size_t(kCtrCount)));
-  YC_TRY(devAlloc(own, &ctx->dCounters, size_t(1)));
+  for (int l = 0; l < kLanes; l++) {
+    Lane& L = ctx->lanes[l];
+    L.capacity = std::max<uint32_t>(1u, ctx->capacity / kLanes);
+    const size_t P = L.capacity;
+    YC_TRY(devAlloc(own, &L.ps.rayO, P));
+    YC_TRY(devAlloc(own, &L.ps.rayD, P));
+    YC_TRY(devAlloc(own, &L.ps.L, P));
+    YC_TRY(devAlloc(own, &L.ps.att, P));
+    YC_TRY(devAlloc(own, &L.ps.dim, P));
+    YC_TRY(devAlloc(own, &L.ps.flags, P));
+    YC_TRY(devAlloc(own, &L.ps.hitA, P));
+    YC_TRY(devAlloc(own, &L.ps.hitB, P));
+    YC_TRY(devAlloc(own, &L.sq.o, P));
+    YC_TRY(devAlloc(own, &L.sq.d, P));
+    YC_TRY(devAlloc(own, &L.sq.lif, P));
+    YC_TRY(devAlloc(own, &L.sq.att, P));
+    YC_TRY(devAlloc(own, &L.qA, P));
+    YC_TRY(devAlloc(own, &L.qH, P));
+    YC_TRY(devAlloc(own, &L.qM, P));
+    YC_TRY(devAlloc(own, &L.ctr, size_t(kCtrCount)));
+    YC_TRY(rt::zero(ctx->st, L.ctr, kCtrCount * sizeof(uint32_t)));
+    void* hp = nullptr;
+    YC_TRY(rt::hostAlloc(&hp, kCtrCount * sizeof(uint32_t)));
+    L.hCtr = static_cast<uint32_t*>(hp);
 #ifndef YB_HOSTSIM
-  {
     uint2* sp = nullptr;
     YC_TRY(devAlloc(own, &sp, size_t(traceGridMax(ctx)) * kTraceBlock * (kMaxStack - kShStack)));
-    ctx->dSpill = sp;
-  }
+    L.spill = sp;
 #endif
+  }
+  ctx->dCtr = ctx->lanes[0].ctr;
+  ctx->dSpill = ctx->lanes[0].spill;
+  YC_TRY(devAlloc(own, &ctx->dCounters, size_t(1)));
   YC_TRY(rt::zero(ctx->st, ctx->dCounters, sizeof(Counters)));
-  YC_TRY(rt::zero(ctx->st, ctx->dCtr, kCtrCount * sizeof(uint32_t)));
+  YC_TRY(rt::sync(ctx->st));
   return YC_OK;
 }
 
@@ -676,6 +733,32 @@ extern "C" int yc_begin_frame(yc_ctx* ctx, const YcFrameDesc* f) {
   return YC_OK;
 }
 
+// One bounce of one lane's chunk: extend → sort → shade-miss → shade → shadow, then (unless it is the last
+// possible bounce) an asynchronous read-back of the counters that size the next bounce.
+template <bool ALPHA>
+static int issueBounce(yc_ctx* ctx, Lane& L) {
+  const uint32_t n = L.n;
+  YC_TRY(rt::zero(L.st, L.ctr, kCtrCount * sizeof(uint32_t)));
+  if (ctx->countTraversal) runExtend<ALPHA, true>(ctx, L, n);
+  else runExtend<ALPHA, false>(ctx, L, n);
+  rt::launchFor(L.st, n, SortK{L.ps, L.qA, L.qH, L.qM, L.ctr});
+  rt::launchFor(L.st, n, ShadeMissK{ctx->ds, L.w, L.ps, L.qM, L.ctr, ctx->dCounters});
+  rt::launchFor<YB_SHADE_MIN_BLOCKS>(L.st, n, ShadeK<ALPHA>{ctx->ds, L.w, L.ps, L.sq, L.qH, L.qA, L.ctr, ctx->dCounters});
+  if (ctx->countTraversal) runShadow<ALPHA, true>(ctx, L, n);
+  else runShadow<ALPHA, false>(ctx, L, n);
+  ctx->launches += 5;
+  ctx->raysExtend += n;  // every queue entry is one closest-hit ray
+  if (L.bounce + 1 < ctx->opts.maxDepth) {
+    YC_TRY(rt::d2hAsync(L.st, L.hCtr, L.ctr, kCtrCount * sizeof(uint32_t)));
+    rt::eventRecord(L.st, L.evCtr);
+    L.waiting = true;
+  } else {
+    L.waiting = false;  // the bounce loop ends here whatever the counts are: no host round trip
+    L.done = true;
+  }
+  return YC_OK;
+}
+
 template <bool ALPHA>
 static int renderChunks(yc_ctx* ctx, const uint32_t* dList, uint32_t nPixCall, uint32_t sampleOffset, uint32_t waveSamples,
                         uint32_t m) {
@@ -689,62 +772,107 @@ static int renderChunks(yc_ctx* ctx, const uint32_t* dList, uint32_t nPixCall, u
   w.maxDepth = ctx->opts.maxDepth;
   w.pixelList = dList;
   const float exposureScale = std::exp2(ctx->cam.exposure);  // integrator.cpp:23
-  const uint32_t B = std::min<uint32_t>(nPixCall, ctx->capacity);
-  const uint32_t Kmax = std::max<uint32_t>(1u, ctx->capacity / B);
+
+  // chunk list: pixel blocks x sample groups, each at most one lane's capacity of paths
+  struct Chunk {
+    uint32_t pixBase, nPix, sDone, K;
+  };
+  std::vector<Chunk> chunks;
+  const uint32_t cap = ctx->lanes[0].capacity;
+  const uint32_t B = std::min<uint32_t>(nPixCall, cap);
+  const uint32_t Kmax = std::max<uint32_t>(1u, cap / B);
   for (uint32_t pixBase = 0; pixBase < nPixCall; pixBase += B) {
     const uint32_t nPix = std::min(B, nPixCall - pixBase);
     for (uint32_t sDone = 0; sDone < waveSamples;) {
       const uint32_t K = std::min(Kmax, waveSamples - sDone);
-      const uint32_t nPaths = K * nPix;
-      w.pixBase = pixBase, w.nPix = nPix, w.s0 = sampleOffset + sDone;
-      // queues: A = this bounce's paths (rewritten by shade as the next bounce's), H / M = extend's hit / miss sort
-      uint32_t* qCur = ctx->dQueueA;
-      rt::launchFor(ctx->st, nPaths, RaygenK{w, ctx->ps, qCur});
-      ctx->launches++;
-      uint32_t n = nPaths;
-      for (uint32_t bounce = 0; bounce < ctx->opts.maxDepth && n > 0; bounce++) {
-        YC_TRY(rt::zero(ctx->st, ctx->dCtr, kCtrCount * sizeof(uint32_t)));
-        if (ctx->countTraversal) runExtend<ALPHA, true>(ctx, w, qCur, n);
-        else runExtend<ALPHA, false>(ctx, w, qCur, n);
-        rt::launchFor(ctx->st, n, SortK{ctx->ps, qCur, ctx->dQueueH, ctx->dQueueM, ctx->dCtr});
-        rt::launchFor(ctx->st, n, ShadeMissK{ctx->ds, w, ctx->ps, ctx->dQueueM, ctx->dCtr, ctx->dCounters});
-        rt::launchFor<YB_SHADE_MIN_BLOCKS>(ctx->st, n, ShadeK<ALPHA>{ctx->ds, w, ctx->ps, ctx->sq, ctx->dQueueH, qCur, ctx->dCtr,
-                                                                      ctx->dCounters});
-#ifdef YB_HOSTSIM
-        runShadow<ALPHA, false>(ctx, w);
-#else
-        if (ctx->countTraversal) runShadow<ALPHA, true>(ctx, w, n);
-        else runShadow<ALPHA, false>(ctx, w, n);
-#endif
-        ctx->launches += 5;
-        uint32_t ctr[kCtrCount] = {0};
-        // the counts are only needed to size the next bounce: none after the last one (no host round trip
-        // inside a maxDepth-1 chunk at all)
-        static const bool forceSync = getenv("YART_SYNC_LAST_BOUNCE") != nullptr;  // A/B switch (measurement only)
-        if (bounce + 1 < ctx->opts.maxDepth || forceSync) YC_TRY(rt::d2h(ctx->st, ctr, ctx->dCtr, sizeof ctr));
-        if (ctx->timeExtend) {
-          rt::eventSync(ctx->evK1);  // waits for the extend launch only; the kernels behind it are already queued
-          ctx->extendMs += rt::eventElapsedMs(ctx->evK0, ctx->evK1);
-          ctx->extendLaunches++;
-        }
-        ctx->raysExtend += n;  // every queue entry is one closest-hit ray
-        n = ctr[kCtrNextCount];
-#ifndef YB_HOSTSIM
-        if (n > 0 && n <= ctx->tailThreshold && bounce + 1 < ctx->opts.maxDepth) {
-          tailKernel<ALPHA><<<(n + kTailBlock - 1) / kTailBlock, kTailBlock, 0, ctx->st.s>>>(
-            ctx->ds, w, ctx->ps, ctx->sq, qCur, n, bounce + 1, ctx->dCounters);
-          ctx->launches++;
-          n = 0;
-        }
-#endif
-      }
-      rt::launchFor(ctx->st, nPix,
-                    AccumulateK{ctx->ps, ctx->dBuckets, ctx->bucketCapacity, pixBase, nPix, K, sDone, m, f.estimator,
-                                exposureScale});
-      ctx->launches++;
+      chunks.push_back({pixBase, nPix, sDone, K});
       sDone += K;
     }
   }
+
+  // the other lanes' streams start after everything already queued on the main stream (ev0)
+  for (int l = 1; l < kLanes; l++) rt::streamWaitEvent(ctx->lanes[l].st, ctx->ev0);
+  for (int l = 0; l < kLanes; l++) ctx->lanes[l].active = false;
+  size_t next = 0, nextAcc = 0;
+  rt::Event* lastAcc = nullptr;
+  while (nextAcc < chunks.size()) {
+    // start chunks on idle lanes
+    for (int l = 0; l < kLanes && next < chunks.size(); l++) {
+      Lane& L = ctx->lanes[l];
+      if (L.active) continue;
+      const Chunk& c = chunks[next];
+      L.active = true, L.done = false, L.waiting = false;
+      L.chunk = uint32_t(next++);
+      L.w = w;
+      L.w.pixBase = c.pixBase, L.w.nPix = c.nPix, L.w.s0 = sampleOffset + c.sDone;
+      L.K = c.K, L.sDone = c.sDone;
+      L.n = c.K * c.nPix;
+      L.bounce = 0;
+      rt::launchFor(L.st, L.n, RaygenK{L.w, L.ps, L.qA});
+      ctx->launches++;
+      const int rc = issueBounce<ALPHA>(ctx, L);
+      if (rc != YC_OK) return rc;
+    }
+    // accumulate finished chunks in chunk order: Integrator::render adds a pixel's samples in sample order
+    // (integrator.cpp:19-24), and the buckets' rounding sequence depends on it
+    bool progressed = true;
+    while (progressed) {
+      progressed = false;
+      for (int l = 0; l < kLanes; l++) {
+        Lane& L = ctx->lanes[l];
+        if (!(L.active && L.done && L.chunk == nextAcc)) continue;
+        if (lastAcc && lastAcc != &L.evAcc) rt::streamWaitEvent(L.st, *lastAcc);
+        rt::launchFor(L.st, L.w.nPix,
+                      AccumulateK{L.ps, ctx->dBuckets, ctx->bucketCapacity, L.w.pixBase, L.w.nPix, L.K, L.sDone, m,
+                                  f.estimator, exposureScale});
+        rt::eventRecord(L.st, L.evAcc);
+        lastAcc = &L.evAcc;
+        ctx->launches++;
+        L.active = false;
+        nextAcc++;
+        progressed = true;
+      }
+    }
+    if (nextAcc >= chunks.size()) break;
+    if (next < chunks.size()) {
+      bool idle = false;
+      for (int l = 0; l < kLanes; l++) idle |= !ctx->lanes[l].active;
+      if (idle) continue;  // a lane was freed: give it the next chunk before blocking
+    }
+    // service whichever waiting lane's counters arrive first: they size its next bounce
+    Lane* W = nullptr;
+    int waiting = 0;
+    for (int l = 0; l < kLanes; l++) waiting += ctx->lanes[l].active && ctx->lanes[l].waiting;
+    if (!waiting) return fail(ctx, YC_ERR_STATE, "wavefront scheduler stalled");
+    for (int spin = 0; !W; spin++) {
+      for (int l = 0; l < kLanes && !W; l++) {
+        Lane& L = ctx->lanes[l];
+        if (L.active && L.waiting && (waiting == 1 || rt::eventReady(L.evCtr))) W = &L;
+      }
+    }
+    Lane& L = *W;
+    rt::eventSync(L.evCtr);
+    L.waiting = false;
+    L.n = L.hCtr[kCtrNextCount];
+    L.bounce++;
+    if (L.n == 0 || L.bounce >= ctx->opts.maxDepth) {
+      L.done = true;
+      continue;
+    }
+#ifndef YB_HOSTSIM
+    if (L.n <= ctx->tailThreshold) {
+      tailKernel<ALPHA><<<(L.n + kTailBlock - 1) / kTailBlock, kTailBlock, 0, L.st.s>>>(ctx->ds, L.w, L.ps, L.sq, L.qA, L.n,
+                                                                                      L.bounce, ctx->dCounters);
+      ctx->launches++;
+      L.done = true;
+      continue;
+    }
+#endif
+    const int rc = issueBounce<ALPHA>(ctx, L);
+    if (rc != YC_OK) return rc;
+  }
+  // the main stream continues (finalize) after the last accumulate, which waited for all earlier ones
+  if (lastAcc && lastAcc != &ctx->lanes[0].evAcc) rt::streamWaitEvent(ctx->st, *lastAcc);
   YC_TRY(rt::lastError());
   return YC_OK;
 }
@@ -785,6 +913,11 @@ extern "C" int yc_render_wave(yc_ctx* ctx, YcRect px, uint32_t sampleOffset, uin
   YC_TRY(rt::sync(ctx->st));
   YC_TRY(rt::lastError());
   ctx->gpuMs += rt::eventElapsedMs(ctx->ev0, ctx->ev1);
+  for (size_t i = 0; i < ctx->extendEventsUsed; i++) {
+    ctx->extendMs += rt::eventElapsedMs(ctx->extendEvents[i].first, ctx->extendEvents[i].second);
+    ctx->extendLaunches++;
+  }
+  ctx->extendEventsUsed = 0;
   return YC_OK;
 }
 
