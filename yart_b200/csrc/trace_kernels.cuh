@@ -27,27 +27,48 @@ struct TraceTuning {
   int innerMin;   // keep stepping inner nodes while at least this many lanes sit on one
 };
 
+// Per-lane traversal stack of the persistent kernels: packed (ref, d) entries, [entry][thread] in shared
+// memory (one 64-bit access per push / pop, conflict-free), global spill area beyond kPsStack entries.
+// The stack pointer is the shared-memory byte address of the next free slot, so push / pop are one
+// add and one LDS.64 / STS.64; entry 0 holds a sentinel (kNoRef) written when a mesh is entered, so a
+// pop never tests for "empty": popping the sentinel yields kNoRef = "this mesh is walked".
+constexpr int kPsStack = kShStack + 1;
+constexpr uint32_t kPsStride = kTraceBlock * 8;  // bytes between consecutive entries of one thread
 struct WarpStack {
-  uint32_t* shRef;  // + threadIdx.x
-  float* shD;
-  uint2* spill;     // this thread's kMaxStack - kShStack entries in global memory
-  __device__ __forceinline__ void push(int sp, uint32_t ref, float d) {
-    if (sp < kShStack) {
-      shRef[sp * kTraceBlock] = ref;
-      shD[sp * kTraceBlock] = d;
-    } else if (sp < kMaxStack) {
-      spill[sp - kShStack] = make_uint2(ref, __float_as_uint(d));
-    }
+  uint32_t base;   // shared address of this thread's entry 0
+  uint32_t limit;  // base + kPsStack * kPsStride: first address that lives in the spill area
+  uint2** spillBase;  // in shared memory: the spill area's base pointer (only the rare path reads it)
+  __device__ __forceinline__ void init(uint2* shStack, uint2** shSpill, uint2* spill) {
+    uint32_t a = uint32_t(__cvta_generic_to_shared(shStack + threadIdx.x));
+    asm volatile("mov.u32 %0, %1;" : "=r"(base) : "r"(a));  // opaque: kept in a register, not recomputed
+    limit = base + uint32_t(kPsStack) * kPsStride;
+    if (threadIdx.x == 0) *shSpill = spill;
+    __syncthreads();
+    spillBase = shSpill;
   }
-  __device__ __forceinline__ void pop(int sp, uint32_t& ref, float& d) const {
-    if (sp < kShStack) {
-      ref = shRef[sp * kTraceBlock];
-      d = shD[sp * kTraceBlock];
+  // rare path (trees deeper than kShStack): everything is derived here so nothing of it stays live
+  __device__ __noinline__ static uint2* spillSlot(uint2** spillBase, uint32_t off) {
+    return *spillBase + size_t(blockIdx.x * kTraceBlock + threadIdx.x) * (kMaxStack - kShStack) + off / kPsStride;
+  }
+  __device__ __forceinline__ void put(uint32_t sa, uint32_t ref, float d) const {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(sa), "r"(ref), "r"(__float_as_uint(d)));
+  }
+  __device__ __forceinline__ void push(uint32_t& sa, uint32_t ref, float d) const {
+    if (sa < limit) put(sa, ref, d);
+    else if (sa < limit + uint32_t(kMaxStack - kShStack) * kPsStride) *spillSlot(spillBase, sa - limit) = make_uint2(ref, __float_as_uint(d));
+    sa += kPsStride;
+  }
+  __device__ __forceinline__ void pop(uint32_t& sa, uint32_t& ref, float& d) const {
+    sa -= kPsStride;
+    uint32_t x, y;
+    if (sa < limit) {
+      asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "r"(sa));
     } else {
-      const uint2 v = spill[sp - kShStack];
-      ref = v.x;
-      d = __uint_as_float(v.y);
+      const uint2 v = *spillSlot(spillBase, sa - limit);
+      x = v.x, y = v.y;
     }
+    ref = x;
+    d = __uint_as_float(y);
   }
 };
 
@@ -87,19 +108,18 @@ enum : int { kLaneIdle = 0, kLaneNode = 1, kLaneTrav = 2 };
 template <bool NEE, bool ALPHA, bool COUNT, bool EARLY_OUT, class IO>
 __device__ __forceinline__ void tracePersistent(const DScene& sc, IO& io, uint32_t n, uint32_t* head, uint2* spillBase,
                                                 const TraceTuning tune, TraceCounters& cnt) {
-  __shared__ uint32_t shRef[kShStack * kTraceBlock];
-  __shared__ float shD[kShStack * kTraceBlock];
+  __shared__ uint2 shStack[kPsStack * kTraceBlock];
+  __shared__ uint2* shSpill;
   WarpStack stack;
-  stack.shRef = shRef + threadIdx.x;
-  stack.shD = shD + threadIdx.x;
-  stack.spill = spillBase + size_t(blockIdx.x * kTraceBlock + threadIdx.x) * (kMaxStack - kShStack);
+  stack.init(shStack, &shSpill, spillBase);
   const unsigned FULL = 0xffffffffu;
   const unsigned lane = threadIdx.x & 31u, ltMask = (1u << lane) - 1u;
 
   int state = kLaneIdle;
   bool exhausted = false;
   uint32_t item = 0, nextNode = 0, cur = 0;
-  int sp = 0, curNode = 0;
+  uint32_t sp = 0;  // stack pointer: shared byte address of the next free slot (WarpStack)
+  int curNode = 0;
   float dcur = 0.0f;
   bool didHit = false, meshHit = false, rayIsWorld = false, worldFinite = false;
   V3 wo, wd;
@@ -110,7 +130,8 @@ __device__ __forceinline__ void tracePersistent(const DScene& sc, IO& io, uint32
   const float4* __restrict__ tris = nullptr;
   uint32_t meshIdx = 0;
   constexpr bool SPEC = !COUNT;           // counting builds reproduce the reference's box-test counts
-  constexpr uint32_t kNoRef = 0xffffffffu;  // "no current node" (has the leaf bit: never stepped as inner)
+  constexpr uint32_t kNoRef = 0xffffffffu;   // "no current node" (has the leaf bit: never stepped as inner)
+  constexpr uint32_t kPopRef = 0xfffffffeu;  // "pop at the top of the next inner step" (leaf bit set as well)
   uint32_t pend = 0u;                     // parked leaf (0 = none; leaf refs carry bit 31)
   float pendD = 0.0f;
 
@@ -179,7 +200,8 @@ __device__ __forceinline__ void tracePersistent(const DScene& sc, IO& io, uint32
         tris = sc.bvhTris + 3 * size_t(mesh.triOffset);
         cur = mesh.rootRef;
         dcur = dd;
-        sp = 0;
+        stack.put(stack.base, kNoRef, 0.0f);  // sentinel
+        sp = stack.base + kPsStride;
         pend = 0u;
         meshHit = false;
         entered = true;
@@ -195,68 +217,61 @@ __device__ __forceinline__ void tracePersistent(const DScene& sc, IO& io, uint32
 
     // ---- inner-node steps ------------------------------------------------------------------------
     // SPEC (all non-counting builds): a lane that reaches a leaf parks it in `pend` and keeps walking;
-    // it only blocks when it reaches a second leaf (or runs out of stack) with one still parked.
+    // it only blocks when it reaches a second leaf (or has walked the mesh) with one still parked.
     // Parked leaves are tested in the order they were reached, before any later leaf, so the sequence
     // of triangle tests — and with it the accepted hit, exact ties and alpha-test draws — is the
     // reference's.  Only box culling sees a slightly older hit.t, i.e. a few extra box tests.
+    // The loop body is branch-free apart from the `inner` guard: descend / push / pop are selects and
+    // predicated 64-bit shared-memory accesses, and the stack sentinel stands in for the "empty" test.
     for (;;) {
-      if (SPEC && state == kLaneTrav && (cur & YC_REF_LEAF) && cur != kNoRef && pend == 0u) {
+      const bool trav = state == kLaneTrav;
+      bool doPop = trav && cur == kPopRef;  // left by the previous step: one pop site per iteration
+      if (SPEC && trav && pend == 0u && int32_t(cur) < -2) {  // a leaf (bit 31) other than kNoRef / kPopRef
         pend = cur, pendD = dcur;
-        if (sp == 0) cur = kNoRef;
-        else stack.pop(--sp, cur, dcur);
+        doPop = true;
       }
-      const bool inner = state == kLaneTrav && !(cur & YC_REF_LEAF);
+      if (doPop) stack.pop(sp, cur, dcur);  // the sentinel ends the mesh: cur = kNoRef
+      const bool inner = trav && int32_t(cur) >= 0;
       const unsigned im = __ballot_sync(FULL, inner);
       if (im == 0) break;
-      if (__popc(im) < tune.innerMin && __ballot_sync(FULL, state == kLaneTrav && (cur & YC_REF_LEAF))) break;
+      if (__popc(im) < tune.innerMin && __ballot_sync(FULL, trav && !inner)) break;
       if (inner) {
+        const NodeRec nr = loadNode(nodes + 4 * size_t(cur));
+        // testBVH's pop-time cull `d < hit.t` (ray-integrator.cpp:100): an entry that fails it is
+        // dropped without testing its children — here both tests are made to fail (tmax = -inf)
         const bool live = dcur < st.hit.t;
-        bool hit1 = false, hit2 = false;
-        float d1 = 0.0f, d2 = 0.0f;
-        uint32_t c1 = 0, c2 = 0;
-        if (live) {
-          const NodeRec nr = loadNode(nodes + 4 * size_t(cur));
-          hit1 = slabLive<COUNT>(r, V3(nr.f[0], nr.f[1], nr.f[2]), V3(nr.f[3], nr.f[4], nr.f[5]), kTMin, st.hit.t, d1, cnt);
-          hit2 = slabLive<COUNT>(r, V3(nr.f[6], nr.f[7], nr.f[8]), V3(nr.f[9], nr.f[10], nr.f[11]), kTMin, st.hit.t, d2, cnt);
-          c1 = __float_as_uint(nr.f[12]), c2 = __float_as_uint(nr.f[13]);
-        }
+        const float tmx = live ? st.hit.t : -INFINITY;
+        float d1, d2;
+        const bool hit1 = slabLive(r, V3(nr.f[0], nr.f[1], nr.f[2]), V3(nr.f[3], nr.f[4], nr.f[5]), kTMin, tmx, d1);
+        const bool hit2 = slabLive(r, V3(nr.f[6], nr.f[7], nr.f[8]), V3(nr.f[9], nr.f[10], nr.f[11]), kTMin, tmx, d2);
+        if (COUNT && live) cnt.box += 2;
+        const uint32_t c1 = __float_as_uint(nr.f[12]), c2 = __float_as_uint(nr.f[13]);
         // testBVH's descend / push / pop decisions (ray-integrator.cpp:131-152) as selects
         const bool both = hit1 && hit2;
         const bool swapped = both && d1 > d2;
+        const bool first = hit1 && !swapped;
         const uint32_t farRef = swapped ? c1 : c2;
         const float farD = swapped ? d1 : d2;
-        const uint32_t nearRef = (hit1 && !swapped) ? c1 : c2;
-        const float nearD = (hit1 && !swapped) ? d1 : d2;
-        if (both) stack.push(sp++, farRef, farD);
-        if (hit1 || hit2) {
-          cur = nearRef, dcur = nearD;
-        } else if (sp == 0) {
-          if (SPEC && pend != 0u) cur = kNoRef;  // mesh walked, one leaf still parked
-          else state = kLaneNode;                // this mesh is done: on to the next scene node
-        } else {
-          stack.pop(--sp, cur, dcur);
-        }
+        const uint32_t nearRef = first ? c1 : c2;
+        const float nearD = first ? d1 : d2;
+        if (both) stack.push(sp, farRef, farD);
+        cur = (hit1 || hit2) ? nearRef : kPopRef;
+        dcur = nearD;
       }
     }
 
     // ---- leaf step -------------------------------------------------------------------------------
-    // kNoRef carries the leaf bit, so "cur is a leaf" also covers "nothing left but a parked leaf".
-    if (state == kLaneTrav && ((cur & YC_REF_LEAF) || (SPEC && pend != 0u))) {
+    // kNoRef carries the leaf bit, so "cur is a leaf" also covers "mesh walked" (with or without a
+    // parked leaf); a lane still on an inner node uses the break to test its parked leaf.
+    if (state == kLaneTrav && (int32_t(cur) < 0 || (SPEC && pend != 0u))) {
       uint32_t leaf = cur;
       float leafD = dcur;
       if (SPEC) {
-        if (pend != 0u) {
-          leaf = pend, leafD = pendD;
-          pend = 0u;
-        } else {
-          // only reachable for cur == kNoRef with nothing parked (cannot happen) or a fresh leaf
-          if (cur != kNoRef) {
-            if (sp == 0) cur = kNoRef;
-            else stack.pop(--sp, cur, dcur);
-          }
-        }
+        // a real leaf in `cur` with nothing parked cannot leave the loop above (it is parked at once)
+        leaf = pend, leafD = pendD;
+        pend = 0u;
       }
-      if (leaf != kNoRef && leafD < st.hit.t) {
+      if (int32_t(leaf) < -1 && leafD < st.hit.t) {
         const YcMesh& mesh = sc.meshes[meshIdx];
         uint32_t ti = leaf & ~YC_REF_LEAF;
         while (true) {
@@ -273,12 +288,9 @@ __device__ __forceinline__ void tracePersistent(const DScene& sc, IO& io, uint32
         io.store(item, st, true, smp);
         state = kLaneIdle;
         pend = 0u;
-      } else if (SPEC) {
-        if (cur == kNoRef) state = kLaneNode;  // stack empty and nothing parked any more
-      } else if (sp == 0) {
-        state = kLaneNode;
       } else {
-        stack.pop(--sp, cur, dcur);
+        if (!SPEC && cur != kNoRef) stack.pop(sp, cur, dcur);
+        if (cur == kNoRef) state = kLaneNode;  // mesh walked and nothing parked any more
       }
     }
   }

@@ -18,7 +18,10 @@
 
 namespace yb {
 
-constexpr int kShStack = 24;   // shared-memory stack entries per thread
+#ifndef YB_SH_STACK
+#define YB_SH_STACK 24
+#endif
+constexpr int kShStack = YB_SH_STACK;   // shared-memory stack entries per thread
 constexpr int kMaxStack = 64;  // reference: stack[64], ray-integrator.cpp:92-93
 constexpr float kTMin = 0.001f;
 
@@ -62,9 +65,7 @@ YB_DEV bool slab(const LocalRay& r, V3 lo, V3 hi, float tmn, float tmx, float& d
 // fmaxf(m, n) and `m < n ? m : n` equals fminf(m, n) for every m including NaN (both return n), up to
 // the sign of a zero that can never be selected (t0 >= tMin > 0) or never matters (t1 = ±0 < t0).
 // One FMNMX instead of FSETP + FSEL per fold.
-template <bool COUNT>
-YB_DEV bool slabLive(const LocalRay& r, V3 lo, V3 hi, float tmn, float tmx, float& d, TraceCounters& cnt) {
-  if (COUNT) cnt.box++;
+YB_DEV bool slabLive(const LocalRay& r, V3 lo, V3 hi, float tmn, float tmx, float& d) {
   const bool sx = r.d.x < 0.0f, sy = r.d.y < 0.0f, sz = r.d.z < 0.0f;
   V3 bmin(sx ? hi.x : lo.x, sy ? hi.y : lo.y, sz ? hi.z : lo.z);
   V3 bmax(sx ? lo.x : hi.x, sy ? lo.y : hi.y, sz ? lo.z : hi.z);
