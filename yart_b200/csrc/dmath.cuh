@@ -10,11 +10,13 @@
 #define YB_DEV inline
 #define YB_DEV_NI inline
 #define YB_CONST static const
+#define YB_TABLE static const
 #else
 #include <cuda_runtime.h>
 #define YB_DEV __device__ __forceinline__
 #define YB_DEV_NI __device__ __noinline__
 #define YB_CONST __device__ __constant__
+#define YB_TABLE __device__ const  // global memory: for tables indexed differently per lane
 #endif
 #include <math.h>
 #include <stdint.h>

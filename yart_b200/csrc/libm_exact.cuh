@@ -118,7 +118,7 @@ YB_DEV float cosfExact(float y) {
 
 namespace libm {
 // __logf_data (e_logf_data.c): 16 x {invc, logc}
-YB_CONST double kLogTab[32] = {
+YB_TABLE double kLogTab[32] = {
   0x1.661ec79f8f3bep+0, -0x1.57bf7808caadep-2, 0x1.571ed4aaf883dp+0, -0x1.2bef0a7c06ddbp-2,
   0x1.49539f0f010bp+0,  -0x1.01eae7f513a67p-2, 0x1.3c995b0b80385p+0, -0x1.b31d8a68224e9p-3,
   0x1.30d190c8864a5p+0, -0x1.6574f0ac07758p-3, 0x1.25e227b0b8eap+0,  -0x1.1aa2bc79c81p-3,
@@ -158,7 +158,7 @@ YB_DEV float logfExact(float x) {
 
 namespace libm {
 // __exp2f_data.tab (e_exp2f_data.c): asuint64(2^(i/32)) - (i << 47), i = 0..31
-YB_CONST uint64_t kExp2Tab[32] = {
+YB_TABLE uint64_t kExp2Tab[32] = {
   0x3ff0000000000000ull, 0x3fefd9b0d3158574ull, 0x3fefb5586cf9890full, 0x3fef9301d0125b51ull, 0x3fef72b83c7d517bull,
   0x3fef54873168b9aaull, 0x3fef387a6e756238ull, 0x3fef1e9df51fdee1ull, 0x3fef06fe0a31b715ull, 0x3feef1a7373aa9cbull,
   0x3feedea64c123422ull, 0x3feece086061892dull, 0x3feebfdad5362a27ull, 0x3feeb42b569d4f82ull, 0x3feeab07dd485429ull,
@@ -196,7 +196,7 @@ YB_DEV float expfExact(float x) {
 
 namespace libm {
 // __log2f_data (e_log2f_data.c): 16 x {invc, log2(c)}; __powf_log2_data.tab holds the same pairs
-YB_CONST double kLog2Tab[32] = {
+YB_TABLE double kLog2Tab[32] = {
   0x1.661ec79f8f3bep+0, -0x1.efec65b963019p-2, 0x1.571ed4aaf883dp+0, -0x1.b0b6832d4fca4p-2,
   0x1.49539f0f010bp+0,  -0x1.7418b0a1fb77bp-2, 0x1.3c995b0b80385p+0, -0x1.39de91a6dcf7bp-2,
   0x1.30d190c8864a5p+0, -0x1.01d9bf3f2b631p-2, 0x1.25e227b0b8eap+0,  -0x1.97c1d1b3b7afp-3,

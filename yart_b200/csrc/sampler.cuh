@@ -16,10 +16,17 @@ struct SamplerConfig {
 };
 
 // permutations[24][4], sampler.hpp:116-141 (the 24 permutations of {0,1,2,3} in the order the
-// reference lists them), packed 2 bits per digit: entry p, digit d → (kPerm[p] >> (2*d)) & 3.
-YB_CONST uint8_t kPerm[24] = {
-  0xE4, 0xB4, 0xD8, 0x78, 0x6C, 0x9C, 0xE1, 0xB1, 0xC9, 0x39, 0x2D, 0x8D,
-  0xC6, 0x36, 0xD2, 0x72, 0x4E, 0x1E, 0x27, 0x87, 0x1B, 0x4B, 0x63, 0x93};
+// reference lists them), packed 2 bits per digit: entry p, digit d → (kPermPacked[p] >> (2*d)) & 3.
+// On the device the table is one byte per (p, digit) in GLOBAL memory, read through the read-only
+// path: the index differs per lane, and a __constant__ table would serialise a warp's lookup into one
+// pass per distinct address (up to 24), while these 96 bytes are three L1 sectors.
+#define YB_PERM_ROW(b) (b) & 3, ((b) >> 2) & 3, ((b) >> 4) & 3, ((b) >> 6) & 3
+YB_TABLE uint8_t kPerm[96] = {
+  YB_PERM_ROW(0xE4), YB_PERM_ROW(0xB4), YB_PERM_ROW(0xD8), YB_PERM_ROW(0x78), YB_PERM_ROW(0x6C), YB_PERM_ROW(0x9C),
+  YB_PERM_ROW(0xE1), YB_PERM_ROW(0xB1), YB_PERM_ROW(0xC9), YB_PERM_ROW(0x39), YB_PERM_ROW(0x2D), YB_PERM_ROW(0x8D),
+  YB_PERM_ROW(0xC6), YB_PERM_ROW(0x36), YB_PERM_ROW(0xD2), YB_PERM_ROW(0x72), YB_PERM_ROW(0x4E), YB_PERM_ROW(0x1E),
+  YB_PERM_ROW(0x27), YB_PERM_ROW(0x87), YB_PERM_ROW(0x1B), YB_PERM_ROW(0x4B), YB_PERM_ROW(0x63), YB_PERM_ROW(0x93)};
+#undef YB_PERM_ROW
 
 // rng.hpp:93-100
 YB_DEV uint64_t mixBits(uint64_t v) {
@@ -70,19 +77,19 @@ YB_DEV uint32_t fastOwen(uint32_t v, uint32_t seed) {
   return reverseBits32(v);
 }
 
-// Sobol dimension 1 generator matrix column i (sobol.tables entries 52..103): the Pascal-mod-2
-// columns v_0 = 2^31, v_i = v_{i-1} ^ (v_{i-1} >> 1), repeating with period 32 in the table.
-YB_DEV uint32_t sobolDim1Column(uint32_t i) {
-  // closed form of the recurrence: bit-reversed row (i & 31) of Pascal's triangle mod 2
-  uint32_t k = i & 31u;
-  uint32_t v = 0x80000000u;
-  // v_k = Π (1 + S)^k applied to v_0 where S is a right shift; use binary decomposition of k
-  if (k & 1u) v ^= v >> 1;
-  if (k & 2u) v ^= v >> 2;
-  if (k & 4u) v ^= v >> 4;
-  if (k & 8u) v ^= v >> 8;
-  if (k & 16u) v ^= v >> 16;
-  return v;
+// Sobol dimension 1 (sobol.tables entries 52..103): generator-matrix column i is the Pascal-mod-2
+// column v_0 = 2^31, v_i = v_{i-1} ^ (v_{i-1} >> 1) = (1 + S)^i v_0 (S = shift right by one), repeating
+// with period 32 in the table.  Bit (31 - j) of column i is C(i, j) mod 2 = [j ⊆ i] (Lucas), so the
+// XOR of the columns selected by the bits of `d` (sampler.hpp:143-153) is the superset-sum transform
+// over GF(2) of those bits — five butterfly steps — followed by a bit reversal.
+YB_DEV uint32_t sobolDim1Closed(uint64_t d) {
+  uint32_t x = uint32_t(d) ^ uint32_t(d >> 32);  // columns repeat with period 32
+  x ^= (x >> 1) & 0x55555555u;
+  x ^= (x >> 2) & 0x33333333u;
+  x ^= (x >> 4) & 0x0f0f0f0fu;
+  x ^= (x >> 8) & 0x00ff00ffu;
+  x ^= (x >> 16) & 0x0000ffffu;
+  return reverseBits32(x);
 }
 
 struct Sampler {
@@ -107,10 +114,10 @@ struct Sampler {
       uint32_t digitShift = 2 * i - lastDigit;
       uint32_t digit = uint32_t(morton >> digitShift) & 3u;
       uint64_t higherDigits = morton >> (digitShift + 2);
-      // (mixBits(..) >> 24) % 24 on the 40-bit quotient, in 32-bit pieces: 2^32 mod 24 = 16
+      // (mixBits(..) >> 24) % 24 on the 40-bit quotient, in 32-bit pieces: 2^32 mod 24 = 16, hi < 256
       uint64_t mb = mixBits(higherDigits ^ dimMix) >> 24;
-      uint32_t p = (((uint32_t(mb >> 32) % 24u) * 16u) + (uint32_t(mb) % 24u)) % 24u;
-      digit = (kPerm[p] >> (2 * digit)) & 3u;
+      uint32_t p = ((uint32_t(mb >> 32) * 16u) + (uint32_t(mb) % 24u)) % 24u;
+      digit = __ldg(&kPerm[4u * p + digit]);
       index |= uint64_t(digit) << digitShift;
     }
     if (pow2Samples) {
@@ -125,12 +132,7 @@ struct Sampler {
     v = fastOwen(v, seed);
     return fminf(float(v) * 0x1p-32f, 0x1.fffffep-1f);
   }
-  static YB_DEV uint32_t sobolDim1(uint64_t d) {
-    uint32_t v = 0;
-    for (uint32_t i = 0; d != 0; d >>= 1, i++)
-      if (d & 1ull) v ^= sobolDim1Column(i);
-    return v;
-  }
+  static YB_DEV uint32_t sobolDim1(uint64_t d) { return sobolDim1Closed(d); }
 
   // sampler.hpp:89-94: index uses the CURRENT dim, the hash the incremented one
   YB_DEV float get1D() {
