@@ -165,3 +165,23 @@ def test_camera_make_defaults_and_up_vector():
     assert abs(a.apertureRadius - (50.0 / 2000.0) / 2.0) < 1e-9
     pin = Y.make_camera(640, 480, 50.0, 0.0, (1, 2, 3), (0, 0, 0))
     assert pin.apertureRadius == 0.0
+
+
+def test_u8_unit_conversion_is_the_division():
+    """csrc/texture.cuh u8ToUnit: q = b*r, rem = fma(-q, 255, b), q' = fma(rem, r, q) with r = fl(1/255) equals the
+    correctly rounded float(b) / 255.0f for every byte (the reference's conversion, texture.hpp:108-116)."""
+    from fractions import Fraction
+    f32 = np.float32
+
+    def rn(x: Fraction) -> np.float32:  # exact round-to-nearest-even of a rational to float32
+        c = f32(float(x))
+        cands = [c, np.nextafter(c, f32(np.inf)), np.nextafter(c, f32(-np.inf))]
+        return min(cands, key=lambda v: (abs(Fraction(float(v)) - x), int(v.view(np.uint32)) & 1))
+
+    r = f32(1.0) / f32(255.0)
+    for b in range(256):
+        fb = f32(b)
+        q = rn(Fraction(float(fb)) * Fraction(float(r)))
+        rem = rn(-Fraction(float(q)) * 255 + Fraction(float(fb)))
+        q2 = rn(Fraction(float(rem)) * Fraction(float(r)) + Fraction(float(q)))
+        assert q2 == fb / f32(255.0), b

@@ -37,9 +37,20 @@ YB_DEV float bilerp1(float a0, float a1, float b0, float b1, float u, float v) {
   return a0 * (1.0f - u) * (1.0f - v) + a1 * (1.0f - u) * v + b0 * u * (1.0f - v) + b1 * u * v;
 }
 
+// float(b) / 255.0f for a byte b, correctly rounded, without the general division sequence: one
+// Newton correction of b * fl(1/255) with fused multiply-adds (the standard division fast path; its
+// range checks are unnecessary for 0..255).  Checked against the division for all 256 inputs
+// (tests/test_host_logic.py::test_u8_unit_conversion_is_the_division).
+YB_DEV float u8ToUnit(uint32_t b) {
+  const float fb = float(b), r = 1.0f / 255.0f;
+  const float q = fb * r;
+  const float rem = fmaf(-q, 255.0f, fb);
+  return fmaf(rem, r, q);
+}
+
 // one channel of an 8-bit texture
 YB_DEV float texelU8(const DScene& s, const YcTexture& t, size_t idx, uint32_t c, bool gamma2) {
-  float v = float(s.texU8[t.offset + idx * t.channels + c]) / 255.0f;
+  float v = u8ToUnit(s.texU8[t.offset + idx * t.channels + c]);
   return gamma2 ? v * v : v;
 }
 

@@ -53,23 +53,27 @@ struct WarpStack {
   __device__ __forceinline__ void put(uint32_t sa, uint32_t ref, float d) const {
     asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(sa), "r"(ref), "r"(__float_as_uint(d)));
   }
-  __device__ __forceinline__ void push(uint32_t& sa, uint32_t ref, float d) const {
-    if (sa < limit) put(sa, ref, d);
-    else if (sa < limit + uint32_t(kMaxStack - kShStack) * kPsStride) *spillSlot(spillBase, sa - limit) = make_uint2(ref, __float_as_uint(d));
-    sa += kPsStride;
+  // push / pop under a lane predicate: the shared-memory access is a single predicated instruction and
+  // only the (rare) spill case branches.
+  __device__ __forceinline__ void pushIf(bool on, uint32_t& sa, uint32_t ref, float d) const {
+    if (on && sa < limit) put(sa, ref, d);
+    if (on && sa >= limit) {
+      if (sa < limit + uint32_t(kMaxStack - kShStack) * kPsStride) *spillSlot(spillBase, sa - limit) = make_uint2(ref, __float_as_uint(d));
+    }
+    if (on) sa += kPsStride;
   }
-  __device__ __forceinline__ void pop(uint32_t& sa, uint32_t& ref, float& d) const {
-    sa -= kPsStride;
-    uint32_t x, y;
-    if (sa < limit) {
-      asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "r"(sa));
-    } else {
+  __device__ __forceinline__ void popIf(bool on, uint32_t& sa, uint32_t& ref, float& d) const {
+    if (on) sa -= kPsStride;
+    uint32_t x = ref, y = __float_as_uint(d);
+    if (on && sa < limit) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "r"(sa));
+    if (on && sa >= limit) {
       const uint2 v = *spillSlot(spillBase, sa - limit);
       x = v.x, y = v.y;
     }
     ref = x;
     d = __uint_as_float(y);
   }
+  __device__ __forceinline__ void pop(uint32_t& sa, uint32_t& ref, float& d) const { popIf(true, sa, ref, d); }
 };
 
 // Ray in the object space of scene node `node`: the chain of inverse transforms root → node, applied
@@ -230,7 +234,7 @@ __device__ __forceinline__ void tracePersistent(const DScene& sc, IO& io, uint32
         pend = cur, pendD = dcur;
         doPop = true;
       }
-      if (doPop) stack.pop(sp, cur, dcur);  // the sentinel ends the mesh: cur = kNoRef
+      stack.popIf(doPop, sp, cur, dcur);  // the sentinel ends the mesh: cur = kNoRef
       const bool inner = trav && int32_t(cur) >= 0;
       const unsigned im = __ballot_sync(FULL, inner);
       if (im == 0) break;
@@ -254,7 +258,7 @@ __device__ __forceinline__ void tracePersistent(const DScene& sc, IO& io, uint32
         const float farD = swapped ? d1 : d2;
         const uint32_t nearRef = first ? c1 : c2;
         const float nearD = first ? d1 : d2;
-        if (both) stack.push(sp, farRef, farD);
+        stack.pushIf(both, sp, farRef, farD);
         cur = (hit1 || hit2) ? nearRef : kPopRef;
         dcur = nearD;
       }

@@ -31,7 +31,7 @@ using namespace yb;
 #define YB_TRACE_MIN_BLOCKS 8  // 8 CTAs x 4 warps per SM: caps the traversal kernels at 64 registers
 #endif
 #ifndef YB_SHADE_MIN_BLOCKS
-#define YB_SHADE_MIN_BLOCKS 2
+#define YB_SHADE_MIN_BLOCKS 6  // 6 x 256 threads per SM (40 registers + local-memory spills): shading is latency-bound, warps beat registers (2: 35.6, 4: 33.7, 6: 32.4, 8: 32.3 ms on the Sponza-shaped step)
 #endif
 
 // ---------------------------------------------------------------------------------------
