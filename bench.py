@@ -217,6 +217,16 @@ def run_ours(args):
     ctx.begin_frame(W, H, total_spp, 64, (0, 0, 0), Y.TONEMAP_AGX)
 
     frame_t = None
+    buckets = world > 1 and args.sharding == "buckets"
+    bucket_t, ar_events = None, []
+    if buckets:
+        import torch
+        b_ptr, b_bytes, _, plane_pix = ctx.bucket_device_ptrs()
+        m_wave = ctx.wave_buckets(spp * world)
+
+        class _BAlias:  # zero-copy int32 view of the planes a wave of spp * world samples uses
+            __cuda_array_interface__ = {"shape": (m_wave * plane_pix * 4,), "typestr": "<i4", "data": (b_ptr, False), "version": 3}
+        bucket_t = torch.as_tensor(_BAlias(), device=f"cuda:{local}")
     if dist:
         import torch
         hdr_ptr, _, nbytes = ctx.frame_device_ptrs()
@@ -236,13 +246,28 @@ def run_ours(args):
         """One pass: wave (k * world + rank) of the job — `spp` samples of every pixel — blended into this
         rank's HDR frame with finishTile's sample-count weights."""
         k = min(k, waves_per_rank - 1)
+        if buckets:
+            # sample sharding inside a wave of spp * world samples by estimator bucket: every rank accumulates
+            # the samples of its buckets, the GMoN accumulation buffers are summed with NCCL (int32: disjoint
+            # planes, bitwise exact), every rank finalizes — bit-identical to one GPU rendering the wave
+            import torch
+            S = spp * world
+            ctx.accumulate_wave(k * S, S, bucket_shard=rank, bucket_shard_count=world)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            dist.all_reduce(bucket_t)
+            e1.record()
+            torch.cuda.synchronize()
+            ar_events.append((e0, e1))
+            ctx.finalize_wave(S, k * S)
+            return
         ctx.render_wave((k * world + rank) * spp, spp, k * spp)
 
     def combine(scratch=False):
         """N > 1: the per-GPU HDR frames (equal sample counts) are averaged with one NCCL all-reduce over
         NVLink and re-tonemapped — once per job, inside the timed region.  scratch=True (warm-up) runs the
         same collective on a copy so the frames being accumulated are left alone."""
-        if not dist:
+        if not dist or buckets:
             return 0.0
         import torch
         t = frame_t.clone() if scratch else frame_t
@@ -265,10 +290,11 @@ def run_ours(args):
         combine(scratch=True)  # warms NCCL up (parity of this path: tests/test_multi_gpu_cpu.py)
     sync_all()
     s0 = ctx.stats()
+    ar_events.clear()
     w0 = time.time()
     for k in range(args.steps):
         step(n_warm + k)
-    ar_total = combine()
+    ar_total = combine() + sum(a.elapsed_time(b) for a, b in ar_events)
     sync_all()
     w1 = time.time()
     s1 = ctx.stats()
@@ -371,8 +397,11 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD_TEXT,
                        "step": f"one wave of {spp} spp per GPU ({W * H * spp} camera paths)",
-                       "parallelism": f"sample-wave sharding x{world}: rank r renders waves r, r+N, ... of the job; scene replicated; "
-                                      "one NCCL all-reduce of the HDR frames per job (inside the timed region)",
+                       "parallelism": (f"bucket sharding x{world}: every wave of {spp * world} samples is split by GMoN bucket "
+                                       "(rank r takes buckets b % N == r); scene replicated; NCCL all-reduce(int32 sum) of the "
+                                       "accumulation buffers per wave, inside the timed region") if buckets else
+                                      (f"sample-wave sharding x{world}: rank r renders waves r, r+N, ... of the job; scene replicated; "
+                                       "one NCCL all-reduce of the HDR frames per job (inside the timed region)"),
                        "l2": "inputs larger than L2: BVH + 0.8 GB of path state streamed per step exceed the 126 MB L2; no flush"},
             "wall_ms_per_step": wall_ms / args.steps,
             "traced_mrays_per_s": traced / dev_ms / 1e3,
@@ -412,6 +441,8 @@ def main():
     ap.add_argument("--workload", default="soup", choices=sorted(WORKLOADS))
     ap.add_argument("--tris", type=int, default=0, help="triangle count (default: the workload's BASELINE.json size)")
     ap.add_argument("--spp", type=int, default=4)
+    ap.add_argument("--sharding", default="waves", choices=["waves", "buckets"],
+                    help="N > 1: whole waves per rank (default) or the samples of one wave split by GMoN bucket")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if not args.tris:

@@ -267,6 +267,25 @@ int yc_begin_frame(yc_ctx* ctx, const YcFrameDesc* frame);
  * (takenBefore = samples already blended) and tonemaps. */
 int yc_render_wave(yc_ctx* ctx, YcRect pixels, uint32_t sampleOffset, uint32_t waveSamples,
                    uint32_t takenBefore);
+/* The same wave in two steps, for sample sharding across GPUs (SURVEY §8e alternative B; north_star:
+ * "per-GPU ... median-of-means and GMoN accumulation buffers are combined with NCCL"):
+ *   yc_accumulate_wave  Integrator::render's sample loop (integrator.cpp:19-24) for the samples of the wave
+ *                       whose estimator bucket b = (index in the wave) % m satisfies
+ *                       b % bucketShardCount == bucketShard; each owned bucket receives its samples in
+ *                       sample order (the reference's rounding sequence), the others stay zero, so the
+ *                       bucket buffers of all shards add up exactly (bitwise, as 32-bit integers).
+ *                       bucketShardCount = 1 takes every sample.
+ *   yc_bucket_device_ptrs  the accumulation buffer, for the caller's NCCL all-reduce(sum) as int32:
+ *                       `planes` planes of `planePixels` float4 {sum r, g, b, count (uint32 bits)}.
+ *   yc_wave_buckets     how many of those planes (the first m) a wave of `waveSamples` samples uses
+ *                       (GMoN / MoN: m = min(15, max(1, 1 + 2 * ((n - 5) / 10))), estimator.hpp:94-141; Mean: 1).
+ *   yc_finalize_wave    Estimator::getValue per pixel + finishTile's blend and tonemap
+ *                       (estimator.hpp:23-141, tile-renderer.hpp:220-239); clears the buckets. */
+int yc_accumulate_wave(yc_ctx* ctx, YcRect pixels, uint32_t sampleOffset, uint32_t waveSamples,
+                       uint32_t bucketShard, uint32_t bucketShardCount);
+int yc_bucket_device_ptrs(yc_ctx* ctx, void** buckets, size_t* bytes, uint32_t* planes, size_t* planePixels);
+int yc_wave_buckets(yc_ctx* ctx, uint32_t waveSamples, uint32_t* m);
+int yc_finalize_wave(yc_ctx* ctx, YcRect pixels, uint32_t waveSamples, uint32_t takenBefore);
 /* Copies the frames to host (either pointer may be NULL).  width*height*4 floats each.
  * Replaces reading Renderer::m_buffer (RenderData::buffer, renderer.hpp:22-28). */
 int yc_resolve(yc_ctx* ctx, float* hdrRGBA, float* ldrRGBA, YcStats* stats);

@@ -37,6 +37,25 @@ def run(rank: int, world: int, port: int, mode: str, out_dir: str):
         t_hdr, t_ldr = torch.from_numpy(hdr), torch.from_numpy(ldr)
         dist.all_reduce(t_hdr)
         dist.all_reduce(t_ldr)
+    elif mode == "buckets":
+        # sample sharding inside a wave by estimator bucket (SURVEY §8e alternative B): every rank accumulates
+        # the samples of its buckets, the GMoN accumulation buffers are summed across ranks as 32-bit
+        # integers (disjoint planes: bitwise exact), every rank finalizes the wave
+        waves = [16, 16]
+        ctx.begin_frame(w, h, sum(waves), 16, (0, 0, 0), Y.TONEMAP_AGX)
+        ptr, nbytes, _, _ = ctx.bucket_device_ptrs()
+        taken = 0
+        for wv in waves:
+            ctx.accumulate_wave(taken, wv, bucket_shard=rank, bucket_shard_count=world)
+            acc = np.empty(nbytes // 4, np.int32)
+            ctx.d2h(acc, ptr)
+            t = torch.from_numpy(acc)
+            dist.all_reduce(t)
+            ctx.h2d(ptr, acc)
+            ctx.finalize_wave(wv, taken)
+            taken += wv
+        hdr, ldr, st = ctx.resolve()
+        t_hdr, t_ldr = torch.from_numpy(hdr), torch.from_numpy(ldr)  # identical on every rank
     else:
         # sample-wave sharding (bench.py's N > 1 path): rank r renders wave r of spp samples of the
         # whole frame; equal wave sizes → finishTile's weights collapse to 1 / world

@@ -234,3 +234,47 @@ def test_c5_4k_progressive_gmon_sharded_equals_unsharded():
     assert H.bits_equal(parts[0][1] + parts[1][1], full[1]).all()
     assert parts[0][2].raysReference + parts[1][2].raysReference == full[2].raysReference
     assert np.isfinite(full[0]).all()
+
+
+def test_bucket_shards_combine_to_the_unsharded_render_bitwise():
+    """Sample sharding by estimator bucket (yc_accumulate_wave / yc_bucket_device_ptrs / yc_finalize_wave):
+    three contexts stand in for three GPUs, their GMoN accumulation buffers are added as int32 (what the NCCL
+    all-reduce does) and the finalized frames must be bit-identical to yc_render_wave's, wave after wave
+    (zoo scene: every material class; 64 + 128 samples → m = 11 then 15 buckets)."""
+    sp, cam = H.scene_file("material_zoo"), H.scene_camera("material_zoo")
+    sc = Y.Scene(sp)
+    w, h, waves, G = 160, 90, [64, 128], 3
+    c = Y.make_camera(w, h, cam["focal"], cam["fnum"], cam["pos"], cam["target"], (0, 0, 0), cam["exposure"])
+
+    def ctx_new():
+        ctx = Y.Context(max_depth=6)
+        ctx.upload_scene(sc)
+        ctx.set_camera(c)
+        ctx.begin_frame(w, h, sum(waves), 64, (0, 0, 0), Y.TONEMAP_AGX)
+        return ctx
+
+    ref = ctx_new()
+    shards = [ctx_new() for _ in range(G)]
+    taken = 0
+    for wv in waves:
+        ref.render_wave(taken, wv, taken)
+        total = None
+        for g, ctx in enumerate(shards):
+            ctx.accumulate_wave(taken, wv, bucket_shard=g, bucket_shard_count=G)
+            ptr, nbytes, _, _ = ctx.bucket_device_ptrs()
+            acc = np.empty(nbytes // 4, np.int32)
+            ctx.d2h(acc, ptr)
+            total = acc if total is None else total + acc
+        for ctx in shards:
+            ptr, _, _, _ = ctx.bucket_device_ptrs()
+            ctx.h2d(ptr, total)
+            ctx.finalize_wave(wv, taken)
+        taken += wv
+    hdr0, ldr0, st0 = ref.resolve()
+    rays = 0
+    for ctx in shards:
+        hdr, ldr, st = ctx.resolve()
+        assert H.bits_equal(hdr, hdr0).all() and H.bits_equal(ldr, ldr0).all()
+        rays += st.raysReference
+    assert rays == st0.raysReference
+    assert np.isfinite(hdr0).all() and hdr0[..., :3].mean() > 0

@@ -63,3 +63,13 @@ def test_two_ranks_wave_sharding_equals_progressive_render(tmp_path):
     # 0.5 * a + 0.5 * b on both sides: identical rounding for two equal waves
     assert H.bits_equal(got, hdr1).all()
     assert int(np.load(tmp_path / "waves_rays.npy")[0]) == st.raysReference
+
+
+def test_two_ranks_bucket_sharding_equals_one_rank_bitwise(tmp_path):
+    """GMoN accumulation buffers combined across ranks (all-reduce of the bucket planes as int32), two
+    progressive waves of 16 samples (m = 3 buckets: rank 0 owns buckets 0 and 2, rank 1 bucket 1)."""
+    launch("buckets", tmp_path)
+    hdr1, ldr1, st = single(32, [16, 16])
+    assert H.bits_equal(np.load(tmp_path / "buckets_hdr.npy"), hdr1).all()
+    assert H.bits_equal(np.load(tmp_path / "buckets_ldr.npy"), ldr1).all()
+    assert int(np.load(tmp_path / "buckets_rays.npy")[0]) == st.raysReference

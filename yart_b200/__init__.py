@@ -179,6 +179,30 @@ class Context:
         r = capi.YcRect(0, 0, self.frame.width, self.frame.height) if rect is None else capi.YcRect(*rect)
         self._ck(lib().yc_render_wave(self._h, r, sample_offset, wave_samples, taken_before), "yc_render_wave")
 
+    def _rect(self, rect):
+        return capi.YcRect(0, 0, self.frame.width, self.frame.height) if rect is None else capi.YcRect(*rect)
+
+    def accumulate_wave(self, sample_offset, wave_samples, bucket_shard=0, bucket_shard_count=1, rect=None):
+        """Sample loop of a wave into the estimator buckets; with bucket_shard_count > 1 only the samples of
+        the buckets b with b % bucket_shard_count == bucket_shard (yc_accumulate_wave)."""
+        self._ck(lib().yc_accumulate_wave(self._h, self._rect(rect), sample_offset, wave_samples, bucket_shard,
+                                          bucket_shard_count), "yc_accumulate_wave")
+
+    def finalize_wave(self, wave_samples, taken_before, rect=None):
+        self._ck(lib().yc_finalize_wave(self._h, self._rect(rect), wave_samples, taken_before), "yc_finalize_wave")
+
+    def wave_buckets(self, wave_samples) -> int:
+        m = C.c_uint32()
+        self._ck(lib().yc_wave_buckets(self._h, wave_samples, C.byref(m)), "yc_wave_buckets")
+        return m.value
+
+    def bucket_device_ptrs(self):
+        """(device pointer, bytes, planes, pixels per plane) of the estimator accumulation buffer."""
+        p, n, planes, pix = C.c_void_p(), C.c_size_t(), C.c_uint32(), C.c_size_t()
+        self._ck(lib().yc_bucket_device_ptrs(self._h, C.byref(p), C.byref(n), C.byref(planes), C.byref(pix)),
+                 "yc_bucket_device_ptrs")
+        return p.value, n.value, planes.value, pix.value
+
     def resolve(self, want_hdr=True, want_ldr=True):
         h, w = self.frame.height, self.frame.width
         hdr = np.empty((h, w, 4), np.float32) if want_hdr else None

@@ -105,6 +105,10 @@ PROTOTYPES = {
     "yc_set_camera": (C.c_int, [P, C.POINTER(YcCamera)]),
     "yc_begin_frame": (C.c_int, [P, C.POINTER(YcFrameDesc)]),
     "yc_render_wave": (C.c_int, [P, YcRect, u32, u32, u32]),
+    "yc_accumulate_wave": (C.c_int, [P, YcRect, u32, u32, u32, u32]),
+    "yc_bucket_device_ptrs": (C.c_int, [P, C.POINTER(P), C.POINTER(C.c_size_t), C.POINTER(u32), C.POINTER(C.c_size_t)]),
+    "yc_finalize_wave": (C.c_int, [P, YcRect, u32, u32]),
+    "yc_wave_buckets": (C.c_int, [P, u32, C.POINTER(u32)]),
     "yc_resolve": (C.c_int, [P, P, P, C.POINTER(YcStats)]),
     "yc_frame_device_ptrs": (C.c_int, [P, C.POINTER(P), C.POINTER(P), C.POINTER(C.c_size_t)]),
     "yc_retonemap": (C.c_int, [P]),

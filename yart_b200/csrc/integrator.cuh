@@ -59,16 +59,17 @@ struct WaveParams {
   SamplerConfig smp;
   float bg[3];
   uint32_t maxDepth;
-  // chunk geometry: path i ↔ pixel pixelList[pixBase + i % nPix], sample s0 + i / nPix
+  // chunk geometry: path i ↔ pixel pixelList[pixBase + i % nPix], sample s0 + (i / nPix) * (sStrideM1 + 1)
   const uint32_t* pixelList;  // x | y << 16
   uint32_t pixBase, nPix, s0;
+  uint32_t sStrideM1;  // sample stride - 1: 0 for consecutive samples, m - 1 when a chunk holds one estimator bucket's samples
 };
 
 YB_DEV void pathPixelSample(const WaveParams& w, uint32_t i, uint32_t& px, uint32_t& py, uint32_t& sample) {
   const uint32_t pix = w.pixelList[w.pixBase + i % w.nPix];
   px = pix & 0xffffu;
   py = pix >> 16;
-  sample = w.s0 + i / w.nPix;
+  sample = w.s0 + (i / w.nPix) * (w.sStrideM1 + 1u);
 }
 
 YB_DEV Sampler pathSampler(const WaveParams& w, uint32_t i, uint32_t dim) {

@@ -30,6 +30,9 @@ using namespace yb;
 #ifndef YB_TRACE_MIN_BLOCKS
 #define YB_TRACE_MIN_BLOCKS 8  // 8 CTAs x 4 warps per SM: caps the traversal kernels at 64 registers
 #endif
+#ifndef YB_SHADOW_MIN_BLOCKS
+#define YB_SHADOW_MIN_BLOCKS 1
+#endif
 #ifndef YB_SHADE_MIN_BLOCKS
 #define YB_SHADE_MIN_BLOCKS 6  // 6 x 256 threads per SM (40 registers + local-memory spills): shading is latency-bound, warps beat registers (2: 35.6, 4: 33.7, 6: 32.4, 8: 32.3 ms on the Sponza-shaped step)
 #endif
@@ -221,13 +224,13 @@ struct AccumulateK {
   PathState ps;
   float4* buckets;
   size_t planeStride;
-  uint32_t pixBase, nPix, K, waveSampleBase, m, estimator;
+  uint32_t pixBase, nPix, K, waveSampleBase, sampleStride, m, estimator;
   float exposureScale;
   YB_DEV void operator()(uint32_t p) const {
     for (uint32_t k = 0; k < K; k++) {
       const float4 L4 = ps.L[size_t(k) * nPix + p];
       const V3 s = V3(L4.x, L4.y, L4.z) * exposureScale;
-      const uint32_t b = estimator == YC_ESTIMATOR_MEAN ? 0u : (waveSampleBase + k) % m;
+      const uint32_t b = estimator == YC_ESTIMATOR_MEAN ? 0u : (waveSampleBase + k * sampleStride) % m;
       if (estimatorAccepts(int(estimator), s)) {
         float4* slot = buckets + size_t(b) * planeStride + (pixBase + p);
         float4 v = *slot;
@@ -367,7 +370,7 @@ struct ShadowIO {
 };
 
 template <bool ALPHA, bool COUNT>
-__global__ void __launch_bounds__(kTraceBlock) shadowKernel(DScene sc, WaveParams w, PathState ps, ShadowQueue sq,
+__global__ void __launch_bounds__(kTraceBlock, YB_SHADOW_MIN_BLOCKS) shadowKernel(DScene sc, WaveParams w, PathState ps, ShadowQueue sq,
                                                             uint32_t* ctr, Counters* counters, uint2* spill, TraceTuning tune) {
   const uint32_t n = ctr[kCtrShadowCount];
   ShadowIO<ALPHA> io{w, ps, sq};
@@ -761,7 +764,7 @@ static int issueBounce(yc_ctx* ctx, Lane& L) {
 
 template <bool ALPHA>
 static int renderChunks(yc_ctx* ctx, const uint32_t* dList, uint32_t nPixCall, uint32_t sampleOffset, uint32_t waveSamples,
-                        uint32_t m) {
+                        uint32_t m, uint32_t bucketShard, uint32_t bucketShardCount) {
   const YcFrameDesc& f = ctx->frame;
   WaveParams w{};
   w.cam = ctx->cam;
@@ -774,8 +777,12 @@ static int renderChunks(yc_ctx* ctx, const uint32_t* dList, uint32_t nPixCall, u
   const float exposureScale = std::exp2(ctx->cam.exposure);  // integrator.cpp:23
 
   // chunk list: pixel blocks x sample groups, each at most one lane's capacity of paths
+  // Bucket sharding (bucketShardCount > 1): this context takes only the samples of the estimator buckets
+  // b with b % bucketShardCount == bucketShard, one bucket at a time (samples b, b + m, b + 2m, ...), so each
+  // bucket it owns receives its samples in sample order — the reference's rounding sequence — and the
+  // buckets it does not own stay zero: the per-GPU bucket buffers add up exactly.
   struct Chunk {
-    uint32_t pixBase, nPix, sDone, K;
+    uint32_t pixBase, nPix, sDone, K, stride;  // samples sDone, sDone + stride, ... (K of them) of the wave
   };
   std::vector<Chunk> chunks;
   const uint32_t cap = ctx->lanes[0].capacity;
@@ -783,12 +790,24 @@ static int renderChunks(yc_ctx* ctx, const uint32_t* dList, uint32_t nPixCall, u
   const uint32_t Kmax = std::max<uint32_t>(1u, cap / B);
   for (uint32_t pixBase = 0; pixBase < nPixCall; pixBase += B) {
     const uint32_t nPix = std::min(B, nPixCall - pixBase);
-    for (uint32_t sDone = 0; sDone < waveSamples;) {
-      const uint32_t K = std::min(Kmax, waveSamples - sDone);
-      chunks.push_back({pixBase, nPix, sDone, K});
-      sDone += K;
+    if (bucketShardCount <= 1) {
+      for (uint32_t sDone = 0; sDone < waveSamples;) {
+        const uint32_t K = std::min(Kmax, waveSamples - sDone);
+        chunks.push_back({pixBase, nPix, sDone, K, 1u});
+        sDone += K;
+      }
+    } else {
+      for (uint32_t b = bucketShard; b < m && b < waveSamples; b += bucketShardCount) {
+        const uint32_t nb = (waveSamples - b + m - 1) / m;  // samples of the wave that fall into bucket b
+        for (uint32_t j = 0; j < nb;) {
+          const uint32_t K = std::min(Kmax, nb - j);
+          chunks.push_back({pixBase, nPix, b + j * m, K, m});
+          j += K;
+        }
+      }
     }
   }
+  if (chunks.empty()) return YC_OK;
 
   // the other lanes' streams start after everything already queued on the main stream (ev0)
   for (int l = 1; l < kLanes; l++) rt::streamWaitEvent(ctx->lanes[l].st, ctx->ev0);
@@ -805,6 +824,7 @@ static int renderChunks(yc_ctx* ctx, const uint32_t* dList, uint32_t nPixCall, u
       L.chunk = uint32_t(next++);
       L.w = w;
       L.w.pixBase = c.pixBase, L.w.nPix = c.nPix, L.w.s0 = sampleOffset + c.sDone;
+      L.w.sStrideM1 = c.stride - 1u;
       L.K = c.K, L.sDone = c.sDone;
       L.n = c.K * c.nPix;
       L.bounce = 0;
@@ -823,8 +843,8 @@ static int renderChunks(yc_ctx* ctx, const uint32_t* dList, uint32_t nPixCall, u
         if (!(L.active && L.done && L.chunk == nextAcc)) continue;
         if (lastAcc && lastAcc != &L.evAcc) rt::streamWaitEvent(L.st, *lastAcc);
         rt::launchFor(L.st, L.w.nPix,
-                      AccumulateK{L.ps, ctx->dBuckets, ctx->bucketCapacity, L.w.pixBase, L.w.nPix, L.K, L.sDone, m,
-                                  f.estimator, exposureScale});
+                      AccumulateK{L.ps, ctx->dBuckets, ctx->bucketCapacity, L.w.pixBase, L.w.nPix, L.K, L.sDone,
+                                  L.w.sStrideM1 + 1u, m, f.estimator, exposureScale});
         rt::eventRecord(L.st, L.evAcc);
         lastAcc = &L.evAcc;
         ctx->launches++;
@@ -877,38 +897,31 @@ static int renderChunks(yc_ctx* ctx, const uint32_t* dList, uint32_t nPixCall, u
   return YC_OK;
 }
 
-extern "C" int yc_render_wave(yc_ctx* ctx, YcRect px, uint32_t sampleOffset, uint32_t waveSamples, uint32_t takenBefore) {
-  if (!ctx) return YC_ERR_INVALID;
-  if (!ctx->inFrame) return fail(ctx, YC_ERR_STATE, "yc_render_wave before yc_begin_frame");
+// Pixel list of a call: the whole shard, or its intersection with `px` (uploaded to the scratch list).
+static int wavePixels(yc_ctx* ctx, YcRect px, const uint32_t** dList, uint32_t* nPixCall) {
   const YcFrameDesc& f = ctx->frame;
-  if (waveSamples == 0 || px.w == 0 || px.h == 0) return YC_OK;
   if (uint64_t(px.x) + px.w > f.width || uint64_t(px.y) + px.h > f.height)
     return fail(ctx, YC_ERR_INVALID, "pixel rectangle outside the frame");
-  const uint32_t* dList = ctx->dPixels;
-  uint32_t nPixCall = uint32_t(ctx->pixels.size());
+  *dList = ctx->dPixels;
+  *nPixCall = uint32_t(ctx->pixels.size());
   if (!(px.x == 0 && px.y == 0 && px.w == f.width && px.h == f.height)) {
     std::vector<uint32_t> sub;
     for (uint32_t v : ctx->pixels) {
       const uint32_t x = v & 0xffffu, y = v >> 16;
       if (x >= px.x && x < px.x + px.w && y >= px.y && y < px.y + px.h) sub.push_back(v);
     }
-    nPixCall = uint32_t(sub.size());
+    *nPixCall = uint32_t(sub.size());
     YC_TRY(rt::h2d(ctx->st, ctx->dPixelsScratch, sub.data(), sub.size() * 4));
-    dList = ctx->dPixelsScratch;
+    *dList = ctx->dPixelsScratch;
   }
-  if (nPixCall == 0) return YC_OK;
-  rt::eventRecord(ctx->st, ctx->ev0);
-  const uint32_t m = f.estimator == YC_ESTIMATOR_MEAN ? 1u : uint32_t(estimatorBuckets(int(waveSamples), kMaxBuckets));
-  const int rc = ctx->ds.hasAlpha ? renderChunks<true>(ctx, dList, nPixCall, sampleOffset, waveSamples, m)
-                                  : renderChunks<false>(ctx, dList, nPixCall, sampleOffset, waveSamples, m);
-  if (rc != YC_OK) return rc;
-  // finishTile's weights, tile-renderer.hpp:220-223
-  const uint32_t takenAfter = takenBefore + waveSamples;
-  const float wCurrent = float(takenBefore) / float(takenAfter), wWave = float(waveSamples) / float(takenAfter);
-  rt::launchFor(ctx->st, nPixCall,
-                FinalizeK{dList, ctx->dBuckets, ctx->bucketCapacity, ctx->dHdr, ctx->dLdr, f.width, m, f.estimator,
-                          waveSamples, f.tonemap, wCurrent, wWave});
-  ctx->launches++;
+  return YC_OK;
+}
+
+static uint32_t waveBuckets(const YcFrameDesc& f, uint32_t waveSamples) {
+  return f.estimator == YC_ESTIMATOR_MEAN ? 1u : uint32_t(estimatorBuckets(int(waveSamples), kMaxBuckets));
+}
+
+static int endTimedRegion(yc_ctx* ctx) {
   rt::eventRecord(ctx->st, ctx->ev1);
   YC_TRY(rt::sync(ctx->st));
   YC_TRY(rt::lastError());
@@ -918,6 +931,86 @@ extern "C" int yc_render_wave(yc_ctx* ctx, YcRect px, uint32_t sampleOffset, uin
     ctx->extendLaunches++;
   }
   ctx->extendEventsUsed = 0;
+  return YC_OK;
+}
+
+// The sample loop of a wave (Integrator::render, integrator.cpp:5-28) into the estimator buckets.
+static int accumulateWave(yc_ctx* ctx, const uint32_t* dList, uint32_t nPixCall, uint32_t sampleOffset, uint32_t waveSamples,
+                          uint32_t bucketShard, uint32_t bucketShardCount) {
+  const uint32_t m = waveBuckets(ctx->frame, waveSamples);
+  return ctx->ds.hasAlpha ? renderChunks<true>(ctx, dList, nPixCall, sampleOffset, waveSamples, m, bucketShard, bucketShardCount)
+                          : renderChunks<false>(ctx, dList, nPixCall, sampleOffset, waveSamples, m, bucketShard, bucketShardCount);
+}
+
+// Estimator value of the wave + finishTile's blend and tonemap (tile-renderer.hpp:220-239).
+static void finalizeWave(yc_ctx* ctx, const uint32_t* dList, uint32_t nPixCall, uint32_t waveSamples, uint32_t takenBefore) {
+  const YcFrameDesc& f = ctx->frame;
+  const uint32_t takenAfter = takenBefore + waveSamples;
+  const float wCurrent = float(takenBefore) / float(takenAfter), wWave = float(waveSamples) / float(takenAfter);
+  rt::launchFor(ctx->st, nPixCall,
+                FinalizeK{dList, ctx->dBuckets, ctx->bucketCapacity, ctx->dHdr, ctx->dLdr, f.width, waveBuckets(f, waveSamples),
+                          f.estimator, waveSamples, f.tonemap, wCurrent, wWave});
+  ctx->launches++;
+}
+
+extern "C" int yc_render_wave(yc_ctx* ctx, YcRect px, uint32_t sampleOffset, uint32_t waveSamples, uint32_t takenBefore) {
+  if (!ctx) return YC_ERR_INVALID;
+  if (!ctx->inFrame) return fail(ctx, YC_ERR_STATE, "yc_render_wave before yc_begin_frame");
+  if (waveSamples == 0 || px.w == 0 || px.h == 0) return YC_OK;
+  const uint32_t* dList;
+  uint32_t nPixCall;
+  if (const int prc = wavePixels(ctx, px, &dList, &nPixCall)) return prc;
+  if (nPixCall == 0) return YC_OK;
+  rt::eventRecord(ctx->st, ctx->ev0);
+  const int rc = accumulateWave(ctx, dList, nPixCall, sampleOffset, waveSamples, 0, 1);
+  if (rc != YC_OK) return rc;
+  finalizeWave(ctx, dList, nPixCall, waveSamples, takenBefore);
+  return endTimedRegion(ctx);
+}
+
+extern "C" int yc_accumulate_wave(yc_ctx* ctx, YcRect px, uint32_t sampleOffset, uint32_t waveSamples, uint32_t bucketShard,
+                                  uint32_t bucketShardCount) {
+  if (!ctx) return YC_ERR_INVALID;
+  if (!ctx->inFrame) return fail(ctx, YC_ERR_STATE, "yc_accumulate_wave before yc_begin_frame");
+  if (bucketShardCount == 0 || bucketShard >= bucketShardCount) return fail(ctx, YC_ERR_INVALID, "bucket shard out of range");
+  if (waveSamples == 0 || px.w == 0 || px.h == 0) return YC_OK;
+  const uint32_t* dList;
+  uint32_t nPixCall;
+  if (const int prc = wavePixels(ctx, px, &dList, &nPixCall)) return prc;
+  if (nPixCall == 0) return YC_OK;
+  rt::eventRecord(ctx->st, ctx->ev0);
+  const int rc = accumulateWave(ctx, dList, nPixCall, sampleOffset, waveSamples, bucketShard, bucketShardCount);
+  if (rc != YC_OK) return rc;
+  return endTimedRegion(ctx);
+}
+
+extern "C" int yc_finalize_wave(yc_ctx* ctx, YcRect px, uint32_t waveSamples, uint32_t takenBefore) {
+  if (!ctx) return YC_ERR_INVALID;
+  if (!ctx->inFrame) return fail(ctx, YC_ERR_STATE, "yc_finalize_wave before yc_begin_frame");
+  if (waveSamples == 0 || px.w == 0 || px.h == 0) return YC_OK;
+  const uint32_t* dList;
+  uint32_t nPixCall;
+  if (const int prc = wavePixels(ctx, px, &dList, &nPixCall)) return prc;
+  if (nPixCall == 0) return YC_OK;
+  rt::eventRecord(ctx->st, ctx->ev0);
+  finalizeWave(ctx, dList, nPixCall, waveSamples, takenBefore);
+  return endTimedRegion(ctx);
+}
+
+extern "C" int yc_wave_buckets(yc_ctx* ctx, uint32_t waveSamples, uint32_t* m) {
+  if (!ctx || !m) return YC_ERR_INVALID;
+  if (!ctx->inFrame) return fail(ctx, YC_ERR_STATE, "no frame");
+  *m = waveBuckets(ctx->frame, waveSamples);
+  return YC_OK;
+}
+
+extern "C" int yc_bucket_device_ptrs(yc_ctx* ctx, void** buckets, size_t* bytes, uint32_t* planes, size_t* planePixels) {
+  if (!ctx) return YC_ERR_INVALID;
+  if (!ctx->inFrame) return fail(ctx, YC_ERR_STATE, "no frame");
+  if (buckets) *buckets = ctx->dBuckets;
+  if (bytes) *bytes = ctx->bucketCapacity * kMaxBuckets * sizeof(float4);
+  if (planes) *planes = kMaxBuckets;
+  if (planePixels) *planePixels = ctx->bucketCapacity;
   return YC_OK;
 }
 
