@@ -189,8 +189,16 @@ typedef struct YcOptions {
    * refill threshold (idle lanes) and inner-step threshold (lanes on inner nodes).  They never
    * change results.  reserved[2]: number of surviving paths at which a chunk's remaining bounces are
    * handed to the per-path tail kernel (0 = default 16384, 0xffffffff = never). */
-  uint32_t reserved[6];
+  uint32_t reserved[3];
+  /* The `Integrator` template argument of TileRenderer (src/main.cpp:17): YC_INTEGRATOR_MIS =
+   * cpu::MISIntegrator (the measured path), YC_INTEGRATOR_NAIVE = cpu::NaiveIntegrator
+   * (src/cpu/naive-integrator.cpp: BSDF sampling only, maxDepth + 1 segments, at most 63). */
+  uint32_t integrator;
+  uint32_t reserved2[2];
 } YcOptions;
+
+#define YC_INTEGRATOR_MIS 0
+#define YC_INTEGRATOR_NAIVE 1
 
 typedef struct YcRect { uint32_t x, y, w, h; } YcRect;
 
@@ -374,6 +382,7 @@ typedef struct YrSettings {
   uint32_t estimator; /* YC_ESTIMATOR_* */
   uint32_t shardIndex, shardCount;
   int32_t device;
+  uint32_t integrator; /* YC_INTEGRATOR_* */
 } YrSettings;
 
 typedef struct YrRenderData {  /* Renderer::RenderData (renderer.hpp:22-28) */

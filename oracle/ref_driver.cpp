@@ -17,6 +17,7 @@
 #include <bsdf/parametric.hpp>
 #include <bsdf/luts.hpp>
 #include <cpu/mis-integrator.hpp>
+#include <cpu/naive-integrator.hpp>
 #include <cpu/tile-renderer.hpp>
 #include <output/ppm.hpp>
 #include <fstream>
@@ -227,6 +228,12 @@ struct DepthIntegrator : cpu::MISIntegrator {
   }
 };
 
+struct DepthNaiveIntegrator : cpu::NaiveIntegrator {  // src/cpu/naive-integrator.cpp
+  DepthNaiveIntegrator(Buffer& b, const Camera& c, Sampler& s) noexcept : cpu::NaiveIntegrator(b, c, s) {
+    m_maxDepth = g_maxDepth;
+  }
+};
+
 struct TraceHarness : cpu::MISIntegrator {
   TraceHarness(Buffer& b, const Camera& c, Sampler& s) noexcept : cpu::MISIntegrator(b, c, s) {}
   bool closest(const Ray& r, float tMin, cpu::Hit& hit) { return testNode(r, tMin, hit, scene->root()); }
@@ -235,8 +242,19 @@ struct TraceHarness : cpu::MISIntegrator {
 // ---------------------------------------------------------------------------------------
 // commands
 // ---------------------------------------------------------------------------------------
+template <class IntegratorT>
+static int cmdRenderWith(int argc, char** argv);
+
+// integrator=mis (default) | naive: the `Integrator` template argument of TileRenderer (src/main.cpp:17)
 static int cmdRender(int argc, char** argv) {
   if (argc < 4) return 1;
+  Args a(argc, argv, 4);
+  if (a.str("integrator", "mis") == "naive") return cmdRenderWith<DepthNaiveIntegrator>(argc, argv);
+  return cmdRenderWith<DepthIntegrator>(argc, argv);
+}
+
+template <class IntegratorT>
+static int cmdRenderWith(int argc, char** argv) {
   Args a(argc, argv, 4);
   ysc::SceneDesc d;
   std::string err;
@@ -249,7 +267,7 @@ static int cmdRender(int argc, char** argv) {
   Camera cam = makeCamera(a, w, h);
   g_maxDepth = uint32_t(a.num("maxdepth", 30));
 
-  cpu::TileRenderer<RefSampler, DepthIntegrator> r(Buffer(w, h), cam);
+  cpu::TileRenderer<RefSampler, IntegratorT> r(Buffer(w, h), cam);
   r.scene = rs.scene.get();
   r.samples = uint32_t(a.num("spp", 16));
   r.firstWaveSamples = uint32_t(a.num("first", r.samples));

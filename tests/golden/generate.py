@@ -76,8 +76,29 @@ def trace_rays(cam, n, seed=3, spread=12.0):
     return r
 
 
+# TileRenderer<SobolSampler<FastOwenScrambler>, NaiveIntegrator>: tag, scene, kwargs, w, h, spp, first, max, depth
+NAIVE_RENDERS = [
+    ("cornell", "cornell", {}, 64, 64, 16, 16, 16, 5),
+    ("zoo", "material_zoo", {}, 96, 54, 16, 8, 8, 8),
+    ("two_quads", "two_quads", {}, 32, 32, 16, 16, 16, 30),
+]
+
+
+def naive_renders():
+    for tag, name, kw, w, h, spp, first, mx, depth in NAIVE_RENDERS:
+        sp, cam = H.scene_file(name, **kw), H.scene_camera(name, **kw)
+        r = H.oracle_render(sp, w, h, spp, cam, first=first, max=mx, maxdepth=depth, tonemap="agx", threads=4,
+                            integrator="naive")
+        np.savez_compressed(os.path.join(OUT, f"naive_{tag}.npz"), scene=name, kwargs=repr(kw),
+                            settings=np.array([w, h, spp, first, mx, depth]), tonemap="agx", hdr=r["hdr"], ldr=r["ldr"],
+                            rays=r["rays"], integrator="naive")
+        print("naive render", tag, r["rays"])
+
+
 def main():
     assert H.have_oracle(), "build oracle/_ref first: make -C oracle ref"
+    if "--only-naive" in sys.argv:
+        return naive_renders()
     for tag, kind, n, kw, scene in KATS:
         blob = H.kat_input(kind, n, **kw)
         sp = H.scene_file(scene) if scene else None
@@ -107,6 +128,7 @@ def main():
                             **{f"nodes{i}": m[0] for i, m in enumerate(meshes)},
                             **{f"idx{i}": m[1] for i, m in enumerate(meshes)})
         print("bvh", name, [len(m[0]) for m in meshes])
+    naive_renders()
 
 
 if __name__ == "__main__":

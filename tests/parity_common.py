@@ -99,6 +99,8 @@ def render_golden(path, **renderer_kw):
     sc = Y.Scene(H.scene_file(name, **kw))
     c = Y.make_camera(w, h, cam["focal"], cam["fnum"], cam["pos"], cam["target"], (0, 0, 0), cam["exposure"],
                       cam.get("sides", 0))
+    if "integrator" in g.files and str(g["integrator"]) == "naive":
+        renderer_kw = dict(renderer_kw, integrator=Y.INTEGRATOR_NAIVE)
     r = Y.Renderer(w, h, c, sc, samples=spp, first_wave_samples=first, max_wave_samples=mx, max_depth=depth,
                    tonemap=TONEMAPS[str(g["tonemap"])], **renderer_kw)
     data = r.render_sync()
@@ -125,4 +127,6 @@ def check_render(path, exact: bool):
         assert H.bits_equal(hdr, g["hdr"]).all(), f"{tag}: HDR differs in {(~H.bits_equal(hdr, g['hdr'])).sum()} words"
         assert H.bits_equal(ldr, g["ldr"]).all(), f"{tag}: LDR differs in {(~H.bits_equal(ldr, g['ldr'])).sum()} words"
     assert st.raysExtend >= data["total_rays"] - st.raysShadow
+    if "integrator" in g.files and str(g["integrator"]) == "naive":
+        assert st.raysShadow == 0 and st.raysExtend == data["total_rays"]  # no NEE: one closest-hit ray per segment
     return hdr, ldr

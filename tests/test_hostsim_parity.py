@@ -42,6 +42,12 @@ def test_render_bit_exact(path):
     PC.check_render(path, exact=True)
 
 
+@pytest.mark.parametrize("path", PC.golden_files("naive"), ids=os.path.basename)
+def test_naive_integrator_render_bit_exact(path):
+    """TileRenderer<SobolSampler<FastOwenScrambler>, NaiveIntegrator> (naive-integrator.cpp), progressive waves included."""
+    PC.check_render(path, exact=True)
+
+
 def test_small_wavefront_capacity_gives_same_image():
     """Chunking (pixel blocks x sample groups) must not change a single bit."""
     path = os.path.join(H.GOLDEN, "render_cornell_waves.npz")

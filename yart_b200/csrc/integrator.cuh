@@ -313,6 +313,82 @@ YB_DEV uint32_t shadeStage(const DScene& sc, const WaveParams& w, const PathStat
   return result;
 }
 
+// ---- NaiveIntegrator ------------------------------------------------------------------
+// src/cpu/naive-integrator.cpp:12-60: no NEE, no MIS, no Russian roulette.  The reference recurses,
+//     Li(depth) = [Le] + Li(depth + 1) * fcos / pdf,
+// i.e. the products are formed on the way BACK from the deepest segment, which does not round like a
+// forward throughput product.  One thread walks the whole path, records (Le, fcos, pdf) per segment and
+// folds them in the recursion's order.  Off the measured path: simplicity over speed.
+constexpr uint32_t kNaiveMaxSegments = 64;  // maxDepth + 1 segments at most (`depth > m_maxDepth` ends the path)
+
+template <bool ALPHA>
+YB_DEV void naiveStage(const DScene& sc, const WaveParams& w, const PathState& ps, uint32_t i, TravStack& stack,
+                       TraceCounters& cnt, uint32_t& raysReference) {
+  V3 segLe[kNaiveMaxSegments], segFcos[kNaiveMaxSegments];
+  float segPdf[kNaiveMaxSegments];
+  uint8_t segFlags[kNaiveMaxSegments];  // 1: emitted, 2: scattered
+  uint32_t n = 0;
+  V3 tail;  // what the deepest call returns
+  for (uint32_t depth = 0;; depth++) {
+    if (depth > w.maxDepth || n == kNaiveMaxSegments) break;  // naive-integrator.cpp:21 (returns {})
+    raysReference += 1;                                       // :22
+    extendStage<ALPHA, false>(sc, w, ps, i, stack, cnt);      // :25 testNode
+    const int32_t hb = ps.hitB[i];
+    const float4 ro4 = ps.rayO[i], rd4 = ps.rayD[i];
+    const V3 rayO(ro4.x, ro4.y, ro4.z), rayD(rd4.x, rd4.y, rd4.z);
+    if (hb == kHitMiss) {
+      // :26-38 (Le(octahedralUV(ray.dir)) of every infinite light, then the background colour)
+      V3 L;
+      for (uint32_t k = 0; k < sc.nInf; k++) L += lightLe(sc, sc.lights[sc.infLights[k]], octahedralUV(rayD));
+      L += V3(w.bg);
+      tail = L;
+      break;
+    }
+    HitRec h;
+    const float4 ha = ps.hitA[i];
+    h.t = ha.x, h.u = ha.y, h.v = ha.z, h.prim = __float_as_uint(ha.w);
+    h.node = int32_t(uint32_t(hb) & ~kBackSideBit);
+    h.backSide = (uint32_t(hb) & kBackSideBit) ? 1u : 0u;
+    const SurfaceHit hit = resolveHit(sc, h, rayO, rayD);
+    const YcMaterial& mat = sc.materials[hit.material];
+    const Bsdf bsdf(sc, mat);
+    Sampler smp = pathSampler(w, i, ps.dim[i]);
+    // :40-48 hit.bsdf->sample(-ray.dir, n, tg, uv, get2D(), get1D(), get1D()) — BSDF::sample, core/bsdf.cpp:27-41.
+    // The three draws are function ARGUMENTS, so their order is the compiler's: g++ on x86-64 (the oracle
+    // build) evaluates them right to left — uc2 first, then uc, then u — and that is the order kept here
+    // (clang evaluates left to right; the reference's source does not pin it).
+    const float uc2 = smp.get1D();
+    const float uc = smp.get1D();
+    const V2 u = smp.get2D();
+    ps.dim[i] = smp.dim;
+    const Frame fr = Bsdf::localFrame(hit.n, hit.tg);
+    const MatEval me = evalMaterialTextures(sc, mat, hit.uv);
+    BSDFSample res = bsdf.sampleImpl(fr.wtl(-rayD), hit.uv, me, u, uc, uc2, false);
+    res.wi = fr.ltw(res.wi);
+    uint8_t fl = 0;
+    if (res.is(Emitted)) fl |= 1, segLe[n] = res.Le;  // :51-53
+    const bool scattered = res.is(Reflected | Transmitted);
+    if (scattered) {
+      // :54-59
+      fl |= 2;
+      segFcos[n] = res.f * absDot(res.wi, hit.n);
+      segPdf[n] = res.pdf;
+      ps.rayO[i] = make_float4(hit.p.x, hit.p.y, hit.p.z, 0.0f);
+      ps.rayD[i] = make_float4(res.wi.x, res.wi.y, res.wi.z, 0.0f);
+    }
+    segFlags[n++] = fl;
+    if (!scattered) break;  // tail stays {}: nothing is added below this segment
+  }
+  V3 L = tail;
+  for (uint32_t k = n; k-- > 0;) {
+    V3 Li;
+    if (segFlags[k] & 1) Li += segLe[k];
+    if (segFlags[k] & 2) Li += L * segFcos[k] / segPdf[k];
+    L = Li;
+  }
+  ps.L[i] = make_float4(L.x, L.y, L.z, 0.0f);
+}
+
 // ---- shadow ---------------------------------------------------------------------------
 template <bool ALPHA>
 YB_DEV uint32_t shadowLoad(const WaveParams& w, const PathState& ps, const ShadowQueue& q, uint32_t j, V3& o, V3& d,

@@ -324,6 +324,15 @@ static void runShadow(yc_ctx* ctx, Lane& L, uint32_t) {
   ctx->dCounters->boxTests += cnt.box;
   ctx->dCounters->triTests += cnt.tri;
 }
+template <bool ALPHA>
+static void runNaive(yc_ctx* ctx, Lane& L) {
+  HostStack hs;
+  TraceCounters cnt;
+  uint32_t rays = 0;
+  for (uint32_t j = 0; j < L.n; j++) naiveStage<ALPHA>(ctx->ds, L.w, L.ps, L.qA[j], hs.ts, cnt, rays);
+  ctx->dCounters->raysReference += rays;
+  ctx->dCounters->raysExtend += rays;
+}
 #else
 // Persistent extend / shadow kernels: IO adapters around tracePersistent (trace_kernels.cuh).
 template <bool ALPHA>
@@ -429,6 +438,31 @@ __global__ void __launch_bounds__(kTailBlock) tailKernel(DScene sc, WaveParams w
   aggregatedCount(&counters->raysShadow, nShadow);
 }
 
+// NaiveIntegrator: one thread per path, whole path (integrator.cuh naiveStage).
+template <bool ALPHA>
+__global__ void __launch_bounds__(kTailBlock) naiveKernel(DScene sc, WaveParams w, PathState ps, const uint32_t* queue, uint32_t n,
+                                                          Counters* counters) {
+  __shared__ uint32_t shRef[kShStack * kTailBlock];
+  __shared__ float shD[kShStack * kTailBlock];
+  TravStack stack;
+  stack.shRef = shRef + threadIdx.x;
+  stack.shD = shD + threadIdx.x;
+  stack.stride = kTailBlock;
+  const uint32_t j = blockIdx.x * kTailBlock + threadIdx.x;
+  uint32_t rays = 0;
+  if (j < n) {
+    TraceCounters cnt;
+    naiveStage<ALPHA>(sc, w, ps, queue[j], stack, cnt, rays);
+  }
+  __syncwarp();
+  aggregatedCount(&counters->raysReference, rays);
+  aggregatedCount(&counters->raysExtend, rays);
+}
+template <bool ALPHA>
+static void runNaive(yc_ctx* ctx, Lane& L) {
+  naiveKernel<ALPHA><<<(L.n + kTailBlock - 1) / kTailBlock, kTailBlock, 0, L.st.s>>>(ctx->ds, L.w, L.ps, L.qA, L.n, ctx->dCounters);
+}
+
 static int traceGridMax(const yc_ctx* ctx) { return ctx->smCount * 8; }
 static TraceTuning tuning(const yc_ctx* ctx) {
   TraceTuning t;
@@ -475,6 +509,11 @@ extern "C" int yc_create(int device, const YcOptions* opts, yc_ctx** out) {
   if (!ctx) return YC_ERR_INVALID;
   if (opts) ctx->opts = *opts;
   if (ctx->opts.maxDepth == 0) ctx->opts.maxDepth = 30;  // RayIntegrator::m_maxDepth, ray-integrator.hpp:14
+  if (ctx->opts.integrator > YC_INTEGRATOR_NAIVE ||
+      (ctx->opts.integrator == YC_INTEGRATOR_NAIVE && ctx->opts.maxDepth + 1 > kNaiveMaxSegments)) {
+    delete ctx;
+    return YC_ERR_INVALID;
+  }
   ctx->capacity = ctx->opts.maxPathsInFlight ? ctx->opts.maxPathsInFlight : (8u << 20);
   if (ctx->opts.reserved[2]) ctx->tailThreshold = ctx->opts.reserved[2] == 0xffffffffu ? 0u : ctx->opts.reserved[2];
   ctx->device = device;
@@ -830,6 +869,12 @@ static int renderChunks(yc_ctx* ctx, const uint32_t* dList, uint32_t nPixCall, u
       L.bounce = 0;
       rt::launchFor(L.st, L.n, RaygenK{L.w, L.ps, L.qA});
       ctx->launches++;
+      if (ctx->opts.integrator == YC_INTEGRATOR_NAIVE) {
+        runNaive<ALPHA>(ctx, L);  // the whole path in one launch: nothing to wait for
+        ctx->launches++;
+        L.done = true;
+        continue;
+      }
       const int rc = issueBounce<ALPHA>(ctx, L);
       if (rc != YC_OK) return rc;
     }

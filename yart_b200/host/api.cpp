@@ -225,6 +225,7 @@ extern "C" int yr_create(const YrSettings* settings, const ys_scene* scene, cons
   r->cam = *camera;
   YcOptions o{};
   o.maxDepth = settings->maxDepth;
+  o.integrator = settings->integrator;
   int rc = yc_create(settings->device, &o, &r->ctx);
   if (rc != YC_OK) {
     delete r;
