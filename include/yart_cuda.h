@@ -210,6 +210,7 @@ typedef struct YcRect { uint32_t x, y, w, h; } YcRect;
 #define YC_ESTIMATOR_GMON 0 /* what Integrator::render instantiates (integrator.cpp:17) */
 #define YC_ESTIMATOR_MON 1
 #define YC_ESTIMATOR_MEAN 2
+#define YC_ESTIMATOR_GMONB 3 /* GMoNbEstimator, estimator.hpp:94-141: mean when the Gini index <= 0.25, else median of means */
 
 typedef struct YcFrameDesc {
   uint32_t width, height;

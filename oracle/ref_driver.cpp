@@ -589,6 +589,14 @@ static int cmdKat(int argc, char** argv) {
       out.f3(m.getValue());
       out.f3(mean.getValue());
     }
+  } else if (kind == "gmonb") {
+    // in: as "gmon".  out: npix×gmonb[3]  (GMoNbEstimator, src/core/estimator.hpp:94-141)
+    uint32_t n = u32(), npix = u32();
+    for (uint32_t i = 0; i < npix; i++) {
+      GMoNbEstimator g(int32_t(n), 15);
+      for (uint32_t s = 0; s < n; s++) g.addSample(v3());
+      out.f3(g.getValue());
+    }
   } else if (kind == "agx") {
     // in: u32 look, u32 n, float3[n]. out float3[n]
     uint32_t look = u32(), n = u32();

@@ -30,6 +30,8 @@ KATS = [  # (file tag, kind, n, kwargs, scene)
     ("gmon64", "gmon", 256, dict(samples=64), None),
     ("gmon128", "gmon", 128, dict(samples=128), None),
     ("gmon3", "gmon", 64, dict(samples=3), None),
+    ("gmonb16", "gmonb", 256, dict(samples=16), None),
+    ("gmonb128", "gmonb", 256, dict(samples=128), None),
     ("agx0", "agx", 1024, dict(look=0), None),
     ("agx1", "agx", 512, dict(look=1), None),
     ("agx2", "agx", 512, dict(look=2), None),
@@ -99,6 +101,16 @@ def main():
     assert H.have_oracle(), "build oracle/_ref first: make -C oracle ref"
     if "--only-naive" in sys.argv:
         return naive_renders()
+    only = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--only-kat=")]
+    if only:  # regenerate single KAT fixtures: --only-kat=gmonb16
+        for tag, kind, n, kw, scene in KATS:
+            if tag in only:
+                blob = H.kat_input(kind, n, **kw)
+                out = H.oracle_kat(kind, blob, H.scene_file(scene) if scene else None)
+                np.savez_compressed(os.path.join(OUT, f"kat_{tag}.npz"), kind=kind, scene=scene or "",
+                                    blob=np.frombuffer(blob, np.uint8), out=out)
+                print("kat", tag, out.size)
+        return
     for tag, kind, n, kw, scene in KATS:
         blob = H.kat_input(kind, n, **kw)
         sp = H.scene_file(scene) if scene else None

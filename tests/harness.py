@@ -197,7 +197,7 @@ def kat_input(kind: str, n: int = 256, seed: int = 7, **kw) -> bytes:
             out += p[i].tobytes() + nn[i].tobytes() + rng.uniform(0, 1, 2).astype(np.float32).tobytes()
             out += wi[i].tobytes() + struct.pack("<f", float(rng.uniform(0, 1)))
         return bytes(out)
-    if kind == "gmon":
+    if kind in ("gmon", "gmonb"):
         ns = kw.get("samples", 16)
         s = rng.gamma(0.5, 2.0, (n, ns, 3)).astype(np.float32)
         s[rng.uniform(size=(n, ns)) < 0.02] *= 500.0  # fireflies
@@ -231,11 +231,11 @@ def kat_input(kind: str, n: int = 256, seed: int = 7, **kw) -> bytes:
     raise KeyError(kind)
 
 
-KAT_OUT_WORDS = dict(sampler=8, lut=8, ggx=8, bsdf=27, light=22, gmon=9, agx=3, camera=6, texture=4)
+KAT_OUT_WORDS = dict(sampler=8, lut=8, ggx=8, bsdf=27, light=22, gmon=9, gmonb=3, agx=3, camera=6, texture=4)
 
 
 def kat_count(kind: str, blob: bytes) -> int:
-    if kind in ("sampler", "gmon", "agx"):
+    if kind in ("sampler", "gmon", "gmonb", "agx"):
         return struct.unpack_from("<I", blob, 4)[0]
     if kind == "camera":
         return struct.unpack_from("<I", blob, 56)[0]

@@ -14,7 +14,7 @@ PRODUCT_LIB = os.path.join(HERE, "libyart_b200.so")
 
 YC_OK, YC_ERR_INVALID, YC_ERR_CUDA, YC_ERR_NO_SCENE, YC_ERR_NO_DEVICE, YC_ERR_STATE, YC_ERR_IO = 0, -1, -2, -3, -4, -5, -6
 TONEMAP_NONE, TONEMAP_AGX, TONEMAP_AGX_GOLDEN, TONEMAP_AGX_PUNCHY = 0, 1, 2, 3
-ESTIMATOR_GMON, ESTIMATOR_MON, ESTIMATOR_MEAN = 0, 1, 2
+ESTIMATOR_GMON, ESTIMATOR_MON, ESTIMATOR_MEAN, ESTIMATOR_GMONB = 0, 1, 2, 3
 TRACE_CLOSEST, TRACE_ANY, TRACE_COUNT, TRACE_USE_TMAX = 0, 1, 16, 32
 
 f32, u32, i32, u64 = C.c_float, C.c_uint32, C.c_int32, C.c_uint64

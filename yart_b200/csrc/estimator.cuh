@@ -63,13 +63,19 @@ YB_DEV V3 estimatorValue(int estimator, V3* acc, const uint32_t* cnt, int m, uin
   for (int i = 0; i < m; i++) acc[i] /= float(cnt[i]);
   sortByLuma(acc, m);
   if (estimator == YC_ESTIMATOR_MON) return acc[m / 2];
-  // GMoN, estimator.hpp:176-191
+  // Gini function, estimator.hpp:123-130 (GMoNb) = :176-183 (GMoN)
   V3 sum, weightedSum;
   for (int i = 0; i < m; i++) {
     sum += acc[i];
     weightedSum += float(i + 1) * acc[i];  // (i + 1) * vec → vec * float(i + 1)
   }
   float G = (2.0f * luma(weightedSum)) / (float(m) * luma(sum)) - float(m + 1) / float(m);
+  if (estimator == YC_ESTIMATOR_GMONB) {
+    // estimator.hpp:132-136: below the threshold the mean of the bucket means, else their median (NaN → median)
+    if (G <= 0.25f) return sum / float(m);
+    return acc[m / 2];
+  }
+  // GMoN, estimator.hpp:184-191
   if (G > 1.0f) G = 1.0f;
   // c = size_t(G * float(m / 2)) as the x86-64 oracle evaluates it.  G in (-1,0) truncates to 0.
   // G = NaN (black pixel: luma(sum) = 0, or an empty bucket) converts to 2^63; the reference loop

@@ -149,6 +149,28 @@ struct KatGmon {
   }
 };
 
+// GMoNbEstimator alone (same input as KatGmon): out = value[3]
+struct KatGmonb {
+  KatIO io;
+  uint32_t n;
+  YB_DEV void operator()(uint32_t i) const {
+    const int m = estimatorBuckets(int(n), kMaxBuckets);
+    V3 acc[kMaxBuckets];
+    uint32_t cnt[kMaxBuckets];
+    for (int b = 0; b < kMaxBuckets; b++) cnt[b] = 0;
+    for (uint32_t s = 0; s < n; s++) {
+      const V3 v = io.v3((size_t(i) * n + s) * 3);
+      if (estimatorAccepts(YC_ESTIMATOR_GMONB, v)) {
+        acc[s % uint32_t(m)] += v;
+        cnt[s % uint32_t(m)]++;
+      }
+    }
+    const V3 val = estimatorValue(YC_ESTIMATOR_GMONB, acc, cnt, m, n);
+    float* o = io.out + size_t(i) * 3;
+    o[0] = val.x, o[1] = val.y, o[2] = val.z;
+  }
+};
+
 struct KatAgx {
   KatIO io;
   uint32_t tonemap;
@@ -208,6 +230,7 @@ extern "C" int yc_kat(yc_ctx* ctx, const char* kind, const void* in, size_t inBy
   else if (k == "bsdf") recWords = 22, outWords = 27;
   else if (k == "light") recWords = 13, outWords = 22;
   else if (k == "gmon") header = 2, n = inWords > 1 ? hin[1] : 0, recWords = size_t(hin[0]) * 3, outWords = 9;
+  else if (k == "gmonb") header = 2, n = inWords > 1 ? hin[1] : 0, recWords = size_t(hin[0]) * 3, outWords = 3;
   else if (k == "agx") header = 2, n = inWords > 1 ? hin[1] : 0, recWords = 3, outWords = 3;
   else if (k == "camera") header = 15, n = inWords > 14 ? hin[14] : 0, recWords = 6, outWords = 6;
   else if (k == "texture") recWords = 3, outWords = 4;
@@ -232,6 +255,7 @@ extern "C" int yc_kat(yc_ctx* ctx, const char* kind, const void* in, size_t inBy
     else if (k == "bsdf") rt::launchFor(ctx->st, n, KatBsdf{io, ctx->ds});
     else if (k == "light") rt::launchFor(ctx->st, n, KatLight{io, ctx->ds});
     else if (k == "gmon") rt::launchFor(ctx->st, n, KatGmon{io, hin[0]});
+    else if (k == "gmonb") rt::launchFor(ctx->st, n, KatGmonb{io, hin[0]});
     else if (k == "agx") rt::launchFor(ctx->st, n, KatAgx{io, hin[0] == 1 ? uint32_t(YC_TONEMAP_AGX_GOLDEN) : hin[0] == 2 ? uint32_t(YC_TONEMAP_AGX_PUNCHY) : uint32_t(YC_TONEMAP_AGX)});
     else if (k == "camera") rt::launchFor(ctx->st, n, KatCamera{io, ctx->cam});
     else rt::launchFor(ctx->st, n, KatTexture{io, ctx->ds});

@@ -716,7 +716,7 @@ extern "C" int yc_begin_frame(yc_ctx* ctx, const YcFrameDesc* f) {
   if (!ctx->hasScene) return fail(ctx, YC_ERR_NO_SCENE, "yc_begin_frame before yc_upload_scene");
   if (!ctx->hasCamera) return fail(ctx, YC_ERR_STATE, "yc_begin_frame before yc_set_camera");
   if (f->width == 0 || f->height == 0 || f->width > 65535 || f->height > 65535 || f->tileSize == 0 ||
-      f->totalSamples == 0 || f->estimator > YC_ESTIMATOR_MEAN || f->tonemap > YC_TONEMAP_AGX_PUNCHY)
+      f->totalSamples == 0 || f->estimator > YC_ESTIMATOR_GMONB || f->tonemap > YC_TONEMAP_AGX_PUNCHY)
     return fail(ctx, YC_ERR_INVALID, "bad frame description");
   const uint32_t shardCount = f->shardCount ? f->shardCount : 1;
   if (f->shardIndex >= shardCount) return fail(ctx, YC_ERR_INVALID, "shardIndex >= shardCount");
