@@ -194,11 +194,17 @@ typedef struct YcOptions {
    * cpu::MISIntegrator (the measured path), YC_INTEGRATOR_NAIVE = cpu::NaiveIntegrator
    * (src/cpu/naive-integrator.cpp: BSDF sampling only, maxDepth + 1 segments, at most 63). */
   uint32_t integrator;
-  uint32_t reserved2[2];
+  /* The scrambler R of the `Sampler = SobolSampler<R>` template argument (src/main.cpp:16):
+   * FastOwenScrambler (the measured path), OwenScrambler or BinaryPermuteScrambler (src/core/scrambler.hpp:35-85). */
+  uint32_t scrambler;
+  uint32_t reserved2[1];
 } YcOptions;
 
 #define YC_INTEGRATOR_MIS 0
 #define YC_INTEGRATOR_NAIVE 1
+#define YC_SCRAMBLER_FAST_OWEN 0
+#define YC_SCRAMBLER_OWEN 1
+#define YC_SCRAMBLER_BINARY_PERMUTE 2
 
 typedef struct YcRect { uint32_t x, y, w, h; } YcRect;
 
@@ -384,6 +390,7 @@ typedef struct YrSettings {
   uint32_t shardIndex, shardCount;
   int32_t device;
   uint32_t integrator; /* YC_INTEGRATOR_* */
+  uint32_t scrambler;  /* YC_SCRAMBLER_* */
 } YrSettings;
 
 typedef struct YrRenderData {  /* Renderer::RenderData (renderer.hpp:22-28) */

@@ -242,18 +242,22 @@ struct TraceHarness : cpu::MISIntegrator {
 // ---------------------------------------------------------------------------------------
 // commands
 // ---------------------------------------------------------------------------------------
-template <class IntegratorT>
+template <class IntegratorT, class SamplerT>
 static int cmdRenderWith(int argc, char** argv);
 
 // integrator=mis (default) | naive: the `Integrator` template argument of TileRenderer (src/main.cpp:17)
+// scrambler=fastowen (default) | owen | binary: the R of `Sampler = SobolSampler<R>` (src/main.cpp:16)
 static int cmdRender(int argc, char** argv) {
   if (argc < 4) return 1;
   Args a(argc, argv, 4);
-  if (a.str("integrator", "mis") == "naive") return cmdRenderWith<DepthNaiveIntegrator>(argc, argv);
-  return cmdRenderWith<DepthIntegrator>(argc, argv);
+  const std::string scr = a.str("scrambler", "fastowen");
+  if (a.str("integrator", "mis") == "naive") return cmdRenderWith<DepthNaiveIntegrator, RefSampler>(argc, argv);
+  if (scr == "owen") return cmdRenderWith<DepthIntegrator, SobolSampler<OwenScrambler>>(argc, argv);
+  if (scr == "binary") return cmdRenderWith<DepthIntegrator, SobolSampler<BinaryPermuteScrambler>>(argc, argv);
+  return cmdRenderWith<DepthIntegrator, RefSampler>(argc, argv);
 }
 
-template <class IntegratorT>
+template <class IntegratorT, class SamplerT>
 static int cmdRenderWith(int argc, char** argv) {
   Args a(argc, argv, 4);
   ysc::SceneDesc d;
@@ -267,7 +271,7 @@ static int cmdRenderWith(int argc, char** argv) {
   Camera cam = makeCamera(a, w, h);
   g_maxDepth = uint32_t(a.num("maxdepth", 30));
 
-  cpu::TileRenderer<RefSampler, IntegratorT> r(Buffer(w, h), cam);
+  cpu::TileRenderer<SamplerT, IntegratorT> r(Buffer(w, h), cam);
   r.scene = rs.scene.get();
   r.samples = uint32_t(a.num("spp", 16));
   r.firstWaveSamples = uint32_t(a.num("first", r.samples));

@@ -97,10 +97,31 @@ def naive_renders():
         print("naive render", tag, r["rays"])
 
 
+# TileRenderer<SobolSampler<OwenScrambler | BinaryPermuteScrambler>, MISIntegrator>
+SCRAMBLER_RENDERS = [
+    ("owen_cornell", "owen", "cornell", {}, 64, 64, 16, 16, 16, 6),
+    ("owen_zoo", "owen", "material_zoo", {}, 96, 54, 12, 4, 8, 8),
+    ("binary_cornell", "binary", "cornell", {}, 64, 64, 16, 16, 16, 6),
+    ("binary_zoo", "binary", "material_zoo", {}, 96, 54, 12, 4, 8, 8),
+]
+
+
+def scrambler_renders():
+    for tag, scr, name, kw, w, h, spp, first, mx, depth in SCRAMBLER_RENDERS:
+        sp, cam = H.scene_file(name, **kw), H.scene_camera(name, **kw)
+        r = H.oracle_render(sp, w, h, spp, cam, first=first, max=mx, maxdepth=depth, tonemap="agx", threads=4, scrambler=scr)
+        np.savez_compressed(os.path.join(OUT, f"scrambler_{tag}.npz"), scene=name, kwargs=repr(kw),
+                            settings=np.array([w, h, spp, first, mx, depth]), tonemap="agx", hdr=r["hdr"], ldr=r["ldr"],
+                            rays=r["rays"], scrambler=scr)
+        print("scrambler render", tag, r["rays"])
+
+
 def main():
     assert H.have_oracle(), "build oracle/_ref first: make -C oracle ref"
     if "--only-naive" in sys.argv:
         return naive_renders()
+    if "--only-scramblers" in sys.argv:
+        return scrambler_renders()
     only = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--only-kat=")]
     if only:  # regenerate single KAT fixtures: --only-kat=gmonb16
         for tag, kind, n, kw, scene in KATS:
@@ -141,6 +162,7 @@ def main():
                             **{f"idx{i}": m[1] for i, m in enumerate(meshes)})
         print("bvh", name, [len(m[0]) for m in meshes])
     naive_renders()
+    scrambler_renders()
 
 
 if __name__ == "__main__":

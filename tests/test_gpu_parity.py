@@ -44,6 +44,12 @@ def test_naive_integrator_render(path):
     PC.check_render(path, exact=False)
 
 
+@pytest.mark.parametrize("path", PC.golden_files("scrambler"), ids=os.path.basename)
+def test_other_scramblers_render(path):
+    """YC_SCRAMBLER_OWEN / _BINARY_PERMUTE against TileRenderer<SobolSampler<R>, MISIntegrator> (relMSE < 1e-3, then bitwise)."""
+    PC.check_render(path, exact=False)
+
+
 def test_render_is_deterministic_and_capacity_independent():
     path = os.path.join(H.GOLDEN, "render_zoo.npz")
     _, d1, hdr1, ldr1, _ = PC.render_golden(path)

@@ -48,6 +48,12 @@ def test_naive_integrator_render_bit_exact(path):
     PC.check_render(path, exact=True)
 
 
+@pytest.mark.parametrize("path", PC.golden_files("scrambler"), ids=os.path.basename)
+def test_other_scramblers_render_bit_exact(path):
+    """TileRenderer<SobolSampler<OwenScrambler | BinaryPermuteScrambler>, MISIntegrator> (scrambler.hpp:35-85)."""
+    PC.check_render(path, exact=True)
+
+
 def test_small_wavefront_capacity_gives_same_image():
     """Chunking (pixel blocks x sample groups) must not change a single bit."""
     path = os.path.join(H.GOLDEN, "render_cornell_waves.npz")

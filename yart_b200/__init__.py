@@ -13,7 +13,7 @@ import ctypes as C
 import numpy as np
 
 from . import capi
-from .capi import (INTEGRATOR_MIS, INTEGRATOR_NAIVE, ESTIMATOR_GMONB, ESTIMATOR_GMON, ESTIMATOR_MEAN, ESTIMATOR_MON, TONEMAP_AGX, TONEMAP_AGX_GOLDEN, TONEMAP_AGX_PUNCHY,
+from .capi import (SCRAMBLER_FAST_OWEN, SCRAMBLER_OWEN, SCRAMBLER_BINARY_PERMUTE, INTEGRATOR_MIS, INTEGRATOR_NAIVE, ESTIMATOR_GMONB, ESTIMATOR_GMON, ESTIMATOR_MEAN, ESTIMATOR_MON, TONEMAP_AGX, TONEMAP_AGX_GOLDEN, TONEMAP_AGX_PUNCHY,
                    TONEMAP_NONE, TRACE_ANY, TRACE_CLOSEST, TRACE_COUNT, TRACE_USE_TMAX)
 
 _lib = None
@@ -139,9 +139,10 @@ class Context:
     """Device layer (yc_*): one CUDA context + stream on one GPU."""
 
     def __init__(self, device: int = 0, max_depth: int = 30, max_paths: int = 0, refill_min: int = 0, inner_min: int = 0,
-                 tail_threshold: int = 0, integrator: int = capi.INTEGRATOR_MIS):
+                 tail_threshold: int = 0, integrator: int = capi.INTEGRATOR_MIS,
+                 scrambler: int = capi.SCRAMBLER_FAST_OWEN):
         self._h = C.c_void_p()
-        opts = capi.YcOptions(maxDepth=max_depth, maxPathsInFlight=max_paths, integrator=integrator)
+        opts = capi.YcOptions(maxDepth=max_depth, maxPathsInFlight=max_paths, integrator=integrator, scrambler=scrambler)
         opts.reserved[0], opts.reserved[1] = refill_min, inner_min  # traversal scheduling knobs (0 = default)
         opts.reserved[2] = 0xffffffff if tail_threshold < 0 else tail_threshold  # tail kernel hand-over (-1 = never)
         _check(lib().yc_create(device, C.byref(opts), C.byref(self._h)), "yc_create",
@@ -280,11 +281,11 @@ class Renderer:
     def __init__(self, width, height, camera: capi.YcCamera, scene: Scene | None = None, samples=64,
                  first_wave_samples=None, max_wave_samples=None, tile_size=64, max_depth=30, background=(0, 0, 0),
                  tonemap=TONEMAP_AGX, estimator=ESTIMATOR_GMON, shard_index=0, shard_count=1, device=0,
-                 integrator=capi.INTEGRATOR_MIS):
+                 integrator=capi.INTEGRATOR_MIS, scrambler=capi.SCRAMBLER_FAST_OWEN):
         # TileRenderer defaults: samples 64, firstWaveSamples 64, maxWaveSamples 128, tileSize 64 (:11-14)
         s = capi.YrSettings(width, height, samples, 64 if first_wave_samples is None else first_wave_samples,
                             128 if max_wave_samples is None else max_wave_samples, tile_size, max_depth,
-                            _f3(background), tonemap, estimator, shard_index, shard_count, device, integrator)
+                            _f3(background), tonemap, estimator, shard_index, shard_count, device, integrator, scrambler)
         self.settings = s
         self.scene = scene
         self._h = C.c_void_p()

@@ -27,11 +27,12 @@ class YcCamera(C.Structure):
 
 
 INTEGRATOR_MIS, INTEGRATOR_NAIVE = 0, 1
+SCRAMBLER_FAST_OWEN, SCRAMBLER_OWEN, SCRAMBLER_BINARY_PERMUTE = 0, 1, 2
 
 
 class YcOptions(C.Structure):
     _fields_ = [("maxDepth", u32), ("maxPathsInFlight", u32), ("reserved", u32 * 3), ("integrator", u32),
-                ("reserved2", u32 * 2)]
+                ("scrambler", u32), ("reserved2", u32 * 1)]
 
 
 class YcRect(C.Structure):
@@ -81,7 +82,7 @@ class YcScene(C.Structure):
 class YrSettings(C.Structure):
     _fields_ = [("width", u32), ("height", u32), ("samples", u32), ("firstWaveSamples", u32), ("maxWaveSamples", u32),
                 ("tileSize", u32), ("maxDepth", u32), ("background", f32 * 3), ("tonemap", u32), ("estimator", u32),
-                ("shardIndex", u32), ("shardCount", u32), ("device", i32), ("integrator", u32)]
+                ("shardIndex", u32), ("shardCount", u32), ("device", i32), ("integrator", u32), ("scrambler", u32)]
 
 
 class YrRenderData(C.Structure):

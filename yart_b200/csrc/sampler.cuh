@@ -13,7 +13,9 @@ namespace yb {
 struct SamplerConfig {
   uint32_t log2spp;       // log2Int(float(totalSamples))
   uint32_t nBase4Digits;  // log2Int(roundUpPow2(tileSize)) + (log2spp + 1) / 2
+  uint32_t scrambler;     // the R of SobolSampler<R>: 0 FastOwenScrambler (the measured path), 1 OwenScrambler, 2 BinaryPermuteScrambler
 };
+enum : uint32_t { kScrambleFastOwen = 0, kScrambleOwen = 1, kScrambleBinaryPermute = 2 };
 
 // permutations[24][4], sampler.hpp:116-141 (the 24 permutations of {0,1,2,3} in the order the
 // reference lists them), packed 2 bits per digit: entry p, digit d → (kPermPacked[p] >> (2*d)) & 3.
@@ -77,6 +79,16 @@ YB_DEV uint32_t fastOwen(uint32_t v, uint32_t seed) {
   return reverseBits32(v);
 }
 
+// scrambler.hpp:71-85 (OwenScrambler): one hashed flip decision per bit, each depending on the bits above it
+YB_DEV uint32_t owenScramble(uint32_t v, uint32_t seed) {
+  if (seed & 1u) v ^= 1u << 31;
+  for (uint32_t b = 1; b < 32; b++) {
+    const uint32_t mask = (~0u) << (32 - b);
+    if (uint32_t(mixBits(uint64_t(v & mask)) ^ uint64_t(seed)) & (1u << b)) v ^= 1u << (31 - b);
+  }
+  return v;
+}
+
 // Sobol dimension 1 (sobol.tables entries 52..103): generator-matrix column i is the Pascal-mod-2
 // column v_0 = 2^31, v_i = v_{i-1} ^ (v_{i-1} >> 1) = (1 + S)^i v_0 (S = shift right by one), repeating
 // with period 32 in the table.  Bit (31 - j) of column i is C(i, j) mod 2 = [j ⊆ i] (Lucas), so the
@@ -95,11 +107,12 @@ YB_DEV uint32_t sobolDim1Closed(uint64_t d) {
 struct Sampler {
   uint64_t morton;
   uint32_t dim;
-  uint32_t log2spp, nBase4Digits;
+  uint32_t log2spp, nBase4Digits, scrambler;
 
   YB_DEV void start(const SamplerConfig& c, uint32_t px, uint32_t py, uint32_t sample) {
     log2spp = c.log2spp;
     nBase4Digits = c.nBase4Digits;
+    scrambler = c.scrambler;
     dim = 0;
     morton = (encodeMorton2(px, py) << log2spp) | uint64_t(sample);  // sampler.hpp:84-87
   }
@@ -128,8 +141,10 @@ struct Sampler {
   }
 
   // sampler.hpp:143-153, dimension 0: v = reverseBits32(uint32(d))
-  static YB_DEV float finish(uint32_t v, uint32_t seed) {
-    v = fastOwen(v, seed);
+  YB_DEV float finish(uint32_t v, uint32_t seed) const {
+    if (scrambler == kScrambleFastOwen) v = fastOwen(v, seed);
+    else if (scrambler == kScrambleOwen) v = owenScramble(v, seed);
+    else v = seed ^ v;  // BinaryPermuteScrambler, scrambler.hpp:35-46
     return fminf(float(v) * 0x1p-32f, 0x1.fffffep-1f);
   }
   static YB_DEV uint32_t sobolDim1(uint64_t d) { return sobolDim1Closed(d); }

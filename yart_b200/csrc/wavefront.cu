@@ -509,7 +509,7 @@ extern "C" int yc_create(int device, const YcOptions* opts, yc_ctx** out) {
   if (!ctx) return YC_ERR_INVALID;
   if (opts) ctx->opts = *opts;
   if (ctx->opts.maxDepth == 0) ctx->opts.maxDepth = 30;  // RayIntegrator::m_maxDepth, ray-integrator.hpp:14
-  if (ctx->opts.integrator > YC_INTEGRATOR_NAIVE ||
+  if (ctx->opts.integrator > YC_INTEGRATOR_NAIVE || ctx->opts.scrambler > YC_SCRAMBLER_BINARY_PERMUTE ||
       (ctx->opts.integrator == YC_INTEGRATOR_NAIVE && ctx->opts.maxDepth + 1 > kNaiveMaxSegments)) {
     delete ctx;
     return YC_ERR_INVALID;
@@ -810,6 +810,7 @@ static int renderChunks(yc_ctx* ctx, const uint32_t* dList, uint32_t nPixCall, u
   // SobolSampler ctor (sampler.hpp:74-82) as TileRenderer calls it: (totalSamples, {tileSize, tileSize})
   w.smp.log2spp = log2IntU(f.totalSamples);
   w.smp.nBase4Digits = log2IntU(roundUpPow2(f.tileSize)) + (w.smp.log2spp + 1) / 2;
+  w.smp.scrambler = ctx->opts.scrambler;
   memcpy(w.bg, f.background, sizeof w.bg);
   w.maxDepth = ctx->opts.maxDepth;
   w.pixelList = dList;
@@ -1120,6 +1121,7 @@ YB_DEV Sampler traceHookSampler() {
   SamplerConfig c;
   c.log2spp = 4;
   c.nBase4Digits = 6 + 2;
+  c.scrambler = kScrambleFastOwen;
   Sampler s;
   s.start(c, 0, 0, 0);
   return s;
@@ -1370,6 +1372,7 @@ extern "C" int yc_generate_primary_rays(yc_ctx* ctx, uint32_t sampleOffset, uint
   w.cam = ctx->cam;
   w.smp.log2spp = log2IntU(f.totalSamples);
   w.smp.nBase4Digits = log2IntU(roundUpPow2(f.tileSize)) + (w.smp.log2spp + 1) / 2;
+  w.smp.scrambler = ctx->opts.scrambler;
   w.pixelList = ctx->dPixels;
   w.pixBase = 0, w.nPix = uint32_t(ctx->pixels.size()), w.s0 = sampleOffset;
   const uint64_t n = uint64_t(w.nPix) * spp;

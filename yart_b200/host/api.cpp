@@ -226,6 +226,7 @@ extern "C" int yr_create(const YrSettings* settings, const ys_scene* scene, cons
   YcOptions o{};
   o.maxDepth = settings->maxDepth;
   o.integrator = settings->integrator;
+  o.scrambler = settings->scrambler;
   int rc = yc_create(settings->device, &o, &r->ctx);
   if (rc != YC_OK) {
     delete r;
