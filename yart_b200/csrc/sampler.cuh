@@ -89,6 +89,12 @@ YB_DEV uint32_t owenScramble(uint32_t v, uint32_t seed) {
   return v;
 }
 
+// The scramblers other than FastOwen, out of line: they are off the measured path and must not grow every draw site.
+YB_DEV_NI uint32_t scrambleOther(uint32_t v, uint32_t seed, uint32_t scrambler) {
+  if (scrambler == kScrambleOwen) return owenScramble(v, seed);
+  return seed ^ v;  // BinaryPermuteScrambler, scrambler.hpp:35-46
+}
+
 // Sobol dimension 1 (sobol.tables entries 52..103): generator-matrix column i is the Pascal-mod-2
 // column v_0 = 2^31, v_i = v_{i-1} ^ (v_{i-1} >> 1) = (1 + S)^i v_0 (S = shift right by one), repeating
 // with period 32 in the table.  Bit (31 - j) of column i is C(i, j) mod 2 = [j ⊆ i] (Lucas), so the
@@ -142,9 +148,7 @@ struct Sampler {
 
   // sampler.hpp:143-153, dimension 0: v = reverseBits32(uint32(d))
   YB_DEV float finish(uint32_t v, uint32_t seed) const {
-    if (scrambler == kScrambleFastOwen) v = fastOwen(v, seed);
-    else if (scrambler == kScrambleOwen) v = owenScramble(v, seed);
-    else v = seed ^ v;  // BinaryPermuteScrambler, scrambler.hpp:35-46
+    v = scrambler == kScrambleFastOwen ? fastOwen(v, seed) : scrambleOther(v, seed, scrambler);
     return fminf(float(v) * 0x1p-32f, 0x1.fffffep-1f);
   }
   static YB_DEV uint32_t sobolDim1(uint64_t d) { return sobolDim1Closed(d); }

@@ -34,7 +34,7 @@ using namespace yb;
 #define YB_SHADOW_MIN_BLOCKS 1
 #endif
 #ifndef YB_SHADE_MIN_BLOCKS
-#define YB_SHADE_MIN_BLOCKS 6  // 6 x 256 threads per SM (40 registers + local-memory spills): shading is latency-bound, warps beat registers (2: 35.6, 4: 33.7, 6: 32.4, 8: 32.3 ms on the Sponza-shaped step)
+#define YB_SHADE_MIN_BLOCKS 8  // 8 x 256 threads per SM (32 registers + local-memory spills): shading is latency-bound, resident warps beat registers (CTAs/SM 2: 35.6, 4: 33.7, 6: 32.4-34.5, 8: 32.3-34.0 ms on the Sponza-shaped step)
 #endif
 
 // ---------------------------------------------------------------------------------------
