@@ -430,7 +430,10 @@ def run_ours(args):
                          "traffic": traffic if args.workload == "soup" else None, "kernel": roof_kernel, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": algo_bytes, "rays_per_launch": n_rays, "avg_launch_ms": roof_ms,
                          "box_tests_per_ray": box / n_rays, "tri_tests_per_ray": tri / n_rays,
-                         "in_step_extend_launches": in_step},
+                         "in_step_extend_launches": in_step,
+                         "note": "frac > 1 is possible: the algorithmic bytes (SURVEY 8d: the reference BVH2's node and triangle "
+                                 "bytes per test) are served by the L2, where the BVH is resident; DRAM moves only `traffic`. ncu: "
+                                 "issue slots 65 %, L1/TEX 77 %, 18.7 of 32 lanes active, top stall L2 latency (profiles/README.md)"},
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), file=_REAL_STDOUT, flush=True)

@@ -197,6 +197,8 @@ typedef struct YcOptions {
   /* The scrambler R of the `Sampler = SobolSampler<R>` template argument (src/main.cpp:16):
    * FastOwenScrambler (the measured path), OwenScrambler or BinaryPermuteScrambler (src/core/scrambler.hpp:35-85). */
   uint32_t scrambler;
+  /* reserved2[0]: entries of the traversal kernels' shared-memory stack actually used (0 = default, all 25);
+   * the rest goes to the global spill area.  Never changes results; tests shrink it to exercise the spill path. */
   uint32_t reserved2[1];
 } YcOptions;
 

@@ -290,3 +290,50 @@ def test_bucket_shards_combine_to_the_unsharded_render_bitwise():
         rays += st.raysReference
     assert rays == st0.raysReference
     assert np.isfinite(hdr0).all() and hdr0[..., :3].mean() > 0
+
+
+def test_traversal_stack_spill_path_gives_identical_hits_and_frames(soup_100k):
+    """The persistent kernels keep 25 stack entries per lane in shared memory and spill deeper ones to global
+    memory.  With 3 shared entries (YcOptions.reserved2[0]) nearly every push spills: closest-hit and any-hit
+    records of 1080p primary rays and a full-path render must not change by a bit."""
+    sc, ctx = soup_100k
+    cam = H.scene_camera("soup")
+    W, Hh = 1920, 1080
+    c = Y.make_camera(W, Hh, cam["focal"], cam["fnum"], cam["pos"], cam["target"])
+    n = W * Hh
+    out = []
+    for entries in (0, 3):
+        cx = Y.Context(max_depth=4, sh_stack_entries=entries)
+        cx.upload_scene(sc)
+        cx.set_camera(c)
+        cx.begin_frame(W, Hh, 1, 64, (0, 0, 0), Y.TONEMAP_NONE)
+        rays_dev, hits_dev = cx.device_alloc(n * 32), cx.device_alloc(n * 20)
+        cx.generate_primary_rays(0, 1, rays_dev)
+        rec = []
+        for mode in (Y.TRACE_CLOSEST, Y.TRACE_ANY):
+            cx.trace_device(rays_dev, n, hits_dev, mode)
+            hits = np.empty(n, Y.COMPACT_HIT_DTYPE)
+            cx.d2h(hits, hits_dev)
+            rec.append(hits.tobytes())
+        cx.device_free(rays_dev)
+        cx.device_free(hits_dev)
+        cx.render_wave(0, 1, 0)
+        hdr, _, st = cx.resolve()
+        out.append((rec, hdr, st.raysReference))
+        cx.close()
+    assert out[0][0][0] == out[1][0][0] and out[0][0][1] == out[1][0][1]
+    assert H.bits_equal(out[0][1], out[1][1]).all() and out[0][2] == out[1][2]
+
+    # and against the reference on a scene with nested transforms, alpha-tested and NEE-transparent materials
+    path = os.path.join(H.GOLDEN, "render_zoo.npz")
+    g = PC.load(path)
+    name, kw = PC.scene_from_golden(g)
+    w, h, spp, first, mx, depth = (int(v) for v in g["settings"])
+    zc = H.scene_camera(name)
+    cx = Y.Context(max_depth=depth, sh_stack_entries=2)
+    cx.upload_scene(Y.Scene(H.scene_file(name)))
+    cx.set_camera(Y.make_camera(w, h, zc["focal"], zc["fnum"], zc["pos"], zc["target"], (0, 0, 0), zc["exposure"]))
+    cx.begin_frame(w, h, spp, 64, (0, 0, 0), Y.TONEMAP_AGX)
+    cx.render_wave(0, spp, 0)
+    hdr, _, st = cx.resolve()
+    assert H.bits_equal(hdr, g["hdr"]).all() and st.raysReference == int(g["rays"])

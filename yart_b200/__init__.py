@@ -140,11 +140,12 @@ class Context:
 
     def __init__(self, device: int = 0, max_depth: int = 30, max_paths: int = 0, refill_min: int = 0, inner_min: int = 0,
                  tail_threshold: int = 0, integrator: int = capi.INTEGRATOR_MIS,
-                 scrambler: int = capi.SCRAMBLER_FAST_OWEN):
+                 scrambler: int = capi.SCRAMBLER_FAST_OWEN, sh_stack_entries: int = 0):
         self._h = C.c_void_p()
         opts = capi.YcOptions(maxDepth=max_depth, maxPathsInFlight=max_paths, integrator=integrator, scrambler=scrambler)
         opts.reserved[0], opts.reserved[1] = refill_min, inner_min  # traversal scheduling knobs (0 = default)
         opts.reserved[2] = 0xffffffff if tail_threshold < 0 else tail_threshold  # tail kernel hand-over (-1 = never)
+        opts.reserved2[0] = sh_stack_entries  # shared traversal-stack entries in use (0 = default; small = spill-path test)
         _check(lib().yc_create(device, C.byref(opts), C.byref(self._h)), "yc_create",
                b"(no usable CUDA device: yart_b200 has no CPU fallback)")
         self.frame = None

@@ -8,12 +8,16 @@
 //     mesh's BVH: current ref is an inner node or a leaf) → … → IDLE;
 //   * idle lanes are refilled from the work queue with ONE atomic per warp (ballot + popc), as soon
 //     as enough lanes are idle, instead of waiting for the slowest ray of a batch of 32;
-//   * inner-node steps run in a tight loop while enough lanes sit on inner nodes; lanes that reach a
-//     leaf wait there (their own test order is unchanged) and all leaves are processed together, so
-//     the two code paths do not serialise against each other on every iteration;
-//   * the traversal stack lives in shared memory ([entry][thread], conflict-free) with a spill area
-//     in global memory for trees deeper than kShStack; no local memory is used.
-// Node and triangle records are fetched as 128-bit read-only loads (4 per inner node, 3 per triangle).
+//   * inner-node steps run in a tight loop while enough lanes sit on inner nodes; a lane that reaches a
+//     leaf parks it and keeps walking (its own test order is unchanged: parked leaves are tested in the
+//     order they were reached, before any later leaf), and all leaves are processed together, so the two
+//     code paths do not serialise against each other on every iteration;
+//   * the inner step is branch-free apart from its `inner` guard: packed (ref, d) stack entries in shared
+//     memory ([entry][thread], conflict-free, one LDS.64 / STS.64 per pop / push), the stack pointer is
+//     the shared byte address, a sentinel at the bottom replaces the "empty" test, one predicated pop
+//     site per iteration, descend / push as selects; trees deeper than kShStack spill to global memory
+//     through an out-of-line path; no local memory is used.
+// Node records are fetched as two 256-bit read-only loads, triangles as three 128-bit loads.
 #pragma once
 #include "integrator.cuh"
 
@@ -25,6 +29,7 @@ constexpr int kTraceBlock = 128;       // 4 warps per CTA
 struct TraceTuning {
   int refillMin;  // refill the warp from the queue when at least this many lanes are idle
   int innerMin;   // keep stepping inner nodes while at least this many lanes sit on one
+  int shEntries;  // shared-memory stack entries in use (2..kPsStack; the rest spills): tests shrink it to exercise the spill path
 };
 
 // Per-lane traversal stack of the persistent kernels: packed (ref, d) entries, [entry][thread] in shared
@@ -34,21 +39,22 @@ struct TraceTuning {
 // pop never tests for "empty": popping the sentinel yields kNoRef = "this mesh is walked".
 constexpr int kPsStack = kShStack + 1;
 constexpr uint32_t kPsStride = kTraceBlock * 8;  // bytes between consecutive entries of one thread
+constexpr int kSpillEntries = kMaxStack;         // global spill entries per thread (covers the smallest shared stack)
 struct WarpStack {
   uint32_t base;   // shared address of this thread's entry 0
   uint32_t limit;  // base + kPsStack * kPsStride: first address that lives in the spill area
   uint2** spillBase;  // in shared memory: the spill area's base pointer (only the rare path reads it)
-  __device__ __forceinline__ void init(uint2* shStack, uint2** shSpill, uint2* spill) {
-    uint32_t a = uint32_t(__cvta_generic_to_shared(shStack + threadIdx.x));
-    asm volatile("mov.u32 %0, %1;" : "=r"(base) : "r"(a));  // opaque: kept in a register, not recomputed
-    limit = base + uint32_t(kPsStack) * kPsStride;
+  __device__ __forceinline__ void init(uint2* shStack, uint2** shSpill, uint2* spill, int shEntries) {
+    base = uint32_t(__cvta_generic_to_shared(shStack + threadIdx.x));  // rarely needed: may be recomputed
+    const uint32_t l = base + uint32_t(shEntries) * kPsStride;
+    asm volatile("mov.u32 %0, %1;" : "=r"(limit) : "r"(l));  // opaque: compared at every push / pop, kept in a register
     if (threadIdx.x == 0) *shSpill = spill;
     __syncthreads();
     spillBase = shSpill;
   }
   // rare path (trees deeper than kShStack): everything is derived here so nothing of it stays live
   __device__ __noinline__ static uint2* spillSlot(uint2** spillBase, uint32_t off) {
-    return *spillBase + size_t(blockIdx.x * kTraceBlock + threadIdx.x) * (kMaxStack - kShStack) + off / kPsStride;
+    return *spillBase + size_t(blockIdx.x * kTraceBlock + threadIdx.x) * kSpillEntries + off / kPsStride;
   }
   __device__ __forceinline__ void put(uint32_t sa, uint32_t ref, float d) const {
     asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(sa), "r"(ref), "r"(__float_as_uint(d)));
@@ -58,7 +64,7 @@ struct WarpStack {
   __device__ __forceinline__ void pushIf(bool on, uint32_t& sa, uint32_t ref, float d) const {
     if (on && sa < limit) put(sa, ref, d);
     if (on && sa >= limit) {
-      if (sa < limit + uint32_t(kMaxStack - kShStack) * kPsStride) *spillSlot(spillBase, sa - limit) = make_uint2(ref, __float_as_uint(d));
+      if (sa < base + uint32_t(kMaxStack + 1) * kPsStride) *spillSlot(spillBase, sa - limit) = make_uint2(ref, __float_as_uint(d));
     }
     if (on) sa += kPsStride;
   }
@@ -115,7 +121,7 @@ __device__ __forceinline__ void tracePersistent(const DScene& sc, IO& io, uint32
   __shared__ uint2 shStack[kPsStack * kTraceBlock];
   __shared__ uint2* shSpill;
   WarpStack stack;
-  stack.init(shStack, &shSpill, spillBase);
+  stack.init(shStack, &shSpill, spillBase, tune.shEntries);
   const unsigned FULL = 0xffffffffu;
   const unsigned lane = threadIdx.x & 31u, ltMask = (1u << lane) - 1u;
 

@@ -468,6 +468,8 @@ static TraceTuning tuning(const yc_ctx* ctx) {
   TraceTuning t;
   t.refillMin = ctx->opts.reserved[0] ? int(ctx->opts.reserved[0]) : 8;
   t.innerMin = ctx->opts.reserved[1] ? int(ctx->opts.reserved[1]) : 20;
+  const int e = ctx->opts.reserved2[0] ? int(ctx->opts.reserved2[0]) : kPsStack;
+  t.shEntries = std::max(2, std::min(kPsStack, e));
   return t;
 }
 static int traceGrid(const yc_ctx* ctx, uint32_t n) {
@@ -679,7 +681,7 @@ static int ensureWaveStorage(yc_ctx* ctx) {
     L.hCtr = static_cast<uint32_t*>(hp);
 #ifndef YB_HOSTSIM
     uint2* sp = nullptr;
-    YC_TRY(devAlloc(own, &sp, size_t(traceGridMax(ctx)) * kTraceBlock * (kMaxStack - kShStack)));
+    YC_TRY(devAlloc(own, &sp, size_t(traceGridMax(ctx)) * kTraceBlock * kSpillEntries));
     L.spill = sp;
 #endif
   }
