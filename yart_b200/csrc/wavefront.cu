@@ -31,7 +31,7 @@ using namespace yb;
 #define YB_TRACE_MIN_BLOCKS 8  // 8 CTAs x 4 warps per SM: caps the traversal kernels at 64 registers
 #endif
 #ifndef YB_SHADOW_MIN_BLOCKS
-#define YB_SHADOW_MIN_BLOCKS 1
+#define YB_SHADOW_MIN_BLOCKS 7  // 72 registers, no spills (uncapped: 96 registers, 5 CTAs — C2 step 11.5 ms; 7: 10.9; 8 spills: 11.9)
 #endif
 #ifndef YB_SHADE_MIN_BLOCKS
 #define YB_SHADE_MIN_BLOCKS 8  // 8 x 256 threads per SM (32 registers + local-memory spills): shading is latency-bound, resident warps beat registers (CTAs/SM 2: 35.6, 4: 33.7, 6: 32.4-34.5, 8: 32.3-34.0 ms on the Sponza-shaped step)
