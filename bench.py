@@ -316,10 +316,11 @@ def run_ours(args):
     launches = s1.kernelLaunches - s0.kernelLaunches
 
     # ---- extend-kernel roofline: algorithmic bytes of the reference traversal on these rays ------
-    n_rays = W * H * spp
+    rspp = min(spp, max(1, (1 << 23) // (W * H)))  # roofline launch: at most 8 Mi primary rays (4 spp at 1080p)
+    n_rays = W * H * rspp
     rays_dev, hits_dev = ctx.device_alloc(n_rays * 32), ctx.device_alloc(n_rays * 20)
     ctx.begin_frame(W, H, total_spp, 64, (0, 0, 0), Y.TONEMAP_AGX)
-    ctx.generate_primary_rays((n_warm * world + rank) * spp, spp, rays_dev)  # the first timed wave's rays
+    ctx.generate_primary_rays((n_warm * world + rank) * spp, rspp, rays_dev)  # the first timed wave's rays
     one = np.array([[0, 0, 40, 0.001, 0.01, 0.02, -0.99975, np.inf]], np.float32)  # any ordinary ray
     ctx.trace(one, Y.TRACE_CLOSEST | Y.TRACE_COUNT)  # zeroes the work counters
     c0 = ctx.stats()
@@ -461,7 +462,13 @@ def main():
     ap.add_argument("--sharding", default="waves", choices=["waves", "buckets"],
                     help="N > 1: whole waves per rank (default) or the samples of one wave split by GMoN bucket")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080, help="3840 x 2160 for the BASELINE.json configs[4] shape")
     args = ap.parse_args()
+    global W, H, METRIC
+    W, H = args.width, args.height
+    if (W, H) != (1920, 1080):
+        METRIC = METRIC.replace("1080p", f"{W}x{H}")
     if not args.tris:
         args.tris = DEFAULT_TRIS[args.workload]
     select_workload(args.workload, args.tris)
