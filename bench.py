@@ -247,9 +247,9 @@ def run_ours(args):
         rank's HDR frame with finishTile's sample-count weights."""
         k = min(k, waves_per_rank - 1)
         if buckets:
-            # sample sharding inside a wave of spp * world samples by estimator bucket: every rank accumulates
-            # the samples of its buckets, the GMoN accumulation buffers are summed with NCCL (int32: disjoint
-            # planes, bitwise exact), every rank finalizes — bit-identical to one GPU rendering the wave
+            # sample sharding inside a wave of spp * world samples by (estimator bucket, pixel class) units: every
+            # rank accumulates its units, the GMoN accumulation buffers are summed with NCCL (int32: disjoint
+            # slots, bitwise exact), every rank finalizes — bit-identical to one GPU rendering the wave
             import torch
             S = spp * world
             ctx.accumulate_wave(k * S, S, bucket_shard=rank, bucket_shard_count=world)
@@ -412,9 +412,9 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD_TEXT,
                        "step": f"one wave of {spp} spp per GPU ({W * H * spp} camera paths)",
-                       "parallelism": (f"bucket sharding x{world}: every wave of {spp * world} samples is split by GMoN bucket "
-                                       "(rank r takes buckets b % N == r); scene replicated; NCCL all-reduce(int32 sum) of the "
-                                       "accumulation buffers per wave, inside the timed region") if buckets else
+                       "parallelism": (f"bucket sharding x{world}: every wave of {spp * world} samples is split into (GMoN bucket b, pixel "
+                                       "class c) units, rank r takes (b + c) % N == r; scene replicated; NCCL all-reduce(int32 sum) "
+                                       "of the accumulation buffers per wave, inside the timed region") if buckets else
                                       (f"sample-wave sharding x{world}: rank r renders waves r, r+N, ... of the job; scene replicated; "
                                        "one NCCL all-reduce of the HDR frames per job (inside the timed region)"),
                        "l2": "inputs larger than L2: BVH + 0.8 GB of path state streamed per step exceed the 126 MB L2; no flush"},

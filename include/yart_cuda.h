@@ -286,12 +286,13 @@ int yc_render_wave(yc_ctx* ctx, YcRect pixels, uint32_t sampleOffset, uint32_t w
                    uint32_t takenBefore);
 /* The same wave in two steps, for sample sharding across GPUs (SURVEY §8e alternative B; north_star:
  * "per-GPU ... median-of-means and GMoN accumulation buffers are combined with NCCL"):
- *   yc_accumulate_wave  Integrator::render's sample loop (integrator.cpp:19-24) for the samples of the wave
- *                       whose estimator bucket b = (index in the wave) % m satisfies
- *                       b % bucketShardCount == bucketShard; each owned bucket receives its samples in
- *                       sample order (the reference's rounding sequence), the others stay zero, so the
- *                       bucket buffers of all shards add up exactly (bitwise, as 32-bit integers).
- *                       bucketShardCount = 1 takes every sample.
+ *   yc_accumulate_wave  Integrator::render's sample loop (integrator.cpp:19-24) for this GPU's share of the wave:
+ *                       the work is cut into units (estimator bucket b = (index in the wave) % m, pixel class c =
+ *                       the c-th of bucketShardCount equal ranges of the frame's pixel list) and the call takes
+ *                       the units with (b + c) % bucketShardCount == bucketShard.  Each (bucket, pixel) slot
+ *                       receives its samples on one GPU, in sample order (the reference's rounding sequence), the
+ *                       others stay zero, so the bucket buffers of all shards add up exactly (bitwise, as 32-bit
+ *                       integers).  bucketShardCount = 1 takes every sample.
  *   yc_bucket_device_ptrs  the accumulation buffer, for the caller's NCCL all-reduce(sum) as int32:
  *                       `planes` planes of `planePixels` float4 {sum r, g, b, count (uint32 bits)}.
  *   yc_wave_buckets     how many of those planes (the first m) a wave of `waveSamples` samples uses

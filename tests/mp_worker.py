@@ -38,9 +38,9 @@ def run(rank: int, world: int, port: int, mode: str, out_dir: str):
         dist.all_reduce(t_hdr)
         dist.all_reduce(t_ldr)
     elif mode == "buckets":
-        # sample sharding inside a wave by estimator bucket (SURVEY §8e alternative B): every rank accumulates
-        # the samples of its buckets, the GMoN accumulation buffers are summed across ranks as 32-bit
-        # integers (disjoint planes: bitwise exact), every rank finalizes the wave
+        # sample sharding inside a wave by (estimator bucket, pixel class) units (SURVEY §8e alternative B): every
+        # rank accumulates its units, the GMoN accumulation buffers are summed across ranks as 32-bit
+        # integers (disjoint slots: bitwise exact), every rank finalizes the wave
         waves = [16, 16]
         ctx.begin_frame(w, h, sum(waves), 16, (0, 0, 0), Y.TONEMAP_AGX)
         ptr, nbytes, _, _ = ctx.bucket_device_ptrs()

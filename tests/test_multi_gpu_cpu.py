@@ -67,7 +67,7 @@ def test_two_ranks_wave_sharding_equals_progressive_render(tmp_path):
 
 def test_two_ranks_bucket_sharding_equals_one_rank_bitwise(tmp_path):
     """GMoN accumulation buffers combined across ranks (all-reduce of the bucket planes as int32), two
-    progressive waves of 16 samples (m = 3 buckets: rank 0 owns buckets 0 and 2, rank 1 bucket 1)."""
+    progressive waves of 16 samples (m = 3 buckets x 2 pixel classes: every rank owns one class of each bucket)."""
     launch("buckets", tmp_path)
     hdr1, ldr1, st = single(32, [16, 16])
     assert H.bits_equal(np.load(tmp_path / "buckets_hdr.npy"), hdr1).all()

@@ -819,28 +819,39 @@ static int renderChunks(yc_ctx* ctx, const uint32_t* dList, uint32_t nPixCall, u
   const float exposureScale = std::exp2(ctx->cam.exposure);  // integrator.cpp:23
 
   // chunk list: pixel blocks x sample groups, each at most one lane's capacity of paths
-  // Bucket sharding (bucketShardCount > 1): this context takes only the samples of the estimator buckets
-  // b with b % bucketShardCount == bucketShard, one bucket at a time (samples b, b + m, b + 2m, ...), so each
-  // bucket it owns receives its samples in sample order — the reference's rounding sequence — and the
-  // buckets it does not own stay zero: the per-GPU bucket buffers add up exactly.
+  // Bucket sharding (bucketShardCount = G > 1): the wave's work is cut into units (estimator bucket b, pixel class c)
+  // — class c = the c-th of G equal contiguous ranges of the pixel list — and this context takes the units with
+  // (b + c) % G == bucketShard.  Every GPU gets one unit per bucket (balanced for any m, and each GPU sees every
+  // part of the image), each (bucket, pixel) slot is written by exactly one GPU, with that bucket's samples
+  // b, b + m, b + 2m, ... in sample order — the reference's rounding sequence — and everything else stays zero:
+  // the per-GPU bucket buffers add up exactly.
   struct Chunk {
     uint32_t pixBase, nPix, sDone, K, stride;  // samples sDone, sDone + stride, ... (K of them) of the wave
   };
   std::vector<Chunk> chunks;
   const uint32_t cap = ctx->lanes[0].capacity;
-  const uint32_t B = std::min<uint32_t>(nPixCall, cap);
-  const uint32_t Kmax = std::max<uint32_t>(1u, cap / B);
-  for (uint32_t pixBase = 0; pixBase < nPixCall; pixBase += B) {
-    const uint32_t nPix = std::min(B, nPixCall - pixBase);
-    if (bucketShardCount <= 1) {
+  if (bucketShardCount <= 1) {
+    const uint32_t B = std::min<uint32_t>(nPixCall, cap);
+    const uint32_t Kmax = std::max<uint32_t>(1u, cap / B);
+    for (uint32_t pixBase = 0; pixBase < nPixCall; pixBase += B) {
+      const uint32_t nPix = std::min(B, nPixCall - pixBase);
       for (uint32_t sDone = 0; sDone < waveSamples;) {
         const uint32_t K = std::min(Kmax, waveSamples - sDone);
         chunks.push_back({pixBase, nPix, sDone, K, 1u});
         sDone += K;
       }
-    } else {
-      for (uint32_t b = bucketShard; b < m && b < waveSamples; b += bucketShardCount) {
-        const uint32_t nb = (waveSamples - b + m - 1) / m;  // samples of the wave that fall into bucket b
+    }
+  } else {
+    const uint32_t G = bucketShardCount;
+    for (uint32_t b = 0; b < m && b < waveSamples; b++) {
+      const uint32_t c = (bucketShard + G - b % G) % G;
+      const uint32_t p0 = uint32_t(uint64_t(c) * nPixCall / G), p1 = uint32_t(uint64_t(c + 1) * nPixCall / G);
+      if (p1 == p0) continue;
+      const uint32_t nb = (waveSamples - b + m - 1) / m;  // samples of the wave that fall into bucket b
+      const uint32_t B = std::min<uint32_t>(p1 - p0, cap);
+      const uint32_t Kmax = std::max<uint32_t>(1u, cap / B);
+      for (uint32_t pixBase = p0; pixBase < p1; pixBase += B) {
+        const uint32_t nPix = std::min(B, p1 - pixBase);
         for (uint32_t j = 0; j < nb;) {
           const uint32_t K = std::min(Kmax, nb - j);
           chunks.push_back({pixBase, nPix, b + j * m, K, m});
