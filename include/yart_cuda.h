@@ -344,6 +344,11 @@ typedef struct ys_scene ys_scene;
  * same steps gltf::load performs on the reference API (materials, meshes + SAH BVH, node tree,
  * lights).  Stands in for `gltf::load(path)` (src/gltf/gltf.cpp:319-358). */
 int ys_scene_load(const char* path, ys_scene** out);
+/* The same with Mesh::BVHType chosen (src/core/mesh.hpp:17): YS_BVH_SAH = SahBVH (what the reference instantiates,
+ * bvh.hpp:266-347), YS_BVH_MEDIAN_SPLIT = MedianSplitBVH (bvh.hpp:237-264, its baseline builder). */
+#define YS_BVH_SAH 0
+#define YS_BVH_MEDIAN_SPLIT 1
+int ys_scene_load_bvh(const char* path, uint32_t bvhKind, ys_scene** out);
 /* Environment map handed to the GLB entry points: main.cpp:81-84 adds an ImageInfiniteLight(sceneRadius,
  * &hdri) after gltf::load.  rgb = width*height*3 floats in octahedral layout; transform row-major 4x4. */
 typedef struct YsEnvLight {

@@ -409,8 +409,20 @@ static int cmdBvh(int argc, char** argv) {
   RefScene rs = buildScene(d);
   Writer out(argv[3]);
   out.put(uint32_t(rs.meshes.size()));
+  // kind=median: MedianSplitBVH (bvh.hpp:237-264) built over each mesh's data the way Mesh's constructor builds
+  // its BVHType (mesh.hpp:54-61: m_bvh.init(&m_vertices, &m_triangles, &m_centroids)); Mesh does not expose
+  // m_centroids, so they are recomputed with createTriangle's expression (primitives.hpp:46).
+  Args a(argc, argv, 4);
+  const bool median = a.str("kind", "sah") == "median";
   for (Mesh* m : rs.meshes) {
-    const BVH& bvh = m->bvh();
+    MedianSplitBVH medianBvh;
+    std::vector<float3> centroids;
+    if (median) {
+      for (const Triangle& t : m->triangles())
+        centroids.push_back((m->vertices()[t.i0] + m->vertices()[t.i1] + m->vertices()[t.i2]) / 3.0f);
+      medianBvh.init(&m->vertices(), &m->triangles(), &centroids);
+    }
+    const BVH& bvh = median ? static_cast<const BVH&>(medianBvh) : m->bvh();
     // nodes are allocated contiguously in creation order; highest reachable index + 1 = nodes used
     uint32_t maxIdx = 0;
     std::vector<uint32_t> stack{0};

@@ -86,6 +86,16 @@ NAIVE_RENDERS = [
 ]
 
 
+def median_bvhs():
+    """MedianSplitBVH (bvh.hpp:237-264) over the same meshes."""
+    for name, kw in [("cornell", {}), ("material_zoo", {}), ("soup", dict(n_tris=3000))]:
+        meshes = H.oracle_bvh(H.scene_file(name, **kw), kind="median")
+        np.savez_compressed(os.path.join(OUT, f"medianbvh_{name}.npz"), scene=name, kwargs=repr(kw),
+                            **{f"nodes{i}": m[0] for i, m in enumerate(meshes)},
+                            **{f"idx{i}": m[1] for i, m in enumerate(meshes)})
+        print("median bvh", name, [len(m[0]) for m in meshes])
+
+
 def naive_renders():
     for tag, name, kw, w, h, spp, first, mx, depth in NAIVE_RENDERS:
         sp, cam = H.scene_file(name, **kw), H.scene_camera(name, **kw)
@@ -122,6 +132,8 @@ def main():
         return naive_renders()
     if "--only-scramblers" in sys.argv:
         return scrambler_renders()
+    if "--only-median-bvh" in sys.argv:
+        return median_bvhs()
     only = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--only-kat=")]
     if only:  # regenerate single KAT fixtures: --only-kat=gmonb16
         for tag, kind, n, kw, scene in KATS:
@@ -161,6 +173,7 @@ def main():
                             **{f"nodes{i}": m[0] for i, m in enumerate(meshes)},
                             **{f"idx{i}": m[1] for i, m in enumerate(meshes)})
         print("bvh", name, [len(m[0]) for m in meshes])
+    median_bvhs()
     naive_renders()
     scrambler_renders()
 

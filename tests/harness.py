@@ -117,10 +117,10 @@ def oracle_render(scene: str, w: int, h: int, spp: int, cam: dict, binary=ORACLE
     return dict(hdr=hdr, ldr=ldr, rays=rays, ms=ms, threads=threads, build_ms=build_ms)
 
 
-def oracle_bvh(scene: str):
+def oracle_bvh(scene: str, kind: str = "sah"):
     with tempfile.TemporaryDirectory() as d:
         fout = os.path.join(d, "bvh.bin")
-        run_oracle("bvh", scene, fout)
+        run_oracle("bvh", scene, fout, f"kind={kind}")
         raw = open(fout, "rb").read()
     (n_meshes,) = struct.unpack_from("<I", raw, 0)
     off = 4

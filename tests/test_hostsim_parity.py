@@ -32,6 +32,35 @@ def test_bvh_builder_reproduces_reference_tree(path):
     assert i == sc.flat.nMeshes
 
 
+@pytest.mark.parametrize("path", PC.golden_files("medianbvh"), ids=os.path.basename)
+def test_median_split_builder_reproduces_reference_tree(path):
+    """YS_BVH_MEDIAN_SPLIT against MedianSplitBVH (bvh.hpp:237-264) built by the oracle over the same meshes; a render
+    through that tree must give the SAH tree's image (same triangles, same arithmetic per test; no ties in this scene)."""
+    g = PC.load(path)
+    name, kw = PC.scene_from_golden(g)
+    sc = Y.Scene(H.scene_file(name, **kw), bvh_kind=Y.BVH_MEDIAN_SPLIT)
+    i = 0
+    while f"nodes{i}" in g.files:
+        nodes, idx = sc.bvh(i)
+        assert nodes.tobytes() == g[f"nodes{i}"].tobytes(), f"{name} mesh {i}: nodes differ"
+        assert np.array_equal(idx, g[f"idx{i}"]), f"{name} mesh {i}: index permutation differs"
+        i += 1
+    assert i == sc.flat.nMeshes
+    if name == "cornell":
+        cam = H.scene_camera(name)
+        c = Y.make_camera(32, 32, cam["focal"], cam["fnum"], cam["pos"], cam["target"])
+        frames = []
+        for scene in (sc, Y.Scene(H.scene_file(name, **kw))):
+            ctx = Y.Context(max_depth=4)
+            ctx.upload_scene(scene)
+            ctx.set_camera(c)
+            ctx.begin_frame(32, 32, 4, 64, (0, 0, 0), Y.TONEMAP_AGX)
+            ctx.render_wave(0, 4, 0)
+            frames.append(ctx.resolve()[0])
+            ctx.close()
+        assert H.bits_equal(frames[0], frames[1]).all()
+
+
 @pytest.mark.parametrize("path", PC.golden_files("trace"), ids=os.path.basename)
 def test_trace_bit_exact(path):
     PC.check_trace(Y.Context, path)

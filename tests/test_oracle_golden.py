@@ -22,6 +22,7 @@ def test_golden_fixtures_present():
     assert len(PC.golden_files("bvh")) >= 3
     assert len(PC.golden_files("naive")) >= 3
     assert len(PC.golden_files("scrambler")) >= 4
+    assert len(PC.golden_files("medianbvh")) >= 3
 
 
 @needs_oracle

@@ -13,7 +13,7 @@ import ctypes as C
 import numpy as np
 
 from . import capi
-from .capi import (SCRAMBLER_FAST_OWEN, SCRAMBLER_OWEN, SCRAMBLER_BINARY_PERMUTE, INTEGRATOR_MIS, INTEGRATOR_NAIVE, ESTIMATOR_GMONB, ESTIMATOR_GMON, ESTIMATOR_MEAN, ESTIMATOR_MON, TONEMAP_AGX, TONEMAP_AGX_GOLDEN, TONEMAP_AGX_PUNCHY,
+from .capi import (BVH_SAH, BVH_MEDIAN_SPLIT, SCRAMBLER_FAST_OWEN, SCRAMBLER_OWEN, SCRAMBLER_BINARY_PERMUTE, INTEGRATOR_MIS, INTEGRATOR_NAIVE, ESTIMATOR_GMONB, ESTIMATOR_GMON, ESTIMATOR_MEAN, ESTIMATOR_MON, TONEMAP_AGX, TONEMAP_AGX_GOLDEN, TONEMAP_AGX_PUNCHY,
                    TONEMAP_NONE, TRACE_ANY, TRACE_CLOSEST, TRACE_COUNT, TRACE_USE_TMAX)
 
 _lib = None
@@ -88,15 +88,15 @@ def write_ppm(path: str, rgba: np.ndarray):
 class Scene:
     """yart::Scene built from a .ysc description or a binary glTF file (stands in for gltf::load)."""
 
-    def __init__(self, path: str, env=None, env_radius=100.0, env_transform=None):
+    def __init__(self, path: str, env=None, env_radius=100.0, env_transform=None, bvh_kind: int = capi.BVH_SAH):
         self._h = C.c_void_p()
         if path.lower().endswith(".glb"):
             e, keep = _env_struct(env, env_radius, env_transform)
             rc = lib().ys_scene_load_glb(path.encode(), C.byref(e) if e is not None else None, C.byref(self._h))
             _check(rc, f"ys_scene_load_glb({path})", lib().ys_last_error() or b"")
         else:
-            rc = lib().ys_scene_load(path.encode(), C.byref(self._h))
-            _check(rc, f"ys_scene_load({path})", lib().ys_last_error() or b"")
+            rc = lib().ys_scene_load_bvh(path.encode(), bvh_kind, C.byref(self._h))
+            _check(rc, f"ys_scene_load_bvh({path})", lib().ys_last_error() or b"")
         self.flat = lib().ys_scene_flat(self._h).contents
         self.build_ms = lib().ys_scene_build_ms(self._h)
 

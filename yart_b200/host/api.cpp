@@ -34,8 +34,11 @@ static thread_local std::string g_ysError;
 
 extern "C" const char* ys_last_error(void) { return g_ysError.c_str(); }
 
-extern "C" int ys_scene_load(const char* path, ys_scene** out) {
-  if (!path || !out) return YC_ERR_INVALID;
+extern "C" int ys_scene_load_bvh(const char* path, uint32_t bvhKind, ys_scene** out);
+extern "C" int ys_scene_load(const char* path, ys_scene** out) { return ys_scene_load_bvh(path, YS_BVH_SAH, out); }
+
+extern "C" int ys_scene_load_bvh(const char* path, uint32_t bvhKind, ys_scene** out) {
+  if (!path || !out || bvhKind > YS_BVH_MEDIAN_SPLIT) return YC_ERR_INVALID;
   *out = nullptr;
   ysc::SceneDesc d;
   std::string err;
@@ -45,6 +48,7 @@ extern "C" int ys_scene_load(const char* path, ys_scene** out) {
   }
   ys_scene* s = new (std::nothrow) ys_scene();
   if (!s) return YC_ERR_INVALID;
+  s->host.bvhKind = bvhKind;
   if (!s->host.build(d, &err)) {
     g_ysError = err;
     delete s;

@@ -34,6 +34,10 @@ class SahBvhBuilder {
  public:
   static constexpr uint32_t kMaxLeafSize = 20;  // MAX_LEAF_SIZE, bvh.hpp:14
   static constexpr uint32_t kBins = 20;         // nBins, bvh.hpp:283
+  // Mesh::BVHType (mesh.hpp:17): SahBVH is what the reference instantiates; MedianSplitBVH (bvh.hpp:237-264)
+  // is its baseline alternative — same init / subdivide, a different getSplit.
+  enum Kind : uint32_t { kSah = 0, kMedianSplit = 1 };
+  Kind kind = kSah;
 
   BvhBuildResult build(const float* positions, size_t nVerts, const uint32_t* faces /*stride 4*/, size_t nTris,
                        unsigned threads = 0) {
@@ -96,7 +100,21 @@ class SahBvhBuilder {
     return uint32_t(int64_t(x));
   }
 
+  // MedianSplitBVH::getSplit, bvh.hpp:239-263: longest axis of the centroid bounds, split in the middle
+  bool getSplitMedian(const TNode& node, uint8_t& axis, float& splitPos) const {
+    if (node.span <= 2) return false;
+    Bounds3 cb;
+    for (uint32_t i = node.first; i < node.first + node.span; i++) cb.expandToInclude(centroids_[idx_[i]]);
+    axis = 0;
+    const f3 size = cb.mx - cb.mn;
+    if (size[1] > size[0]) axis = 1;
+    if (size[2] > size[axis]) axis = 2;
+    splitPos = cb.mn[axis] + size[axis] * 0.5f;
+    return true;
+  }
+
   bool getSplit(const TNode& node, uint8_t& axis, float& splitPos) const {
+    if (kind == kMedianSplit) return getSplitMedian(node, axis, splitPos);
     float minCost = std::numeric_limits<float>::infinity();
     Bounds3 cb;
     for (uint32_t i = node.first; i < node.first + node.span; i++) cb.expandToInclude(centroids_[idx_[i]]);

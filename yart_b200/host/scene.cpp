@@ -145,6 +145,7 @@ bool HostScene::build(const ysc::SceneDesc& d, std::string* err) {
     meshVertexBounds.push_back(vb);
 
     SahBvhBuilder builder;
+    builder.kind = bvhKind == 1 ? SahBvhBuilder::kMedianSplit : SahBvhBuilder::kSah;
     BvhBuildResult ref = builder.build(m.positions.data(), nv, m.faces.data(), nf);
 
     // reference nodes → inner-node records with both children inlined; leaves → contiguous tri runs

@@ -44,6 +44,7 @@ struct HostScene {
   double buildMs = 0;
   YcScene flat{};
 
+  uint32_t bvhKind = 0;  // YS_BVH_* (Mesh::BVHType, mesh.hpp:17)
   bool build(const ysc::SceneDesc& d, std::string* err);
   bool loadLuts(std::string* err);
 };
