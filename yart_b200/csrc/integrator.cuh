@@ -201,16 +201,56 @@ YB_DEV void shadeMissStage(const DScene& sc, const WaveParams& w, const PathStat
   ps.L[i] = make_float4(L.x, L.y, L.z, 0.0f);
 }
 
+// Surface shading is cut in two so that each kernel's instruction footprint stays near the instruction cache
+// (one fused kernel touched 134 KB of SASS per launch and stalled on instruction fetch more than on anything else):
+//   shadeSurface  hit resolution, textures, the BSDF sample, emission MIS, throughput, next ray, Russian roulette
+//                 (mis-integrator.cpp:46-73, 83-102) — and, when the bounce takes a NEE sample, a NeeRecord;
+//   shadeNee      Ld up to the shadow ray (mis-integrator.cpp:79-80 → :111-124, 135-148) from that record.
+// The sampler dimensions of the NEE draws are reserved by shadeSurface (they precede the roulette draw), so both
+// halves draw exactly what the fused loop drew; L is only touched by shadeSurface (emission) and later by the shadow
+// stage, in the reference's order.
+struct NeeRecord {
+  V3 p, n, fx, fy;  // hit point, shading normal (= frame z), frame x / y
+  V3 woLocal, att;  // outgoing direction in the frame; path throughput before this bounce's update
+  MatEval me;       // material parameters with their textures applied
+  int32_t material;
+  uint32_t dim;     // sampler dimension of the first NEE draw
+};
+
+// SoA storage of NeeRecords, one slot per path slot (7 x float4 = 112 B).
+struct NeeState {
+  float4 *r0, *r1, *r2, *r3, *r4, *r5, *r6;
+};
+YB_DEV void storeNee(const NeeState& ns, uint32_t i, const NeeRecord& r) {
+  ns.r0[i] = make_float4(r.p.x, r.p.y, r.p.z, __uint_as_float(uint32_t(r.material)));
+  ns.r1[i] = make_float4(r.n.x, r.n.y, r.n.z, __uint_as_float(r.dim));
+  ns.r2[i] = make_float4(r.fx.x, r.fx.y, r.fx.z, r.me.r);
+  ns.r3[i] = make_float4(r.fy.x, r.fy.y, r.fy.z, r.me.m);
+  ns.r4[i] = make_float4(r.woLocal.x, r.woLocal.y, r.woLocal.z, r.me.t);
+  ns.r5[i] = make_float4(r.me.base.x, r.me.base.y, r.me.base.z, r.me.c);
+  ns.r6[i] = make_float4(r.att.x, r.att.y, r.att.z, r.me.cr);
+}
+YB_DEV NeeRecord loadNee(const NeeState& ns, uint32_t i) {
+  const float4 a = ns.r0[i], b = ns.r1[i], c = ns.r2[i], d = ns.r3[i], e = ns.r4[i], f = ns.r5[i], g = ns.r6[i];
+  NeeRecord r;
+  r.p = V3(a.x, a.y, a.z), r.material = int32_t(__float_as_uint(a.w));
+  r.n = V3(b.x, b.y, b.z), r.dim = __float_as_uint(b.w);
+  r.fx = V3(c.x, c.y, c.z), r.me.r = c.w;
+  r.fy = V3(d.x, d.y, d.z), r.me.m = d.w;
+  r.woLocal = V3(e.x, e.y, e.z), r.me.t = e.w;
+  r.me.base = V3(f.x, f.y, f.z), r.me.c = f.w;
+  r.att = V3(g.x, g.y, g.z), r.me.cr = g.w;
+  return r;
+}
+
+enum : uint32_t { kShadeNee = 4u };  // shadeSurface: `nee` was filled, run shadeNee on it
+
+// Returns kShadeContinue / kShadeNee bits.  DEFER_RR ⇔ scene has alpha.
 template <bool DEFER_RR>
-YB_DEV uint32_t shadeStage(const DScene& sc, const WaveParams& w, const PathState& ps, uint32_t i, ShadowRequest& rq,
-                           uint32_t& raysReference) {
-  const int32_t hb = ps.hitB[i];
-  if (hb == kHitDead) return 0u;
-  if (hb == kHitMiss) {
-    shadeMissStage(sc, w, ps, i, raysReference);
-    return 0u;
-  }
+YB_DEV uint32_t shadeSurface(const DScene& sc, const WaveParams& w, const PathState& ps, uint32_t i, NeeRecord& nee,
+                             uint32_t& raysReference) {
   raysReference += 1;  // mis-integrator.cpp:22
+  const int32_t hb = ps.hitB[i];
   const float4 ro4 = ps.rayO[i], rd4 = ps.rayD[i], L4 = ps.L[i], a4 = ps.att[i];
   const V3 rayO(ro4.x, ro4.y, ro4.z), rayD(rd4.x, rd4.y, rd4.z);
   float lastPdf = ro4.w, accRoughness = rd4.w;
@@ -257,30 +297,14 @@ YB_DEV uint32_t shadeStage(const DScene& sc, const WaveParams& w, const PathStat
 
   uint32_t result = 0u;
   if (res.is(Reflected | Transmitted)) {
-    // mis-integrator.cpp:79-80 → Ld, :111-133
+    // mis-integrator.cpp:79-80 → Ld: its three draws (get1D, get2D) come next in the sampler's order
     if (!res.is(Emitted | Specular) && sc.nLights != 0) {
-      const float ucl = smp.get1D();
-      const V2 ul = smp.get2D();
-      const PickedLight pick = pickLight(sc, ucl);
-      const YcLight& light = sc.lights[pick.index];
-      const LightSample ls = lightSample(sc, light, hit.p, ul);
-      const V3 wiLocal = fr.wtl(ls.wi);
-      const V3 f = bsdf.fImpl(woLocal, wiLocal, me);
-      if (length2(f) != 0.0f) {
-        // unoccluded(), :135-148
-        const V3 to = ls.p - hit.p;
-        rq.o = hit.p;
-        rq.d = normalized(to);
-        rq.tMax = length(to) - 0.001f;
-        const float pdfBSDF = bsdf.pdfImpl(woLocal, wiLocal, me);
-        float pdfLight = pick.p * ls.pdf / absDot(ls.n, ls.wi);
-        if (light.type == YC_LIGHT_AREA) pdfLight *= length2(hit.p - ls.p);
-        rq.lif = ls.Li * f;
-        rq.absDotN = absDot(ls.wi, hit.n);
-        rq.denom = pdfBSDF + pdfLight;
-        rq.att = att;
-        result |= kShadeShadow;
-      }
+      nee.p = hit.p, nee.n = hit.n, nee.fx = fr.x, nee.fy = fr.y;
+      nee.woLocal = woLocal, nee.att = att, nee.me = me;
+      nee.material = hit.material;
+      nee.dim = smp.dim;
+      smp.dim += 3;
+      result |= kShadeNee;
     }
     // mis-integrator.cpp:83-95
     const V3 fcos = res.f * absDot(res.wi, hit.n);
@@ -311,6 +335,51 @@ YB_DEV uint32_t shadeStage(const DScene& sc, const WaveParams& w, const PathStat
   ps.dim[i] = smp.dim;
   ps.L[i] = make_float4(L.x, L.y, L.z, 0.0f);
   return result;
+}
+
+// Ld (mis-integrator.cpp:111-133) up to the shadow ray.  Returns true when `rq` holds a request.
+YB_DEV bool shadeNee(const DScene& sc, const WaveParams& w, uint32_t i, const NeeRecord& nee, ShadowRequest& rq) {
+  const Bsdf bsdf(sc, sc.materials[nee.material]);
+  Frame fr;
+  fr.x = nee.fx, fr.y = nee.fy, fr.z = nee.n;
+  Sampler smp = pathSampler(w, i, nee.dim);
+  const float ucl = smp.get1D();
+  const V2 ul = smp.get2D();
+  const PickedLight pick = pickLight(sc, ucl);
+  const YcLight& light = sc.lights[pick.index];
+  const LightSample ls = lightSample(sc, light, nee.p, ul);
+  const V3 wiLocal = fr.wtl(ls.wi);
+  const V3 f = bsdf.fImpl(nee.woLocal, wiLocal, nee.me);
+  if (length2(f) == 0.0f) return false;
+  // unoccluded(), :135-148
+  const V3 to = ls.p - nee.p;
+  rq.o = nee.p;
+  rq.d = normalized(to);
+  rq.tMax = length(to) - 0.001f;
+  const float pdfBSDF = bsdf.pdfImpl(nee.woLocal, wiLocal, nee.me);
+  float pdfLight = pick.p * ls.pdf / absDot(ls.n, ls.wi);
+  if (light.type == YC_LIGHT_AREA) pdfLight *= length2(nee.p - ls.p);
+  rq.lif = ls.Li * f;
+  rq.absDotN = absDot(ls.wi, nee.n);
+  rq.denom = pdfBSDF + pdfLight;
+  rq.att = nee.att;
+  return true;
+}
+
+// Both halves back to back (the per-path tail kernel).  Returns kShade* bits; `rq` is filled when kShadeShadow is set.
+template <bool DEFER_RR>
+YB_DEV uint32_t shadeStage(const DScene& sc, const WaveParams& w, const PathState& ps, uint32_t i, ShadowRequest& rq,
+                           uint32_t& raysReference) {
+  const int32_t hb = ps.hitB[i];
+  if (hb == kHitDead) return 0u;
+  if (hb == kHitMiss) {
+    shadeMissStage(sc, w, ps, i, raysReference);
+    return 0u;
+  }
+  NeeRecord nee;
+  uint32_t result = shadeSurface<DEFER_RR>(sc, w, ps, i, nee, raysReference);
+  if ((result & kShadeNee) && shadeNee(sc, w, i, nee, rq)) result |= kShadeShadow;
+  return result & (kShadeContinue | kShadeShadow);
 }
 
 // ---- NaiveIntegrator ------------------------------------------------------------------

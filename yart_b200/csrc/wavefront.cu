@@ -41,7 +41,7 @@ using namespace yb;
 // context
 // ---------------------------------------------------------------------------------------
 enum { kCtrExtendHead = 0, kCtrNextCount = 1, kCtrShadowCount = 2, kCtrShadowHead = 3, kCtrHitCount = 4, kCtrMissCount = 5,
-       kCtrCount = 8 };
+       kCtrNeeCount = 6, kCtrCount = 8 };
 
 // Two chunks of a wave are in flight at a time, each on its own stream with its own path state: while one
 // chunk waits for the slowest ray of a traversal launch (a single ray with a zero direction component can walk
@@ -51,7 +51,8 @@ struct Lane {
   rt::Stream st;       // lane 0 shares the context's main stream
   PathState ps{};
   ShadowQueue sq{};
-  uint32_t *qA = nullptr, *qH = nullptr, *qM = nullptr, *ctr = nullptr;  // cur/next, hit, miss queues; counters
+  NeeState ns{};
+  uint32_t *qA = nullptr, *qH = nullptr, *qM = nullptr, *qN = nullptr, *ctr = nullptr;  // cur/next, hit, miss, NEE queues; counters
   uint32_t* hCtr = nullptr;  // page-locked copy of the counters
   void* spill = nullptr;     // traversal-stack spill area of the persistent kernels
   rt::Event evCtr, evAcc;
@@ -158,26 +159,47 @@ struct RaygenK {
 };
 
 // Surface shading over the HIT queue extend produced (count on the device: the launch is sized for the
-// upper bound and surplus threads leave at once).
+// upper bound and surplus threads leave at once), in two kernels (integrator.cuh: shadeSurface / shadeNee) so
+// that neither outgrows the instruction cache: the first appends the surviving paths to the next queue and the
+// paths that take a NEE sample, with their NeeRecord, to the NEE queue; the second turns NEE records into shadow
+// requests.
 template <bool DEFER_RR>
-struct ShadeK {
+struct ShadeSurfaceK {
   DScene sc;
   WaveParams w;
   PathState ps;
-  ShadowQueue sq;
+  NeeState ns;
   const uint32_t* queue;
-  uint32_t* nextQueue;
+  uint32_t *nextQueue, *neeQueue;
   uint32_t* ctr;
   Counters* counters;
   YB_DEV void operator()(uint32_t j) const {
     if (j >= ctr[kCtrHitCount]) return;
     const uint32_t i = queue[j];
-    ShadowRequest rq;
+    NeeRecord nee;
     uint32_t rays = 0;
-    const uint32_t r = shadeStage<DEFER_RR>(sc, w, ps, i, rq, rays);
+    const uint32_t r = shadeSurface<DEFER_RR>(sc, w, ps, i, nee, rays);
     aggregatedCount(&counters->raysReference, rays);
     if (r & kShadeContinue) nextQueue[aggregatedAppend(ctr + kCtrNextCount)] = i;
-    if (r & kShadeShadow) {
+    if (r & kShadeNee) {
+      storeNee(ns, i, nee);
+      neeQueue[aggregatedAppend(ctr + kCtrNeeCount)] = i;
+    }
+  }
+};
+
+struct ShadeNeeK {
+  DScene sc;
+  WaveParams w;
+  NeeState ns;
+  ShadowQueue sq;
+  const uint32_t* neeQueue;
+  uint32_t* ctr;
+  YB_DEV void operator()(uint32_t j) const {
+    if (j >= ctr[kCtrNeeCount]) return;
+    const uint32_t i = neeQueue[j];
+    ShadowRequest rq;
+    if (shadeNee(sc, w, i, loadNee(ns, i), rq)) {
       const uint32_t k = aggregatedAppend(ctr + kCtrShadowCount);
       sq.o[k] = make_float4(rq.o.x, rq.o.y, rq.o.z, rq.tMax);
       sq.d[k] = make_float4(rq.d.x, rq.d.y, rq.d.z, rq.absDotN);
@@ -674,6 +696,14 @@ static int ensureWaveStorage(yc_ctx* ctx) {
     YC_TRY(devAlloc(own, &L.qA, P));
     YC_TRY(devAlloc(own, &L.qH, P));
     YC_TRY(devAlloc(own, &L.qM, P));
+    YC_TRY(devAlloc(own, &L.qN, P));
+    YC_TRY(devAlloc(own, &L.ns.r0, P));
+    YC_TRY(devAlloc(own, &L.ns.r1, P));
+    YC_TRY(devAlloc(own, &L.ns.r2, P));
+    YC_TRY(devAlloc(own, &L.ns.r3, P));
+    YC_TRY(devAlloc(own, &L.ns.r4, P));
+    YC_TRY(devAlloc(own, &L.ns.r5, P));
+    YC_TRY(devAlloc(own, &L.ns.r6, P));
     YC_TRY(devAlloc(own, &L.ctr, size_t(kCtrCount)));
     YC_TRY(rt::zero(ctx->st, L.ctr, kCtrCount * sizeof(uint32_t)));
     void* hp = nullptr;
@@ -787,10 +817,11 @@ static int issueBounce(yc_ctx* ctx, Lane& L) {
   else runExtend<ALPHA, false>(ctx, L, n);
   rt::launchFor(L.st, n, SortK{L.ps, L.qA, L.qH, L.qM, L.ctr});
   rt::launchFor(L.st, n, ShadeMissK{ctx->ds, L.w, L.ps, L.qM, L.ctr, ctx->dCounters});
-  rt::launchFor<YB_SHADE_MIN_BLOCKS>(L.st, n, ShadeK<ALPHA>{ctx->ds, L.w, L.ps, L.sq, L.qH, L.qA, L.ctr, ctx->dCounters});
+  rt::launchFor<YB_SHADE_MIN_BLOCKS>(L.st, n, ShadeSurfaceK<ALPHA>{ctx->ds, L.w, L.ps, L.ns, L.qH, L.qA, L.qN, L.ctr, ctx->dCounters});
+  rt::launchFor<YB_SHADE_MIN_BLOCKS>(L.st, n, ShadeNeeK{ctx->ds, L.w, L.ns, L.sq, L.qN, L.ctr});
   if (ctx->countTraversal) runShadow<ALPHA, true>(ctx, L, n);
   else runShadow<ALPHA, false>(ctx, L, n);
-  ctx->launches += 5;
+  ctx->launches += 6;
   ctx->raysExtend += n;  // every queue entry is one closest-hit ray
   if (L.bounce + 1 < ctx->opts.maxDepth) {
     YC_TRY(rt::d2hAsync(L.st, L.hCtr, L.ctr, kCtrCount * sizeof(uint32_t)));
