@@ -31,6 +31,9 @@ extern "C" {
 #define YC_ERR_NO_DEVICE (-4) /* no usable CUDA device: there is NO CPU fallback */
 #define YC_ERR_STATE (-5)     /* call order violated (e.g. render_wave before begin_frame) */
 #define YC_ERR_IO (-6)
+#define YC_ERR_UNSUPPORTED (-7) /* a variant this build of the library folds away: every sampler / scrambler other than
+                                   YC_SAMPLER_SOBOL + YC_SCRAMBLER_FAST_OWEN needs libyart_b200_samplers.so (the same
+                                   sources built with -DYB_RNG_SAMPLERS, same ABI) */
 
 #define YC_MAX_NODE_DEPTH 16
 
@@ -200,6 +203,11 @@ typedef struct YcOptions {
   /* reserved2[0]: entries of the traversal kernels' shared-memory stack actually used (0 = default, all 25);
    * the rest goes to the global spill area.  Never changes results; tests shrink it to exercise the spill path. */
   uint32_t reserved2[1];
+  /* The `Sampler` template argument of TileRenderer (src/main.cpp:16): YC_SAMPLER_SOBOL = SobolSampler<R> with the
+   * scrambler above (the measured path), YC_SAMPLER_NAIVE = NaiveSampler, YC_SAMPLER_STRATIFIED = StratifiedSampler
+   * (src/core/sampler.cpp:5-50; xoshiro256++ seeded per pixel sample, re-derived per draw from the dimension). */
+  uint32_t sampler;
+  uint32_t reserved3[3];
 } YcOptions;
 
 #define YC_INTEGRATOR_MIS 0
@@ -207,6 +215,9 @@ typedef struct YcOptions {
 #define YC_SCRAMBLER_FAST_OWEN 0
 #define YC_SCRAMBLER_OWEN 1
 #define YC_SCRAMBLER_BINARY_PERMUTE 2
+#define YC_SAMPLER_SOBOL 0
+#define YC_SAMPLER_NAIVE 1
+#define YC_SAMPLER_STRATIFIED 2
 
 typedef struct YcRect { uint32_t x, y, w, h; } YcRect;
 
@@ -399,6 +410,7 @@ typedef struct YrSettings {
   int32_t device;
   uint32_t integrator; /* YC_INTEGRATOR_* */
   uint32_t scrambler;  /* YC_SCRAMBLER_* */
+  uint32_t sampler;    /* YC_SAMPLER_* */
 } YrSettings;
 
 typedef struct YrRenderData {  /* Renderer::RenderData (renderer.hpp:22-28) */

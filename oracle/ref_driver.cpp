@@ -252,6 +252,9 @@ static int cmdRender(int argc, char** argv) {
   Args a(argc, argv, 4);
   const std::string scr = a.str("scrambler", "fastowen");
   if (a.str("integrator", "mis") == "naive") return cmdRenderWith<DepthNaiveIntegrator, RefSampler>(argc, argv);
+  const std::string smp = a.str("sampler", "sobol");  // the `Sampler` template argument (src/main.cpp:16)
+  if (smp == "naive") return cmdRenderWith<DepthIntegrator, NaiveSampler>(argc, argv);
+  if (smp == "stratified") return cmdRenderWith<DepthIntegrator, StratifiedSampler>(argc, argv);
   if (scr == "owen") return cmdRenderWith<DepthIntegrator, SobolSampler<OwenScrambler>>(argc, argv);
   if (scr == "binary") return cmdRenderWith<DepthIntegrator, SobolSampler<BinaryPermuteScrambler>>(argc, argv);
   return cmdRenderWith<DepthIntegrator, RefSampler>(argc, argv);

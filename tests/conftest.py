@@ -31,3 +31,14 @@ def cuda_lib():
     lib = capi.load()  # raises if libyart_b200.so is not built
     yart_b200.use_library(lib)
     yield lib
+
+
+@pytest.fixture
+def cuda_samplers_lib():
+    """The YB_RNG_SAMPLERS build of the product library (NaiveSampler / StratifiedSampler compiled in)."""
+    import yart_b200
+    from yart_b200 import capi
+    lib = capi.load(capi.SAMPLERS_LIB)
+    yart_b200.use_library(lib)
+    yield lib
+    yart_b200.use_library(capi.load())

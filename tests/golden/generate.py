@@ -116,6 +116,25 @@ SCRAMBLER_RENDERS = [
 ]
 
 
+# TileRenderer<NaiveSampler | StratifiedSampler, MISIntegrator>
+SAMPLER_RENDERS = [
+    ("naive_cornell", "naive", "cornell", {}, 64, 64, 16, 16, 16, 6),
+    ("naive_zoo", "naive", "material_zoo", {}, 96, 54, 12, 4, 8, 8),
+    ("stratified_cornell", "stratified", "cornell", {}, 64, 64, 16, 16, 16, 6),
+    ("stratified_zoo", "stratified", "material_zoo", {}, 96, 54, 12, 4, 8, 8),
+]
+
+
+def sampler_renders():
+    for tag, smp, name, kw, w, h, spp, first, mx, depth in SAMPLER_RENDERS:
+        sp, cam = H.scene_file(name, **kw), H.scene_camera(name, **kw)
+        r = H.oracle_render(sp, w, h, spp, cam, first=first, max=mx, maxdepth=depth, tonemap="agx", threads=4, sampler=smp)
+        np.savez_compressed(os.path.join(OUT, f"sampler_{tag}.npz"), scene=name, kwargs=repr(kw),
+                            settings=np.array([w, h, spp, first, mx, depth]), tonemap="agx", hdr=r["hdr"], ldr=r["ldr"],
+                            rays=r["rays"], sampler=smp)
+        print("sampler render", tag, r["rays"])
+
+
 def scrambler_renders():
     for tag, scr, name, kw, w, h, spp, first, mx, depth in SCRAMBLER_RENDERS:
         sp, cam = H.scene_file(name, **kw), H.scene_camera(name, **kw)
@@ -132,6 +151,8 @@ def main():
         return naive_renders()
     if "--only-scramblers" in sys.argv:
         return scrambler_renders()
+    if "--only-samplers" in sys.argv:
+        return sampler_renders()
     if "--only-median-bvh" in sys.argv:
         return median_bvhs()
     only = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--only-kat=")]
@@ -176,6 +197,7 @@ def main():
     median_bvhs()
     naive_renders()
     scrambler_renders()
+    sampler_renders()
 
 
 if __name__ == "__main__":

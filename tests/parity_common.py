@@ -101,6 +101,8 @@ def render_golden(path, **renderer_kw):
                       cam.get("sides", 0))
     if "integrator" in g.files and str(g["integrator"]) == "naive":
         renderer_kw = dict(renderer_kw, integrator=Y.INTEGRATOR_NAIVE)
+    if "sampler" in g.files:
+        renderer_kw = dict(renderer_kw, sampler={"naive": Y.SAMPLER_NAIVE, "stratified": Y.SAMPLER_STRATIFIED}[str(g["sampler"])])
     if "scrambler" in g.files:
         renderer_kw = dict(renderer_kw, scrambler={"owen": Y.SCRAMBLER_OWEN, "binary": Y.SCRAMBLER_BINARY_PERMUTE}[str(g["scrambler"])])
     r = Y.Renderer(w, h, c, sc, samples=spp, first_wave_samples=first, max_wave_samples=mx, max_depth=depth,

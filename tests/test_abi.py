@@ -35,6 +35,13 @@ def test_product_library_exports_every_declared_symbol():
     assert not missing, f"declared in include/yart_cuda.h but not exported: {missing}"
 
 
+def test_samplers_build_exports_the_same_abi():
+    assert os.path.exists(capi.SAMPLERS_LIB), "libyart_b200_samplers.so not built: run __graft_entry__.build()"
+    lib = C.CDLL(capi.SAMPLERS_LIB)
+    missing = [f for f in declared_functions() if not hasattr(lib, f)]
+    assert not missing, f"declared in include/yart_cuda.h but not exported by the samplers build: {missing}"
+
+
 def test_python_prototypes_cover_the_header():
     assert sorted(capi.PROTOTYPES) == declared_functions()
     capi.load()  # binds restype/argtypes of all of them

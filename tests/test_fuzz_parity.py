@@ -14,7 +14,7 @@ TONEMAPS = ["agx", "golden", "punchy", "none"]
 TM = {"none": Y.TONEMAP_NONE, "agx": Y.TONEMAP_AGX, "golden": Y.TONEMAP_AGX_GOLDEN, "punchy": Y.TONEMAP_AGX_PUNCHY}
 
 
-def run_case(seed, integrator="mis", scrambler="fastowen"):
+def run_case(seed, integrator="mis", scrambler="fastowen", sampler="sobol"):
     sc_py = scenes.random_scene(seed)
     cam = sc_py.camera
     path = H.scene_file("random_scene", seed=seed)
@@ -24,13 +24,14 @@ def run_case(seed, integrator="mis", scrambler="fastowen"):
     tm = TONEMAPS[seed % 4]
     depth = 30 if seed % 5 else 3
     ref = H.oracle_render(path, w, h, spp, cam, first=first, max=mx, maxdepth=depth, tonemap=tm,
-                          bg="%g,%g,%g" % bg, tile=16 if seed % 2 else 64, integrator=integrator, scrambler=scrambler)
+                          bg="%g,%g,%g" % bg, tile=16 if seed % 2 else 64, integrator=integrator, scrambler=scrambler, sampler=sampler)
     s = Y.Scene(path)
     c = Y.make_camera(w, h, cam["focal"], cam["fnum"], cam["pos"], cam["target"], (0, 0, 0), cam["exposure"], cam["sides"])
     r = Y.Renderer(w, h, c, s, samples=spp, first_wave_samples=first, max_wave_samples=mx, max_depth=depth, background=bg,
                    tonemap=TM[tm], tile_size=16 if seed % 2 else 64,
                    integrator=Y.INTEGRATOR_NAIVE if integrator == "naive" else Y.INTEGRATOR_MIS,
-                   scrambler={"fastowen": Y.SCRAMBLER_FAST_OWEN, "owen": Y.SCRAMBLER_OWEN, "binary": Y.SCRAMBLER_BINARY_PERMUTE}[scrambler])
+                   scrambler={"fastowen": Y.SCRAMBLER_FAST_OWEN, "owen": Y.SCRAMBLER_OWEN, "binary": Y.SCRAMBLER_BINARY_PERMUTE}[scrambler],
+                   sampler={"sobol": Y.SAMPLER_SOBOL, "naive": Y.SAMPLER_NAIVE, "stratified": Y.SAMPLER_STRATIFIED}[sampler])
     d = r.render_sync()
     hdr, ldr, _ = r.read()
     r.close()
@@ -76,5 +77,18 @@ def test_random_scene_other_scramblers_bit_exact_hostsim(seed, hostsim_lib):
 @needs_oracle
 @pytest.mark.gpu
 @pytest.mark.parametrize("seed", range(206, 214))
-def test_random_scene_other_scramblers_bit_exact_cuda(seed, cuda_lib):
+def test_random_scene_other_scramblers_bit_exact_cuda(seed, cuda_samplers_lib):
     run_case(seed, scrambler="owen" if seed % 2 else "binary")
+
+
+@needs_oracle
+@pytest.mark.parametrize("seed", range(300, 306))
+def test_random_scene_rng_samplers_bit_exact_hostsim(seed, hostsim_lib):
+    run_case(seed, sampler="naive" if seed % 2 else "stratified")
+
+
+@needs_oracle
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(306, 314))
+def test_random_scene_rng_samplers_bit_exact_cuda(seed, cuda_samplers_lib):
+    run_case(seed, sampler="naive" if seed % 2 else "stratified")

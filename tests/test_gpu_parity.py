@@ -45,9 +45,23 @@ def test_naive_integrator_render(path):
 
 
 @pytest.mark.parametrize("path", PC.golden_files("scrambler"), ids=os.path.basename)
-def test_other_scramblers_render(path):
-    """YC_SCRAMBLER_OWEN / _BINARY_PERMUTE against TileRenderer<SobolSampler<R>, MISIntegrator> (relMSE < 1e-3, then bitwise)."""
+def test_other_scramblers_render(path, cuda_samplers_lib):
+    """YC_SCRAMBLER_OWEN / _BINARY_PERMUTE (libyart_b200_samplers.so) against TileRenderer<SobolSampler<R>, MISIntegrator> (relMSE < 1e-3, then bitwise)."""
     PC.check_render(path, exact=False)
+
+
+@pytest.mark.parametrize("path", PC.golden_files("sampler"), ids=os.path.basename)
+def test_rng_samplers_render(path, cuda_samplers_lib):
+    """YC_SAMPLER_NAIVE / _STRATIFIED (libyart_b200_samplers.so) against TileRenderer<NaiveSampler | StratifiedSampler,
+    MISIntegrator> (relMSE < 1e-3, then bitwise)."""
+    PC.check_render(path, exact=False)
+
+
+def test_default_library_refuses_rng_samplers_loudly():
+    with pytest.raises(Y.YartError, match="UNSUPPORTED"):
+        Y.Context(sampler=Y.SAMPLER_NAIVE)
+    with pytest.raises(Y.YartError, match="UNSUPPORTED"):
+        Y.Context(scrambler=Y.SCRAMBLER_OWEN)
 
 
 def test_render_is_deterministic_and_capacity_independent():

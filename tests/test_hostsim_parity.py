@@ -83,6 +83,13 @@ def test_other_scramblers_render_bit_exact(path):
     PC.check_render(path, exact=True)
 
 
+@pytest.mark.parametrize("path", PC.golden_files("sampler"), ids=os.path.basename)
+def test_rng_samplers_render_bit_exact(path):
+    """TileRenderer<NaiveSampler | StratifiedSampler, MISIntegrator> (sampler.cpp:5-50, xoshiro256++ + libstdc++'s
+    uniform_real_distribution<float>), progressive waves included."""
+    PC.check_render(path, exact=True)
+
+
 def test_small_wavefront_capacity_gives_same_image():
     """Chunking (pixel blocks x sample groups) must not change a single bit."""
     path = os.path.join(H.GOLDEN, "render_cornell_waves.npz")

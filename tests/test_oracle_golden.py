@@ -23,6 +23,7 @@ def test_golden_fixtures_present():
     assert len(PC.golden_files("naive")) >= 3
     assert len(PC.golden_files("scrambler")) >= 4
     assert len(PC.golden_files("medianbvh")) >= 3
+    assert len(PC.golden_files("sampler")) >= 4
 
 
 @needs_oracle
@@ -76,6 +77,18 @@ def test_oracle_reproduces_scrambler_render(path):
     w, h, spp, first, mx, depth = (int(v) for v in g["settings"])
     r = H.oracle_render(H.scene_file(name, **kw), w, h, spp, H.scene_camera(name, **kw), first=first, max=mx,
                         maxdepth=depth, tonemap=str(g["tonemap"]), threads=2, scrambler=str(g["scrambler"]))
+    assert r["rays"] == int(g["rays"])
+    assert H.bits_equal(r["hdr"], g["hdr"]).all() and H.bits_equal(r["ldr"], g["ldr"]).all()
+
+
+@needs_oracle
+@pytest.mark.parametrize("path", PC.golden_files("sampler"), ids=os.path.basename)
+def test_oracle_reproduces_rng_sampler_render(path):
+    g = PC.load(path)
+    name, kw = PC.scene_from_golden(g)
+    w, h, spp, first, mx, depth = (int(v) for v in g["settings"])
+    r = H.oracle_render(H.scene_file(name, **kw), w, h, spp, H.scene_camera(name, **kw), first=first, max=mx,
+                        maxdepth=depth, tonemap=str(g["tonemap"]), threads=2, sampler=str(g["sampler"]))
     assert r["rays"] == int(g["rays"])
     assert H.bits_equal(r["hdr"], g["hdr"]).all() and H.bits_equal(r["ldr"], g["ldr"]).all()
 

@@ -13,7 +13,7 @@ import ctypes as C
 import numpy as np
 
 from . import capi
-from .capi import (BVH_SAH, BVH_MEDIAN_SPLIT, SCRAMBLER_FAST_OWEN, SCRAMBLER_OWEN, SCRAMBLER_BINARY_PERMUTE, INTEGRATOR_MIS, INTEGRATOR_NAIVE, ESTIMATOR_GMONB, ESTIMATOR_GMON, ESTIMATOR_MEAN, ESTIMATOR_MON, TONEMAP_AGX, TONEMAP_AGX_GOLDEN, TONEMAP_AGX_PUNCHY,
+from .capi import (SAMPLER_SOBOL, SAMPLER_NAIVE, SAMPLER_STRATIFIED, BVH_SAH, BVH_MEDIAN_SPLIT, SCRAMBLER_FAST_OWEN, SCRAMBLER_OWEN, SCRAMBLER_BINARY_PERMUTE, INTEGRATOR_MIS, INTEGRATOR_NAIVE, ESTIMATOR_GMONB, ESTIMATOR_GMON, ESTIMATOR_MEAN, ESTIMATOR_MON, TONEMAP_AGX, TONEMAP_AGX_GOLDEN, TONEMAP_AGX_PUNCHY,
                    TONEMAP_NONE, TRACE_ANY, TRACE_CLOSEST, TRACE_COUNT, TRACE_USE_TMAX)
 
 _lib = None
@@ -39,7 +39,8 @@ class YartError(RuntimeError):
 
 def _check(rc, what, detail=b""):
     if rc != 0:
-        names = {-1: "INVALID", -2: "CUDA", -3: "NO_SCENE", -4: "NO_DEVICE", -5: "STATE", -6: "IO"}
+        names = {-1: "INVALID", -2: "CUDA", -3: "NO_SCENE", -4: "NO_DEVICE", -5: "STATE", -6: "IO",
+                 -7: "UNSUPPORTED (this build folds the variant away: load capi.SAMPLERS_LIB for the RNG samplers)"}
         msg = detail.decode() if isinstance(detail, bytes) else str(detail)
         raise YartError(f"{what} failed: YC_ERR_{names.get(rc, rc)} {msg}")
 
@@ -140,9 +141,11 @@ class Context:
 
     def __init__(self, device: int = 0, max_depth: int = 30, max_paths: int = 0, refill_min: int = 0, inner_min: int = 0,
                  tail_threshold: int = 0, integrator: int = capi.INTEGRATOR_MIS,
-                 scrambler: int = capi.SCRAMBLER_FAST_OWEN, sh_stack_entries: int = 0):
+                 scrambler: int = capi.SCRAMBLER_FAST_OWEN, sh_stack_entries: int = 0,
+                 sampler: int = capi.SAMPLER_SOBOL):
         self._h = C.c_void_p()
-        opts = capi.YcOptions(maxDepth=max_depth, maxPathsInFlight=max_paths, integrator=integrator, scrambler=scrambler)
+        opts = capi.YcOptions(maxDepth=max_depth, maxPathsInFlight=max_paths, integrator=integrator, scrambler=scrambler,
+                              sampler=sampler)
         opts.reserved[0], opts.reserved[1] = refill_min, inner_min  # traversal scheduling knobs (0 = default)
         opts.reserved[2] = 0xffffffff if tail_threshold < 0 else tail_threshold  # tail kernel hand-over (-1 = never)
         opts.reserved2[0] = sh_stack_entries  # shared traversal-stack entries in use (0 = default; small = spill-path test)
@@ -282,11 +285,11 @@ class Renderer:
     def __init__(self, width, height, camera: capi.YcCamera, scene: Scene | None = None, samples=64,
                  first_wave_samples=None, max_wave_samples=None, tile_size=64, max_depth=30, background=(0, 0, 0),
                  tonemap=TONEMAP_AGX, estimator=ESTIMATOR_GMON, shard_index=0, shard_count=1, device=0,
-                 integrator=capi.INTEGRATOR_MIS, scrambler=capi.SCRAMBLER_FAST_OWEN):
+                 integrator=capi.INTEGRATOR_MIS, scrambler=capi.SCRAMBLER_FAST_OWEN, sampler=capi.SAMPLER_SOBOL):
         # TileRenderer defaults: samples 64, firstWaveSamples 64, maxWaveSamples 128, tileSize 64 (:11-14)
         s = capi.YrSettings(width, height, samples, 64 if first_wave_samples is None else first_wave_samples,
                             128 if max_wave_samples is None else max_wave_samples, tile_size, max_depth,
-                            _f3(background), tonemap, estimator, shard_index, shard_count, device, integrator, scrambler)
+                            _f3(background), tonemap, estimator, shard_index, shard_count, device, integrator, scrambler, sampler)
         self.settings = s
         self.scene = scene
         self._h = C.c_void_p()

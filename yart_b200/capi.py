@@ -11,8 +11,12 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 PRODUCT_LIB = os.path.join(HERE, "libyart_b200.so")
+# the same sources built with -DYB_RNG_SAMPLERS: adds the Owen / BinaryPermute scramblers and YC_SAMPLER_NAIVE /
+# YC_SAMPLER_STRATIFIED (same C ABI)
+SAMPLERS_LIB = os.path.join(HERE, "libyart_b200_samplers.so")
 
 YC_OK, YC_ERR_INVALID, YC_ERR_CUDA, YC_ERR_NO_SCENE, YC_ERR_NO_DEVICE, YC_ERR_STATE, YC_ERR_IO = 0, -1, -2, -3, -4, -5, -6
+YC_ERR_UNSUPPORTED = -7
 TONEMAP_NONE, TONEMAP_AGX, TONEMAP_AGX_GOLDEN, TONEMAP_AGX_PUNCHY = 0, 1, 2, 3
 ESTIMATOR_GMON, ESTIMATOR_MON, ESTIMATOR_MEAN, ESTIMATOR_GMONB = 0, 1, 2, 3
 TRACE_CLOSEST, TRACE_ANY, TRACE_COUNT, TRACE_USE_TMAX = 0, 1, 16, 32
@@ -29,11 +33,12 @@ class YcCamera(C.Structure):
 BVH_SAH, BVH_MEDIAN_SPLIT = 0, 1
 INTEGRATOR_MIS, INTEGRATOR_NAIVE = 0, 1
 SCRAMBLER_FAST_OWEN, SCRAMBLER_OWEN, SCRAMBLER_BINARY_PERMUTE = 0, 1, 2
+SAMPLER_SOBOL, SAMPLER_NAIVE, SAMPLER_STRATIFIED = 0, 1, 2
 
 
 class YcOptions(C.Structure):
     _fields_ = [("maxDepth", u32), ("maxPathsInFlight", u32), ("reserved", u32 * 3), ("integrator", u32),
-                ("scrambler", u32), ("reserved2", u32 * 1)]
+                ("scrambler", u32), ("reserved2", u32 * 1), ("sampler", u32), ("reserved3", u32 * 3)]
 
 
 class YcRect(C.Structure):
@@ -83,7 +88,7 @@ class YcScene(C.Structure):
 class YrSettings(C.Structure):
     _fields_ = [("width", u32), ("height", u32), ("samples", u32), ("firstWaveSamples", u32), ("maxWaveSamples", u32),
                 ("tileSize", u32), ("maxDepth", u32), ("background", f32 * 3), ("tonemap", u32), ("estimator", u32),
-                ("shardIndex", u32), ("shardCount", u32), ("device", i32), ("integrator", u32), ("scrambler", u32)]
+                ("shardIndex", u32), ("shardCount", u32), ("device", i32), ("integrator", u32), ("scrambler", u32), ("sampler", u32)]
 
 
 class YrRenderData(C.Structure):

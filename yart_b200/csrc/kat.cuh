@@ -250,6 +250,8 @@ extern "C" int yc_kat(yc_ctx* ctx, const char* kind, const void* in, size_t inBy
       cfg.log2spp = log2IntU(hin[0]);
       cfg.nBase4Digits = 6 + (cfg.log2spp + 1) / 2;  // renderSize {64, 64}
       cfg.scrambler = ctx->opts.scrambler;
+      cfg.kind = ctx->opts.sampler;
+      cfg.strata = uint32_t(std::ceil(std::sqrt(double(hin[0]))));
       rt::launchFor(ctx->st, n, KatSampler{io, cfg});
     } else if (k == "lut") rt::launchFor(ctx->st, n, KatLut{io, ctx->ds.lut});
     else if (k == "ggx") rt::launchFor(ctx->st, n, KatGgx{io});

@@ -14,7 +14,15 @@ struct SamplerConfig {
   uint32_t log2spp;       // log2Int(float(totalSamples))
   uint32_t nBase4Digits;  // log2Int(roundUpPow2(tileSize)) + (log2spp + 1) / 2
   uint32_t scrambler;     // the R of SobolSampler<R>: 0 FastOwenScrambler (the measured path), 1 OwenScrambler, 2 BinaryPermuteScrambler
+  uint32_t kind;          // the `Sampler` template argument: 0 SobolSampler<R>, 1 NaiveSampler, 2 StratifiedSampler
+  uint32_t strata;        // StratifiedSampler: m_xSamples = m_ySamples = ceil(sqrt(samplesPerPixel)), sampler.hpp:49-51
+  // One word for the per-lane copy (the persistent traversal kernels of alpha-tested scenes keep a Sampler per lane):
+  // log2spp [0,6) | nBase4Digits [6,12) | scrambler [12,14) | kind [14,16) | strata [16,32)
+  YB_DEV uint32_t packed() const {
+    return log2spp | (nBase4Digits << 6) | (scrambler << 12) | (kind << 14) | (strata << 16);
+  }
 };
+enum : uint32_t { kSamplerSobol = 0, kSamplerNaive = 1, kSamplerStratified = 2 };
 enum : uint32_t { kScrambleFastOwen = 0, kScrambleOwen = 1, kScrambleBinaryPermute = 2 };
 
 // permutations[24][4], sampler.hpp:116-141 (the 24 permutations of {0,1,2,3} in the order the
@@ -110,26 +118,152 @@ YB_DEV uint32_t sobolDim1Closed(uint64_t d) {
   return reverseBits32(x);
 }
 
+// ---- NaiveSampler / StratifiedSampler (src/core/sampler.cpp:5-50) -------------------------------------------------
+// Both draw from an xoshiro256++ generator seeded per pixel sample with hash(pixel, sample) and advance it once per
+// 1-D value.  The path state carries no generator: the stream position equals the sampler dimension (1 per get1D,
+// 2 per get2D, exactly the number of uniform() calls so far), so a draw re-seeds and skips `dim` outputs.  Off the
+// measured path, kept out of line.
+
+// hash(uint2 p, uint32_t v): MurmurHash64A over 12 bytes, seed 0 (rng.hpp:25-91): one 8-byte block, a 4-byte tail
+YB_DEV uint64_t hashPixel(uint32_t px, uint32_t py, uint32_t v) {
+  const uint64_t m = 0xc6a4a7935bd1e995ull;
+  uint64_t h = 12ull * m;
+  uint64_t k = uint64_t(px) | (uint64_t(py) << 32);
+  k *= m;
+  k ^= k >> 47;
+  k *= m;
+  h ^= k;
+  h *= m;
+  h ^= uint64_t(v);
+  h *= m;
+  h ^= h >> 47;
+  h *= m;
+  h ^= h >> 47;
+  return h;
+}
+
+// xoshiro-rng/xoshiro.hpp:119-124
+YB_DEV uint64_t splitmix64(uint64_t seed) {
+  uint64_t z = seed + 0x9e3779b97f4a7c15ull;
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  return z ^ (z >> 31);
+}
+
+// Xoshiro::Xoshiro256PP (xoshiro.hpp:136-214) + RNG::uniform (rng.cpp:7-9): std::uniform_real_distribution<float>
+// over a 64-bit generator is libstdc++'s generate_canonical<float, 24>: ONE draw, float(u64) / 2^64 (the conversion
+// rounds to nearest, so it can reach 1), and a result >= 1 is replaced by nextafter(1, 0).
+struct Xoshiro256pp {
+  uint64_t s0, s1, s2, s3;
+  YB_DEV void seed(uint64_t v) {
+    s0 = splitmix64(splitmix64(v));
+    s1 = splitmix64(s0);
+    s2 = splitmix64(s1);
+    s3 = splitmix64(s2);
+  }
+  static YB_DEV uint64_t rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+  YB_DEV uint64_t next() {
+    const uint64_t result = rotl(s0 + s3, 23) + s0;
+    const uint64_t t = s1 << 17;
+    s2 ^= s0;
+    s3 ^= s1;
+    s1 ^= s2;
+    s0 ^= s3;
+    s2 ^= t;
+    s3 = rotl(s3, 45);
+    return result;
+  }
+  YB_DEV float uniform() {
+    const float r = float(next()) * 0x1p-64f;
+    return r >= 1.0f ? 0x1.fffffep-1f : r;
+  }
+};
+
+// rng.hpp:103-133
+YB_DEV uint32_t permel(uint32_t i, uint32_t l, uint32_t p) {
+  uint32_t w = l - 1;
+  w |= w >> 1;
+  w |= w >> 2;
+  w |= w >> 4;
+  w |= w >> 8;
+  w |= w >> 16;
+  do {
+    i ^= p;
+    i *= 0xe170893du;
+    i ^= p >> 16;
+    i ^= (i & w) >> 4;
+    i ^= p >> 8;
+    i *= 0x0929eb3fu;
+    i ^= p >> 23;
+    i ^= (i & w) >> 1;
+    i *= 1u | p >> 27;
+    i *= 0x6935fa69u;
+    i ^= (i & w) >> 11;
+    i *= 0x74dcb303u;
+    i ^= (i & w) >> 2;
+    i *= 0x9e501cc3u;
+    i ^= (i & w) >> 2;
+    i *= 0xc860a3dfu;
+    i &= w;
+    i ^= i >> 5;
+  } while (i >= l);
+  return (i + p) % l;
+}
+
+// One get1D (two = false) or get2D of the RNG-based samplers at stream position `dim` of pixel sample (px, py, sample).
+YB_DEV_NI V2 rngSamplerDraw(uint32_t px, uint32_t py, uint32_t sample, uint32_t dim, uint32_t kind, uint32_t strata, bool two) {
+  Xoshiro256pp rng;
+  rng.seed(hashPixel(px, py, sample));  // startPixelSample, sampler.cpp:5-7 / 21-26
+  for (uint32_t k = 0; k < dim; k++) rng.next();
+  const float d0 = rng.uniform();
+  const float d1 = two ? rng.uniform() : 0.0f;
+  if (kind == kSamplerNaive) return V2(d0, d1);  // sampler.cpp:9-15
+  // StratifiedSampler, sampler.cpp:28-46
+  const uint32_t n = strata * strata;
+  const uint32_t stratum = permel(sample, n, uint32_t(hashPixel(px, py, dim)));
+  if (!two) return V2((float(stratum) + d0) / float(n), 0.0f);
+  const uint32_t x = stratum % strata, y = stratum / strata;
+  return V2((float(x) + d0) / float(strata), (float(y) + d1) / float(strata));
+}
+
 struct Sampler {
   uint64_t morton;
   uint32_t dim;
-  uint32_t log2spp, nBase4Digits, scrambler;
+  uint32_t cfg;  // SamplerConfig::packed()
+  YB_DEV uint32_t log2spp() const { return cfg & 63u; }
+  YB_DEV uint32_t nBase4Digits() const { return (cfg >> 6) & 63u; }
+  // Every `Sampler` template argument other than SobolSampler<FastOwenScrambler> (the Owen / BinaryPermute scramblers,
+  // NaiveSampler, StratifiedSampler) lives in the YB_RNG_SAMPLERS build of the library (libyart_b200_samplers.so,
+  // same ABI): in the default build kind() and scrambler() are constants and every branch on them folds away —
+  // measured, even a never-taken call or an inlined cold path in the persistent traversal kernels of alpha-tested
+  // scenes costs 4-11 % of a Sponza-shaped step (the scrambler switch alone 1-2 % of a McLaren-shaped one).
+#ifdef YB_RNG_SAMPLERS
+  YB_DEV uint32_t kind() const { return (cfg >> 14) & 3u; }
+  YB_DEV uint32_t scrambler() const { return (cfg >> 12) & 3u; }
+#else
+  YB_DEV uint32_t kind() const { return kSamplerSobol; }
+  YB_DEV uint32_t scrambler() const { return kScrambleFastOwen; }
+#endif
+  YB_DEV uint32_t strata() const { return cfg >> 16; }
 
   YB_DEV void start(const SamplerConfig& c, uint32_t px, uint32_t py, uint32_t sample) {
-    log2spp = c.log2spp;
-    nBase4Digits = c.nBase4Digits;
-    scrambler = c.scrambler;
+    cfg = c.packed();
     dim = 0;
-    morton = (encodeMorton2(px, py) << log2spp) | uint64_t(sample);  // sampler.hpp:84-87
+    if (kind() == kSamplerSobol) morton = (encodeMorton2(px, py) << c.log2spp) | uint64_t(sample);  // sampler.hpp:84-87
+    else morton = (uint64_t(px | (py << 16)) << 32) | uint64_t(sample);  // RNG samplers: the pixel sample itself
+  }
+  YB_DEV V2 drawOther(bool two) const {
+    const uint32_t pix = uint32_t(morton >> 32);
+    return rngSamplerDraw(pix & 0xffffu, pix >> 16, uint32_t(morton), dim, kind(), strata(), two);
   }
 
   // sampler.hpp:155-173
   YB_DEV uint64_t sampleIndex() const {
     uint64_t index = 0;
-    const bool pow2Samples = log2spp & 1u;
+    const bool pow2Samples = log2spp() & 1u;
     const int lastDigit = pow2Samples ? 1 : 0;
     const uint64_t dimMix = uint64_t(0x55555555u * dim);
-    for (int i = int(nBase4Digits) - 1; i >= lastDigit; i--) {
+    for (int i = int(nBase4Digits()) - 1; i >= lastDigit; i--) {
       uint32_t digitShift = 2 * i - lastDigit;
       uint32_t digit = uint32_t(morton >> digitShift) & 3u;
       uint64_t higherDigits = morton >> (digitShift + 2);
@@ -148,13 +282,18 @@ struct Sampler {
 
   // sampler.hpp:143-153, dimension 0: v = reverseBits32(uint32(d))
   YB_DEV float finish(uint32_t v, uint32_t seed) const {
-    v = scrambler == kScrambleFastOwen ? fastOwen(v, seed) : scrambleOther(v, seed, scrambler);
+    v = scrambler() == kScrambleFastOwen ? fastOwen(v, seed) : scrambleOther(v, seed, scrambler());
     return fminf(float(v) * 0x1p-32f, 0x1.fffffep-1f);
   }
   static YB_DEV uint32_t sobolDim1(uint64_t d) { return sobolDim1Closed(d); }
 
   // sampler.hpp:89-94: index uses the CURRENT dim, the hash the incremented one
   YB_DEV float get1D() {
+    if (kind() != kSamplerSobol) {
+      const V2 r = drawOther(false);
+      dim++;
+      return r.x;
+    }
     uint64_t idx = sampleIndex();
     dim++;
     uint32_t h = uint32_t(hashDim(dim));
@@ -163,6 +302,11 @@ struct Sampler {
 
   // sampler.hpp:96-107
   YB_DEV V2 get2D() {
+    if (kind() != kSamplerSobol) {
+      const V2 r = drawOther(true);
+      dim += 2;
+      return r;
+    }
     uint64_t idx = sampleIndex();
     dim += 2;
     uint64_t hb = hashDim(dim);

@@ -534,10 +534,18 @@ extern "C" int yc_create(int device, const YcOptions* opts, yc_ctx** out) {
   if (opts) ctx->opts = *opts;
   if (ctx->opts.maxDepth == 0) ctx->opts.maxDepth = 30;  // RayIntegrator::m_maxDepth, ray-integrator.hpp:14
   if (ctx->opts.integrator > YC_INTEGRATOR_NAIVE || ctx->opts.scrambler > YC_SCRAMBLER_BINARY_PERMUTE ||
+      ctx->opts.sampler > YC_SAMPLER_STRATIFIED ||
       (ctx->opts.integrator == YC_INTEGRATOR_NAIVE && ctx->opts.maxDepth + 1 > kNaiveMaxSegments)) {
     delete ctx;
     return YC_ERR_INVALID;
   }
+#ifndef YB_RNG_SAMPLERS
+  if (ctx->opts.sampler != YC_SAMPLER_SOBOL || ctx->opts.scrambler != YC_SCRAMBLER_FAST_OWEN) {
+    // this build folds the sampler choice away (sampler.cuh); the other samplers are in libyart_b200_samplers.so
+    delete ctx;
+    return YC_ERR_UNSUPPORTED;
+  }
+#endif
   ctx->capacity = ctx->opts.maxPathsInFlight ? ctx->opts.maxPathsInFlight : (8u << 20);
   if (ctx->opts.reserved[2]) ctx->tailThreshold = ctx->opts.reserved[2] == 0xffffffffu ? 0u : ctx->opts.reserved[2];
   ctx->device = device;
@@ -844,6 +852,8 @@ static int renderChunks(yc_ctx* ctx, const uint32_t* dList, uint32_t nPixCall, u
   w.smp.log2spp = log2IntU(f.totalSamples);
   w.smp.nBase4Digits = log2IntU(roundUpPow2(f.tileSize)) + (w.smp.log2spp + 1) / 2;
   w.smp.scrambler = ctx->opts.scrambler;
+  w.smp.kind = ctx->opts.sampler;
+  w.smp.strata = uint32_t(std::ceil(std::sqrt(double(f.totalSamples))));  // StratifiedSampler ctor, sampler.hpp:49-51
   memcpy(w.bg, f.background, sizeof w.bg);
   w.maxDepth = ctx->opts.maxDepth;
   w.pixelList = dList;
@@ -1166,6 +1176,8 @@ YB_DEV Sampler traceHookSampler() {
   c.log2spp = 4;
   c.nBase4Digits = 6 + 2;
   c.scrambler = kScrambleFastOwen;
+  c.kind = kSamplerSobol;
+  c.strata = 4;
   Sampler s;
   s.start(c, 0, 0, 0);
   return s;
@@ -1417,6 +1429,8 @@ extern "C" int yc_generate_primary_rays(yc_ctx* ctx, uint32_t sampleOffset, uint
   w.smp.log2spp = log2IntU(f.totalSamples);
   w.smp.nBase4Digits = log2IntU(roundUpPow2(f.tileSize)) + (w.smp.log2spp + 1) / 2;
   w.smp.scrambler = ctx->opts.scrambler;
+  w.smp.kind = ctx->opts.sampler;
+  w.smp.strata = uint32_t(std::ceil(std::sqrt(double(f.totalSamples))));  // StratifiedSampler ctor, sampler.hpp:49-51
   w.pixelList = ctx->dPixels;
   w.pixBase = 0, w.nPix = uint32_t(ctx->pixels.size()), w.s0 = sampleOffset;
   const uint64_t n = uint64_t(w.nPix) * spp;
