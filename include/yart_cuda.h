@@ -207,6 +207,8 @@ typedef struct YcOptions {
    * scrambler above (the measured path), YC_SAMPLER_NAIVE = NaiveSampler, YC_SAMPLER_STRATIFIED = StratifiedSampler
    * (src/core/sampler.cpp:5-50; xoshiro256++ seeded per pixel sample, re-derived per draw from the dimension). */
   uint32_t sampler;
+  /* reserved3[0]: YC_LIGHT_SAMPLER_* — the m_lightSampler member of MISIntegrator (mis-integrator.hpp:20 hard-codes
+   * PowerLightSampler; UniformLightSampler, light-sampler.cpp:11-31, is its alternative; variants build only). */
   uint32_t reserved3[3];
 } YcOptions;
 
@@ -215,6 +217,8 @@ typedef struct YcOptions {
 #define YC_SCRAMBLER_FAST_OWEN 0
 #define YC_SCRAMBLER_OWEN 1
 #define YC_SCRAMBLER_BINARY_PERMUTE 2
+#define YC_LIGHT_SAMPLER_POWER 0
+#define YC_LIGHT_SAMPLER_UNIFORM 1
 #define YC_SAMPLER_SOBOL 0
 #define YC_SAMPLER_NAIVE 1
 #define YC_SAMPLER_STRATIFIED 2

@@ -608,6 +608,28 @@ static int cmdKat(int argc, char** argv) {
       out.f3(m.getValue());
       out.f3(mean.getValue());
     }
+  } else if (kind == "lightuniform") {
+    // argv[5] = scene.ysc.  in: as "light".  out: n×{picked(i32) pPick pOf(light)}  (UniformLightSampler, light-sampler.cpp:11-31)
+    if (argc < 6) return 1;
+    ysc::SceneDesc d;
+    if (!ysc::load(argv[5], d)) return 2;
+    RefScene rs = buildScene(d);
+    UniformLightSampler ls;
+    ls.init(rs.scene.get());
+    std::map<const Light*, int> lidx;
+    for (size_t i = 0; i < rs.scene->nLights(); i++) lidx[&rs.scene->light(i)] = int(i);
+    uint32_t n = u32();
+    for (uint32_t i = 0; i < n; i++) {
+      uint32_t li = u32();
+      float3 pp = v3(), nn = v3();
+      v2();
+      v3();
+      float uc = f32();
+      SampledLight sl = ls.sample(pp, nn, uc);
+      out.put(int32_t(lidx[&sl.light]));
+      out.put(sl.p);
+      out.put(ls.p(pp, nn, li));
+    }
   } else if (kind == "gmonb") {
     // in: as "gmon".  out: npix×gmonb[3]  (GMoNbEstimator, src/core/estimator.hpp:94-141)
     uint32_t n = u32(), npix = u32();

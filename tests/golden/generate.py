@@ -86,6 +86,15 @@ NAIVE_RENDERS = [
 ]
 
 
+def variant_kats():
+    """KATs of code that only the variants build carries (libyart_b200_samplers.so / hostsim): UniformLightSampler."""
+    blob = H.kat_input("lightuniform", 2048, **dict(n_lights=6))
+    out = H.oracle_kat("lightuniform", blob, H.scene_file("material_zoo"))
+    np.savez_compressed(os.path.join(OUT, "variantkat_lightuniform.npz"), kind="lightuniform", scene="material_zoo",
+                        blob=np.frombuffer(blob, np.uint8), out=out)
+    print("variant kat lightuniform", out.size)
+
+
 def median_bvhs():
     """MedianSplitBVH (bvh.hpp:237-264) over the same meshes."""
     for name, kw in [("cornell", {}), ("material_zoo", {}), ("soup", dict(n_tris=3000))]:
@@ -155,6 +164,8 @@ def main():
         return sampler_renders()
     if "--only-median-bvh" in sys.argv:
         return median_bvhs()
+    if "--only-variant-kats" in sys.argv:
+        return variant_kats()
     only = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--only-kat=")]
     if only:  # regenerate single KAT fixtures: --only-kat=gmonb16
         for tag, kind, n, kw, scene in KATS:
@@ -195,6 +206,7 @@ def main():
                             **{f"idx{i}": m[1] for i, m in enumerate(meshes)})
         print("bvh", name, [len(m[0]) for m in meshes])
     median_bvhs()
+    variant_kats()
     naive_renders()
     scrambler_renders()
     sampler_renders()

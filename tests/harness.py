@@ -187,7 +187,7 @@ def kat_input(kind: str, n: int = 256, seed: int = 7, **kw) -> bytes:
             out += struct.pack("<I", int(rng.integers(0, 2)))
             out += struct.pack("<ff", 1.0 if rng.uniform() < 0.5 else -1.0, float(rng.uniform(0, 5)))
         return bytes(out)
-    if kind == "light":
+    if kind in ("light", "lightuniform"):
         n_lights = kw["n_lights"]
         out = bytearray(struct.pack("<I", n))
         p = rng.uniform(-4, 4, (n, 3)).astype(np.float32)
@@ -231,7 +231,7 @@ def kat_input(kind: str, n: int = 256, seed: int = 7, **kw) -> bytes:
     raise KeyError(kind)
 
 
-KAT_OUT_WORDS = dict(sampler=8, lut=8, ggx=8, bsdf=27, light=22, gmon=9, gmonb=3, agx=3, camera=6, texture=4)
+KAT_OUT_WORDS = dict(sampler=8, lut=8, ggx=8, bsdf=27, light=22, gmon=9, gmonb=3, lightuniform=3, agx=3, camera=6, texture=4)
 
 
 def kat_count(kind: str, blob: bytes) -> int:

@@ -57,11 +57,39 @@ def test_rng_samplers_render(path, cuda_samplers_lib):
     PC.check_render(path, exact=False)
 
 
+@pytest.mark.parametrize("path", PC.golden_files("variantkat"), ids=os.path.basename)
+def test_variant_kat(path, cuda_samplers_lib):
+    PC.check_kat(Y.Context, path, exact=True)
+
+
+def test_uniform_light_sampler_renders_and_differs_only_in_noise(cuda_samplers_lib):
+    """No frame of the reference exists for UniformLightSampler (MISIntegrator hard-codes PowerLightSampler); the
+    render must run, stay finite, and agree with the power sampler's image on average (both are unbiased)."""
+    name = "material_zoo"
+    cam = H.scene_camera(name)
+    sc = Y.Scene(H.scene_file(name))
+    c = Y.make_camera(96, 54, cam["focal"], cam["fnum"], cam["pos"], cam["target"], (0, 0, 0), cam["exposure"])
+    means = []
+    for ls in (Y.LIGHT_SAMPLER_POWER, Y.LIGHT_SAMPLER_UNIFORM):
+        ctx = Y.Context(max_depth=6, light_sampler=ls)
+        ctx.upload_scene(sc)
+        ctx.set_camera(c)
+        ctx.begin_frame(96, 54, 64, 64, (0, 0, 0), Y.TONEMAP_AGX, estimator=Y.ESTIMATOR_MEAN)
+        ctx.render_wave(0, 64, 0)
+        hdr, _, _ = ctx.resolve()
+        assert np.isfinite(hdr).all()
+        means.append(hdr[..., :3].mean())
+        ctx.close()
+    assert abs(means[0] - means[1]) < 0.1 * means[0]
+
+
 def test_default_library_refuses_rng_samplers_loudly():
     with pytest.raises(Y.YartError, match="UNSUPPORTED"):
         Y.Context(sampler=Y.SAMPLER_NAIVE)
     with pytest.raises(Y.YartError, match="UNSUPPORTED"):
         Y.Context(scrambler=Y.SCRAMBLER_OWEN)
+    with pytest.raises(Y.YartError, match="UNSUPPORTED"):
+        Y.Context(light_sampler=Y.LIGHT_SAMPLER_UNIFORM)
 
 
 def test_render_is_deterministic_and_capacity_independent():

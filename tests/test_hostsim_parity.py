@@ -32,6 +32,12 @@ def test_bvh_builder_reproduces_reference_tree(path):
     assert i == sc.flat.nMeshes
 
 
+@pytest.mark.parametrize("path", PC.golden_files("variantkat"), ids=os.path.basename)
+def test_variant_kat_bit_exact(path):
+    """UniformLightSampler (light-sampler.cpp:11-31) against the reference's class."""
+    PC.check_kat(Y.Context, path, exact=True)
+
+
 @pytest.mark.parametrize("path", PC.golden_files("medianbvh"), ids=os.path.basename)
 def test_median_split_builder_reproduces_reference_tree(path):
     """YS_BVH_MEDIAN_SPLIT against MedianSplitBVH (bvh.hpp:237-264) built by the oracle over the same meshes; a render

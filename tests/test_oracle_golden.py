@@ -36,6 +36,14 @@ def test_oracle_reproduces_kat(path):
 
 
 @needs_oracle
+@pytest.mark.parametrize("path", PC.golden_files("variantkat"), ids=os.path.basename)
+def test_oracle_reproduces_variant_kat(path):
+    g = PC.load(path)
+    out = H.oracle_kat(str(g["kind"]), g["blob"].tobytes(), H.scene_file(str(g["scene"])))
+    assert H.bits_equal(out, g["out"]).all()
+
+
+@needs_oracle
 @pytest.mark.parametrize("path", PC.golden_files("trace"), ids=os.path.basename)
 def test_oracle_reproduces_trace(path):
     g = PC.load(path)

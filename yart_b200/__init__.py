@@ -13,7 +13,7 @@ import ctypes as C
 import numpy as np
 
 from . import capi
-from .capi import (SAMPLER_SOBOL, SAMPLER_NAIVE, SAMPLER_STRATIFIED, BVH_SAH, BVH_MEDIAN_SPLIT, SCRAMBLER_FAST_OWEN, SCRAMBLER_OWEN, SCRAMBLER_BINARY_PERMUTE, INTEGRATOR_MIS, INTEGRATOR_NAIVE, ESTIMATOR_GMONB, ESTIMATOR_GMON, ESTIMATOR_MEAN, ESTIMATOR_MON, TONEMAP_AGX, TONEMAP_AGX_GOLDEN, TONEMAP_AGX_PUNCHY,
+from .capi import (LIGHT_SAMPLER_POWER, LIGHT_SAMPLER_UNIFORM, SAMPLER_SOBOL, SAMPLER_NAIVE, SAMPLER_STRATIFIED, BVH_SAH, BVH_MEDIAN_SPLIT, SCRAMBLER_FAST_OWEN, SCRAMBLER_OWEN, SCRAMBLER_BINARY_PERMUTE, INTEGRATOR_MIS, INTEGRATOR_NAIVE, ESTIMATOR_GMONB, ESTIMATOR_GMON, ESTIMATOR_MEAN, ESTIMATOR_MON, TONEMAP_AGX, TONEMAP_AGX_GOLDEN, TONEMAP_AGX_PUNCHY,
                    TONEMAP_NONE, TRACE_ANY, TRACE_CLOSEST, TRACE_COUNT, TRACE_USE_TMAX)
 
 _lib = None
@@ -142,12 +142,13 @@ class Context:
     def __init__(self, device: int = 0, max_depth: int = 30, max_paths: int = 0, refill_min: int = 0, inner_min: int = 0,
                  tail_threshold: int = 0, integrator: int = capi.INTEGRATOR_MIS,
                  scrambler: int = capi.SCRAMBLER_FAST_OWEN, sh_stack_entries: int = 0,
-                 sampler: int = capi.SAMPLER_SOBOL):
+                 sampler: int = capi.SAMPLER_SOBOL, light_sampler: int = capi.LIGHT_SAMPLER_POWER):
         self._h = C.c_void_p()
         opts = capi.YcOptions(maxDepth=max_depth, maxPathsInFlight=max_paths, integrator=integrator, scrambler=scrambler,
                               sampler=sampler)
         opts.reserved[0], opts.reserved[1] = refill_min, inner_min  # traversal scheduling knobs (0 = default)
         opts.reserved[2] = 0xffffffff if tail_threshold < 0 else tail_threshold  # tail kernel hand-over (-1 = never)
+        opts.reserved3[0] = light_sampler
         opts.reserved2[0] = sh_stack_entries  # shared traversal-stack entries in use (0 = default; small = spill-path test)
         _check(lib().yc_create(device, C.byref(opts), C.byref(self._h)), "yc_create",
                b"(no usable CUDA device: yart_b200 has no CPU fallback)")

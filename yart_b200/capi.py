@@ -34,6 +34,7 @@ BVH_SAH, BVH_MEDIAN_SPLIT = 0, 1
 INTEGRATOR_MIS, INTEGRATOR_NAIVE = 0, 1
 SCRAMBLER_FAST_OWEN, SCRAMBLER_OWEN, SCRAMBLER_BINARY_PERMUTE = 0, 1, 2
 SAMPLER_SOBOL, SAMPLER_NAIVE, SAMPLER_STRATIFIED = 0, 1, 2
+LIGHT_SAMPLER_POWER, LIGHT_SAMPLER_UNIFORM = 0, 1
 
 
 class YcOptions(C.Structure):

@@ -124,6 +124,22 @@ struct KatLight {
   }
 };
 
+#ifdef YB_RNG_SAMPLERS
+// UniformLightSampler (same input records as KatLight): out = {picked index, pick probability, p(light)}
+struct KatLightUniform {
+  KatIO io;
+  DScene sc;
+  YB_DEV void operator()(uint32_t i) const {
+    const size_t r = size_t(i) * 13;
+    const PickedLight pk = pickLightUniform(sc, io.f(r + 12));
+    float* o = io.out + size_t(i) * 3;
+    o[0] = __uint_as_float(pk.index);
+    o[1] = pk.p;
+    o[2] = 1.0f / float(sc.nLights);
+  }
+};
+#endif
+
 struct KatGmon {
   KatIO io;
   uint32_t n;
@@ -222,13 +238,16 @@ extern "C" int yc_kat(yc_ctx* ctx, const char* kind, const void* in, size_t inBy
   const size_t inWords = inBytes / 4;
   size_t header = 1, recWords = 0, outWords = 0;
   uint32_t n = hin[0];
-  const bool needsScene = k == "bsdf" || k == "light" || k == "texture" || k == "lut";
+  const bool needsScene = k == "bsdf" || k == "light" || k == "lightuniform" || k == "texture" || k == "lut";
   if (needsScene && !ctx->hasScene) return fail(ctx, YC_ERR_NO_SCENE, "yc_kat(%s) needs an uploaded scene", kind);
   if (k == "sampler") header = 2, n = inWords > 1 ? hin[1] : 0, recWords = 3, outWords = 8;
   else if (k == "lut") recWords = 4, outWords = 8;
   else if (k == "ggx") recWords = 10, outWords = 8;
   else if (k == "bsdf") recWords = 22, outWords = 27;
   else if (k == "light") recWords = 13, outWords = 22;
+#ifdef YB_RNG_SAMPLERS
+  else if (k == "lightuniform") recWords = 13, outWords = 3;
+#endif
   else if (k == "gmon") header = 2, n = inWords > 1 ? hin[1] : 0, recWords = size_t(hin[0]) * 3, outWords = 9;
   else if (k == "gmonb") header = 2, n = inWords > 1 ? hin[1] : 0, recWords = size_t(hin[0]) * 3, outWords = 3;
   else if (k == "agx") header = 2, n = inWords > 1 ? hin[1] : 0, recWords = 3, outWords = 3;
@@ -257,6 +276,9 @@ extern "C" int yc_kat(yc_ctx* ctx, const char* kind, const void* in, size_t inBy
     else if (k == "ggx") rt::launchFor(ctx->st, n, KatGgx{io});
     else if (k == "bsdf") rt::launchFor(ctx->st, n, KatBsdf{io, ctx->ds});
     else if (k == "light") rt::launchFor(ctx->st, n, KatLight{io, ctx->ds});
+#ifdef YB_RNG_SAMPLERS
+    else if (k == "lightuniform") rt::launchFor(ctx->st, n, KatLightUniform{io, ctx->ds});
+#endif
     else if (k == "gmon") rt::launchFor(ctx->st, n, KatGmon{io, hin[0]});
     else if (k == "gmonb") rt::launchFor(ctx->st, n, KatGmonb{io, hin[0]});
     else if (k == "agx") rt::launchFor(ctx->st, n, KatAgx{io, hin[0] == 1 ? uint32_t(YC_TONEMAP_AGX_GOLDEN) : hin[0] == 2 ? uint32_t(YC_TONEMAP_AGX_PUNCHY) : uint32_t(YC_TONEMAP_AGX)});

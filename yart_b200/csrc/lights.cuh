@@ -132,8 +132,25 @@ YB_DEV float pInfinite(const DScene& sc) {
   return sc.nArea == 0 ? 1.0f : float(sc.nInf) / float(sc.nInf + 1);
 }
 
+// UniformLightSampler::sample / p, light-sampler.cpp:11-31.  `size_t(u * nl - 0.01f)` as x86-64 evaluates it
+// (truncation; a negative value in (-1, 0) gives 0).  Variants build only: the reference's MISIntegrator hard-codes
+// PowerLightSampler (mis-integrator.hpp:20), so this one can be checked against the reference's class, not its frames.
+YB_DEV PickedLight pickLightUniform(const DScene& sc, float u) {
+  const uint32_t nl = sc.nLights;
+  const float x = u * float(nl) - 0.01f;
+  uint32_t idx = x != x ? 0u : uint32_t((long long)x);
+  if (nl - 1 < idx) idx = nl - 1;
+  PickedLight r;
+  r.index = idx;
+  r.p = 1.0f / float(nl);
+  return r;
+}
+
 // PowerLightSampler::sample, light-sampler.cpp:52-78
 YB_DEV PickedLight pickLight(const DScene& sc, float u) {
+#ifdef YB_RNG_SAMPLERS
+  if (sc.uniformLights) return pickLightUniform(sc, u);
+#endif
   const uint32_t infCount = sc.nInf;
   const float pInf = pInfinite(sc);
   PickedLight r;
@@ -165,6 +182,9 @@ YB_DEV PickedLight pickLight(const DScene& sc, float u) {
 
 // PowerLightSampler::p, light-sampler.cpp:80-93
 YB_DEV float lightPickProbability(const DScene& sc, uint32_t lightIdx) {
+#ifdef YB_RNG_SAMPLERS
+  if (sc.uniformLights) return 1.0f / float(sc.nLights);
+#endif
   const float pInf = pInfinite(sc);
   const YcLight& l = sc.lights[lightIdx];
   if (l.type != YC_LIGHT_AREA) return pInf / float(sc.nInf);

@@ -42,6 +42,7 @@ struct DScene {
   uint32_t nArea;
   const float* powerCdf;
   float totalPower;
+  uint32_t uniformLights;  // YB_RNG_SAMPLERS build: UniformLightSampler instead of PowerLightSampler (light-sampler.cpp:11-31)
   const float* lut;
   int hasAlpha;
 };

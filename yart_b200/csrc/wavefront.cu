@@ -534,13 +534,14 @@ extern "C" int yc_create(int device, const YcOptions* opts, yc_ctx** out) {
   if (opts) ctx->opts = *opts;
   if (ctx->opts.maxDepth == 0) ctx->opts.maxDepth = 30;  // RayIntegrator::m_maxDepth, ray-integrator.hpp:14
   if (ctx->opts.integrator > YC_INTEGRATOR_NAIVE || ctx->opts.scrambler > YC_SCRAMBLER_BINARY_PERMUTE ||
-      ctx->opts.sampler > YC_SAMPLER_STRATIFIED ||
+      ctx->opts.sampler > YC_SAMPLER_STRATIFIED || ctx->opts.reserved3[0] > YC_LIGHT_SAMPLER_UNIFORM ||
       (ctx->opts.integrator == YC_INTEGRATOR_NAIVE && ctx->opts.maxDepth + 1 > kNaiveMaxSegments)) {
     delete ctx;
     return YC_ERR_INVALID;
   }
 #ifndef YB_RNG_SAMPLERS
-  if (ctx->opts.sampler != YC_SAMPLER_SOBOL || ctx->opts.scrambler != YC_SCRAMBLER_FAST_OWEN) {
+  if (ctx->opts.sampler != YC_SAMPLER_SOBOL || ctx->opts.scrambler != YC_SCRAMBLER_FAST_OWEN ||
+      ctx->opts.reserved3[0] != YC_LIGHT_SAMPLER_POWER) {
     // this build folds the sampler choice away (sampler.cuh); the other samplers are in libyart_b200_samplers.so
     delete ctx;
     return YC_ERR_UNSUPPORTED;
@@ -670,6 +671,7 @@ extern "C" int yc_upload_scene(yc_ctx* ctx, const YcScene* s) {
   YC_TRY(devUpload(ctx, s->lutTables, 14112, &d.lut));
   d.nNodes = s->nNodes, d.nMeshes = s->nMeshes, d.nLights = s->nLights;
   d.nInf = s->nInfinite, d.nArea = s->nArea, d.totalPower = s->totalPower, d.hasAlpha = s->hasAlpha;
+  d.uniformLights = ctx->opts.reserved3[0] == YC_LIGHT_SAMPLER_UNIFORM ? 1u : 0u;
   ctx->ds = d;
   ctx->hasScene = true;
   return YC_OK;
