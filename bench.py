@@ -207,7 +207,8 @@ def run_ours(args):
     spp = args.spp
 
     # ---- device-resident arm ---------------------------------------------------------------
-    ctx = Y.Context(device=local, max_depth=MAX_DEPTH)
+    trav = {"auto": Y.TRAVERSAL_AUTO, "reference": Y.TRAVERSAL_REFERENCE_ORDER, "wide": Y.TRAVERSAL_WIDE}[args.traversal]
+    ctx = Y.Context(device=local, max_depth=MAX_DEPTH, traversal=trav)
     ctx.upload_scene(scene)
     ctx.set_camera(cam)
     ctx.set_profiling(os.environ.get('YART_BENCH_NO_PROFILE') is None)
@@ -363,7 +364,7 @@ def run_ours(args):
 
     # ---- end-to-end arm: public Renderer API, host buffers ------------------------------------
     r = Y.Renderer(W, H, cam, scene, samples=spp, first_wave_samples=spp, max_wave_samples=spp, max_depth=MAX_DEPTH,
-                   tonemap=Y.TONEMAP_AGX, device=local)
+                   tonemap=Y.TONEMAP_AGX, device=local, traversal=trav)
     e2e_rays = 0
 
     def e2e_step():
@@ -462,6 +463,9 @@ def main():
     ap.add_argument("--sharding", default="waves", choices=["waves", "buckets"],
                     help="N > 1: whole waves per rank (default) or the samples of one wave split by GMoN bucket")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--traversal", default="auto", choices=["auto", "reference", "wide"],
+                    help="YcOptions::traversal: auto = the 4-wide BVH for scenes without alpha-tested materials (default), "
+                         "reference = the reference-order BVH2 walk (bit-identical frames)")
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080, help="3840 x 2160 for the BASELINE.json configs[4] shape")
     args = ap.parse_args()

@@ -188,11 +188,13 @@ typedef struct YcCamera {
 typedef struct YcOptions {
   uint32_t maxDepth;        /* RayIntegrator::m_maxDepth (default 30) */
   uint32_t maxPathsInFlight; /* wavefront capacity; 0 = default (8 Mi paths) */
-  /* reserved[0], reserved[1]: warp-scheduling knobs of the traversal kernels (0 = default):
-   * refill threshold (idle lanes) and inner-step threshold (lanes on inner nodes).  They never
-   * change results.  reserved[2]: number of surviving paths at which a chunk's remaining bounces are
-   * handed to the per-path tail kernel (0 = default 16384, 0xffffffff = never). */
-  uint32_t reserved[3];
+  /* Warp-scheduling knobs of the traversal kernels (0 = default); they never change results:
+   * traceRefillMin — idle lanes at which a warp fetches new rays (default 8);
+   * traceInnerMin  — lanes on inner nodes below which a warp leaves the inner-node loop (default 20). */
+  uint32_t traceRefillMin, traceInnerMin;
+  /* Surviving paths of a chunk at which its remaining bounces go to the per-path tail kernel
+   * (0 = default 16384, 0xffffffff = never).  Never changes results. */
+  uint32_t tailThreshold;
   /* The `Integrator` template argument of TileRenderer (src/main.cpp:17): YC_INTEGRATOR_MIS =
    * cpu::MISIntegrator (the measured path), YC_INTEGRATOR_NAIVE = cpu::NaiveIntegrator
    * (src/cpu/naive-integrator.cpp: BSDF sampling only, maxDepth + 1 segments, at most 63). */
@@ -200,16 +202,27 @@ typedef struct YcOptions {
   /* The scrambler R of the `Sampler = SobolSampler<R>` template argument (src/main.cpp:16):
    * FastOwenScrambler (the measured path), OwenScrambler or BinaryPermuteScrambler (src/core/scrambler.hpp:35-85). */
   uint32_t scrambler;
-  /* reserved2[0]: entries of the traversal kernels' shared-memory stack actually used (0 = default, all 25);
-   * the rest goes to the global spill area.  Never changes results; tests shrink it to exercise the spill path. */
-  uint32_t reserved2[1];
+  /* Entries of the traversal kernels' shared-memory stack actually used (0 = default, all 25); the rest goes to
+   * the global spill area.  Never changes results; tests shrink it to exercise the spill path. */
+  uint32_t sharedStackEntries;
   /* The `Sampler` template argument of TileRenderer (src/main.cpp:16): YC_SAMPLER_SOBOL = SobolSampler<R> with the
    * scrambler above (the measured path), YC_SAMPLER_NAIVE = NaiveSampler, YC_SAMPLER_STRATIFIED = StratifiedSampler
    * (src/core/sampler.cpp:5-50; xoshiro256++ seeded per pixel sample, re-derived per draw from the dimension). */
   uint32_t sampler;
-  /* reserved3[0]: YC_LIGHT_SAMPLER_* — the m_lightSampler member of MISIntegrator (mis-integrator.hpp:20 hard-codes
+  /* YC_LIGHT_SAMPLER_* — the m_lightSampler member of MISIntegrator (mis-integrator.hpp:20 hard-codes
    * PowerLightSampler; UniformLightSampler, light-sampler.cpp:11-31, is its alternative; variants build only). */
-  uint32_t reserved3[3];
+  uint32_t lightSampler;
+  /* YC_TRAVERSAL_* — how RayIntegrator::testBVH (ray-integrator.cpp:84-160) is walked:
+   *   AUTO             the 4-wide collapsed BVH (csrc/wide_bvh.cuh) for scenes without alpha-tested materials,
+   *                    the reference-order BVH2 walk otherwise;
+   *   REFERENCE_ORDER  always the BVH2 walk: same boxes, same order, same two-rounding slab test as the reference —
+   *                    every hit, frame and ray count is bit-identical to the reference;
+   *   WIDE             the wide walk or YC_ERR_UNSUPPORTED at yc_upload_scene (alpha-tested materials: the order of
+   *                    triangle tests would move sampler draws).
+   * The wide walk tests the reference's triangles with the reference's arithmetic and differs only in box culling
+   * (hit ids / t identical except last-bit ties and box-boundary hits; frames within the north-star tolerance). */
+  uint32_t traversal;
+  uint32_t reserved;
 } YcOptions;
 
 #define YC_INTEGRATOR_MIS 0
@@ -222,6 +235,9 @@ typedef struct YcOptions {
 #define YC_SAMPLER_SOBOL 0
 #define YC_SAMPLER_NAIVE 1
 #define YC_SAMPLER_STRATIFIED 2
+#define YC_TRAVERSAL_AUTO 0
+#define YC_TRAVERSAL_REFERENCE_ORDER 1
+#define YC_TRAVERSAL_WIDE 2
 
 typedef struct YcRect { uint32_t x, y, w, h; } YcRect;
 
@@ -255,7 +271,8 @@ typedef struct YcStats {
   uint64_t samples;         /* pixel samples taken */
   uint64_t kernelLaunches;  /* CUDA kernels launched by this context since begin_frame */
   double gpuMs;             /* CUDA-event time spent inside yc_render_wave since begin_frame */
-  uint64_t boxTests, triTests; /* only filled by counting traces (yc_trace with YC_TRACE_COUNT) */
+  uint64_t boxTests, triTests; /* only filled by counting traces (yc_trace with YC_TRACE_COUNT): the reference-order
+                                  walk's tests unless YC_TRACE_WIDE is OR-ed in (then: wide child boxes tested) */
   double extendMs;          /* CUDA-event time of the extend (closest-hit) launches, when yc_set_profiling(1) */
   uint64_t extendLaunches;
 } YcStats;
@@ -278,6 +295,8 @@ typedef struct YcHit {
 #define YC_TRACE_ANY 1     /* NEE ray: Ray::nee = true, hit.t preset to tmax */
 #define YC_TRACE_COUNT 16  /* OR-ed in: also count box / triangle tests into YcStats */
 #define YC_TRACE_USE_TMAX 32 /* OR-ed in (closest): preset hit.t = ray.tmax instead of infinity */
+#define YC_TRACE_REFERENCE_ORDER 64 /* OR-ed in: force the reference-order BVH2 walk for this call */
+#define YC_TRACE_WIDE 128           /* OR-ed in: force the 4-wide walk (YC_ERR_STATE if the scene has none) */
 
 typedef struct yc_ctx yc_ctx;
 
@@ -415,6 +434,7 @@ typedef struct YrSettings {
   uint32_t integrator; /* YC_INTEGRATOR_* */
   uint32_t scrambler;  /* YC_SCRAMBLER_* */
   uint32_t sampler;    /* YC_SAMPLER_* */
+  uint32_t traversal;  /* YC_TRAVERSAL_* */
 } YrSettings;
 
 typedef struct YrRenderData {  /* Renderer::RenderData (renderer.hpp:22-28) */

@@ -13,6 +13,19 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+@pytest.fixture(autouse=True)
+def reference_order_by_default():
+    """The parity suites assert BITWISE equality with the reference, which is what YC_TRAVERSAL_REFERENCE_ORDER
+    delivers; contexts created without an explicit `traversal` use it.  The wide walk (the library's default for
+    scenes without alpha-tested materials) is tested by name in test_wide_bvh.py / test_gpu_parity.py with the
+    north-star tolerances (ids exact bar ties, t <= 1e-5, relMSE < 1e-3)."""
+    import yart_b200
+    old = yart_b200.default_traversal
+    yart_b200.default_traversal = yart_b200.TRAVERSAL_REFERENCE_ORDER
+    yield
+    yart_b200.default_traversal = old
+
+
 @pytest.fixture
 def hostsim_lib():
     """The product sources compiled for the CPU (tests/hostsim) bound as the active library."""

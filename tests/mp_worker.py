@@ -25,7 +25,7 @@ def run(rank: int, world: int, port: int, mode: str, out_dir: str):
     sc = Y.Scene(H.scene_file("cornell"))
     w = h = 48
     c = Y.make_camera(w, h, cam["focal"], cam["fnum"], cam["pos"], cam["target"])
-    ctx = Y.Context()
+    ctx = Y.Context(traversal=Y.TRAVERSAL_REFERENCE_ORDER)  # the parent compares bitwise with a reference-order render
     ctx.upload_scene(sc)
     ctx.set_camera(c)
     spp = 8

@@ -14,7 +14,8 @@ import numpy as np
 
 from . import capi
 from .capi import (LIGHT_SAMPLER_POWER, LIGHT_SAMPLER_UNIFORM, SAMPLER_SOBOL, SAMPLER_NAIVE, SAMPLER_STRATIFIED, BVH_SAH, BVH_MEDIAN_SPLIT, SCRAMBLER_FAST_OWEN, SCRAMBLER_OWEN, SCRAMBLER_BINARY_PERMUTE, INTEGRATOR_MIS, INTEGRATOR_NAIVE, ESTIMATOR_GMONB, ESTIMATOR_GMON, ESTIMATOR_MEAN, ESTIMATOR_MON, TONEMAP_AGX, TONEMAP_AGX_GOLDEN, TONEMAP_AGX_PUNCHY,
-                   TONEMAP_NONE, TRACE_ANY, TRACE_CLOSEST, TRACE_COUNT, TRACE_USE_TMAX)
+                   TONEMAP_NONE, TRACE_ANY, TRACE_CLOSEST, TRACE_COUNT, TRACE_USE_TMAX, TRACE_REFERENCE_ORDER, TRACE_WIDE,
+                   TRAVERSAL_AUTO, TRAVERSAL_REFERENCE_ORDER, TRAVERSAL_WIDE)
 
 _lib = None
 
@@ -31,6 +32,11 @@ def use_library(handle):
     """Tests only: bind another build of the same C ABI (tests/hostsim)."""
     global _lib
     _lib = handle
+
+
+# YcOptions::traversal used by Context / Renderer when none is passed (the bit-exact parity suites set
+# TRAVERSAL_REFERENCE_ORDER here; the library's own default is TRAVERSAL_AUTO).
+default_traversal = capi.TRAVERSAL_AUTO
 
 
 class YartError(RuntimeError):
@@ -142,14 +148,15 @@ class Context:
     def __init__(self, device: int = 0, max_depth: int = 30, max_paths: int = 0, refill_min: int = 0, inner_min: int = 0,
                  tail_threshold: int = 0, integrator: int = capi.INTEGRATOR_MIS,
                  scrambler: int = capi.SCRAMBLER_FAST_OWEN, sh_stack_entries: int = 0,
-                 sampler: int = capi.SAMPLER_SOBOL, light_sampler: int = capi.LIGHT_SAMPLER_POWER):
+                 sampler: int = capi.SAMPLER_SOBOL, light_sampler: int = capi.LIGHT_SAMPLER_POWER,
+                 traversal: int | None = None):
         self._h = C.c_void_p()
+        traversal = default_traversal if traversal is None else traversal
         opts = capi.YcOptions(maxDepth=max_depth, maxPathsInFlight=max_paths, integrator=integrator, scrambler=scrambler,
-                              sampler=sampler)
-        opts.reserved[0], opts.reserved[1] = refill_min, inner_min  # traversal scheduling knobs (0 = default)
-        opts.reserved[2] = 0xffffffff if tail_threshold < 0 else tail_threshold  # tail kernel hand-over (-1 = never)
-        opts.reserved3[0] = light_sampler
-        opts.reserved2[0] = sh_stack_entries  # shared traversal-stack entries in use (0 = default; small = spill-path test)
+                              sampler=sampler, lightSampler=light_sampler, traversal=traversal)
+        opts.traceRefillMin, opts.traceInnerMin = refill_min, inner_min  # traversal scheduling knobs (0 = default)
+        opts.tailThreshold = 0xffffffff if tail_threshold < 0 else tail_threshold  # tail kernel hand-over (-1 = never)
+        opts.sharedStackEntries = sh_stack_entries  # shared traversal-stack entries in use (0 = default; small = spill-path test)
         _check(lib().yc_create(device, C.byref(opts), C.byref(self._h)), "yc_create",
                b"(no usable CUDA device: yart_b200 has no CPU fallback)")
         self.frame = None
@@ -286,11 +293,14 @@ class Renderer:
     def __init__(self, width, height, camera: capi.YcCamera, scene: Scene | None = None, samples=64,
                  first_wave_samples=None, max_wave_samples=None, tile_size=64, max_depth=30, background=(0, 0, 0),
                  tonemap=TONEMAP_AGX, estimator=ESTIMATOR_GMON, shard_index=0, shard_count=1, device=0,
-                 integrator=capi.INTEGRATOR_MIS, scrambler=capi.SCRAMBLER_FAST_OWEN, sampler=capi.SAMPLER_SOBOL):
+                 integrator=capi.INTEGRATOR_MIS, scrambler=capi.SCRAMBLER_FAST_OWEN, sampler=capi.SAMPLER_SOBOL,
+                 traversal=None):
+        traversal = default_traversal if traversal is None else traversal
         # TileRenderer defaults: samples 64, firstWaveSamples 64, maxWaveSamples 128, tileSize 64 (:11-14)
         s = capi.YrSettings(width, height, samples, 64 if first_wave_samples is None else first_wave_samples,
                             128 if max_wave_samples is None else max_wave_samples, tile_size, max_depth,
-                            _f3(background), tonemap, estimator, shard_index, shard_count, device, integrator, scrambler, sampler)
+                            _f3(background), tonemap, estimator, shard_index, shard_count, device, integrator, scrambler, sampler,
+                            traversal)
         self.settings = s
         self.scene = scene
         self._h = C.c_void_p()

@@ -19,7 +19,7 @@ YC_OK, YC_ERR_INVALID, YC_ERR_CUDA, YC_ERR_NO_SCENE, YC_ERR_NO_DEVICE, YC_ERR_ST
 YC_ERR_UNSUPPORTED = -7
 TONEMAP_NONE, TONEMAP_AGX, TONEMAP_AGX_GOLDEN, TONEMAP_AGX_PUNCHY = 0, 1, 2, 3
 ESTIMATOR_GMON, ESTIMATOR_MON, ESTIMATOR_MEAN, ESTIMATOR_GMONB = 0, 1, 2, 3
-TRACE_CLOSEST, TRACE_ANY, TRACE_COUNT, TRACE_USE_TMAX = 0, 1, 16, 32
+TRACE_CLOSEST, TRACE_ANY, TRACE_COUNT, TRACE_USE_TMAX, TRACE_REFERENCE_ORDER, TRACE_WIDE = 0, 1, 16, 32, 64, 128
 
 f32, u32, i32, u64 = C.c_float, C.c_uint32, C.c_int32, C.c_uint64
 
@@ -35,11 +35,13 @@ INTEGRATOR_MIS, INTEGRATOR_NAIVE = 0, 1
 SCRAMBLER_FAST_OWEN, SCRAMBLER_OWEN, SCRAMBLER_BINARY_PERMUTE = 0, 1, 2
 SAMPLER_SOBOL, SAMPLER_NAIVE, SAMPLER_STRATIFIED = 0, 1, 2
 LIGHT_SAMPLER_POWER, LIGHT_SAMPLER_UNIFORM = 0, 1
+TRAVERSAL_AUTO, TRAVERSAL_REFERENCE_ORDER, TRAVERSAL_WIDE = 0, 1, 2
 
 
 class YcOptions(C.Structure):
-    _fields_ = [("maxDepth", u32), ("maxPathsInFlight", u32), ("reserved", u32 * 3), ("integrator", u32),
-                ("scrambler", u32), ("reserved2", u32 * 1), ("sampler", u32), ("reserved3", u32 * 3)]
+    _fields_ = [("maxDepth", u32), ("maxPathsInFlight", u32), ("traceRefillMin", u32), ("traceInnerMin", u32),
+                ("tailThreshold", u32), ("integrator", u32), ("scrambler", u32), ("sharedStackEntries", u32),
+                ("sampler", u32), ("lightSampler", u32), ("traversal", u32), ("reserved", u32)]
 
 
 class YcRect(C.Structure):
@@ -89,7 +91,8 @@ class YcScene(C.Structure):
 class YrSettings(C.Structure):
     _fields_ = [("width", u32), ("height", u32), ("samples", u32), ("firstWaveSamples", u32), ("maxWaveSamples", u32),
                 ("tileSize", u32), ("maxDepth", u32), ("background", f32 * 3), ("tonemap", u32), ("estimator", u32),
-                ("shardIndex", u32), ("shardCount", u32), ("device", i32), ("integrator", u32), ("scrambler", u32), ("sampler", u32)]
+                ("shardIndex", u32), ("shardCount", u32), ("device", i32), ("integrator", u32), ("scrambler", u32), ("sampler", u32),
+                ("traversal", u32)]
 
 
 class YrRenderData(C.Structure):

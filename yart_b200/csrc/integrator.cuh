@@ -17,7 +17,7 @@
 #pragma once
 #include "camera.cuh"
 #include "lights.cuh"
-#include "traverse.cuh"
+#include "wide_bvh.cuh"
 
 namespace yb {
 
@@ -153,15 +153,19 @@ YB_DEV void initTraceState(TraceState& st, float tMax) {
   st.attenuation = V3(1.0f);
 }
 
-template <bool ALPHA, bool COUNT>
+// WIDE: walk the collapsed 4-wide BVH (wide_bvh.cuh; scenes without alpha-tested materials only) instead of the
+// reference-order BVH2.
+template <bool ALPHA, bool COUNT, bool WIDE = false>
 YB_DEV void extendStage(const DScene& sc, const WaveParams& w, const PathState& ps, uint32_t i, TravStack& stack,
                         TraceCounters& cnt) {
+  static_assert(!(ALPHA && WIDE), "the wide walk does not reproduce the order of alpha-test sampler draws");
   V3 o, d;
   Sampler smp;
   if (!extendLoad<ALPHA>(w, ps, i, o, d, smp)) return;
   TraceState st;
   initTraceState(st, INFINITY);
-  traceScene<false, ALPHA, COUNT, false>(sc, o, d, st, stack, &smp, cnt);
+  if (WIDE) traceSceneWide<false, COUNT, false>(sc, o, d, st, stack, cnt);
+  else traceScene<false, ALPHA, COUNT, false>(sc, o, d, st, stack, &smp, cnt);
   extendStore<ALPHA>(ps, i, st, smp);
 }
 
@@ -490,7 +494,7 @@ YB_DEV uint32_t shadowFinish(const PathState& ps, const ShadowQueue& q, uint32_t
 // Without alpha-tested materials nothing observable depends on what an occluded NEE ray finds
 // after its first occluder, so the any-hit walk may stop there (EARLY_OUT = !ALPHA); with them the
 // sampler draws must match the reference's, which keeps walking (ray-integrator.cpp:121).
-template <bool ALPHA, bool COUNT>
+template <bool ALPHA, bool COUNT, bool WIDE = false>
 YB_DEV uint32_t shadowStage(const DScene& sc, const WaveParams& w, const PathState& ps, const ShadowQueue& q,
                             uint32_t j, TravStack& stack, TraceCounters& cnt) {
   V3 o, d;
@@ -499,7 +503,8 @@ YB_DEV uint32_t shadowStage(const DScene& sc, const WaveParams& w, const PathSta
   const uint32_t i = shadowLoad<ALPHA>(w, ps, q, j, o, d, tMax, smp);
   TraceState st;
   initTraceState(st, tMax);
-  const bool occluded = traceScene<true, ALPHA, COUNT, !ALPHA>(sc, o, d, st, stack, &smp, cnt);
+  const bool occluded = WIDE ? traceSceneWide<true, COUNT, true>(sc, o, d, st, stack, cnt)
+                             : traceScene<true, ALPHA, COUNT, !ALPHA>(sc, o, d, st, stack, &smp, cnt);
   return shadowFinish<ALPHA>(ps, q, j, i, st, occluded, smp);
 }
 

@@ -233,6 +233,7 @@ struct KatTexture {
 
 extern "C" int yc_kat(yc_ctx* ctx, const char* kind, const void* in, size_t inBytes, void* out, size_t outBytes) {
   if (!ctx || !kind || !in || !out || inBytes < 4 || (inBytes & 3)) return YC_ERR_INVALID;
+  rt::useDevice(ctx->device);
   const std::string k = kind;
   const uint32_t* hin = static_cast<const uint32_t*>(in);
   const size_t inWords = inBytes / 4;

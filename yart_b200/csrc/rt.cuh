@@ -22,6 +22,7 @@ inline const char* init(int, Stream&, int& smCount) {
   return nullptr;
 }
 inline void destroy(Stream&) {}
+inline void useDevice(int) {}
 inline const char* alloc(void** p, size_t bytes) {
   *p = malloc(bytes ? bytes : 1);
   return *p ? nullptr : "out of host memory (hostsim)";
@@ -84,6 +85,9 @@ inline void destroy(Stream& st) {
   if (st.s) cudaStreamDestroy(st.s);
   st.s = nullptr;
 }
+// The current CUDA device is per-thread state: every yc_* entry point re-selects its context's device, so a
+// context may be driven from any thread (yr_render's worker) and contexts on several devices may share a process.
+inline void useDevice(int device) { cudaSetDevice(device); }
 inline const char* alloc(void** p, size_t bytes) { return errstr(cudaMalloc(p, bytes ? bytes : 1)); }
 inline void release(void* p) {
   if (p) cudaFree(p);

@@ -5,6 +5,7 @@
 //   meshes     YcMesh[nMeshes]
 //   bvhNodes   float4[4 * nBvhNodes]     inner BVH2 nodes, both child boxes inlined (64 B, 4 × LDG.128)
 //   bvhTris    float4[3 * nBvhTris]      leaf-ordered triangles, positions pre-gathered (48 B, 3 × LDG.128)
+//   wideNodes  float4[8 * nWide]         the same tree collapsed to 4-wide nodes (128 B, wide_bvh.cuh), scenes without alpha
 //   positions/normals/tangents/uvs       per-vertex attributes (shade-time gathers)
 //   primIndices/primMaterial/primLight   per-primitive, original order
 //   materials, textures, texels, lights, envDist, light-sampler tables, LUTs
@@ -14,6 +15,12 @@
 
 namespace yb {
 
+// Per-mesh entry into the wide (4-ary) node array built by yc_upload_scene (wide_bvh.cuh).
+struct WideMesh {
+  uint32_t rootRef;     // like YcMesh::rootRef, relative to this mesh's first WideNode
+  uint32_t nodeOffset;  // first WideNode of this mesh
+};
+
 struct DScene {
   const YcNode* nodes;
   uint32_t nNodes;
@@ -22,6 +29,8 @@ struct DScene {
   uint32_t nMeshes;
   const float4* bvhNodes;
   const float4* bvhTris;
+  const float4* wideNodes;      // float4[8 * nWideNodes]: the collapsed 4-wide nodes (128 B each), null when not built
+  const WideMesh* wideMeshes;   // [nMeshes]
   const float* positions;
   const float* normals;
   const float* tangents;

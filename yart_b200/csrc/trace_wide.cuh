@@ -1,0 +1,222 @@
+// trace_wide.cuh — persistent-warp traversal of the 4-wide BVH (wide_bvh.cuh), CUDA only: the extend, shadow and
+// ray-hook kernels of scenes without alpha-tested materials.
+//
+// Same warp scheduling as trace_kernels.cuh (lane state machine IDLE → NODE → TRAV, one atomic per warp to
+// refill idle lanes, inner-node steps in a tight loop while enough lanes sit on inner nodes, speculative leaf
+// parking, packed (ref, d) stack entries in shared memory with a sentinel at the bottom); what changes is the
+// inner step: one 128-byte node, four boxes, no selects —
+//     6 x LDG.128 (near / far planes, the row picked by the ray's direction signs) + 1 x LDG.128 (child refs)
+//     24 FFMA  (t = plane * 1/d - o/d, one rounding)
+//     16 FMNMX (FMNMX3 where ptxas finds it) + 4 FSETP
+//     4 keys (entry distance | slot), unsigned min → nearest hit child; the other hit children are pushed with
+//     their entry distances (predicated STS.64), popped entries are culled by `d < hit.t`.
+// Triangles are the reference's arithmetic (testTriangle).  Results versus the reference-order walk: see the
+// header of wide_bvh.cuh.
+#pragma once
+#include "trace_kernels.cuh"
+
+namespace yb {
+
+struct Planes4 {
+  float x, y, z, w;
+};
+__device__ __forceinline__ Planes4 loadRow(const float4* p) {
+  Planes4 r;
+  asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+
+// IO policy as in tracePersistent; the sampler argument of load / store is a dummy (no alpha-tested materials).
+template <bool NEE, bool COUNT, class IO>
+__device__ __forceinline__ void traceWidePersistent(const DScene& sc, IO& io, uint32_t n, uint32_t* head, uint2* spillBase,
+                                                    const TraceTuning tune, TraceCounters& cnt) {
+  __shared__ uint2 shStack[kPsStack * kTraceBlock];
+  __shared__ uint2* shSpill;
+  WarpStack stack;
+  stack.init(shStack, &shSpill, spillBase, tune.shEntries);
+  const unsigned FULL = 0xffffffffu;
+  const unsigned lane = threadIdx.x & 31u, ltMask = (1u << lane) - 1u;
+
+  int state = kLaneIdle;
+  bool exhausted = false;
+  uint32_t item = 0, nextNode = 0, cur = 0;
+  uint32_t sp = 0;
+  int curNode = 0;
+  float dcur = 0.0f;
+  bool didHit = false, meshHit = false, rayIsWorld = false, worldFinite = false;
+  V3 wo, wd;
+  LocalRay r;  // o and d only (triangle tests); the box tests use `wr`
+  WideRay wr;
+  TraceState st;
+  Sampler smp;
+  const float4* __restrict__ nodes = nullptr;
+  const float4* __restrict__ tris = nullptr;
+  uint32_t meshIdx = 0;
+  constexpr uint32_t kNoRef = 0xffffffffu;   // "no current node" (leaf bit set: never stepped as inner)
+  constexpr uint32_t kPopRef = 0xfffffffeu;  // "pop at the top of the next inner step"
+  uint32_t pend = 0u;                        // parked leaf (0 = none)
+  float pendD = 0.0f;
+
+  for (;;) {
+    // ---- refill idle lanes -------------------------------------------------------------------
+    const unsigned idle = __ballot_sync(FULL, state == kLaneIdle);
+    if (idle) {
+      if (!exhausted && (__popc(idle) >= tune.refillMin || idle == FULL)) {
+        const uint32_t want = uint32_t(__popc(idle));
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(head, want);
+        base = __shfl_sync(FULL, base, 0);
+        if (state == kLaneIdle) {
+          const uint32_t j = base + uint32_t(__popc(idle & ltMask));
+          if (j < n) {
+            float tMax;
+            if (io.load(j, wo, wd, tMax, smp)) {
+              item = j;
+              rayIsWorld = false;
+              worldFinite = isfinite(wo.x) && isfinite(wo.y) && isfinite(wo.z) && isfinite(wd.x) && isfinite(wd.y) &&
+                            isfinite(wd.z);
+              initTraceState(st, tMax);
+              nextNode = 0;
+              didHit = false;
+              state = kLaneNode;
+            }
+          }
+        }
+        if (base + want >= n) exhausted = true;
+      }
+      if (exhausted && __ballot_sync(FULL, state != kLaneIdle) == 0) break;
+    }
+
+    // ---- scene-graph step (testNode): next node whose box the ray enters ---------------------------
+    if (state == kLaneNode) {
+      bool entered = false;
+      while (nextNode < sc.nNodes) {
+        const YcNode& nd = sc.nodes[nextNode];
+        if (nd.identityChain && worldFinite) {
+          if (!rayIsWorld) {
+            r.o = wo + 0.0f, r.d = wd + 0.0f;  // what the identity matrix products leave (trace_kernels.cuh)
+            wr.set(r.o, r.d);
+            rayIsWorld = true;
+          }
+        } else {
+          V3 o = wo, d = wd;
+          nodeLocalRay(sc, nextNode, nd.depth, o, d);
+          r.o = o, r.d = d;
+          wr.set(o, d);
+          rayIsWorld = false;
+        }
+        float dd;
+        if (COUNT) cnt.box++;
+        if (!slabWideBox(wr, V3(nd.bmin), V3(nd.bmax), kTMin, st.hit.t, dd) || st.hit.t < dd) {
+          nextNode = uint32_t(nd.skip);
+          continue;
+        }
+        const int mi = nd.mesh;
+        curNode = int(nextNode);
+        nextNode++;
+        if (mi < 0) continue;
+        const YcMesh& mesh = sc.meshes[mi];
+        if (COUNT) cnt.box++;
+        if (!slabWideBox(wr, V3(mesh.rootMin), V3(mesh.rootMax), kTMin, st.hit.t, dd)) continue;
+        const WideMesh wm = sc.wideMeshes[mi];
+        meshIdx = uint32_t(mi);
+        nodes = sc.wideNodes + 8 * size_t(wm.nodeOffset);
+        tris = sc.bvhTris + 3 * size_t(mesh.triOffset);
+        cur = wm.rootRef;
+        dcur = dd;
+        stack.put(stack.base, kNoRef, 0.0f);  // sentinel
+        sp = stack.base + kPsStride;
+        pend = 0u;
+        meshHit = false;
+        entered = true;
+        break;
+      }
+      if (entered) {
+        state = kLaneTrav;
+      } else {
+        io.store(item, st, didHit, smp);
+        state = kLaneIdle;
+      }
+    }
+
+    // ---- inner-node steps --------------------------------------------------------------------------
+    for (;;) {
+      const bool trav = state == kLaneTrav;
+      bool doPop = trav && cur == kPopRef;
+      if (trav && pend == 0u && int32_t(cur) < -3) {  // a leaf (bit 31) other than kNoRef / kPopRef / kWideEmpty: park it
+        pend = cur, pendD = dcur;
+        doPop = true;
+      }
+      stack.popIf(doPop, sp, cur, dcur);  // the sentinel ends the mesh: cur = kNoRef
+      const bool inner = trav && int32_t(cur) >= 0;
+      const unsigned im = __ballot_sync(FULL, inner);
+      if (im == 0) break;
+      if (__popc(im) < tune.innerMin && __ballot_sync(FULL, trav && !inner)) break;
+      if (inner) {
+        const float4* np = nodes + 8 * size_t(cur);
+        const Planes4 nX = loadRow(np + wr.nx), fX = loadRow(np + (wr.nx ^ 1u));
+        const Planes4 nY = loadRow(np + wr.ny), fY = loadRow(np + (wr.ny ^ 1u));
+        const Planes4 nZ = loadRow(np + wr.nz), fZ = loadRow(np + (wr.nz ^ 1u));
+        const uint4 rf = __ldg(reinterpret_cast<const uint4*>(np + 6));
+        // pop-time cull `d < hit.t`: a dead entry fails all four tests (tmx = -inf)
+        const bool live = dcur < st.hit.t;
+        const float tmx = live ? st.hit.t : -INFINITY;
+        float t0, t1, t2, t3;
+        const bool h0 = slabWide(wr, V3(nX.x, nY.x, nZ.x), V3(fX.x, fY.x, fZ.x), kTMin, tmx, t0);
+        const bool h1 = slabWide(wr, V3(nX.y, nY.y, nZ.y), V3(fX.y, fY.y, fZ.y), kTMin, tmx, t1);
+        const bool h2 = slabWide(wr, V3(nX.z, nY.z, nZ.z), V3(fX.z, fY.z, fZ.z), kTMin, tmx, t2) && rf.z != kWideEmpty;
+        const bool h3 = slabWide(wr, V3(nX.w, nY.w, nZ.w), V3(fX.w, fY.w, fZ.w), kTMin, tmx, t3) && rf.w != kWideEmpty;
+        if (COUNT && live) cnt.box += 2u + (rf.z != kWideEmpty) + (rf.w != kWideEmpty);
+        const uint32_t k0 = wideKey(h0, t0, 0u), k1 = wideKey(h1, t1, 1u), k2 = wideKey(h2, t2, 2u), k3 = wideKey(h3, t3, 3u);
+        const uint32_t best = min(min(k0, k1), min(k2, k3));
+        const bool p0 = k0 == best, p1 = k1 == best, p2 = k2 == best;
+        const uint32_t nearRef = p0 ? rf.x : (p1 ? rf.y : (p2 ? rf.z : rf.w));
+        // push the other hit children (slot order) with their entry distances
+        const bool q0 = h0 && !p0, q1 = h1 && !p1, q2 = h2 && !p2, q3 = h3 && k3 != best;
+        if (sp + 3u * kPsStride < stack.limit) {  // the (at most three) pushes fit in shared memory
+          uint32_t a = sp;
+          if (q0) stack.put(a, rf.x, t0), a += kPsStride;
+          if (q1) stack.put(a, rf.y, t1), a += kPsStride;
+          if (q2) stack.put(a, rf.z, t2), a += kPsStride;
+          if (q3) stack.put(a, rf.w, t3), a += kPsStride;
+          sp = a;
+        } else {
+          stack.pushIf(q0, sp, rf.x, t0);
+          stack.pushIf(q1, sp, rf.y, t1);
+          stack.pushIf(q2, sp, rf.z, t2);
+          stack.pushIf(q3, sp, rf.w, t3);
+        }
+        cur = best == kWideMiss ? kPopRef : nearRef;
+        dcur = __uint_as_float(best & ~3u);
+      }
+    }
+
+    // ---- leaf step ---------------------------------------------------------------------------------
+    if (state == kLaneTrav && (int32_t(cur) < 0 || pend != 0u)) {
+      const uint32_t leaf = pend;
+      const float leafD = pendD;
+      pend = 0u;
+      if (int32_t(leaf) < -3 && leafD < st.hit.t) {
+        const YcMesh& mesh = sc.meshes[meshIdx];
+        uint32_t ti = leaf & ~YC_REF_LEAF;
+        while (true) {
+          const float4 a = __ldg(tris + 3 * size_t(ti)), b = __ldg(tris + 3 * size_t(ti) + 1),
+                       c = __ldg(tris + 3 * size_t(ti) + 2);
+          meshHit |= testTriangle<NEE, false, COUNT>(sc, mesh, r, a, b, c, curNode, st, &smp, cnt);
+          if (NEE && meshHit) break;
+          if (__float_as_uint(c.z) & YC_TRI_LAST) break;
+          ti++;
+        }
+        didHit |= meshHit;
+      }
+      if (NEE && didHit) {  // no alpha-tested materials: the first occluder decides (shadowStage, integrator.cuh)
+        io.store(item, st, true, smp);
+        state = kLaneIdle;
+      } else if (cur == kNoRef) {
+        state = kLaneNode;  // mesh walked and nothing parked any more
+      }
+    }
+  }
+}
+
+}  // namespace yb

@@ -22,7 +22,7 @@
 #include "integrator.cuh"
 #include "rt.cuh"
 #ifndef YB_HOSTSIM
-#include "trace_kernels.cuh"
+#include "trace_wide.cuh"
 #endif
 
 using namespace yb;
@@ -86,6 +86,7 @@ struct yc_ctx {
   uint32_t* dPixelsScratch = nullptr;
   float4 *dHdr = nullptr, *dLdr = nullptr, *dBuckets = nullptr;
   size_t bucketCapacity = 0;  // pixels per bucket plane
+  bool bucketsDirty = false;  // an accumulate was not (or only partly) followed by a finalize: the planes hold sums
 
   // wavefront storage lives in the lanes; the ray hooks (yc_trace*) use lane 0's counters and spill area
   uint32_t* dCtr = nullptr;
@@ -101,6 +102,9 @@ struct yc_ctx {
   uint64_t extendLaunches = 0, raysExtend = 0;
   bool timeExtend = false, countTraversal = false;
   uint32_t tailThreshold = 16384;  // paths left in a chunk at which the tail kernel takes over (0 = never)
+  bool wide = false;               // the scene's wide BVH is built and the kernels walk it (YcOptions::traversal)
+  int wideDepth = 0;               // deepest wide level over all meshes
+  uint64_t nWideNodes = 0;
 };
 
 static int fail(yc_ctx* c, int code, const char* fmt, ...) {
@@ -330,7 +334,10 @@ template <bool ALPHA, bool COUNT>
 static void runExtend(yc_ctx* ctx, Lane& L, uint32_t n) {
   HostStack hs;
   TraceCounters cnt;
-  for (uint32_t j = 0; j < n; j++) extendStage<ALPHA, COUNT>(ctx->ds, L.w, L.ps, L.qA[j], hs.ts, cnt);
+  if (!ALPHA && ctx->wide && !COUNT)
+    for (uint32_t j = 0; j < n; j++) extendStage<false, false, true>(ctx->ds, L.w, L.ps, L.qA[j], hs.ts, cnt);
+  else
+    for (uint32_t j = 0; j < n; j++) extendStage<ALPHA, COUNT>(ctx->ds, L.w, L.ps, L.qA[j], hs.ts, cnt);
   ctx->dCounters->boxTests += cnt.box;
   ctx->dCounters->triTests += cnt.tri;
 }
@@ -340,7 +347,10 @@ static void runShadow(yc_ctx* ctx, Lane& L, uint32_t) {
   TraceCounters cnt;
   const uint32_t n = L.ctr[kCtrShadowCount];
   uint32_t contributed = 0;
-  for (uint32_t j = 0; j < n; j++) contributed += shadowStage<ALPHA, COUNT>(ctx->ds, L.w, L.ps, L.sq, j, hs.ts, cnt);
+  if (!ALPHA && ctx->wide && !COUNT)
+    for (uint32_t j = 0; j < n; j++) contributed += shadowStage<false, false, true>(ctx->ds, L.w, L.ps, L.sq, j, hs.ts, cnt);
+  else
+    for (uint32_t j = 0; j < n; j++) contributed += shadowStage<ALPHA, COUNT>(ctx->ds, L.w, L.ps, L.sq, j, hs.ts, cnt);
   ctx->dCounters->raysShadow += n;
   ctx->dCounters->raysReference += contributed;
   ctx->dCounters->boxTests += cnt.box;
@@ -416,13 +426,45 @@ __global__ void __launch_bounds__(kTraceBlock, YB_SHADOW_MIN_BLOCKS) shadowKerne
   }
 }
 
+// The same two kernels over the 4-wide BVH (trace_wide.cuh): scenes without alpha-tested materials.
+#ifndef YB_WIDE_MIN_BLOCKS
+#define YB_WIDE_MIN_BLOCKS 6
+#endif
+template <bool COUNT>
+__global__ void __launch_bounds__(kTraceBlock, YB_WIDE_MIN_BLOCKS) extendWideKernel(DScene sc, WaveParams w, PathState ps, const uint32_t* queue,
+                                                              uint32_t n, uint32_t* ctr, Counters* counters, uint2* spill,
+                                                              TraceTuning tune) {
+  ExtendIO<false> io{w, ps, queue};
+  TraceCounters cnt;
+  traceWidePersistent<false, COUNT>(sc, io, n, ctr + kCtrExtendHead, spill, tune, cnt);
+  if (COUNT) {
+    aggregatedCount(&counters->boxTests, cnt.box);
+    aggregatedCount(&counters->triTests, cnt.tri);
+  }
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(kTraceBlock, YB_WIDE_MIN_BLOCKS) shadowWideKernel(DScene sc, WaveParams w, PathState ps, ShadowQueue sq,
+                                                              uint32_t* ctr, Counters* counters, uint2* spill, TraceTuning tune) {
+  const uint32_t n = ctr[kCtrShadowCount];
+  ShadowIO<false> io{w, ps, sq};
+  TraceCounters cnt;
+  traceWidePersistent<true, COUNT>(sc, io, n, ctr + kCtrShadowHead, spill, tune, cnt);
+  aggregatedCount(&counters->raysReference, io.contributed);
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counters->raysShadow, (unsigned long long)n);
+  if (COUNT) {
+    aggregatedCount(&counters->boxTests, cnt.box);
+    aggregatedCount(&counters->triTests, cnt.tri);
+  }
+}
+
 // Tail of a chunk: once only a few thousand paths survive, every further bounce of the wavefront is
 // bound by the latency of its slowest ray (launch after launch).  The tail kernel gives each surviving
 // path one thread that runs its remaining bounces to the end — extend → shade → shadow in the same
 // order and with the same stage functions as the wavefront, so results are unchanged — and all the
 // slow rays overlap instead of adding up.
 constexpr int kTailBlock = 128;
-template <bool ALPHA>
+template <bool ALPHA, bool WIDE>
 __global__ void __launch_bounds__(kTailBlock) tailKernel(DScene sc, WaveParams w, PathState ps, ShadowQueue sq,
                                                          const uint32_t* queue, uint32_t n, uint32_t firstBounce,
                                                          Counters* counters) {
@@ -438,7 +480,7 @@ __global__ void __launch_bounds__(kTailBlock) tailKernel(DScene sc, WaveParams w
     const uint32_t i = queue[j];
     TraceCounters cnt;
     for (uint32_t bounce = firstBounce; bounce < w.maxDepth; bounce++) {
-      extendStage<ALPHA, false>(sc, w, ps, i, stack, cnt);
+      extendStage<ALPHA, false, WIDE>(sc, w, ps, i, stack, cnt);
       nExtend++;
       ShadowRequest rq;
       const uint32_t r = shadeStage<ALPHA>(sc, w, ps, i, rq, raysRef);
@@ -448,7 +490,7 @@ __global__ void __launch_bounds__(kTailBlock) tailKernel(DScene sc, WaveParams w
         sq.d[j] = make_float4(rq.d.x, rq.d.y, rq.d.z, rq.absDotN);
         sq.lif[j] = make_float4(rq.lif.x, rq.lif.y, rq.lif.z, rq.denom);
         sq.att[j] = make_float4(rq.att.x, rq.att.y, rq.att.z, __uint_as_float(i));
-        raysRef += shadowStage<ALPHA, false>(sc, w, ps, sq, j, stack, cnt);
+        raysRef += shadowStage<ALPHA, false, WIDE>(sc, w, ps, sq, j, stack, cnt);
         nShadow++;
       }
       if (!(r & kShadeContinue)) break;
@@ -488,9 +530,9 @@ static void runNaive(yc_ctx* ctx, Lane& L) {
 static int traceGridMax(const yc_ctx* ctx) { return ctx->smCount * 8; }
 static TraceTuning tuning(const yc_ctx* ctx) {
   TraceTuning t;
-  t.refillMin = ctx->opts.reserved[0] ? int(ctx->opts.reserved[0]) : 8;
-  t.innerMin = ctx->opts.reserved[1] ? int(ctx->opts.reserved[1]) : 20;
-  const int e = ctx->opts.reserved2[0] ? int(ctx->opts.reserved2[0]) : kPsStack;
+  t.refillMin = ctx->opts.traceRefillMin ? int(ctx->opts.traceRefillMin) : 8;
+  t.innerMin = ctx->opts.traceInnerMin ? int(ctx->opts.traceInnerMin) : 20;
+  const int e = ctx->opts.sharedStackEntries ? int(ctx->opts.sharedStackEntries) : kPsStack;
   t.shEntries = std::max(2, std::min(kPsStack, e));
   return t;
 }
@@ -512,14 +554,22 @@ static void runExtend(yc_ctx* ctx, Lane& L, uint32_t n) {
     ev = &ctx->extendEvents[ctx->extendEventsUsed++];
     rt::eventRecord(L.st, ev->first);
   }
-  extendKernel<ALPHA, COUNT><<<traceGrid(ctx, n), kTraceBlock, 0, L.st.s>>>(ctx->ds, L.w, L.ps, L.qA, n, L.ctr, ctx->dCounters,
-                                                                            static_cast<uint2*>(L.spill), tuning(ctx));
+  if (!ALPHA && !COUNT && ctx->wide)
+    extendWideKernel<false><<<traceGrid(ctx, n), kTraceBlock, 0, L.st.s>>>(ctx->ds, L.w, L.ps, L.qA, n, L.ctr, ctx->dCounters,
+                                                                           static_cast<uint2*>(L.spill), tuning(ctx));
+  else
+    extendKernel<ALPHA, COUNT><<<traceGrid(ctx, n), kTraceBlock, 0, L.st.s>>>(ctx->ds, L.w, L.ps, L.qA, n, L.ctr, ctx->dCounters,
+                                                                              static_cast<uint2*>(L.spill), tuning(ctx));
   if (ev) rt::eventRecord(L.st, ev->second);
 }
 template <bool ALPHA, bool COUNT>
 static void runShadow(yc_ctx* ctx, Lane& L, uint32_t upperBound) {
-  shadowKernel<ALPHA, COUNT><<<traceGrid(ctx, upperBound), kTraceBlock, 0, L.st.s>>>(
-    ctx->ds, L.w, L.ps, L.sq, L.ctr, ctx->dCounters, static_cast<uint2*>(L.spill), tuning(ctx));
+  if (!ALPHA && !COUNT && ctx->wide)
+    shadowWideKernel<false><<<traceGrid(ctx, upperBound), kTraceBlock, 0, L.st.s>>>(
+      ctx->ds, L.w, L.ps, L.sq, L.ctr, ctx->dCounters, static_cast<uint2*>(L.spill), tuning(ctx));
+  else
+    shadowKernel<ALPHA, COUNT><<<traceGrid(ctx, upperBound), kTraceBlock, 0, L.st.s>>>(
+      ctx->ds, L.w, L.ps, L.sq, L.ctr, ctx->dCounters, static_cast<uint2*>(L.spill), tuning(ctx));
 }
 #endif
 
@@ -534,21 +584,22 @@ extern "C" int yc_create(int device, const YcOptions* opts, yc_ctx** out) {
   if (opts) ctx->opts = *opts;
   if (ctx->opts.maxDepth == 0) ctx->opts.maxDepth = 30;  // RayIntegrator::m_maxDepth, ray-integrator.hpp:14
   if (ctx->opts.integrator > YC_INTEGRATOR_NAIVE || ctx->opts.scrambler > YC_SCRAMBLER_BINARY_PERMUTE ||
-      ctx->opts.sampler > YC_SAMPLER_STRATIFIED || ctx->opts.reserved3[0] > YC_LIGHT_SAMPLER_UNIFORM ||
+      ctx->opts.sampler > YC_SAMPLER_STRATIFIED || ctx->opts.lightSampler > YC_LIGHT_SAMPLER_UNIFORM ||
+      ctx->opts.traversal > YC_TRAVERSAL_WIDE ||
       (ctx->opts.integrator == YC_INTEGRATOR_NAIVE && ctx->opts.maxDepth + 1 > kNaiveMaxSegments)) {
     delete ctx;
     return YC_ERR_INVALID;
   }
 #ifndef YB_RNG_SAMPLERS
   if (ctx->opts.sampler != YC_SAMPLER_SOBOL || ctx->opts.scrambler != YC_SCRAMBLER_FAST_OWEN ||
-      ctx->opts.reserved3[0] != YC_LIGHT_SAMPLER_POWER) {
+      ctx->opts.lightSampler != YC_LIGHT_SAMPLER_POWER) {
     // this build folds the sampler choice away (sampler.cuh); the other samplers are in libyart_b200_samplers.so
     delete ctx;
     return YC_ERR_UNSUPPORTED;
   }
 #endif
   ctx->capacity = ctx->opts.maxPathsInFlight ? ctx->opts.maxPathsInFlight : (8u << 20);
-  if (ctx->opts.reserved[2]) ctx->tailThreshold = ctx->opts.reserved[2] == 0xffffffffu ? 0u : ctx->opts.reserved[2];
+  if (ctx->opts.tailThreshold) ctx->tailThreshold = ctx->opts.tailThreshold == 0xffffffffu ? 0u : ctx->opts.tailThreshold;
   ctx->device = device;
   const char* e = rt::init(device, ctx->st, ctx->smCount);
   if (e) {
@@ -587,6 +638,7 @@ static void freeFrame(yc_ctx* ctx) {
 
 extern "C" void yc_destroy(yc_ctx* ctx) {
   if (!ctx) return;
+  rt::useDevice(ctx->device);
   rt::sync(ctx->st);
   freeFrame(ctx);
   freeAll(ctx->sceneAllocs);
@@ -613,12 +665,14 @@ extern "C" const char* yc_last_error(const yc_ctx* ctx) { return ctx ? ctx->err.
 
 extern "C" int yc_synchronize(yc_ctx* ctx) {
   if (!ctx) return YC_ERR_INVALID;
+  rt::useDevice(ctx->device);
   YC_TRY(rt::sync(ctx->st));
   return YC_OK;
 }
 
 extern "C" int yc_upload_scene(yc_ctx* ctx, const YcScene* s) {
   if (!ctx || !s) return YC_ERR_INVALID;
+  rt::useDevice(ctx->device);
   if (!s->nodes || s->nNodes == 0 || !s->lutTables) return fail(ctx, YC_ERR_INVALID, "scene has no nodes or no LUT tables");
   for (uint32_t i = 0; i < s->nNodes; i++) {
     const YcNode& n = s->nodes[i];
@@ -629,6 +683,25 @@ extern "C" int yc_upload_scene(yc_ctx* ctx, const YcScene* s) {
   }
   for (uint64_t i = 0; i < s->nPrims; i++)
     if (s->primMaterial[i] >= s->nMaterials) return fail(ctx, YC_ERR_INVALID, "primitive %llu: bad material", (unsigned long long)i);
+  // The traversal stack holds at most one entry per level (testBVH pushes the far child and descends into the near
+  // one), the reference's is `stack[64]` (ray-integrator.cpp:92-93) and overflows silently beyond that; here a
+  // deeper tree is refused instead of walking off the spill area.
+  for (uint32_t mi = 0; mi < s->nMeshes; mi++) {
+    const YcMesh& m = s->meshes[mi];
+    if (uint64_t(m.nodeOffset) + m.nInner > s->nBvhNodes) return fail(ctx, YC_ERR_INVALID, "mesh %u: BVH nodes out of range", mi);
+    if (m.rootRef & YC_REF_LEAF) continue;
+    std::vector<std::pair<uint32_t, int>> todo{{m.rootRef, 1}};
+    size_t visited = 0;
+    while (!todo.empty()) {
+      const auto [ref, depth] = todo.back();
+      todo.pop_back();
+      if (ref >= m.nInner || ++visited > m.nInner) return fail(ctx, YC_ERR_INVALID, "mesh %u: BVH is not a tree", mi);
+      if (depth > kMaxStack) return fail(ctx, YC_ERR_INVALID, "mesh %u: BVH deeper than %d levels", mi, kMaxStack);
+      const YcBvhNode& n = s->bvhNodes[size_t(m.nodeOffset) + ref];
+      if (!(n.ref0 & YC_REF_LEAF)) todo.push_back({n.ref0, depth + 1});
+      if (!(n.ref1 & YC_REF_LEAF)) todo.push_back({n.ref1, depth + 1});
+    }
+  }
   YC_TRY(rt::sync(ctx->st));
   freeAll(ctx->sceneAllocs);
   ctx->hasScene = false;
@@ -652,6 +725,28 @@ extern "C" int yc_upload_scene(yc_ctx* ctx, const YcScene* s) {
   YC_TRY(devUpload(ctx, s->bvhTris, size_t(s->nBvhTris), &bt));
   d.bvhNodes = reinterpret_cast<const float4*>(bn);
   d.bvhTris = reinterpret_cast<const float4*>(bt);
+  // the wide (4-ary) layout of the same trees (wide_bvh.cuh), for scenes whose triangle-test order cannot move
+  // sampler draws; a wide walk pushes up to three entries per level
+  ctx->wide = false, ctx->wideDepth = 0, ctx->nWideNodes = 0;
+  if (ctx->opts.traversal == YC_TRAVERSAL_WIDE && s->hasAlpha)
+    return fail(ctx, YC_ERR_UNSUPPORTED, "YC_TRAVERSAL_WIDE: the scene has alpha-tested materials");
+  if (ctx->opts.traversal != YC_TRAVERSAL_REFERENCE_ORDER && !s->hasAlpha && s->nMeshes) {
+    std::vector<WideNode> wn;
+    std::vector<WideMesh> wm(s->nMeshes);
+    int depth = 0;
+    for (uint32_t mi = 0; mi < s->nMeshes; mi++)
+      depth = std::max(depth, collapseToWide(s->bvhNodes + s->meshes[mi].nodeOffset, s->meshes[mi], wn, wm[mi]));
+    if (3 * depth <= kMaxStack) {
+      const WideNode* dw = nullptr;
+      if (wn.empty()) wn.emplace_back();
+      YC_TRY(devUpload(ctx, wn.data(), wn.size(), &dw));
+      YC_TRY(devUpload(ctx, wm.data(), wm.size(), &d.wideMeshes));
+      d.wideNodes = reinterpret_cast<const float4*>(dw);
+      ctx->wide = true, ctx->wideDepth = depth, ctx->nWideNodes = wn.size();
+    } else if (ctx->opts.traversal == YC_TRAVERSAL_WIDE) {
+      return fail(ctx, YC_ERR_UNSUPPORTED, "YC_TRAVERSAL_WIDE: wide tree of %d levels exceeds the traversal stack", depth);
+    }
+  }
   YC_TRY(devUpload(ctx, s->positions, size_t(s->nVerts) * 3, &d.positions));
   YC_TRY(devUpload(ctx, s->normals, size_t(s->nVerts) * 3, &d.normals));
   YC_TRY(devUpload(ctx, s->tangents, size_t(s->nVerts) * 4, &d.tangents));
@@ -671,7 +766,7 @@ extern "C" int yc_upload_scene(yc_ctx* ctx, const YcScene* s) {
   YC_TRY(devUpload(ctx, s->lutTables, 14112, &d.lut));
   d.nNodes = s->nNodes, d.nMeshes = s->nMeshes, d.nLights = s->nLights;
   d.nInf = s->nInfinite, d.nArea = s->nArea, d.totalPower = s->totalPower, d.hasAlpha = s->hasAlpha;
-  d.uniformLights = ctx->opts.reserved3[0] == YC_LIGHT_SAMPLER_UNIFORM ? 1u : 0u;
+  d.uniformLights = ctx->opts.lightSampler == YC_LIGHT_SAMPLER_UNIFORM ? 1u : 0u;
   ctx->ds = d;
   ctx->hasScene = true;
   return YC_OK;
@@ -679,6 +774,7 @@ extern "C" int yc_upload_scene(yc_ctx* ctx, const YcScene* s) {
 
 extern "C" int yc_set_camera(yc_ctx* ctx, const YcCamera* cam) {
   if (!ctx || !cam) return YC_ERR_INVALID;
+  rt::useDevice(ctx->device);
   ctx->cam = *cam;
   ctx->hasCamera = true;
   return YC_OK;
@@ -755,6 +851,7 @@ static uint32_t roundUpPow2(uint32_t v) {  // math_base.hpp:164-170
 
 extern "C" int yc_begin_frame(yc_ctx* ctx, const YcFrameDesc* f) {
   if (!ctx || !f) return YC_ERR_INVALID;
+  rt::useDevice(ctx->device);
   if (!ctx->hasScene) return fail(ctx, YC_ERR_NO_SCENE, "yc_begin_frame before yc_upload_scene");
   if (!ctx->hasCamera) return fail(ctx, YC_ERR_STATE, "yc_begin_frame before yc_set_camera");
   if (f->width == 0 || f->height == 0 || f->width > 65535 || f->height > 65535 || f->tileSize == 0 ||
@@ -770,11 +867,12 @@ extern "C" int yc_begin_frame(yc_ctx* ctx, const YcFrameDesc* f) {
                           ctx->frame.tileSize == f->tileSize && ctx->frame.shardIndex == f->shardIndex &&
                           ctx->frame.shardCount == shardCount;
   ctx->inFrame = false;
-  ctx->frame = *f;
-  ctx->frame.shardCount = shardCount;
   const size_t frameTexels = size_t(f->width) * f->height;
   if (!sameLayout) {
+    // a failure part-way must not leave a half-allocated frame that the next call's sameLayout test accepts:
+    // the descriptor is committed only after every allocation succeeded
     freeFrame(ctx);
+    ctx->frame = YcFrameDesc{};
     // tile list as TileRenderer::renderImpl builds it (tile-renderer.hpp:127-144), sharded by index
     ctx->pixels.clear();
     const uint32_t ts = f->tileSize;
@@ -789,21 +887,28 @@ extern "C" int yc_begin_frame(yc_ctx* ctx, const YcFrameDesc* f) {
           for (uint32_t x = 0; x < tw; x++) ctx->pixels.push_back((x0 + x) | ((y0 + y) << 16));
       }
     const size_t nPixNew = ctx->pixels.size();
-    void* p = nullptr;
-    YC_TRY(rt::alloc(&p, std::max<size_t>(nPixNew, 1) * 4));
-    ctx->dPixels = static_cast<uint32_t*>(p);
-    YC_TRY(rt::alloc(&p, std::max<size_t>(nPixNew, 1) * 4));
-    ctx->dPixelsScratch = static_cast<uint32_t*>(p);
-    YC_TRY(rt::alloc(&p, frameTexels * sizeof(float4)));
-    ctx->dHdr = static_cast<float4*>(p);
-    YC_TRY(rt::alloc(&p, frameTexels * sizeof(float4)));
-    ctx->dLdr = static_cast<float4*>(p);
     ctx->bucketCapacity = std::max<size_t>(nPixNew, 1);
-    YC_TRY(rt::alloc(&p, ctx->bucketCapacity * kMaxBuckets * sizeof(float4)));
-    ctx->dBuckets = static_cast<float4*>(p);
-    YC_TRY(rt::h2d(ctx->st, ctx->dPixels, ctx->pixels.data(), nPixNew * 4));
-    // finalize leaves every bucket it reads zeroed, so the planes only need clearing once
+    const char* e = nullptr;
+    void* p = nullptr;
+    if (!e && !(e = rt::alloc(&p, std::max<size_t>(nPixNew, 1) * 4))) ctx->dPixels = static_cast<uint32_t*>(p);
+    if (!e && !(e = rt::alloc(&p, std::max<size_t>(nPixNew, 1) * 4))) ctx->dPixelsScratch = static_cast<uint32_t*>(p);
+    if (!e && !(e = rt::alloc(&p, frameTexels * sizeof(float4)))) ctx->dHdr = static_cast<float4*>(p);
+    if (!e && !(e = rt::alloc(&p, frameTexels * sizeof(float4)))) ctx->dLdr = static_cast<float4*>(p);
+    if (!e && !(e = rt::alloc(&p, ctx->bucketCapacity * kMaxBuckets * sizeof(float4)))) ctx->dBuckets = static_cast<float4*>(p);
+    if (!e) e = rt::h2d(ctx->st, ctx->dPixels, ctx->pixels.data(), nPixNew * 4);
+    if (e) {
+      freeFrame(ctx);
+      return fail(ctx, YC_ERR_CUDA, "yc_begin_frame: %s", e);
+    }
+    ctx->bucketsDirty = true;  // fresh planes: clear below
+  }
+  ctx->frame = *f;
+  ctx->frame.shardCount = shardCount;
+  // finalize leaves every bucket it reads zeroed, so the planes only need clearing when an accumulate was not
+  // followed by its finalize (an error or abort mid-wave, a partial-rectangle finalize) or when they are new
+  if (ctx->bucketsDirty) {
     YC_TRY(rt::zero(ctx->st, ctx->dBuckets, ctx->bucketCapacity * kMaxBuckets * sizeof(float4)));
+    ctx->bucketsDirty = false;
   }
   YC_TRY(rt::zero(ctx->st, ctx->dHdr, frameTexels * sizeof(float4)));
   YC_TRY(rt::zero(ctx->st, ctx->dLdr, frameTexels * sizeof(float4)));
@@ -983,8 +1088,11 @@ static int renderChunks(yc_ctx* ctx, const uint32_t* dList, uint32_t nPixCall, u
     }
 #ifndef YB_HOSTSIM
     if (L.n <= ctx->tailThreshold) {
-      tailKernel<ALPHA><<<(L.n + kTailBlock - 1) / kTailBlock, kTailBlock, 0, L.st.s>>>(ctx->ds, L.w, L.ps, L.sq, L.qA, L.n,
-                                                                                      L.bounce, ctx->dCounters);
+      const dim3 tg((L.n + kTailBlock - 1) / kTailBlock);
+      if (!ALPHA && ctx->wide)
+        tailKernel<false, true><<<tg, kTailBlock, 0, L.st.s>>>(ctx->ds, L.w, L.ps, L.sq, L.qA, L.n, L.bounce, ctx->dCounters);
+      else
+        tailKernel<ALPHA, false><<<tg, kTailBlock, 0, L.st.s>>>(ctx->ds, L.w, L.ps, L.sq, L.qA, L.n, L.bounce, ctx->dCounters);
       ctx->launches++;
       L.done = true;
       continue;
@@ -1040,6 +1148,7 @@ static int endTimedRegion(yc_ctx* ctx) {
 static int accumulateWave(yc_ctx* ctx, const uint32_t* dList, uint32_t nPixCall, uint32_t sampleOffset, uint32_t waveSamples,
                           uint32_t bucketShard, uint32_t bucketShardCount) {
   const uint32_t m = waveBuckets(ctx->frame, waveSamples);
+  ctx->bucketsDirty = true;
   return ctx->ds.hasAlpha ? renderChunks<true>(ctx, dList, nPixCall, sampleOffset, waveSamples, m, bucketShard, bucketShardCount)
                           : renderChunks<false>(ctx, dList, nPixCall, sampleOffset, waveSamples, m, bucketShard, bucketShardCount);
 }
@@ -1053,10 +1162,12 @@ static void finalizeWave(yc_ctx* ctx, const uint32_t* dList, uint32_t nPixCall, 
                 FinalizeK{dList, ctx->dBuckets, ctx->bucketCapacity, ctx->dHdr, ctx->dLdr, f.width, waveBuckets(f, waveSamples),
                           f.estimator, waveSamples, f.tonemap, wCurrent, wWave});
   ctx->launches++;
+  if (dList == ctx->dPixels) ctx->bucketsDirty = false;  // every plane this shard touches was read and zeroed
 }
 
 extern "C" int yc_render_wave(yc_ctx* ctx, YcRect px, uint32_t sampleOffset, uint32_t waveSamples, uint32_t takenBefore) {
   if (!ctx) return YC_ERR_INVALID;
+  rt::useDevice(ctx->device);
   if (!ctx->inFrame) return fail(ctx, YC_ERR_STATE, "yc_render_wave before yc_begin_frame");
   if (waveSamples == 0 || px.w == 0 || px.h == 0) return YC_OK;
   const uint32_t* dList;
@@ -1073,6 +1184,7 @@ extern "C" int yc_render_wave(yc_ctx* ctx, YcRect px, uint32_t sampleOffset, uin
 extern "C" int yc_accumulate_wave(yc_ctx* ctx, YcRect px, uint32_t sampleOffset, uint32_t waveSamples, uint32_t bucketShard,
                                   uint32_t bucketShardCount) {
   if (!ctx) return YC_ERR_INVALID;
+  rt::useDevice(ctx->device);
   if (!ctx->inFrame) return fail(ctx, YC_ERR_STATE, "yc_accumulate_wave before yc_begin_frame");
   if (bucketShardCount == 0 || bucketShard >= bucketShardCount) return fail(ctx, YC_ERR_INVALID, "bucket shard out of range");
   if (waveSamples == 0 || px.w == 0 || px.h == 0) return YC_OK;
@@ -1088,6 +1200,7 @@ extern "C" int yc_accumulate_wave(yc_ctx* ctx, YcRect px, uint32_t sampleOffset,
 
 extern "C" int yc_finalize_wave(yc_ctx* ctx, YcRect px, uint32_t waveSamples, uint32_t takenBefore) {
   if (!ctx) return YC_ERR_INVALID;
+  rt::useDevice(ctx->device);
   if (!ctx->inFrame) return fail(ctx, YC_ERR_STATE, "yc_finalize_wave before yc_begin_frame");
   if (waveSamples == 0 || px.w == 0 || px.h == 0) return YC_OK;
   const uint32_t* dList;
@@ -1101,6 +1214,7 @@ extern "C" int yc_finalize_wave(yc_ctx* ctx, YcRect px, uint32_t waveSamples, ui
 
 extern "C" int yc_wave_buckets(yc_ctx* ctx, uint32_t waveSamples, uint32_t* m) {
   if (!ctx || !m) return YC_ERR_INVALID;
+  rt::useDevice(ctx->device);
   if (!ctx->inFrame) return fail(ctx, YC_ERR_STATE, "no frame");
   *m = waveBuckets(ctx->frame, waveSamples);
   return YC_OK;
@@ -1108,6 +1222,7 @@ extern "C" int yc_wave_buckets(yc_ctx* ctx, uint32_t waveSamples, uint32_t* m) {
 
 extern "C" int yc_bucket_device_ptrs(yc_ctx* ctx, void** buckets, size_t* bytes, uint32_t* planes, size_t* planePixels) {
   if (!ctx) return YC_ERR_INVALID;
+  rt::useDevice(ctx->device);
   if (!ctx->inFrame) return fail(ctx, YC_ERR_STATE, "no frame");
   if (buckets) *buckets = ctx->dBuckets;
   if (bytes) *bytes = ctx->bucketCapacity * kMaxBuckets * sizeof(float4);
@@ -1135,6 +1250,7 @@ static int readStats(yc_ctx* ctx, YcStats* stats) {
 
 extern "C" int yc_resolve(yc_ctx* ctx, float* hdrRGBA, float* ldrRGBA, YcStats* stats) {
   if (!ctx) return YC_ERR_INVALID;
+  rt::useDevice(ctx->device);
   if (!ctx->inFrame) return fail(ctx, YC_ERR_STATE, "yc_resolve before yc_begin_frame");
   const size_t bytes = size_t(ctx->frame.width) * ctx->frame.height * sizeof(float4);
   if (hdrRGBA) YC_TRY(rt::d2h(ctx->st, hdrRGBA, ctx->dHdr, bytes));
@@ -1144,6 +1260,7 @@ extern "C" int yc_resolve(yc_ctx* ctx, float* hdrRGBA, float* ldrRGBA, YcStats* 
 
 extern "C" int yc_frame_device_ptrs(yc_ctx* ctx, void** hdr, void** ldr, size_t* bytes) {
   if (!ctx) return YC_ERR_INVALID;
+  rt::useDevice(ctx->device);
   if (!ctx->inFrame) return fail(ctx, YC_ERR_STATE, "no frame");
   if (hdr) *hdr = ctx->dHdr;
   if (ldr) *ldr = ctx->dLdr;
@@ -1153,6 +1270,7 @@ extern "C" int yc_frame_device_ptrs(yc_ctx* ctx, void** hdr, void** ldr, size_t*
 
 extern "C" int yc_retonemap(yc_ctx* ctx) {
   if (!ctx) return YC_ERR_INVALID;
+  rt::useDevice(ctx->device);
   if (!ctx->inFrame) return fail(ctx, YC_ERR_STATE, "no frame");
   rt::launchFor(ctx->st, ctx->frame.width * ctx->frame.height, RetonemapK{ctx->dHdr, ctx->dLdr, ctx->frame.tonemap});
   ctx->launches++;
@@ -1163,6 +1281,7 @@ extern "C" int yc_retonemap(yc_ctx* ctx) {
 
 extern "C" int yc_set_profiling(yc_ctx* ctx, int timeExtendKernel) {
   if (!ctx) return YC_ERR_INVALID;
+  rt::useDevice(ctx->device);
   ctx->timeExtend = (timeExtendKernel & 1) != 0;
   ctx->countTraversal = (timeExtendKernel & 2) != 0;  // counting builds of extend / shadow (box / triangle tests)
   return YC_OK;
@@ -1185,7 +1304,7 @@ YB_DEV Sampler traceHookSampler() {
   return s;
 }
 
-template <bool NEE, bool ALPHA, bool COUNT>
+template <bool NEE, bool ALPHA, bool COUNT, bool WIDE = false>
 YB_DEV void traceOne(const DScene& sc, const YcRay& ray, bool useTMax, YcHit& out, TravStack& stack, TraceCounters& cnt) {
   Sampler smp = traceHookSampler();
   TraceState st;
@@ -1196,7 +1315,8 @@ YB_DEV void traceOne(const DScene& sc, const YcRay& ray, bool useTMax, YcHit& ou
   st.hit.backSide = 0;
   st.attenuation = V3(1.0f);
   const V3 o(ray.o), d(ray.d);
-  const bool did = traceScene<NEE, ALPHA, COUNT, false>(sc, o, d, st, stack, &smp, cnt);
+  const bool did = WIDE ? traceSceneWide<NEE, COUNT, NEE>(sc, o, d, st, stack, cnt)
+                        : traceScene<NEE, ALPHA, COUNT, false>(sc, o, d, st, stack, &smp, cnt);
   out.t = st.hit.t;
   out.didHit = did ? 1u : 0u;
   out.prim = did ? st.hit.prim : 0xffffffffu;
@@ -1222,13 +1342,13 @@ struct CompactHit {
 };
 
 #ifdef YB_HOSTSIM
-template <bool NEE, bool ALPHA, bool COUNT>
+template <bool NEE, bool ALPHA, bool COUNT, bool WIDE = false>
 static void runTrace(yc_ctx* ctx, const YcRay* rays, uint32_t n, bool useTMax, YcHit* hits, CompactHit* compact) {
   HostStack hs;
   TraceCounters cnt;
   for (uint32_t i = 0; i < n; i++) {
     YcHit h;
-    traceOne<NEE, ALPHA, COUNT>(ctx->ds, rays[i], useTMax, h, hs.ts, cnt);
+    traceOne<NEE, ALPHA, COUNT, WIDE>(ctx->ds, rays[i], useTMax, h, hs.ts, cnt);
     if (hits) hits[i] = h;
   }
   (void)compact;
@@ -1295,10 +1415,32 @@ __global__ void __launch_bounds__(kTraceBlock, YB_TRACE_MIN_BLOCKS) traceKernel(
   }
 }
 
-template <bool NEE, bool ALPHA, bool COUNT>
+template <bool NEE, bool COUNT, bool COMPACT>
+__global__ void __launch_bounds__(kTraceBlock, YB_WIDE_MIN_BLOCKS) traceWideKernel(DScene sc, const YcRay* rays, uint32_t n, int useTMax, YcHit* hits,
+                                                             CompactHit* compact, uint32_t* head, Counters* counters,
+                                                             uint2* spill, TraceTuning tune) {
+  TraceIO<NEE, false, COMPACT> io{sc, rays, hits, compact, useTMax};
+  TraceCounters cnt;
+  traceWidePersistent<NEE, COUNT>(sc, io, n, head, spill, tune, cnt);
+  if (COUNT) {
+    aggregatedCount(&counters->boxTests, cnt.box);
+    aggregatedCount(&counters->triTests, cnt.tri);
+  }
+}
+
+template <bool NEE, bool ALPHA, bool COUNT, bool WIDE = false>
 static void runTrace(yc_ctx* ctx, const YcRay* rays, uint32_t n, bool useTMax, YcHit* hits, CompactHit* compact) {
   const int grid = traceGrid(ctx, n);
   uint2* spill = static_cast<uint2*>(ctx->dSpill);
+  if (WIDE) {
+    if (compact)
+      traceWideKernel<NEE, COUNT, true><<<grid, kTraceBlock, 0, ctx->st.s>>>(ctx->ds, rays, n, useTMax, hits, compact, ctx->dCtr,
+                                                                             ctx->dCounters, spill, tuning(ctx));
+    else
+      traceWideKernel<NEE, COUNT, false><<<grid, kTraceBlock, 0, ctx->st.s>>>(ctx->ds, rays, n, useTMax, hits, compact, ctx->dCtr,
+                                                                              ctx->dCounters, spill, tuning(ctx));
+    return;
+  }
   if (compact)
     traceKernel<NEE, ALPHA, COUNT, true><<<grid, kTraceBlock, 0, ctx->st.s>>>(ctx->ds, rays, n, useTMax, hits, compact,
                                                                               ctx->dCtr, ctx->dCounters, spill, tuning(ctx));
@@ -1308,11 +1450,24 @@ static void runTrace(yc_ctx* ctx, const YcRay* rays, uint32_t n, bool useTMax, Y
 }
 #endif
 
-static void dispatchTrace(yc_ctx* ctx, int mode, const YcRay* rays, uint32_t n, YcHit* hits, CompactHit* compact) {
+// Which walk a ray hook uses: the context's (YcOptions::traversal) unless the mode forces one; counting traces
+// default to the reference-order walk (their box / triangle counts define the roofline's algorithmic bytes).
+static int traceUsesWide(yc_ctx* ctx, int mode, bool* wide) {
+  const bool count = (mode & YC_TRACE_COUNT) != 0;
+  *wide = (mode & YC_TRACE_WIDE) ? true : (mode & YC_TRACE_REFERENCE_ORDER) ? false : (ctx->wide && !count);
+  if (*wide && !ctx->ds.wideNodes) return fail(ctx, YC_ERR_STATE, "no wide BVH for this scene (alpha-tested materials, or traversal = reference order)");
+  return YC_OK;
+}
+
+static void dispatchTrace(yc_ctx* ctx, int mode, bool wide, const YcRay* rays, uint32_t n, YcHit* hits, CompactHit* compact) {
   const bool nee = (mode & 0xf) == YC_TRACE_ANY, count = (mode & YC_TRACE_COUNT) != 0, alpha = ctx->ds.hasAlpha != 0;
   const bool useTMax = (mode & YC_TRACE_USE_TMAX) != 0;
 #define YB_TR(N, A, C) runTrace<N, A, C>(ctx, rays, n, useTMax, hits, compact)
-  if (nee) {
+#define YB_TW(N, C) runTrace<N, false, C, true>(ctx, rays, n, useTMax, hits, compact)
+  if (wide) {
+    if (nee) count ? YB_TW(true, true) : YB_TW(true, false);
+    else count ? YB_TW(false, true) : YB_TW(false, false);
+  } else if (nee) {
     if (alpha) count ? YB_TR(true, true, true) : YB_TR(true, true, false);
     else count ? YB_TR(true, false, true) : YB_TR(true, false, false);
   } else {
@@ -1320,19 +1475,23 @@ static void dispatchTrace(yc_ctx* ctx, int mode, const YcRay* rays, uint32_t n, 
     else count ? YB_TR(false, false, true) : YB_TR(false, false, false);
   }
 #undef YB_TR
+#undef YB_TW
 }
 
 extern "C" int yc_trace_device(yc_ctx* ctx, const void* raysDev, size_t n, int mode, void* hitsDev, int repeat, float* ms) {
   if (!ctx || !raysDev || !hitsDev || n > 0xffffffffull) return YC_ERR_INVALID;
+  rt::useDevice(ctx->device);
   if (!ctx->hasScene) return fail(ctx, YC_ERR_NO_SCENE, "yc_trace_device before yc_upload_scene");
   int rc = ensureWaveStorage(ctx);
   if (rc != YC_OK) return rc;
   if (repeat < 1) repeat = 1;
+  bool wide;
+  if ((rc = traceUsesWide(ctx, mode, &wide)) != YC_OK) return rc;
   float total = 0.0f;
   for (int r = 0; r < repeat; r++) {
     YC_TRY(rt::zero(ctx->st, ctx->dCtr, kCtrCount * sizeof(uint32_t)));
     rt::eventRecord(ctx->st, ctx->ev0);
-    dispatchTrace(ctx, mode, static_cast<const YcRay*>(raysDev), uint32_t(n), nullptr, static_cast<CompactHit*>(hitsDev));
+    dispatchTrace(ctx, mode, wide, static_cast<const YcRay*>(raysDev), uint32_t(n), nullptr, static_cast<CompactHit*>(hitsDev));
     rt::eventRecord(ctx->st, ctx->ev1);
     ctx->launches++;
     YC_TRY(rt::sync(ctx->st));
@@ -1345,9 +1504,12 @@ extern "C" int yc_trace_device(yc_ctx* ctx, const void* raysDev, size_t n, int m
 
 extern "C" int yc_trace(yc_ctx* ctx, const YcRay* rays, size_t n, int mode, YcHit* hits, YcStats* stats) {
   if (!ctx || (n && (!rays || !hits)) || n > 0xffffffffull) return YC_ERR_INVALID;
+  rt::useDevice(ctx->device);
   if (!ctx->hasScene) return fail(ctx, YC_ERR_NO_SCENE, "yc_trace before yc_upload_scene");
   int rc = ensureWaveStorage(ctx);
   if (rc != YC_OK) return rc;
+  bool wide;
+  if ((rc = traceUsesWide(ctx, mode, &wide)) != YC_OK) return rc;
   if (mode & YC_TRACE_COUNT) YC_TRY(rt::zero(ctx->st, ctx->dCounters, sizeof(Counters)));
   if (n) {
     void *dr = nullptr, *dh = nullptr;
@@ -1360,7 +1522,7 @@ extern "C" int yc_trace(yc_ctx* ctx, const YcRay* rays, size_t n, int mode, YcHi
     e = rt::h2d(ctx->st, dr, rays, n * sizeof(YcRay));
     if (!e) e = rt::zero(ctx->st, ctx->dCtr, kCtrCount * sizeof(uint32_t));
     if (!e) {
-      dispatchTrace(ctx, mode, static_cast<const YcRay*>(dr), uint32_t(n), static_cast<YcHit*>(dh), nullptr);
+      dispatchTrace(ctx, mode, wide, static_cast<const YcRay*>(dr), uint32_t(n), static_cast<YcHit*>(dh), nullptr);
       ctx->launches++;
       e = rt::d2h(ctx->st, hits, dh, n * sizeof(YcHit));
     }
@@ -1374,32 +1536,38 @@ extern "C" int yc_trace(yc_ctx* ctx, const YcRay* rays, size_t n, int mode, YcHi
 
 extern "C" int yc_device_alloc(yc_ctx* ctx, size_t bytes, void** out) {
   if (!ctx || !out) return YC_ERR_INVALID;
+  rt::useDevice(ctx->device);
   YC_TRY(rt::alloc(out, bytes));
   return YC_OK;
 }
 extern "C" int yc_device_free(yc_ctx* ctx, void* p) {
   if (!ctx) return YC_ERR_INVALID;
+  rt::useDevice(ctx->device);
   rt::sync(ctx->st);
   rt::release(p);
   return YC_OK;
 }
 extern "C" int yc_host_alloc(yc_ctx* ctx, size_t bytes, void** out) {
   if (!ctx || !out) return YC_ERR_INVALID;
+  rt::useDevice(ctx->device);
   YC_TRY(rt::hostAlloc(out, bytes));
   return YC_OK;
 }
 extern "C" int yc_host_free(yc_ctx* ctx, void* p) {
   if (!ctx) return YC_ERR_INVALID;
+  rt::useDevice(ctx->device);
   rt::hostRelease(p);
   return YC_OK;
 }
 extern "C" int yc_memcpy_h2d(yc_ctx* ctx, void* dst, const void* src, size_t bytes) {
   if (!ctx || !dst || !src) return YC_ERR_INVALID;
+  rt::useDevice(ctx->device);
   YC_TRY(rt::h2d(ctx->st, dst, src, bytes));
   return YC_OK;
 }
 extern "C" int yc_memcpy_d2h(yc_ctx* ctx, void* dst, const void* src, size_t bytes) {
   if (!ctx || !dst || !src) return YC_ERR_INVALID;
+  rt::useDevice(ctx->device);
   YC_TRY(rt::d2h(ctx->st, dst, src, bytes));
   return YC_OK;
 }
@@ -1424,6 +1592,7 @@ struct PrimaryRayK {
 
 extern "C" int yc_generate_primary_rays(yc_ctx* ctx, uint32_t sampleOffset, uint32_t spp, void* raysDev) {
   if (!ctx || !raysDev) return YC_ERR_INVALID;
+  rt::useDevice(ctx->device);
   if (!ctx->inFrame) return fail(ctx, YC_ERR_STATE, "yc_generate_primary_rays before yc_begin_frame");
   const YcFrameDesc& f = ctx->frame;
   WaveParams w{};

@@ -232,6 +232,7 @@ extern "C" int yr_create(const YrSettings* settings, const ys_scene* scene, cons
   o.integrator = settings->integrator;
   o.scrambler = settings->scrambler;
   o.sampler = settings->sampler;
+  o.traversal = settings->traversal;
   int rc = yc_create(settings->device, &o, &r->ctx);
   if (rc != YC_OK) {
     delete r;
