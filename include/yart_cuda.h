@@ -35,6 +35,8 @@ extern "C" {
                                    YC_SAMPLER_SOBOL + YC_SCRAMBLER_FAST_OWEN needs libyart_b200_samplers.so (the same
                                    sources built with -DYB_RNG_SAMPLERS, same ABI) */
 
+#define YC_ERR_ABORTED (-8)     /* the abort flag (yc_set_abort_flag / yr_abort) was raised: the wave was not finished */
+
 #define YC_MAX_NODE_DEPTH 16
 
 /* ---------------------------------------------------------------------------------------
@@ -368,6 +370,38 @@ int yc_memcpy_d2h(yc_ctx* ctx, void* dst, const void* src, size_t bytes);
  * written to a device YcRay array of width*height*spp entries (sample-major). */
 int yc_generate_primary_rays(yc_ctx* ctx, uint32_t sampleOffset, uint32_t spp, void* raysDev);
 int yc_synchronize(yc_ctx* ctx);
+/* Renderer::abort (src/core/renderer.hpp:77-83, tile-renderer.hpp:40-63): `flag` is polled between chunks and between
+ * bounces of a wave; once it is non-zero the call in progress stops issuing work and returns YC_ERR_ABORTED (the
+ * frame keeps the waves finished before; the next yc_begin_frame clears the half-filled accumulation buffers).
+ * NULL removes the flag. */
+int yc_set_abort_flag(yc_ctx* ctx, const volatile int32_t* flag);
+
+/* --- device layer: combining accumulation buffers across GPUs (north_star: "per-GPU radiance, median-of-means and
+ * GMoN accumulation buffers are combined with NCCL over NVLink") ------------------------------------------------
+ * A context joins a communicator of `world` participants, one per GPU:
+ *   yc_comm_init_all     one process, n contexts on n GPUs (ncclCommInitAll); calls below come from one thread per context
+ *   yc_comm_init_rank    one process per GPU (torchrun): rank 0 makes an id with yc_comm_unique_id and hands it to the
+ *                        others by any control-plane means (ncclCommInitRank)
+ *   yc_comm_init_custom  the caller's own sum collective instead of NCCL (MPI, gloo, a test double): fn(buf, count,
+ *                        dtype, root, user) sums `count` elements of dtype (0 f32, 1 i32, 2 u64) in place over all
+ *                        participants, into `root` only if root >= 0; `buf` is a DEVICE pointer in the CUDA build
+ * NCCL is loaded at the first of these calls (libnccl.so.2 through dlopen: single-GPU users need none). */
+#define YC_COMM_ID_BYTES 128
+typedef int (*yc_collective_fn)(void* buf, size_t count, int dtype, int root, void* user);
+int yc_comm_unique_id(void* id128);
+int yc_comm_init_rank(yc_ctx* ctx, int rank, int world, const void* id128);
+int yc_comm_init_all(yc_ctx** ctxs, int n);
+int yc_comm_init_custom(yc_ctx* ctx, int rank, int world, yc_collective_fn fn, void* user);
+int yc_comm_destroy(yc_ctx* ctx);
+/* Tile sharding (YcFrameDesc.shardIndex / shardCount): every participant's HDR and LDR frames hold its own tiles and
+ * zeros elsewhere; their sum — bit-identical to one GPU's frame — lands in `root`'s combined frames (ncclReduce,
+ * out of place: the participants' own frames keep blending their tiles wave after wave). */
+int yc_comm_reduce_frames(yc_ctx* ctx, int root);
+int yc_resolve_combined(yc_ctx* ctx, float* hdrRGBA, float* ldrRGBA);
+/* Bucket sharding (yc_accumulate_wave): all-reduce(sum, int32) of the planes a wave of `waveSamples` samples uses. */
+int yc_comm_allreduce_buckets(yc_ctx* ctx, uint32_t waveSamples);
+/* Control values (ray counts, abort votes): in-place sum over all participants. */
+int yc_comm_sum_u64(yc_ctx* ctx, uint64_t* values, uint32_t n);
 /* Function-level hooks used by the parity tests (device evaluations of the restated math). */
 int yc_kat(yc_ctx* ctx, const char* kind, const void* in, size_t inBytes, void* out, size_t outBytes);
 
@@ -408,6 +442,8 @@ void ys_scene_destroy(ys_scene* s);
 const char* ys_last_error(void);
 /* Flattened view (valid until ys_scene_destroy). */
 const YcScene* ys_scene_flat(const ys_scene* s);
+/* The library's data tables for YcScene::lutTables (the values of the reference's src/bsdf/luts.hpp, 14112 floats). */
+const float* ys_lut_tables(size_t* count);
 double ys_scene_build_ms(const ys_scene* s);
 /* BVH of mesh `mesh` in the REFERENCE's node numbering/layout (for builder parity tests):
  * nodes = nNodes × {min[3] max[3] leftFirst span} (32 B), indices = nTris × u32. */
@@ -435,7 +471,12 @@ typedef struct YrSettings {
   uint32_t scrambler;  /* YC_SCRAMBLER_* */
   uint32_t sampler;    /* YC_SAMPLER_* */
   uint32_t traversal;  /* YC_TRAVERSAL_* */
+  uint32_t sharding;   /* YR_SHARD_*: how yr_create_multi / yr_create_dist split a wave across GPUs */
 } YrSettings;
+
+#define YR_SHARD_TILES 0   /* tile k of the reference's tile list (tile-renderer.hpp:127-144) → GPU k mod G; frames reduced to rank 0 */
+#define YR_SHARD_BUCKETS 1 /* every GPU holds the frame and takes (estimator bucket, pixel class) units of each wave; the
+                              GMoN accumulation buffers are all-reduced per wave; every GPU ends up with the frame */
 
 typedef struct YrRenderData {  /* Renderer::RenderData (renderer.hpp:22-28) */
   uint64_t samplesTaken, totalSamples, totalRays;
@@ -447,14 +488,45 @@ typedef struct YrWaveData {    /* Renderer::WaveData (renderer.hpp:33-38) */
   double timeMs;
 } YrWaveData;
 
-typedef void (*yr_wave_callback)(const YrRenderData*, const YrWaveData*, void* user);
+typedef struct YrTileData {    /* Renderer::TileData (renderer.hpp:43-50) */
+  uint32_t x, y, w, h;
+  uint64_t index, total, rays;
+  double timeMs;
+} YrTileData;
+
+typedef void (*yr_wave_callback)(const YrRenderData*, const YrWaveData*, void* user);   /* onRenderWaveComplete */
+typedef void (*yr_tile_callback)(const YrRenderData*, const YrTileData*, void* user);   /* onRenderTileComplete */
+typedef void (*yr_done_callback)(const YrRenderData*, int aborted, void* user);         /* onRenderComplete / onRenderAborted */
 
 typedef struct yr_renderer yr_renderer;
 int yr_create(const YrSettings* settings, const ys_scene* scene, const YcCamera* camera, yr_renderer** out);
+/* The same on a caller-flattened scene (what a `yart::Renderer` subclass holding `const Scene* scene`,
+ * renderer.hpp:53, passes: integration/wavefront-renderer.hpp).  The arrays must outlive the renderer. */
+int yr_create_flat(const YrSettings* settings, const YcScene* scene, const YcCamera* camera, yr_renderer** out);
+/* One renderer over several GPUs of this process (scene replicated, one driver thread per GPU, NCCL inside):
+ * render / abort / wait / callbacks / read are unchanged and the frame is bit-identical to one GPU's.
+ * Replaces TileRenderer's worker threads (tile-renderer.hpp:150-197) at the scale of a box. */
+int yr_create_multi(const YrSettings* settings, const ys_scene* scene, const YcCamera* camera, const int* devices,
+                    uint32_t nDevices, yr_renderer** out);
+int yr_create_multi_flat(const YrSettings* settings, const YcScene* scene, const YcCamera* camera, const int* devices,
+                         uint32_t nDevices, yr_renderer** out);
+/* The same with one process per GPU (torchrun): settings->device is this process's GPU, `commId` the bytes rank 0 got
+ * from yc_comm_unique_id.  Rank 0 receives the frame (tile sharding) or every rank does (bucket sharding); ray counts
+ * in YrRenderData / YrWaveData are whole-job figures on every rank. */
+int yr_create_dist(const YrSettings* settings, const ys_scene* scene, const YcCamera* camera, int rank, int world,
+                   const void* commId, yr_renderer** out);
+int yr_create_dist_custom(const YrSettings* settings, const ys_scene* scene, const YcCamera* camera, int rank, int world,
+                          yc_collective_fn fn, void* user, yr_renderer** out);
 void yr_destroy(yr_renderer* r);
 int yr_set_wave_callback(yr_renderer* r, yr_wave_callback cb, void* user);
+int yr_set_tile_callback(yr_renderer* r, yr_tile_callback cb, void* user);
+int yr_set_done_callback(yr_renderer* r, yr_done_callback cb, void* user);
+/* Host frame (width*height*4 floats) that receives the tonemapped frame — the HDR one when tonemap is NONE, like
+ * Renderer::m_buffer (tile-renderer.hpp:238) — after every wave, before the callbacks fire. */
+int yr_set_frame_target(yr_renderer* r, float* ldrRGBA);
+int yr_set_camera(yr_renderer* r, const YcCamera* camera); /* the camera moved between renders */
 int yr_render(yr_renderer* r);     /* Renderer::render(): asynchronous */
-int yr_abort(yr_renderer* r);      /* Renderer::abort() */
+int yr_abort(yr_renderer* r);      /* Renderer::abort(): returns at once, the render stops at its next chunk / bounce */
 int yr_wait(yr_renderer* r);       /* Renderer::wait() */
 int yr_render_sync(yr_renderer* r, YrRenderData* out); /* Renderer::renderSync() */
 /* Result buffers: LDR (what Renderer::m_buffer holds) and HDR accumulation. */

@@ -1,0 +1,119 @@
+// comm.cuh — combining per-GPU accumulation buffers (included by wavefront.cu after yc_ctx is defined).
+//
+// BASELINE.json north_star: "Work is partitioned across the 8 GPUs of one box by image tile or sample wave, with the
+// scene replicated per GPU.  Per-GPU radiance, median-of-means and GMoN accumulation buffers are combined with NCCL
+// over NVLink."  The reference's counterpart is the hand-over of finished tiles between worker threads under
+// m_bufferMutex (src/cpu/tile-renderer.hpp:205-239).
+//
+// Three transports behind the same yc_comm_* entry points:
+//   * NCCL (product build): libnccl.so.2 loaded with dlopen at the first yc_comm_* call — the library has no link-time
+//     dependency on it, and a process that already holds NCCL (PyTorch) shares that copy.  Collectives run on the
+//     context's own stream, so they order after the wave's kernels without a host round trip.
+//   * the caller's sum collective (yc_comm_init_custom): MPI, gloo, a test double.
+//   * an in-process group (CPU build of the product sources only): the contexts of yc_comm_init_all meet at a barrier
+//     and the last one to arrive adds the buffers — lets the multi-GPU renderer logic run in the CPU test-suite.
+// Every data collective is a SUM over buffers in which each element is non-zero on at most one participant (disjoint
+// tiles; disjoint (bucket, pixel) slots, summed as int32), so x + 0 + ... + 0 is exact and the result is bit-identical
+// to one GPU whatever order the transport adds in.
+#pragma once
+#include <condition_variable>
+#include <memory>
+#include <mutex>
+
+#ifndef YB_HOSTSIM
+#include <dlfcn.h>
+#include <nccl.h>
+#endif
+
+namespace yb {
+
+enum { kCommF32 = 0, kCommI32 = 1, kCommU64 = 2 };
+
+#ifndef YB_HOSTSIM
+// The handful of NCCL entry points used, resolved once from libnccl.so.2.
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Reduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  std::string error;
+  bool ok = false;
+};
+inline NcclApi& nccl() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) {
+      api.error = std::string("cannot load libnccl.so.2: ") + dlerror();
+      return;
+    }
+    bool all = true;
+    auto sym = [&](auto& fn, const char* name) {
+      fn = reinterpret_cast<std::remove_reference_t<decltype(fn)>>(dlsym(h, name));
+      all = all && fn != nullptr;
+    };
+    sym(api.GetUniqueId, "ncclGetUniqueId"), sym(api.CommInitRank, "ncclCommInitRank"), sym(api.CommInitAll, "ncclCommInitAll");
+    sym(api.CommDestroy, "ncclCommDestroy"), sym(api.AllReduce, "ncclAllReduce"), sym(api.Reduce, "ncclReduce");
+    sym(api.GroupStart, "ncclGroupStart"), sym(api.GroupEnd, "ncclGroupEnd"), sym(api.GetErrorString, "ncclGetErrorString");
+    api.ok = all;
+    if (!all) api.error = "libnccl.so.2 lacks an expected symbol";
+  });
+  return api;
+}
+static_assert(sizeof(ncclUniqueId) == YC_COMM_ID_BYTES, "YC_COMM_ID_BYTES must match ncclUniqueId");
+#endif
+
+// In-process group (CPU build): n participants, each on its own thread, meet per collective.
+struct HostGroup {
+  std::mutex m;
+  std::condition_variable cv;
+  int n = 0, arrived = 0;
+  uint64_t generation = 0;
+  std::vector<void*> bufs;
+  // Every participant calls with its buffer; the last arrival sums all buffers into bufs[root] (root < 0: into all).
+  void sum(int rank, void* buf, size_t count, int dtype, int root) {
+    std::unique_lock<std::mutex> lk(m);
+    bufs[size_t(rank)] = buf;
+    const uint64_t gen = generation;
+    if (++arrived == n) {
+      auto add = [&](auto* tag) {
+        using T = std::remove_pointer_t<decltype(tag)>;
+        std::vector<T> total(count, T(0));
+        for (int r = 0; r < n; r++)
+          for (size_t i = 0; i < count; i++) total[i] += static_cast<T*>(bufs[size_t(r)])[i];
+        for (int r = 0; r < n; r++)
+          if (root < 0 || r == root) memcpy(bufs[size_t(r)], total.data(), count * sizeof(T));
+      };
+      if (dtype == kCommF32) add(static_cast<float*>(nullptr));
+      else if (dtype == kCommI32) add(static_cast<uint32_t*>(nullptr));  // wrap-around add: bit patterns, x + 0 exact
+      else add(static_cast<uint64_t*>(nullptr));
+      arrived = 0;
+      generation++;
+      cv.notify_all();
+    } else {
+      cv.wait(lk, [&] { return generation != gen; });
+    }
+  }
+};
+
+struct Comm {
+  int rank = 0, world = 1;
+#ifndef YB_HOSTSIM
+  ncclComm_t nccl = nullptr;
+#endif
+  yc_collective_fn custom = nullptr;
+  void* customUser = nullptr;
+  std::shared_ptr<HostGroup> group;
+  float4 *hdrAll = nullptr, *ldrAll = nullptr;  // root's combined frames (tile sharding)
+  size_t frameTexels = 0;
+  uint64_t* scratch = nullptr;                  // device staging for yc_comm_sum_u64
+};
+
+}  // namespace yb

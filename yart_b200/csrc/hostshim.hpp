@@ -21,6 +21,13 @@ static inline uint32_t __brev(uint32_t v) {
   v = ((v >> 8) & 0x00ff00ffu) | ((v & 0x00ff00ffu) << 8);
   return (v >> 16) | (v << 16);
 }
+// PRMT: result byte i = byte (selector nibble i) of the eight bytes {x (0-3), y (4-7)}
+static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) {
+  const uint64_t v = (uint64_t(y) << 32) | x;
+  uint32_t r = 0;
+  for (int i = 0; i < 4; i++) r |= uint32_t((v >> (8 * ((s >> (4 * i)) & 7u))) & 0xffu) << (8 * i);
+  return r;
+}
 static inline uint32_t __float_as_uint(float f) {
   uint32_t u;
   memcpy(&u, &f, 4);

@@ -42,6 +42,10 @@ inline const char* zero(Stream&, void* d, size_t n) {
   memset(d, 0, n);
   return nullptr;
 }
+inline const char* d2d(Stream&, void* d, const void* s, size_t n) {
+  memcpy(d, s, n);
+  return nullptr;
+}
 inline const char* sync(Stream&) { return nullptr; }
 inline void eventCreate(Event&) {}
 inline void eventDestroy(Event&) {}
@@ -109,6 +113,9 @@ inline const char* d2h(Stream& st, void* d, const void* s, size_t n) {
   return errstr(cudaStreamSynchronize(st.s));
 }
 inline const char* zero(Stream& st, void* d, size_t n) { return n ? errstr(cudaMemsetAsync(d, 0, n, st.s)) : nullptr; }
+inline const char* d2d(Stream& st, void* d, const void* s, size_t n) {
+  return n ? errstr(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, st.s)) : nullptr;
+}
 inline const char* sync(Stream& st) { return errstr(cudaStreamSynchronize(st.s)); }
 inline void eventCreate(Event& e) { cudaEventCreate(&e.e); }
 inline void eventDestroy(Event& e) {

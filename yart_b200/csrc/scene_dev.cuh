@@ -5,7 +5,7 @@
 //   meshes     YcMesh[nMeshes]
 //   bvhNodes   float4[4 * nBvhNodes]     inner BVH2 nodes, both child boxes inlined (64 B, 4 × LDG.128)
 //   bvhTris    float4[3 * nBvhTris]      leaf-ordered triangles, positions pre-gathered (48 B, 3 × LDG.128)
-//   wideNodes  float4[8 * nWide]         the same tree collapsed to 4-wide nodes (128 B, wide_bvh.cuh), scenes without alpha
+//   wideNodes  float4[4 * nWide]         the same tree collapsed to 4-wide nodes with quantised boxes (64 B, wide_bvh.cuh), scenes without alpha
 //   positions/normals/tangents/uvs       per-vertex attributes (shade-time gathers)
 //   primIndices/primMaterial/primLight   per-primitive, original order
 //   materials, textures, texels, lights, envDist, light-sampler tables, LUTs
@@ -29,7 +29,7 @@ struct DScene {
   uint32_t nMeshes;
   const float4* bvhNodes;
   const float4* bvhTris;
-  const float4* wideNodes;      // float4[8 * nWideNodes]: the collapsed 4-wide nodes (128 B each), null when not built
+  const float4* wideNodes;      // float4[4 * nWideNodes]: the collapsed 4-wide nodes with quantised child boxes (64 B each), null when not built
   const WideMesh* wideMeshes;   // [nMeshes]
   const float* positions;
   const float* normals;

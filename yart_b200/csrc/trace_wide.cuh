@@ -1,15 +1,13 @@
-// trace_wide.cuh — persistent-warp traversal of the 4-wide BVH (wide_bvh.cuh), CUDA only: the extend, shadow and
-// ray-hook kernels of scenes without alpha-tested materials.
+// trace_wide.cuh — persistent-warp traversal of the 4-wide quantised BVH (wide_bvh.cuh), CUDA only: the extend,
+// shadow and ray-hook kernels of scenes without alpha-tested materials.
 //
 // Same warp scheduling as trace_kernels.cuh (lane state machine IDLE → NODE → TRAV, one atomic per warp to
 // refill idle lanes, inner-node steps in a tight loop while enough lanes sit on inner nodes, speculative leaf
 // parking, packed (ref, d) stack entries in shared memory with a sentinel at the bottom); what changes is the
-// inner step: one 128-byte node, four boxes, no selects —
-//     6 x LDG.128 (near / far planes, the row picked by the ray's direction signs) + 1 x LDG.128 (child refs)
-//     24 FFMA  (t = plane * 1/d - o/d, one rounding)
-//     16 FMNMX (FMNMX3 where ptxas finds it) + 4 FSETP
-//     4 keys (entry distance | slot), unsigned min → nearest hit child; the other hit children are pushed with
-//     their entry distances (predicated STS.64), popped entries are culled by `d < hit.t`.
+// inner step: one 64-byte node = 2 x LDG.256 per lane (two L1 tag look-ups per visit instead of the BVH2 walk's
+// two per HALF as much tree), four boxes decoded with 24 PRMT + 24 FFMA, 6 selects for near / far,
+// 16 FMNMX(3) + 4 FSETP; 4 keys (entry distance | slot), unsigned min → nearest hit child; the other hit children
+// are pushed with their entry distances (predicated STS.64), popped entries are culled by `d < hit.t`.
 // Triangles are the reference's arithmetic (testTriangle).  Results versus the reference-order walk: see the
 // header of wide_bvh.cuh.
 #pragma once
@@ -17,12 +15,14 @@
 
 namespace yb {
 
-struct Planes4 {
-  float x, y, z, w;
+struct Words8 {
+  uint32_t w[8];
 };
-__device__ __forceinline__ Planes4 loadRow(const float4* p) {
-  Planes4 r;
-  asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+__device__ __forceinline__ Words8 loadHalfNode(const float4* p) {  // 32 bytes, one sector
+  Words8 r;
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7])
+               : "l"(p));
   return r;
 }
 
@@ -56,6 +56,9 @@ __device__ __forceinline__ void traceWidePersistent(const DScene& sc, IO& io, ui
   constexpr uint32_t kPopRef = 0xfffffffeu;  // "pop at the top of the next inner step"
   uint32_t pend = 0u;                        // parked leaf (0 = none)
   float pendD = 0.0f;
+  // bits of 1.0f in a register ptxas cannot fold (shEntries <= 25), so that planeUnit's PRMT carries its selector as the
+  // immediate instead of fetching four selectors into registers on every visit
+  const uint32_t one = 0x3f800000u | (uint32_t(tune.shEntries) >> 30);
 
   for (;;) {
     // ---- refill idle lanes -------------------------------------------------------------------
@@ -120,7 +123,7 @@ __device__ __forceinline__ void traceWidePersistent(const DScene& sc, IO& io, ui
         if (!slabWideBox(wr, V3(mesh.rootMin), V3(mesh.rootMax), kTMin, st.hit.t, dd)) continue;
         const WideMesh wm = sc.wideMeshes[mi];
         meshIdx = uint32_t(mi);
-        nodes = sc.wideNodes + 8 * size_t(wm.nodeOffset);
+        nodes = sc.wideNodes + 4 * size_t(wm.nodeOffset);
         tris = sc.bvhTris + 3 * size_t(mesh.triOffset);
         cur = wm.rootRef;
         dcur = dd;
@@ -153,41 +156,39 @@ __device__ __forceinline__ void traceWidePersistent(const DScene& sc, IO& io, ui
       if (im == 0) break;
       if (__popc(im) < tune.innerMin && __ballot_sync(FULL, trav && !inner)) break;
       if (inner) {
-        const float4* np = nodes + 8 * size_t(cur);
-        const Planes4 nX = loadRow(np + wr.nx), fX = loadRow(np + (wr.nx ^ 1u));
-        const Planes4 nY = loadRow(np + wr.ny), fY = loadRow(np + (wr.ny ^ 1u));
-        const Planes4 nZ = loadRow(np + wr.nz), fZ = loadRow(np + (wr.nz ^ 1u));
-        const uint4 rf = __ldg(reinterpret_cast<const uint4*>(np + 6));
-        // pop-time cull `d < hit.t`: a dead entry fails all four tests (tmx = -inf)
+        const float4* np = nodes + 4 * size_t(cur);
+        const Words8 a = loadHalfNode(np), b = loadHalfNode(np + 2);  // {p', S, q.x} and {q.y, q.z, refs}
+        const uint4 rf = make_uint4(b.w[4], b.w[5], b.w[6], b.w[7]);
+        // pop-time cull `d < hit.t`: a dead entry hits nothing
         const bool live = dcur < st.hit.t;
-        const float tmx = live ? st.hit.t : -INFINITY;
-        float t0, t1, t2, t3;
-        const bool h0 = slabWide(wr, V3(nX.x, nY.x, nZ.x), V3(fX.x, fY.x, fZ.x), kTMin, tmx, t0);
-        const bool h1 = slabWide(wr, V3(nX.y, nY.y, nZ.y), V3(fX.y, fY.y, fZ.y), kTMin, tmx, t1);
-        const bool h2 = slabWide(wr, V3(nX.z, nY.z, nZ.z), V3(fX.z, fY.z, fZ.z), kTMin, tmx, t2) && rf.z != kWideEmpty;
-        const bool h3 = slabWide(wr, V3(nX.w, nY.w, nZ.w), V3(fX.w, fY.w, fZ.w), kTMin, tmx, t3) && rf.w != kWideEmpty;
+        const WideSlabs sl = slabWide4(wr, one, __uint_as_float(a.w[0]), __uint_as_float(a.w[1]), __uint_as_float(a.w[2]),
+                                       __uint_as_float(a.w[3]), __uint_as_float(a.w[4]), __uint_as_float(a.w[5]), a.w[6], a.w[7], b.w[0],
+                                       b.w[1], b.w[2], b.w[3], kTMin, st.hit.t, live);
+        const float t0 = sl.tn[0], t1 = sl.tn[1], t2 = sl.tn[2], t3 = sl.tn[3];
+        const bool h0 = sl.hit[0], h1 = sl.hit[1], h2 = sl.hit[2] && rf.z != kWideEmpty, h3 = sl.hit[3] && rf.w != kWideEmpty;
         if (COUNT && live) cnt.box += 2u + (rf.z != kWideEmpty) + (rf.w != kWideEmpty);
-        const uint32_t k0 = wideKey(h0, t0, 0u), k1 = wideKey(h1, t1, 1u), k2 = wideKey(h2, t2, 2u), k3 = wideKey(h3, t3, 3u);
-        const uint32_t best = min(min(k0, k1), min(k2, k3));
-        const bool p0 = k0 == best, p1 = k1 == best, p2 = k2 == best;
+        // nearest hit child (lowest slot among equal entry distances) → next node; the others are pushed in slot order
+        const float a0 = h0 ? t0 : INFINITY, a1 = h1 ? t1 : INFINITY, a2 = h2 ? t2 : INFINITY, a3 = h3 ? t3 : INFINITY;
+        const float best = fminf(fminf(a0, a1), fminf(a2, a3));
+        const bool any = h0 || h1 || h2 || h3;
+        const bool p0 = h0 && a0 == best, p1 = !p0 && h1 && a1 == best, p2 = !p0 && !p1 && h2 && a2 == best;
         const uint32_t nearRef = p0 ? rf.x : (p1 ? rf.y : (p2 ? rf.z : rf.w));
-        // push the other hit children (slot order) with their entry distances
-        const bool q0 = h0 && !p0, q1 = h1 && !p1, q2 = h2 && !p2, q3 = h3 && k3 != best;
+        const bool q0 = h0 && !p0, q1 = h1 && !p1, q2 = h2 && !p2, q3 = h3 && (p0 || p1 || p2);
         if (sp + 3u * kPsStride < stack.limit) {  // the (at most three) pushes fit in shared memory
-          uint32_t a = sp;
-          if (q0) stack.put(a, rf.x, t0), a += kPsStride;
-          if (q1) stack.put(a, rf.y, t1), a += kPsStride;
-          if (q2) stack.put(a, rf.z, t2), a += kPsStride;
-          if (q3) stack.put(a, rf.w, t3), a += kPsStride;
-          sp = a;
+          uint32_t sa = sp;
+          if (q0) stack.put(sa, rf.x, t0), sa += kPsStride;
+          if (q1) stack.put(sa, rf.y, t1), sa += kPsStride;
+          if (q2) stack.put(sa, rf.z, t2), sa += kPsStride;
+          if (q3) stack.put(sa, rf.w, t3), sa += kPsStride;
+          sp = sa;
         } else {
           stack.pushIf(q0, sp, rf.x, t0);
           stack.pushIf(q1, sp, rf.y, t1);
           stack.pushIf(q2, sp, rf.z, t2);
           stack.pushIf(q3, sp, rf.w, t3);
         }
-        cur = best == kWideMiss ? kPopRef : nearRef;
-        dcur = __uint_as_float(best & ~3u);
+        cur = any ? nearRef : kPopRef;
+        dcur = best;
       }
     }
 

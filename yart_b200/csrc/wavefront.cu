@@ -21,6 +21,7 @@
 #include "estimator.cuh"
 #include "integrator.cuh"
 #include "rt.cuh"
+#include "comm.cuh"
 #ifndef YB_HOSTSIM
 #include "trace_wide.cuh"
 #endif
@@ -102,6 +103,8 @@ struct yc_ctx {
   uint64_t extendLaunches = 0, raysExtend = 0;
   bool timeExtend = false, countTraversal = false;
   uint32_t tailThreshold = 16384;  // paths left in a chunk at which the tail kernel takes over (0 = never)
+  const volatile int32_t* abortFlag = nullptr;  // yc_set_abort_flag
+  std::unique_ptr<Comm> comm;      // yc_comm_*: the communicator this context belongs to
   bool wide = false;               // the scene's wide BVH is built and the kernels walk it (YcOptions::traversal)
   int wideDepth = 0;               // deepest wide level over all meshes
   uint64_t nWideNodes = 0;
@@ -428,7 +431,7 @@ __global__ void __launch_bounds__(kTraceBlock, YB_SHADOW_MIN_BLOCKS) shadowKerne
 
 // The same two kernels over the 4-wide BVH (trace_wide.cuh): scenes without alpha-tested materials.
 #ifndef YB_WIDE_MIN_BLOCKS
-#define YB_WIDE_MIN_BLOCKS 6
+#define YB_WIDE_MIN_BLOCKS 7  // 72 registers, no spills (6 CTAs: 80 registers, soup trace 3.32 ms; 7: 3.10 ms; 8 spills: 3.24 ms)
 #endif
 template <bool COUNT>
 __global__ void __launch_bounds__(kTraceBlock, YB_WIDE_MIN_BLOCKS) extendWideKernel(DScene sc, WaveParams w, PathState ps, const uint32_t* queue,
@@ -636,10 +639,13 @@ static void freeFrame(yc_ctx* ctx) {
   ctx->inFrame = false;
 }
 
+static void destroyComm(yc_ctx* ctx);
+
 extern "C" void yc_destroy(yc_ctx* ctx) {
   if (!ctx) return;
   rt::useDevice(ctx->device);
   rt::sync(ctx->st);
+  destroyComm(ctx);
   freeFrame(ctx);
   freeAll(ctx->sceneAllocs);
   freeAll(ctx->waveAllocs);
@@ -1015,7 +1021,14 @@ static int renderChunks(yc_ctx* ctx, const uint32_t* dList, uint32_t nPixCall, u
   for (int l = 0; l < kLanes; l++) ctx->lanes[l].active = false;
   size_t next = 0, nextAcc = 0;
   rt::Event* lastAcc = nullptr;
+  auto abortRequested = [&] { return ctx->abortFlag && *ctx->abortFlag != 0; };
+  auto abortNow = [&] {
+    // stop issuing, let what is in flight drain (the lanes' buffers are reused by the next call)
+    for (int l = 0; l < kLanes; l++) rt::sync(ctx->lanes[l].st);
+    return fail(ctx, YC_ERR_ABORTED, "aborted");
+  };
   while (nextAcc < chunks.size()) {
+    if (abortRequested()) return abortNow();
     // start chunks on idle lanes
     for (int l = 0; l < kLanes && next < chunks.size(); l++) {
       Lane& L = ctx->lanes[l];
@@ -1079,6 +1092,7 @@ static int renderChunks(yc_ctx* ctx, const uint32_t* dList, uint32_t nPixCall, u
     }
     Lane& L = *W;
     rt::eventSync(L.evCtr);
+    if (abortRequested()) return abortNow();
     L.waiting = false;
     L.n = L.hCtr[kCtrNextCount];
     L.bounce++;
@@ -1610,6 +1624,209 @@ extern "C" int yc_generate_primary_rays(yc_ctx* ctx, uint32_t sampleOffset, uint
   ctx->launches++;
   YC_TRY(rt::sync(ctx->st));
   YC_TRY(rt::lastError());
+  return YC_OK;
+}
+
+extern "C" int yc_set_abort_flag(yc_ctx* ctx, const volatile int32_t* flag) {
+  if (!ctx) return YC_ERR_INVALID;
+  ctx->abortFlag = flag;
+  return YC_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// collectives (comm.cuh)
+// ---------------------------------------------------------------------------------------
+static void destroyComm(yc_ctx* ctx) {
+  if (!ctx->comm) return;
+  Comm& c = *ctx->comm;
+#ifndef YB_HOSTSIM
+  if (c.nccl) nccl().CommDestroy(c.nccl);
+#endif
+  rt::release(c.hdrAll);
+  rt::release(c.ldrAll);
+  rt::release(c.scratch);
+  ctx->comm.reset();
+}
+
+#ifndef YB_HOSTSIM
+#define YC_NCCL(expr)                                                                    \
+  do {                                                                                   \
+    const ncclResult_t r_ = (expr);                                                      \
+    if (r_ != ncclSuccess) return fail(ctx, YC_ERR_CUDA, "%s: %s", #expr, nccl().GetErrorString(r_)); \
+  } while (0)
+#endif
+
+extern "C" int yc_comm_unique_id(void* id128) {
+  if (!id128) return YC_ERR_INVALID;
+#ifdef YB_HOSTSIM
+  return YC_ERR_UNSUPPORTED;
+#else
+  if (!nccl().ok) {
+    fprintf(stderr, "yart_b200: %s\n", nccl().error.c_str());
+    return YC_ERR_UNSUPPORTED;
+  }
+  ncclUniqueId id;
+  if (nccl().GetUniqueId(&id) != ncclSuccess) return YC_ERR_CUDA;
+  memcpy(id128, &id, sizeof id);
+  return YC_OK;
+#endif
+}
+
+extern "C" int yc_comm_init_rank(yc_ctx* ctx, int rank, int world, const void* id128) {
+  if (!ctx || !id128 || world < 1 || rank < 0 || rank >= world) return YC_ERR_INVALID;
+  rt::useDevice(ctx->device);
+#ifdef YB_HOSTSIM
+  return fail(ctx, YC_ERR_UNSUPPORTED, "the CPU build has no NCCL: use yc_comm_init_custom or yc_comm_init_all");
+#else
+  if (!nccl().ok) return fail(ctx, YC_ERR_UNSUPPORTED, "%s", nccl().error.c_str());
+  destroyComm(ctx);
+  ctx->comm = std::make_unique<Comm>();
+  ctx->comm->rank = rank, ctx->comm->world = world;
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof id);
+  YC_NCCL(nccl().CommInitRank(&ctx->comm->nccl, world, id, rank));
+  return YC_OK;
+#endif
+}
+
+extern "C" int yc_comm_init_all(yc_ctx** ctxs, int n) {
+  if (!ctxs || n < 1) return YC_ERR_INVALID;
+  for (int i = 0; i < n; i++)
+    if (!ctxs[i]) return YC_ERR_INVALID;
+#ifdef YB_HOSTSIM
+  auto group = std::make_shared<HostGroup>();
+  group->n = n;
+  group->bufs.assign(size_t(n), nullptr);
+  for (int i = 0; i < n; i++) {
+    destroyComm(ctxs[i]);
+    ctxs[i]->comm = std::make_unique<Comm>();
+    ctxs[i]->comm->rank = i, ctxs[i]->comm->world = n, ctxs[i]->comm->group = group;
+  }
+  return YC_OK;
+#else
+  yc_ctx* ctx = ctxs[0];
+  if (!nccl().ok) return fail(ctx, YC_ERR_UNSUPPORTED, "%s", nccl().error.c_str());
+  std::vector<int> devs;
+  std::vector<ncclComm_t> comms(size_t(n), nullptr);
+  for (int i = 0; i < n; i++) devs.push_back(ctxs[i]->device);
+  YC_NCCL(nccl().CommInitAll(comms.data(), n, devs.data()));
+  for (int i = 0; i < n; i++) {
+    destroyComm(ctxs[i]);
+    ctxs[i]->comm = std::make_unique<Comm>();
+    ctxs[i]->comm->rank = i, ctxs[i]->comm->world = n, ctxs[i]->comm->nccl = comms[size_t(i)];
+  }
+  return YC_OK;
+#endif
+}
+
+extern "C" int yc_comm_init_custom(yc_ctx* ctx, int rank, int world, yc_collective_fn fn, void* user) {
+  if (!ctx || !fn || world < 1 || rank < 0 || rank >= world) return YC_ERR_INVALID;
+  destroyComm(ctx);
+  ctx->comm = std::make_unique<Comm>();
+  ctx->comm->rank = rank, ctx->comm->world = world, ctx->comm->custom = fn, ctx->comm->customUser = user;
+  return YC_OK;
+}
+
+extern "C" int yc_comm_destroy(yc_ctx* ctx) {
+  if (!ctx) return YC_ERR_INVALID;
+  rt::useDevice(ctx->device);
+  rt::sync(ctx->st);
+  destroyComm(ctx);
+  return YC_OK;
+}
+
+// Sum of `count` elements over all participants, in place on this context's stream; into `root` only when root >= 0
+// (the other participants' buffers are then unspecified).
+static int commSum(yc_ctx* ctx, void* buf, size_t count, int dtype, int root) {
+  Comm& c = *ctx->comm;
+  if (c.world == 1) return YC_OK;
+  if (c.custom) {
+    YC_TRY(rt::sync(ctx->st));  // the caller's collective knows nothing of our stream
+    if (c.custom(buf, count, dtype, root, c.customUser) != 0) return fail(ctx, YC_ERR_CUDA, "the custom collective failed");
+    return YC_OK;
+  }
+  if (c.group) {
+    YC_TRY(rt::sync(ctx->st));
+    c.group->sum(c.rank, buf, count, dtype, root);
+    return YC_OK;
+  }
+#ifndef YB_HOSTSIM
+  const ncclDataType_t t = dtype == kCommF32 ? ncclFloat32 : dtype == kCommI32 ? ncclInt32 : ncclUint64;
+  if (root < 0) YC_NCCL(nccl().AllReduce(buf, buf, count, t, ncclSum, c.nccl, ctx->st.s));
+  else YC_NCCL(nccl().Reduce(buf, buf, count, t, ncclSum, root, c.nccl, ctx->st.s));
+  return YC_OK;
+#else
+  return fail(ctx, YC_ERR_STATE, "communicator without a transport");
+#endif
+}
+
+extern "C" int yc_comm_reduce_frames(yc_ctx* ctx, int root) {
+  if (!ctx) return YC_ERR_INVALID;
+  rt::useDevice(ctx->device);
+  if (!ctx->comm) return fail(ctx, YC_ERR_STATE, "yc_comm_reduce_frames without a communicator");
+  if (!ctx->inFrame) return fail(ctx, YC_ERR_STATE, "no frame");
+  Comm& c = *ctx->comm;
+  if (root < 0 || root >= c.world) return fail(ctx, YC_ERR_INVALID, "bad root");
+  const size_t texels = size_t(ctx->frame.width) * ctx->frame.height;
+  if (c.frameTexels != texels) {
+    rt::release(c.hdrAll);
+    rt::release(c.ldrAll);
+    c.hdrAll = c.ldrAll = nullptr;
+    void* p = nullptr;
+    YC_TRY(rt::alloc(&p, texels * sizeof(float4)));
+    c.hdrAll = static_cast<float4*>(p);
+    YC_TRY(rt::alloc(&p, texels * sizeof(float4)));
+    c.ldrAll = static_cast<float4*>(p);
+    c.frameTexels = texels;
+  }
+  // out of place: the context's own frames keep blending its tiles in later waves
+  YC_TRY(rt::d2d(ctx->st, c.hdrAll, ctx->dHdr, texels * sizeof(float4)));
+  YC_TRY(rt::d2d(ctx->st, c.ldrAll, ctx->dLdr, texels * sizeof(float4)));
+  int rc = commSum(ctx, c.hdrAll, texels * 4, kCommF32, root);
+  if (rc == YC_OK) rc = commSum(ctx, c.ldrAll, texels * 4, kCommF32, root);
+  if (rc != YC_OK) return rc;
+  YC_TRY(rt::sync(ctx->st));
+  YC_TRY(rt::lastError());
+  return YC_OK;
+}
+
+extern "C" int yc_resolve_combined(yc_ctx* ctx, float* hdrRGBA, float* ldrRGBA) {
+  if (!ctx) return YC_ERR_INVALID;
+  rt::useDevice(ctx->device);
+  if (!ctx->comm || !ctx->comm->hdrAll) return fail(ctx, YC_ERR_STATE, "yc_resolve_combined before yc_comm_reduce_frames");
+  const size_t bytes = ctx->comm->frameTexels * sizeof(float4);
+  if (hdrRGBA) YC_TRY(rt::d2h(ctx->st, hdrRGBA, ctx->comm->hdrAll, bytes));
+  if (ldrRGBA) YC_TRY(rt::d2h(ctx->st, ldrRGBA, ctx->comm->ldrAll, bytes));
+  return YC_OK;
+}
+
+extern "C" int yc_comm_allreduce_buckets(yc_ctx* ctx, uint32_t waveSamples) {
+  if (!ctx) return YC_ERR_INVALID;
+  rt::useDevice(ctx->device);
+  if (!ctx->comm) return fail(ctx, YC_ERR_STATE, "yc_comm_allreduce_buckets without a communicator");
+  if (!ctx->inFrame) return fail(ctx, YC_ERR_STATE, "no frame");
+  const size_t words = size_t(waveBuckets(ctx->frame, waveSamples)) * ctx->bucketCapacity * 4;
+  const int rc = commSum(ctx, ctx->dBuckets, words, kCommI32, -1);
+  if (rc != YC_OK) return rc;
+  YC_TRY(rt::sync(ctx->st));
+  YC_TRY(rt::lastError());
+  return YC_OK;
+}
+
+extern "C" int yc_comm_sum_u64(yc_ctx* ctx, uint64_t* values, uint32_t n) {
+  if (!ctx || !values || n == 0 || n > 64) return YC_ERR_INVALID;
+  rt::useDevice(ctx->device);
+  if (!ctx->comm) return fail(ctx, YC_ERR_STATE, "yc_comm_sum_u64 without a communicator");
+  Comm& c = *ctx->comm;
+  if (!c.scratch) {
+    void* p = nullptr;
+    YC_TRY(rt::alloc(&p, 64 * sizeof(uint64_t)));
+    c.scratch = static_cast<uint64_t*>(p);
+  }
+  YC_TRY(rt::h2d(ctx->st, c.scratch, values, n * sizeof(uint64_t)));
+  const int rc = commSum(ctx, c.scratch, n, kCommU64, -1);
+  if (rc != YC_OK) return rc;
+  YC_TRY(rt::d2h(ctx->st, values, c.scratch, n * sizeof(uint64_t)));
   return YC_OK;
 }
 

@@ -2,25 +2,29 @@
 // "flattens the same SAH BVH into a GPU-friendly wide-node layout") and its traversal.
 //
 // yc_upload_scene collapses every mesh's BVH2 (the reference's tree, src/core/bvh.hpp:21-33, as it arrives in
-// YcScene::bvhNodes) into 4-wide nodes: same leaves (the same contiguous triangle runs of YcScene::bvhTris, so
-// the triangle arithmetic and every accepted hit's t / u / v are the reference's), child boxes taken verbatim
-// from the BVH2 nodes they came from, inner levels removed greedily by surface area.
+// YcScene::bvhNodes) into 4-wide nodes with QUANTISED child boxes (after Ylitie, Karras, Laine, "Efficient
+// incoherent ray traversal on GPUs through compressed wide BVHs", HPG 2017 — here 4-wide with explicit child refs):
+// same leaves (the same contiguous triangle runs of YcScene::bvhTris, so the triangle arithmetic and every
+// accepted hit's t / u / v are the reference's), inner levels removed greedily by surface area.
 //
-//   WideNode (128 B, one L1 line):   row 0  lo.x of children 0..3      row 1  hi.x
-//                                    row 2  lo.y                        row 3  hi.y
-//                                    row 4  lo.z                        row 5  hi.z
-//                                    row 6  child refs (YcBvhNode::ref encoding, kWideEmpty = unused slot)
-//   A ray precomputes, per axis, which row of the pair holds its NEAR planes (row 2a + (d[a] < 0)), so a lane
-//   loads near and far planes directly (6 x LDG.128, addresses differ by the sign bit) and the slab test has no
-//   selects:  t = fma(plane, 1/d, -o/d)  (one rounding),  tn = max(tnx, tny, tnz, tMin),  tf = min(tfx, tfy, tfz, hit.t).
+//   WideNode, 64 B = 2 x LDG.256 (the uncompressed 128-B version of this node — 7 x LDG.128 per visit — ran at 95 %
+//   of the L1's tag-stage throughput and was slower than the BVH2 walk: profiles/README.md, round 2):
+//       S.x S.y S.z            2^15 quanta per axis; the quantum Q = 2^e is the smallest with 255 * Q >= extent    12 B
+//       p'.x p'.y p'.z         grid origin P (at or below the node's low corner) minus S, rounded down            12 B
+//       qlo.x qhi.x qlo.y qhi.y qlo.z qhi.z   one byte per child: plane = P + q * Q, rounded OUTWARDS            24 B
+//                              (floor / ceil with a 1/128-quantum guard), so a quantised box contains the child's box
+//       ref[4]                 YcBvhNode::ref encoding, kWideEmpty = unused slot                                   16 B
+//   Per visit a lane forms, per axis,  Sd = S / d  and  Bd = (p' - o) / d  (one FMUL + one FFMA), and per child plane one
+//   PRMT that drops the byte into mantissa bits 8..15 of 1.0f (v = 1 + q / 32768, exact) and one FFMA  t = v * Sd + Bd
+//   = (P + q * Q - o) / d;  near / far planes are picked per axis on the packed words with the ray's sign masks
+//   (6 bit-selects per visit, not 24).
 //
 // What differs from the reference-order BVH2 walk (traverse.cuh), and why results still match:
 //   * box culling only.  The set of triangles tested is a superset / reordering of the reference's, every
 //     triangle test is the reference's arithmetic (testTriangle, -fmad=false), and the closest hit is the
 //     minimum over accepted tests.  Hit ids / t / u / v are therefore identical except where two triangles tie
-//     in t to the last bit, or where a hit sits on the boundary of a box that one of the two slab
-//     formulations culls (the reference's `bmin * idir + odir` has two roundings and is not conservative
-//     either).  tests/ count those and list them.
+//     in t to the last bit, or where a hit sits on the boundary of a box that the reference's own slab test
+//     (`bmin * idir + odir`, two roundings, not conservative) culls.  tests/ count those.
 //   * a zero direction component is clamped to ±1e-20 for the BOX test only (Aila-Laine), so a ray with
 //     d.x == 0 and o.x == 0 no longer has NaN slabs on that axis and no longer walks every box that overlaps
 //     it in y and z (14 K boxes for one ray of the C2 camera, profiles/README.md "Pathological rays").
@@ -38,11 +42,12 @@ namespace yb {
 constexpr uint32_t kWideEmpty = 0xfffffffdu;  // unused child slot (has the leaf bit; never equals a real leaf ref)
 
 struct WideNode {
-  float plane[6][4];
+  float pS[3];      // p' = P - S per axis (rounded down)
+  float S[3];       // 2^(e + 15)
+  uint32_t q[6];    // qlo.x, qhi.x, qlo.y, qhi.y, qlo.z, qhi.z; byte k = child k
   uint32_t ref[4];
-  uint32_t pad[4];
 };
-static_assert(sizeof(WideNode) == 128, "WideNode is one 128-byte line");
+static_assert(sizeof(WideNode) == 64, "WideNode is two 32-byte sectors");
 
 // ---- host: BVH2 → BVH4 collapse --------------------------------------------------------------------
 // Appends mesh `m`'s wide nodes to `out` (children of a node are allocated together, parents before children)
@@ -95,19 +100,53 @@ inline int collapseToWide(const YcBvhNode* bvh2, const YcMesh& m, std::vector<Wi
       n++;
     }
     WideNode node{};
-    for (int k = 0; k < 4; k++) {
-      if (k < n) {
-        for (int a = 0; a < 3; a++) node.plane[2 * a][k] = c[k].lo[a], node.plane[2 * a + 1][k] = c[k].hi[a];
-        if (c[k].ref & YC_REF_LEAF) {
-          node.ref[k] = c[k].ref;
+    // Quantisation grid per axis: quantum Q = 2^e, S = 2^15 Q, p' = the float at or below (low corner - S), grid
+    // origin P = p' + S (<= the low corner; P, q * Q and their sums are exact in double).  e is the smallest exponent
+    // for which the planes fit in a byte with the guard below.
+    for (int a = 0; a < 3; a++) {
+      double lo = INFINITY, hi = -INFINITY;
+      for (int k = 0; k < n; k++) lo = std::min(lo, double(c[k].lo[a])), hi = std::max(hi, double(c[k].hi[a]));
+      int e = -100;
+      if (hi - lo > 0.0 && std::isfinite(hi - lo)) std::frexp((hi - lo) / 254.0, &e);
+      e = std::max(-100, std::min(100, e));
+      for (;; e++) {
+        const double Q = std::ldexp(1.0, e), S = std::ldexp(1.0, e + 15);
+        float pS = float(lo - S - Q / 64);  // the origin sits 1/64 quantum below the low corner: a guard for q = 0 too
+        if (double(pS) > lo - S - Q / 64) pS = std::nextafterf(pS, -INFINITY);
+        const double P = double(pS) + S;
+        // outward rounding with a 1/128-quantum guard: the device forms t = v * (S / d) + (p' - o) / d in float, whose
+        // rounding (at the magnitude of S / d) is worth up to ~1/512 of a quantum
+        bool fits = e >= 100;
+        uint32_t ql[4], qh[4];
+        if (!fits) {
+          fits = true;
+          for (int k = 0; k < n && fits; k++) {
+            const double l = std::floor((double(c[k].lo[a]) - P) / Q - 1.0 / 128), h = std::ceil((double(c[k].hi[a]) - P) / Q + 1.0 / 128);
+            fits = l >= 0.0 && h <= 255.0;
+            ql[k] = uint32_t(std::max(0.0, l)), qh[k] = uint32_t(std::max(0.0, std::min(255.0, h)));
+          }
         } else {
-          node.ref[k] = uint32_t(out.size() - base);
-          todo.push_back({c[k].ref, node.ref[k], w.depth + 1});
-          out.emplace_back();
+          for (int k = 0; k < n; k++) ql[k] = 0u, qh[k] = 255u;
         }
-      } else {
-        for (int a = 0; a < 3; a++) node.plane[2 * a][k] = INFINITY, node.plane[2 * a + 1][k] = -INFINITY;
+        if (!fits) continue;
+        node.pS[a] = pS, node.S[a] = float(S);
+        for (int k = 0; k < 4; k++) {
+          // unused slots: lo = 255, hi = 0 — an empty interval on every axis
+          node.q[2 * a] |= (k < n ? ql[k] : 255u) << (8 * k);
+          node.q[2 * a + 1] |= (k < n ? qh[k] : 0u) << (8 * k);
+        }
+        break;
+      }
+    }
+    for (int k = 0; k < 4; k++) {
+      if (k >= n) {
         node.ref[k] = kWideEmpty;
+      } else if (c[k].ref & YC_REF_LEAF) {
+        node.ref[k] = c[k].ref;
+      } else {
+        node.ref[k] = uint32_t(out.size() - base);
+        todo.push_back({c[k].ref, node.ref[k], w.depth + 1});
+        out.emplace_back();
       }
     }
     out[base + w.wide] = node;
@@ -118,15 +157,15 @@ inline int collapseToWide(const YcBvhNode* bvh2, const YcMesh& m, std::vector<Wi
 // ---- device ------------------------------------------------------------------------------------------
 // Per-ray constants of the wide slab test.
 struct WideRay {
-  V3 idir, odir;     // 1 / d (zero components clamped to ±1e-20) and -o * idir
-  uint32_t nx, ny, nz;  // row (float4 index inside the node) of the NEAR planes per axis; far = near ^ 1
+  V3 idir, odir;          // 1 / d (zero components clamped to ±1e-20) and -o * idir
+  uint32_t mx, my, mz;    // all ones where d < 0 on that axis (the near plane of a box is its hi plane), else 0
   YB_DEV void set(V3 o, V3 d) {
     const float eps = 1e-20f;
     const float dx = fabsf(d.x) > eps ? d.x : copysignf(eps, d.x), dy = fabsf(d.y) > eps ? d.y : copysignf(eps, d.y),
                 dz = fabsf(d.z) > eps ? d.z : copysignf(eps, d.z);
     idir = V3(1.0f / dx, 1.0f / dy, 1.0f / dz);
     odir = V3(-o.x * idir.x, -o.y * idir.y, -o.z * idir.z);
-    nx = 0u + (dx < 0.0f ? 1u : 0u), ny = 2u + (dy < 0.0f ? 1u : 0u), nz = 4u + (dz < 0.0f ? 1u : 0u);
+    mx = dx < 0.0f ? 0xffffffffu : 0u, my = dy < 0.0f ? 0xffffffffu : 0u, mz = dz < 0.0f ? 0xffffffffu : 0u;
   }
 };
 
@@ -136,9 +175,12 @@ YB_DEV float fmaExact(float a, float b, float c) { return fmaf(a, b, c); }
 YB_DEV float fmaExact(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 #endif
 
-// One box against the ray: entry distance in `tn`, true when the slab interval [max(tn, tMin), min(tf, tmx)] is
-// not empty.  fmaxf / fminf drop NaN operands, like the reference's NaN-tolerant rmin / rmax.
-YB_DEV bool slabWide(const WideRay& w, V3 nearP, V3 farP, float tmn, float tmx, float& tn) {
+// A box given by its float corners (scene-graph node boxes, mesh root boxes): entry distance in `tn`, true when the
+// slab interval [max(tn, tMin), min(tf, tmx)] is not empty.  fmaxf / fminf drop NaN operands, like the reference's
+// NaN-tolerant rmin / rmax.
+YB_DEV bool slabWideBox(const WideRay& w, V3 lo, V3 hi, float tmn, float tmx, float& tn) {
+  const V3 nearP(w.mx ? hi.x : lo.x, w.my ? hi.y : lo.y, w.mz ? hi.z : lo.z);
+  const V3 farP(w.mx ? lo.x : hi.x, w.my ? lo.y : hi.y, w.mz ? lo.z : hi.z);
   const float tnx = fmaExact(nearP.x, w.idir.x, w.odir.x), tny = fmaExact(nearP.y, w.idir.y, w.odir.y),
               tnz = fmaExact(nearP.z, w.idir.z, w.odir.z);
   const float tfx = fmaExact(farP.x, w.idir.x, w.odir.x), tfy = fmaExact(farP.y, w.idir.y, w.odir.y),
@@ -147,28 +189,64 @@ YB_DEV bool slabWide(const WideRay& w, V3 nearP, V3 farP, float tmn, float tmx, 
   const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmx));
   return tn <= tf;
 }
-// lo / hi form (scene-graph node boxes, mesh root boxes)
-YB_DEV bool slabWideBox(const WideRay& w, V3 lo, V3 hi, float tmn, float tmx, float& tn) {
-  const bool sx = w.nx & 1u, sy = w.ny & 1u, sz = w.nz & 1u;
-  return slabWide(w, V3(sx ? hi.x : lo.x, sy ? hi.y : lo.y, sz ? hi.z : lo.z),
-                  V3(sx ? lo.x : hi.x, sy ? lo.y : hi.y, sz ? lo.z : hi.z), tmn, tmx, tn);
+
+// Byte K of `word` as v = 1 + q / 32768: the byte dropped into mantissa bits 8..15 of 1.0f (one PRMT; `one` holds the
+// bits of 1.0f in a register so that the selector can be the instruction's immediate).
+template <int K>
+YB_DEV float planeUnit(uint32_t word, uint32_t one) {
+#ifdef YB_HOSTSIM
+  return __uint_as_float(__byte_perm(word, one, 0x7604u | (uint32_t(K) << 4)));
+#else
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(word), "r"(one), "n"(0x7604 | (K << 4)));
+  return __uint_as_float(r);
+#endif
 }
 
-// Ordering key of a hit child: entry distance with the child slot in the two lowest mantissa bits (distances are
-// >= tMin > 0, so keys order like the distances; ties go to the lower slot).  kWideMiss for a missed child.
-constexpr uint32_t kWideMiss = 0xffffffffu;
-YB_DEV uint32_t wideKey(bool hit, float tn, uint32_t slot) { return hit ? ((__float_as_uint(tn) & ~3u) | slot) : kWideMiss; }
+// The four quantised child boxes of one WideNode against the ray: entry distances and hit flags (`live` false: none).
+struct WideSlabs {
+  float tn[4];
+  bool hit[4];
+};
+template <int K>
+YB_DEV void slabWideChild(WideSlabs& r, uint32_t one, uint32_t nx, uint32_t ny, uint32_t nz, uint32_t fx, uint32_t fy, uint32_t fz,
+                          float Sx, float Sy, float Sz, float Bx, float By, float Bz, float tmn, float tmx, bool live) {
+  const float tnx = fmaExact(planeUnit<K>(nx, one), Sx, Bx), tny = fmaExact(planeUnit<K>(ny, one), Sy, By),
+              tnz = fmaExact(planeUnit<K>(nz, one), Sz, Bz);
+  const float tfx = fmaExact(planeUnit<K>(fx, one), Sx, Bx), tfy = fmaExact(planeUnit<K>(fy, one), Sy, By),
+              tfz = fmaExact(planeUnit<K>(fz, one), Sz, Bz);
+  r.tn[K] = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmn));
+  const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmx));
+  r.hit[K] = live && r.tn[K] <= tf;
+}
+// words: {p'.x, p'.y, p'.z, S.x, S.y, S.z, qlo.x, qhi.x} and {qlo.y, qhi.y, qlo.z, qhi.z}
+YB_DEV WideSlabs slabWide4(const WideRay& w, uint32_t one, float px, float py, float pz, float sx, float sy, float sz, uint32_t qlx,
+                           uint32_t qhx, uint32_t qly, uint32_t qhy, uint32_t qlz, uint32_t qhz, float tmn, float tmx, bool live) {
+  const float Sx = sx * w.idir.x, Sy = sy * w.idir.y, Sz = sz * w.idir.z;
+  const float Bx = fmaExact(px, w.idir.x, w.odir.x), By = fmaExact(py, w.idir.y, w.odir.y), Bz = fmaExact(pz, w.idir.z, w.odir.z);
+  // bit-select: the hi word where the ray runs against the axis
+  const uint32_t nx = (qlx & ~w.mx) | (qhx & w.mx), fx = (qhx & ~w.mx) | (qlx & w.mx);
+  const uint32_t ny = (qly & ~w.my) | (qhy & w.my), fy = (qhy & ~w.my) | (qly & w.my);
+  const uint32_t nz = (qlz & ~w.mz) | (qhz & w.mz), fz = (qhz & ~w.mz) | (qlz & w.mz);
+  WideSlabs r;
+  slabWideChild<0>(r, one, nx, ny, nz, fx, fy, fz, Sx, Sy, Sz, Bx, By, Bz, tmn, tmx, live);
+  slabWideChild<1>(r, one, nx, ny, nz, fx, fy, fz, Sx, Sy, Sz, Bx, By, Bz, tmn, tmx, live);
+  slabWideChild<2>(r, one, nx, ny, nz, fx, fy, fz, Sx, Sy, Sz, Bx, By, Bz, tmn, tmx, live);
+  slabWideChild<3>(r, one, nx, ny, nz, fx, fy, fz, Sx, Sy, Sz, Bx, By, Bz, tmn, tmx, live);
+  return r;
+}
 
 // Sequential walk of one mesh's wide BVH (per-path tail kernel, CPU build of the product sources); the
-// persistent-warp kernels (trace_wide.cuh) make the same decisions: nearest hit child first (by key), the other
-// hit children pushed in slot order with their entry distances, popped entries culled by `d < hit.t`.
+// persistent-warp kernels (trace_wide.cuh) make the same decisions: the hit child with the smallest entry distance
+// first (the lowest slot among equals), the other hit children pushed in slot order with their entry distances,
+// popped entries culled by `d < hit.t`.
 template <bool NEE, bool COUNT, bool EARLY_OUT>
 YB_DEV bool testBVHWide(const DScene& sc, const YcMesh& mesh, const WideMesh& wm, const LocalRay& r, const WideRay& w,
                         int nodeIdx, TraceState& st, TravStack& stack, TraceCounters& cnt) {
   float d;
   if (COUNT) cnt.box++;
   if (!slabWideBox(w, V3(mesh.rootMin), V3(mesh.rootMax), kTMin, st.hit.t, d)) return false;
-  const float4* __restrict__ nodes = sc.wideNodes + 8 * size_t(wm.nodeOffset);
+  const float4* __restrict__ nodes = sc.wideNodes + 4 * size_t(wm.nodeOffset);
   const float4* __restrict__ tris = sc.bvhTris + 3 * size_t(mesh.triOffset);
   uint32_t cur = wm.rootRef;
   int sp = 0;
@@ -189,31 +267,28 @@ YB_DEV bool testBVHWide(const DScene& sc, const YcMesh& mesh, const WideMesh& wm
         if (sp == 0) break;
         stack.pop(--sp, cur, d);
       } else {
-        const float4* n = nodes + 8 * size_t(cur);
-        const float4 nX = __ldg(n + w.nx), fX = __ldg(n + (w.nx ^ 1u)), nY = __ldg(n + w.ny), fY = __ldg(n + (w.ny ^ 1u)),
-                     nZ = __ldg(n + w.nz), fZ = __ldg(n + (w.nz ^ 1u)), rf = __ldg(n + 6);
+        const float4* n = nodes + 4 * size_t(cur);
+        const float4 r0 = __ldg(n), r1 = __ldg(n + 1), r2 = __ldg(n + 2), rf = __ldg(n + 3);
         const uint32_t ref[4] = {__float_as_uint(rf.x), __float_as_uint(rf.y), __float_as_uint(rf.z), __float_as_uint(rf.w)};
-        float tn[4];
-        bool hit[4];
-        hit[0] = slabWide(w, V3(nX.x, nY.x, nZ.x), V3(fX.x, fY.x, fZ.x), kTMin, st.hit.t, tn[0]);
-        hit[1] = slabWide(w, V3(nX.y, nY.y, nZ.y), V3(fX.y, fY.y, fZ.y), kTMin, st.hit.t, tn[1]);
-        hit[2] = slabWide(w, V3(nX.z, nY.z, nZ.z), V3(fX.z, fY.z, fZ.z), kTMin, st.hit.t, tn[2]) && ref[2] != kWideEmpty;
-        hit[3] = slabWide(w, V3(nX.w, nY.w, nZ.w), V3(fX.w, fY.w, fZ.w), kTMin, st.hit.t, tn[3]) && ref[3] != kWideEmpty;
+        WideSlabs sl = slabWide4(w, 0x3f800000u, r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, __float_as_uint(r1.z), __float_as_uint(r1.w),
+                                 __float_as_uint(r2.x), __float_as_uint(r2.y), __float_as_uint(r2.z), __float_as_uint(r2.w), kTMin,
+                                 st.hit.t, true);
+        float* tn = sl.tn;
+        bool* hit = sl.hit;
+        hit[2] = hit[2] && ref[2] != kWideEmpty;
+        hit[3] = hit[3] && ref[3] != kWideEmpty;
         if (COUNT) cnt.box += 2u + (ref[2] != kWideEmpty) + (ref[3] != kWideEmpty);
-        uint32_t best = kWideMiss;
-        for (uint32_t k = 0; k < 4; k++) {
-          const uint32_t key = wideKey(hit[k], tn[k], k);
-          best = key < best ? key : best;
-        }
-        if (best == kWideMiss) {
+        int nearSlot = -1;
+        for (int k = 0; k < 4; k++)
+          if (hit[k] && (nearSlot < 0 || tn[k] < tn[nearSlot])) nearSlot = k;
+        if (nearSlot < 0) {
           if (sp == 0) break;
           stack.pop(--sp, cur, d);
         } else {
-          const uint32_t nearSlot = best & 3u;
-          for (uint32_t k = 0; k < 4; k++)
+          for (int k = 0; k < 4; k++)
             if (hit[k] && k != nearSlot) stack.push(sp++, ref[k], tn[k]);
           cur = ref[nearSlot];
-          d = __uint_as_float(best & ~3u);
+          d = tn[nearSlot];
         }
       }
     } else {
