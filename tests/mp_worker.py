@@ -29,6 +29,39 @@ def run(rank: int, world: int, port: int, mode: str, out_dir: str):
     ctx.upload_scene(sc)
     ctx.set_camera(c)
     spp = 8
+    if mode in ("yr_tiles", "yr_buckets"):
+        # the whole data plane behind yr_* (yr_create_dist_custom): the library drives the waves and calls back into
+        # this process only for its sum collective, which gloo provides here (NCCL on the GPU box)
+        import ctypes as C
+        dt = {0: (np.float32, torch.float32), 1: (np.int32, torch.int32), 2: (np.int64, torch.int64)}
+
+        def collective(buf, count, dtype, root):
+            npd, _ = dt[dtype]
+            arr = np.ctypeslib.as_array(C.cast(buf, C.POINTER(np.ctypeslib.as_ctypes_type(npd))), shape=(count,))
+            t = torch.from_numpy(arr)
+            if root < 0:
+                dist.all_reduce(t)
+            else:
+                dist.reduce(t, dst=root)
+            return 0
+
+        waves = dict(samples=32, first_wave_samples=16, max_wave_samples=16)  # two waves of 16: m = 3 buckets
+        r = Y.Renderer(w, h, c, sc, tile_size=16, tonemap=Y.TONEMAP_AGX, traversal=Y.TRAVERSAL_REFERENCE_ORDER,
+                       sharding=Y.SHARD_BUCKETS if mode == "yr_buckets" else Y.SHARD_TILES, dist=(rank, world, collective), **waves)
+        seen = []
+        r.on_wave_complete(lambda rd, wd: seen.append((wd["wave"], wd["wave_samples"], wd["rays"], rd["total_rays"])))
+        data = r.render_sync()
+        hdr, ldr, _ = r.read()
+        if rank == 0:
+            np.save(os.path.join(out_dir, f"{mode}_hdr.npy"), hdr)
+            np.save(os.path.join(out_dir, f"{mode}_ldr.npy"), ldr)
+            np.save(os.path.join(out_dir, f"{mode}_rays.npy"), np.array([data["total_rays"], len(seen), sum(s[2] for s in seen)], np.int64))
+        elif mode == "yr_buckets":
+            np.save(os.path.join(out_dir, f"{mode}_hdr_rank{rank}.npy"), hdr)  # bucket sharding: every rank ends with the frame
+        r.close()
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     if mode == "tiles":
         # interleaved tile sharding (SURVEY §8e primary): disjoint pixels, sum = full frame, bit-exact
         ctx.begin_frame(w, h, spp, 16, (0, 0, 0), Y.TONEMAP_AGX, shard_index=rank, shard_count=world)

@@ -55,9 +55,9 @@ def test_struct_sizes_match_the_c_definitions():
 #include <stdio.h>
 #include "yart_cuda.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(YcCamera), sizeof(YcOptions), sizeof(YcRect),
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(YcCamera), sizeof(YcOptions), sizeof(YcRect),
          sizeof(YcFrameDesc), sizeof(YcStats), sizeof(YcRay), sizeof(YcHit), sizeof(YcMesh), sizeof(YcScene),
-         sizeof(YrSettings), sizeof(YrRenderData));
+         sizeof(YrSettings), sizeof(YrRenderData), sizeof(YrWaveData), sizeof(YrTileData));
   return 0;
 }'''
     with tempfile.TemporaryDirectory() as d:
@@ -66,7 +66,8 @@ int main(void) {
         subprocess.run(["gcc", "-I", os.path.join(H.ROOT, "include"), src, "-o", exe], check=True)
         sizes = [int(x) for x in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
     py = [C.sizeof(t) for t in (capi.YcCamera, capi.YcOptions, capi.YcRect, capi.YcFrameDesc, capi.YcStats, capi.YcRay,
-                                capi.YcHit, capi.YcMesh, capi.YcScene, capi.YrSettings, capi.YrRenderData)]
+                                capi.YcHit, capi.YcMesh, capi.YcScene, capi.YrSettings, capi.YrRenderData, capi.YrWaveData,
+                                capi.YrTileData)]
     assert py == sizes
 
 

@@ -73,3 +73,80 @@ def test_two_ranks_bucket_sharding_equals_one_rank_bitwise(tmp_path):
     assert H.bits_equal(np.load(tmp_path / "buckets_hdr.npy"), hdr1).all()
     assert H.bits_equal(np.load(tmp_path / "buckets_ldr.npy"), ldr1).all()
     assert int(np.load(tmp_path / "buckets_rays.npy")[0]) == st.raysReference
+
+
+# ------------------------------------------------------------------------------------------
+# the same through yr_* only: the library owns the wave loop, the sharding and the collectives
+# ------------------------------------------------------------------------------------------
+def single_renderer(**kw):
+    cam = H.scene_camera("cornell")
+    sc = Y.Scene(H.scene_file("cornell"))
+    c = Y.make_camera(48, 48, cam["focal"], cam["fnum"], cam["pos"], cam["target"])
+    r = Y.Renderer(48, 48, c, sc, tile_size=16, tonemap=Y.TONEMAP_AGX, samples=32, first_wave_samples=16, max_wave_samples=16, **kw)
+    return r
+
+
+@pytest.mark.parametrize("mode", ["yr_tiles", "yr_buckets"])
+def test_two_processes_through_yr_create_dist_equal_one_renderer_bitwise(tmp_path, mode):
+    """yr_create_dist_custom with gloo as the sum collective (NCCL's place on the GPU box): rank 0's frame, the
+    whole-job ray count and the wave callbacks equal the single renderer's."""
+    launch(mode, tmp_path)
+    r = single_renderer()
+    data = r.render_sync()
+    hdr1, ldr1, _ = r.read()
+    r.close()
+    assert H.bits_equal(np.load(tmp_path / f"{mode}_hdr.npy"), hdr1).all()
+    assert H.bits_equal(np.load(tmp_path / f"{mode}_ldr.npy"), ldr1).all()
+    rays, n_waves, wave_ray_sum = (int(v) for v in np.load(tmp_path / f"{mode}_rays.npy"))
+    assert rays == data["total_rays"] and n_waves == 2 and wave_ray_sum == rays
+    if mode == "yr_buckets":
+        assert H.bits_equal(np.load(tmp_path / f"{mode}_hdr_rank1.npy"), hdr1).all()
+
+
+@pytest.mark.parametrize("sharding", [Y.SHARD_TILES, Y.SHARD_BUCKETS])
+@pytest.mark.parametrize("n", [2, 3])
+def test_one_process_yr_create_multi_equals_one_renderer_bitwise(sharding, n):
+    """yr_create_multi: n contexts, one driver thread each, the in-process group transport (what two contexts on one
+    GPU use); frames, ray counts and callbacks equal the single renderer's."""
+    r1 = single_renderer()
+    d1 = r1.render_sync()
+    hdr1, ldr1, _ = r1.read()
+    r1.close()
+    rn = single_renderer(devices=list(range(n)), sharding=sharding)
+    waves, tiles, done = [], [], []
+    rn.on_wave_complete(lambda rd, wd: waves.append(wd["rays"]))
+    rn.on_tile_complete(lambda rd, td: tiles.append(td["index"]))
+    rn.on_done(lambda rd, aborted: done.append(aborted))
+    dn = rn.render_sync()
+    hdr, ldr, st = rn.read()
+    assert H.bits_equal(hdr, hdr1).all() and H.bits_equal(ldr, ldr1).all()
+    assert dn["total_rays"] == d1["total_rays"] == st.raysReference and sum(waves) == d1["total_rays"]
+    assert len(waves) == 2 and len(tiles) == 2 * 9 and done == [False]
+    # asynchronous render + abort: exactly one completion callback, no hang, the renderer stays usable
+    rn.render()
+    rn.abort()
+    rn.wait()
+    assert len(done) == 2
+    d2 = rn.render_sync()
+    hdr2, _, _ = rn.read()
+    assert d2["total_rays"] == d1["total_rays"] and H.bits_equal(hdr2, hdr1).all()
+    rn.close()
+
+
+def test_abort_stops_a_long_render_between_chunks():
+    """yr_abort returns at once and the wave in flight stops at its next chunk / bounce boundary (the reference
+    stops between tiles): a render that would take many seconds ends early with the aborted callback."""
+    import time
+    cam = H.scene_camera("cornell")
+    sc = Y.Scene(H.scene_file("cornell"))
+    c = Y.make_camera(64, 64, cam["focal"], cam["fnum"], cam["pos"], cam["target"])
+    r = Y.Renderer(64, 64, c, sc, samples=4096, first_wave_samples=4096, max_wave_samples=4096)  # 16.8 M paths: minutes on the CPU build
+    done = []
+    r.on_done(lambda rd, aborted: done.append((aborted, rd["samples_taken"])))
+    t0 = time.time()
+    r.render()
+    time.sleep(0.3)
+    r.abort()
+    assert r.wait() is False
+    assert time.time() - t0 < 90 and done == [(True, 0)]  # one bounce of the chunks in flight at most
+    r.close()

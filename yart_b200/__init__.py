@@ -15,7 +15,7 @@ import numpy as np
 from . import capi
 from .capi import (LIGHT_SAMPLER_POWER, LIGHT_SAMPLER_UNIFORM, SAMPLER_SOBOL, SAMPLER_NAIVE, SAMPLER_STRATIFIED, BVH_SAH, BVH_MEDIAN_SPLIT, SCRAMBLER_FAST_OWEN, SCRAMBLER_OWEN, SCRAMBLER_BINARY_PERMUTE, INTEGRATOR_MIS, INTEGRATOR_NAIVE, ESTIMATOR_GMONB, ESTIMATOR_GMON, ESTIMATOR_MEAN, ESTIMATOR_MON, TONEMAP_AGX, TONEMAP_AGX_GOLDEN, TONEMAP_AGX_PUNCHY,
                    TONEMAP_NONE, TRACE_ANY, TRACE_CLOSEST, TRACE_COUNT, TRACE_USE_TMAX, TRACE_REFERENCE_ORDER, TRACE_WIDE,
-                   TRAVERSAL_AUTO, TRAVERSAL_REFERENCE_ORDER, TRAVERSAL_WIDE)
+                   TRAVERSAL_AUTO, TRAVERSAL_REFERENCE_ORDER, TRAVERSAL_WIDE, SHARD_TILES, SHARD_BUCKETS)
 
 _lib = None
 
@@ -46,7 +46,8 @@ class YartError(RuntimeError):
 def _check(rc, what, detail=b""):
     if rc != 0:
         names = {-1: "INVALID", -2: "CUDA", -3: "NO_SCENE", -4: "NO_DEVICE", -5: "STATE", -6: "IO",
-                 -7: "UNSUPPORTED (this build folds the variant away: load capi.SAMPLERS_LIB for the RNG samplers)"}
+                 -7: "UNSUPPORTED (this build folds the variant away: load capi.SAMPLERS_LIB for the RNG samplers)",
+                 -8: "ABORTED"}
         msg = detail.decode() if isinstance(detail, bytes) else str(detail)
         raise YartError(f"{what} failed: YC_ERR_{names.get(rc, rc)} {msg}")
 
@@ -64,6 +65,13 @@ def _env_struct(env, radius, transform):
     if transform is not None:
         e.transform = (C.c_float * 16)(*np.asarray(transform, np.float32).reshape(-1))
     return e, rgb  # keep rgb alive
+
+
+def comm_unique_id() -> bytes:
+    """ncclGetUniqueId through the library (rank 0 calls it and hands the bytes to the other ranks)."""
+    buf = (C.c_char * capi.COMM_ID_BYTES)()
+    _check(lib().yc_comm_unique_id(buf), "yc_comm_unique_id")
+    return bytes(buf)
 
 
 def glb_to_ysc(glb_path: str, ysc_path: str, env=None, env_radius=100.0, env_transform=None):
@@ -294,19 +302,36 @@ class Renderer:
                  first_wave_samples=None, max_wave_samples=None, tile_size=64, max_depth=30, background=(0, 0, 0),
                  tonemap=TONEMAP_AGX, estimator=ESTIMATOR_GMON, shard_index=0, shard_count=1, device=0,
                  integrator=capi.INTEGRATOR_MIS, scrambler=capi.SCRAMBLER_FAST_OWEN, sampler=capi.SAMPLER_SOBOL,
-                 traversal=None):
+                 traversal=None, sharding=capi.SHARD_TILES, devices=None, dist=None):
+        """devices=[g0, g1, ...]: one renderer over several GPUs of this process (yr_create_multi).
+        dist=(rank, world, comm): one process per GPU (yr_create_dist); comm = the 128 bytes of comm_unique_id() from
+        rank 0, or a callable collective(buf_ptr, count, dtype, root) → 0 (yr_create_dist_custom)."""
         traversal = default_traversal if traversal is None else traversal
         # TileRenderer defaults: samples 64, firstWaveSamples 64, maxWaveSamples 128, tileSize 64 (:11-14)
         s = capi.YrSettings(width, height, samples, 64 if first_wave_samples is None else first_wave_samples,
                             128 if max_wave_samples is None else max_wave_samples, tile_size, max_depth,
                             _f3(background), tonemap, estimator, shard_index, shard_count, device, integrator, scrambler, sampler,
-                            traversal)
+                            traversal, sharding)
         self.settings = s
         self.scene = scene
         self._h = C.c_void_p()
-        self._cb = None
-        _check(lib().yr_create(C.byref(s), scene._h if scene else None, C.byref(camera), C.byref(self._h)), "yr_create",
-               b"(no usable CUDA device: yart_b200 has no CPU fallback)")
+        self._cb = self._tile_cb = self._done_cb = self._coll = None
+        sh = scene._h if scene else None
+        if devices is not None:
+            arr = (C.c_int * len(devices))(*devices)
+            rc, what = lib().yr_create_multi(C.byref(s), sh, C.byref(camera), arr, len(devices), C.byref(self._h)), "yr_create_multi"
+        elif dist is not None:
+            rank, world, comm = dist
+            if callable(comm):
+                self._coll = capi.COLLECTIVE_FN(lambda buf, count, dtype, root, _u: int(comm(buf, count, dtype, root) or 0))
+                rc = lib().yr_create_dist_custom(C.byref(s), sh, C.byref(camera), rank, world, self._coll, None, C.byref(self._h))
+            else:
+                cid = (C.c_char * capi.COMM_ID_BYTES).from_buffer_copy(bytes(comm)) if comm is not None else None
+                rc = lib().yr_create_dist(C.byref(s), sh, C.byref(camera), rank, world, cid, C.byref(self._h))
+            what = "yr_create_dist"
+        else:
+            rc, what = lib().yr_create(C.byref(s), sh, C.byref(camera), C.byref(self._h)), "yr_create"
+        _check(rc, what, b"(no usable CUDA device: yart_b200 has no CPU fallback)")
 
     def close(self):
         if self._h:
@@ -335,14 +360,40 @@ class Renderer:
         self._cb = capi.WAVE_CALLBACK(tramp)
         self._ck(lib().yr_set_wave_callback(self._h, self._cb, None), "yr_set_wave_callback")
 
+    def on_tile_complete(self, fn):
+        """fn(render_data: dict, tile: dict) — Renderer::onRenderTileComplete."""
+        def tramp(rd, td, _user):
+            r, t = rd.contents, td.contents
+            fn(dict(samples_taken=r.samplesTaken, total_samples=r.totalSamples, total_rays=r.totalRays, total_time_ms=r.totalTimeMs),
+               dict(x=t.x, y=t.y, w=t.w, h=t.h, index=t.index, total=t.total, rays=t.rays, time_ms=t.timeMs))
+        self._tile_cb = capi.TILE_CALLBACK(tramp)
+        self._ck(lib().yr_set_tile_callback(self._h, self._tile_cb, None), "yr_set_tile_callback")
+
+    def on_done(self, fn):
+        """fn(render_data: dict, aborted: bool) — Renderer::onRenderComplete / onRenderAborted."""
+        def tramp(rd, aborted, _user):
+            r = rd.contents
+            fn(dict(samples_taken=r.samplesTaken, total_samples=r.totalSamples, total_rays=r.totalRays, total_time_ms=r.totalTimeMs),
+               bool(aborted))
+        self._done_cb = capi.DONE_CALLBACK(tramp)
+        self._ck(lib().yr_set_done_callback(self._h, self._done_cb, None), "yr_set_done_callback")
+
+    def set_camera(self, camera: capi.YcCamera):
+        self._ck(lib().yr_set_camera(self._h, C.byref(camera)), "yr_set_camera")
+
     def render(self):
         self._ck(lib().yr_render(self._h), "yr_render")
 
     def abort(self):
         self._ck(lib().yr_abort(self._h), "yr_abort")
 
-    def wait(self):
-        self._ck(lib().yr_wait(self._h), "yr_wait")
+    def wait(self) -> bool:
+        """Joins the render; False if it was aborted (YC_ERR_ABORTED)."""
+        rc = lib().yr_wait(self._h)
+        if rc == capi.ERR_ABORTED:
+            return False
+        self._ck(rc, "yr_wait")
+        return True
 
     def render_sync(self) -> dict:
         d = capi.YrRenderData()

@@ -92,7 +92,7 @@ class YrSettings(C.Structure):
     _fields_ = [("width", u32), ("height", u32), ("samples", u32), ("firstWaveSamples", u32), ("maxWaveSamples", u32),
                 ("tileSize", u32), ("maxDepth", u32), ("background", f32 * 3), ("tonemap", u32), ("estimator", u32),
                 ("shardIndex", u32), ("shardCount", u32), ("device", i32), ("integrator", u32), ("scrambler", u32), ("sampler", u32),
-                ("traversal", u32)]
+                ("traversal", u32), ("sharding", u32)]
 
 
 class YrRenderData(C.Structure):
@@ -108,7 +108,19 @@ class YsEnvLight(C.Structure):
                 ("transform", f32 * 16)]
 
 
+class YrTileData(C.Structure):
+    _fields_ = [("x", u32), ("y", u32), ("w", u32), ("h", u32), ("index", u64), ("total", u64), ("rays", u64),
+                ("timeMs", C.c_double)]
+
+
 WAVE_CALLBACK = C.CFUNCTYPE(None, C.POINTER(YrRenderData), C.POINTER(YrWaveData), C.c_void_p)
+TILE_CALLBACK = C.CFUNCTYPE(None, C.POINTER(YrRenderData), C.POINTER(YrTileData), C.c_void_p)
+DONE_CALLBACK = C.CFUNCTYPE(None, C.POINTER(YrRenderData), C.c_int, C.c_void_p)
+# yc_collective_fn: fn(buf, count, dtype (0 f32, 1 i32, 2 u64), root (< 0: all), user) → 0 on success
+COLLECTIVE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p)
+COMM_ID_BYTES = 128
+SHARD_TILES, SHARD_BUCKETS = 0, 1
+ERR_ABORTED = -8
 
 P = C.c_void_p
 # name → (restype, argtypes): every entry point include/yart_cuda.h declares
@@ -138,6 +150,16 @@ PROTOTYPES = {
     "yc_memcpy_d2h": (C.c_int, [P, P, P, C.c_size_t]),
     "yc_generate_primary_rays": (C.c_int, [P, u32, u32, P]),
     "yc_synchronize": (C.c_int, [P]),
+    "yc_set_abort_flag": (C.c_int, [P, C.POINTER(i32)]),
+    "yc_comm_unique_id": (C.c_int, [P]),
+    "yc_comm_init_rank": (C.c_int, [P, C.c_int, C.c_int, P]),
+    "yc_comm_init_all": (C.c_int, [C.POINTER(P), C.c_int]),
+    "yc_comm_init_custom": (C.c_int, [P, C.c_int, C.c_int, COLLECTIVE_FN, P]),
+    "yc_comm_destroy": (C.c_int, [P]),
+    "yc_comm_reduce_frames": (C.c_int, [P, C.c_int]),
+    "yc_resolve_combined": (C.c_int, [P, P, P]),
+    "yc_comm_allreduce_buckets": (C.c_int, [P, u32]),
+    "yc_comm_sum_u64": (C.c_int, [P, C.POINTER(u64), u32]),
     "yc_kat": (C.c_int, [P, C.c_char_p, P, C.c_size_t, P, C.c_size_t]),
     "ys_scene_load": (C.c_int, [C.c_char_p, C.POINTER(P)]),
     "ys_scene_load_bvh": (C.c_int, [C.c_char_p, u32, C.POINTER(P)]),
@@ -148,12 +170,24 @@ PROTOTYPES = {
     "ys_scene_destroy": (None, [P]),
     "ys_last_error": (C.c_char_p, []),
     "ys_scene_flat": (C.POINTER(YcScene), [P]),
+    "ys_lut_tables": (C.POINTER(f32), [C.POINTER(C.c_size_t)]),
     "ys_scene_build_ms": (C.c_double, [P]),
     "ys_scene_bvh": (C.c_int, [P, u32, C.POINTER(P), C.POINTER(u32), C.POINTER(C.POINTER(u32)), C.POINTER(u32)]),
     "ys_camera_make": (C.c_int, [u32, u32, f32, f32, f32 * 3, f32 * 3, f32 * 3, f32, u32, C.POINTER(YcCamera)]),
     "yr_create": (C.c_int, [C.POINTER(YrSettings), P, C.POINTER(YcCamera), C.POINTER(P)]),
+    "yr_create_flat": (C.c_int, [C.POINTER(YrSettings), C.POINTER(YcScene), C.POINTER(YcCamera), C.POINTER(P)]),
+    "yr_create_multi": (C.c_int, [C.POINTER(YrSettings), P, C.POINTER(YcCamera), C.POINTER(C.c_int), u32, C.POINTER(P)]),
+    "yr_create_multi_flat": (C.c_int, [C.POINTER(YrSettings), C.POINTER(YcScene), C.POINTER(YcCamera), C.POINTER(C.c_int), u32,
+                                       C.POINTER(P)]),
+    "yr_create_dist": (C.c_int, [C.POINTER(YrSettings), P, C.POINTER(YcCamera), C.c_int, C.c_int, P, C.POINTER(P)]),
+    "yr_create_dist_custom": (C.c_int, [C.POINTER(YrSettings), P, C.POINTER(YcCamera), C.c_int, C.c_int, COLLECTIVE_FN, P,
+                                        C.POINTER(P)]),
     "yr_destroy": (None, [P]),
     "yr_set_wave_callback": (C.c_int, [P, WAVE_CALLBACK, P]),
+    "yr_set_tile_callback": (C.c_int, [P, TILE_CALLBACK, P]),
+    "yr_set_done_callback": (C.c_int, [P, DONE_CALLBACK, P]),
+    "yr_set_frame_target": (C.c_int, [P, P]),
+    "yr_set_camera": (C.c_int, [P, C.POINTER(YcCamera)]),
     "yr_render": (C.c_int, [P]),
     "yr_abort": (C.c_int, [P]),
     "yr_wait": (C.c_int, [P]),

@@ -10,8 +10,10 @@
 //     dependency on it, and a process that already holds NCCL (PyTorch) shares that copy.  Collectives run on the
 //     context's own stream, so they order after the wave's kernels without a host round trip.
 //   * the caller's sum collective (yc_comm_init_custom): MPI, gloo, a test double.
-//   * an in-process group (CPU build of the product sources only): the contexts of yc_comm_init_all meet at a barrier
-//     and the last one to arrive adds the buffers — lets the multi-GPU renderer logic run in the CPU test-suite.
+//   * an in-process group: the contexts of yc_comm_init_all meet at a barrier and the last one to arrive adds the
+//     buffers (a plain loop in the CPU build of the product sources, one kernel over the participants' device
+//     pointers in the CUDA build).  Used when two contexts of a communicator share a GPU — NCCL refuses that — so the
+//     multi-GPU renderer logic runs in the CPU test-suite and on a one-GPU box.
 // Every data collective is a SUM over buffers in which each element is non-zero on at most one participant (disjoint
 // tiles; disjoint (bucket, pixel) slots, summed as int32), so x + 0 + ... + 0 is exact and the result is bit-identical
 // to one GPU whatever order the transport adds in.
@@ -70,38 +72,55 @@ inline NcclApi& nccl() {
 static_assert(sizeof(ncclUniqueId) == YC_COMM_ID_BYTES, "YC_COMM_ID_BYTES must match ncclUniqueId");
 #endif
 
-// In-process group (CPU build): n participants, each on its own thread, meet per collective.
+// In-process group: n participants, each on its own thread, meet per collective.
+constexpr int kGroupMax = 16;
+struct GroupPtrs {
+  void* p[kGroupMax];
+};
+#ifndef YB_HOSTSIM
+template <typename T>
+__global__ void groupSumKernel(GroupPtrs bufs, int n, size_t count, int root) {
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += size_t(gridDim.x) * blockDim.x) {
+    T total = T(0);
+    for (int r = 0; r < n; r++) total += static_cast<const T*>(bufs.p[r])[i];
+    for (int r = 0; r < n; r++)
+      if (root < 0 || r == root) static_cast<T*>(bufs.p[r])[i] = total;
+  }
+}
+#endif
 struct HostGroup {
   std::mutex m;
   std::condition_variable cv;
   int n = 0, arrived = 0;
   uint64_t generation = 0;
-  std::vector<void*> bufs;
-  // Every participant calls with its buffer; the last arrival sums all buffers into bufs[root] (root < 0: into all).
-  void sum(int rank, void* buf, size_t count, int dtype, int root) {
+  GroupPtrs bufs{};
+  const char* error = nullptr;
+  // Every participant calls with its buffer (its own stream drained); the last arrival sums all buffers into
+  // bufs[root] (root < 0: into all) and releases the others.
+  template <class SumFn>
+  const char* sum(int rank, void* buf, SumFn&& doSum) {
     std::unique_lock<std::mutex> lk(m);
-    bufs[size_t(rank)] = buf;
+    bufs.p[rank] = buf;
     const uint64_t gen = generation;
     if (++arrived == n) {
-      auto add = [&](auto* tag) {
-        using T = std::remove_pointer_t<decltype(tag)>;
-        std::vector<T> total(count, T(0));
-        for (int r = 0; r < n; r++)
-          for (size_t i = 0; i < count; i++) total[i] += static_cast<T*>(bufs[size_t(r)])[i];
-        for (int r = 0; r < n; r++)
-          if (root < 0 || r == root) memcpy(bufs[size_t(r)], total.data(), count * sizeof(T));
-      };
-      if (dtype == kCommF32) add(static_cast<float*>(nullptr));
-      else if (dtype == kCommI32) add(static_cast<uint32_t*>(nullptr));  // wrap-around add: bit patterns, x + 0 exact
-      else add(static_cast<uint64_t*>(nullptr));
+      error = doSum(bufs, n);
       arrived = 0;
       generation++;
       cv.notify_all();
     } else {
       cv.wait(lk, [&] { return generation != gen; });
     }
+    return error;
   }
 };
+template <typename T>
+inline void hostSum(const GroupPtrs& bufs, int n, size_t count, int root) {
+  std::vector<T> total(count, T(0));
+  for (int r = 0; r < n; r++)
+    for (size_t i = 0; i < count; i++) total[i] += static_cast<const T*>(bufs.p[r])[i];
+  for (int r = 0; r < n; r++)
+    if (root < 0 || r == root) memcpy(bufs.p[r], total.data(), count * sizeof(T));
+}
 
 struct Comm {
   int rank = 0, world = 1;

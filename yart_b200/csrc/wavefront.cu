@@ -1693,15 +1693,28 @@ extern "C" int yc_comm_init_all(yc_ctx** ctxs, int n) {
   if (!ctxs || n < 1) return YC_ERR_INVALID;
   for (int i = 0; i < n; i++)
     if (!ctxs[i]) return YC_ERR_INVALID;
+  if (n > 1) {
+    bool shared = false;  // two contexts on one GPU: NCCL refuses duplicate devices
+    for (int i = 0; i < n; i++)
+      for (int j = i + 1; j < n; j++) shared |= ctxs[i]->device == ctxs[j]->device;
 #ifdef YB_HOSTSIM
-  auto group = std::make_shared<HostGroup>();
-  group->n = n;
-  group->bufs.assign(size_t(n), nullptr);
-  for (int i = 0; i < n; i++) {
-    destroyComm(ctxs[i]);
-    ctxs[i]->comm = std::make_unique<Comm>();
-    ctxs[i]->comm->rank = i, ctxs[i]->comm->world = n, ctxs[i]->comm->group = group;
+    shared = true;  // the CPU build has no devices at all
+#endif
+    if (shared) {
+      if (n > kGroupMax) return fail(ctxs[0], YC_ERR_INVALID, "at most %d contexts in an in-process group", kGroupMax);
+      auto group = std::make_shared<HostGroup>();
+      group->n = n;
+      for (int i = 0; i < n; i++) {
+        destroyComm(ctxs[i]);
+        ctxs[i]->comm = std::make_unique<Comm>();
+        ctxs[i]->comm->rank = i, ctxs[i]->comm->world = n, ctxs[i]->comm->group = group;
+      }
+      return YC_OK;
+    }
   }
+#ifdef YB_HOSTSIM
+  destroyComm(ctxs[0]);
+  ctxs[0]->comm = std::make_unique<Comm>();
   return YC_OK;
 #else
   yc_ctx* ctx = ctxs[0];
@@ -1746,8 +1759,24 @@ static int commSum(yc_ctx* ctx, void* buf, size_t count, int dtype, int root) {
     return YC_OK;
   }
   if (c.group) {
-    YC_TRY(rt::sync(ctx->st));
-    c.group->sum(c.rank, buf, count, dtype, root);
+    YC_TRY(rt::sync(ctx->st));  // this participant's buffer is final before the group meets
+    const char* e = c.group->sum(c.rank, buf, [&](const GroupPtrs& bufs, int n) -> const char* {
+#ifdef YB_HOSTSIM
+      if (dtype == kCommF32) hostSum<float>(bufs, n, count, root);
+      else if (dtype == kCommI32) hostSum<uint32_t>(bufs, n, count, root);  // wrap-around add of bit patterns: x + 0 is exact
+      else hostSum<uint64_t>(bufs, n, count, root);
+      return nullptr;
+#else
+      // the last arrival adds on its own stream; the contexts share a device (or peer access), so every pointer is valid here
+      const int grid = int(std::min<size_t>((count + 255) / 256, size_t(ctx->smCount) * 8));
+      if (dtype == kCommF32) groupSumKernel<float><<<grid, 256, 0, ctx->st.s>>>(bufs, n, count, root);
+      else if (dtype == kCommI32) groupSumKernel<uint32_t><<<grid, 256, 0, ctx->st.s>>>(bufs, n, count, root);
+      else groupSumKernel<unsigned long long><<<grid, 256, 0, ctx->st.s>>>(bufs, n, count, root);
+      if (const char* se = rt::sync(ctx->st)) return se;
+      return rt::lastError();
+#endif
+    });
+    if (e) return fail(ctx, YC_ERR_CUDA, "in-process group sum: %s", e);
     return YC_OK;
   }
 #ifndef YB_HOSTSIM
