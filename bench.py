@@ -13,9 +13,16 @@ A step = one pass of the hot path over one batch: one wave of SPP samples of eve
   cpu_baseline  the reference's own tile-threaded CPU renderer (oracle/_ref/oracle_ref_perf) on the
              box's host cores, bounded to 1 spp of the same frame
 
-N > 1 (torchrun, one rank per GPU): scene replicated, rank r renders sample wave r of the frame
-(weak scaling: SPP samples per GPU), the per-GPU HDR frames are combined with an NCCL all-reduce
-over NVLink and re-tonemapped; value = rays of all ranks / max-over-ranks time.
+  parity     the frame of this configuration (1 spp) against the reference's parity build run on this box
+  workloads  N = 1: the configs[2] / configs[3] shapes (Sponza- / McLaren-shaped, full MIS+NEE paths) with the
+             surface-shading kernel's roofline
+
+N > 1 (torchrun, one rank per GPU): scene replicated; a step is one wave of SPP x N samples of the frame, split over
+the ranks by tile (or by GMoN bucket, --sharding buckets) INSIDE libyart_b200.so, which also combines the per-GPU
+frames / accumulation buffers with NCCL on its own stream after every wave, inside the timed region (weak scaling:
+W*H*SPP camera paths per GPU and step).  `strong` reports the N = 1 step's job split over the N GPUs.  torch.distributed
+carries no frame data: barriers, the communicator id and the max-over-ranks of the timings only.
+value = rays of all ranks / max-over-ranks device time (CUDA events around every wave and every collective).
 
 --impl reference times the reference CPU renderer alone (all host threads), same metric/config.
 """
@@ -179,6 +186,82 @@ def run_reference(args):
     print(json.dumps(line), file=_REAL_STDOUT, flush=True)
 
 
+SHADE_BYTES_PER_HIT = 592  # surface shading, algorithmic bytes per hit: path state 92 B read + 92 B written,
+# vertex data of the hit triangle 120 B (3 indices + 3 x (normal, tangent, uv)), material record 176 B, NEE record 112 B;
+# + 36 B of texel taps (base colour, metallic-roughness, normal map: 4 taps each) on textured materials
+SHADE_TEXTURE_BYTES = 36
+
+
+def oracle_frame(path: str, spp: int = 1):
+    """One frame from the PARITY build of the unmodified reference (oracle/_ref/oracle_ref: -O2, no FMA contraction —
+    the build every parity test compares with; the throughput baseline uses the -O3 -march build, whose contracted
+    arithmetic is not bit-identical to it).  Returns (hdr, ldr, rays) or None."""
+    import numpy as np
+    import struct
+    exe = os.path.join(ROOT, "oracle", "_ref", "oracle_ref")
+    if not os.path.exists(exe):
+        return None
+    out = f"/tmp/yart_bench_parity_{os.getpid()}.bin"
+    cmd = [exe, "render", path, out, f"w={W}", f"h={H}", f"spp={spp}", f"first={spp}", f"max={spp}", f"maxdepth={MAX_DEPTH}",
+           "tonemap=agx", "pos=%.9g,%.9g,%.9g" % CAM["pos"], "target=%.9g,%.9g,%.9g" % CAM["target"], f"focal={CAM['focal']}",
+           f"fnum={CAM['fnum']}", f"exposure={CAM['exposure']}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        return None
+    raw = open(out, "rb").read()
+    os.unlink(out)
+    ww, hh, rays, _, _, _ = struct.unpack_from("<IIQdId", raw, 0)
+    off, n = struct.calcsize("<IIQdId"), ww * hh * 4
+    hdr = np.frombuffer(raw, np.float32, n, off).reshape(hh, ww, 4)
+    ldr = np.frombuffer(raw, np.float32, n, off + 4 * n).reshape(hh, ww, 4)
+    return hdr, ldr, rays
+
+
+def rel_mse(img, ref, eps=1e-2):
+    import numpy as np
+    a, b = img[..., :3].astype(np.float64), ref[..., :3].astype(np.float64)
+    return float(np.mean((a - b) ** 2 / (b * b + eps)))
+
+
+def workload_record(Y, name: str, local: int, trav: int, spp: int, steps: int) -> dict:
+    """A BASELINE.json configs[2] / configs[3] shape on one GPU: full MIS+NEE paths, `steps` waves of `spp` samples of the
+    1080p frame after 3 warm-up waves, device-timed, with the surface-shading kernel's share and roofline."""
+    global CAM, MAX_DEPTH, WORKLOAD_TEXT
+    saved = (CAM, MAX_DEPTH, WORKLOAD_TEXT)
+    tris = DEFAULT_TRIS[name]
+    select_workload(name, tris)
+    try:
+        scene = Y.Scene(scene_path(tris, name))
+        cam = Y.make_camera(W, H, CAM["focal"], CAM["fnum"], CAM["pos"], CAM["target"], (0, 0, 0), CAM["exposure"])
+        ctx = Y.Context(device=local, max_depth=MAX_DEPTH, traversal=trav)
+        ctx.upload_scene(scene)
+        ctx.set_camera(cam)
+        ctx.set_profiling(1 | 4)
+        ctx.begin_frame(W, H, spp * (steps + 3), 64, (0, 0, 0), Y.TONEMAP_AGX)
+        for k in range(3):
+            ctx.render_wave(k * spp, spp, k * spp)
+        s0 = ctx.stats()
+        for k in range(3, 3 + steps):
+            ctx.render_wave(k * spp, spp, k * spp)
+        s1 = ctx.stats()
+        ctx.close()
+        ms = (s1.gpuMs - s0.gpuMs) / steps
+        rays = s1.raysReference - s0.raysReference
+        hits, shade_ms, n_shade = s1.hitsShaded - s0.hitsShaded, s1.shadeMs - s0.shadeMs, s1.shadeLaunches - s0.shadeLaunches
+        per_hit = SHADE_BYTES_PER_HIT + (SHADE_TEXTURE_BYTES if name == "sponza" else 0)
+        peak, peak_src = peaks()
+        achieved = per_hit * hits / (shade_ms / 1e3) / 1e9 if shade_ms > 0 else 0.0
+        return {"workload": WORKLOAD_TEXT, "value": rays / (ms * steps) / 1e3, "unit": "Mrays/s", "ms_per_step": ms,
+                "samples_per_s": W * H * spp / (ms / 1e3), "steps": steps, "spp_per_step": spp,
+                "traversal": "wide" if (trav != Y.TRAVERSAL_REFERENCE_ORDER and name != "sponza") else "reference order (alpha-tested materials)" if name == "sponza" else "reference order",
+                "extend_ms_per_step": (s1.extendMs - s0.extendMs) / steps, "shade_surface_ms_per_step": shade_ms / steps,
+                "shade_roofline": {"bound": "hbm", "kernel": "ShadeSurfaceK", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                                   "frac": achieved / peak, "bytes_per_hit": per_hit, "hits_per_step": hits / steps,
+                                   "launches_per_step": n_shade / steps, "traffic": None, "peak_source": peak_src}}
+    finally:
+        CAM, MAX_DEPTH, WORKLOAD_TEXT = saved
+
+
 def run_ours(args):
     import numpy as np
     import yart_b200 as Y
@@ -189,6 +272,8 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     dist = None
     if world > 1:
+        # torch.distributed is the CONTROL plane only (barriers, the communicator id, max-over-ranks of the timings);
+        # every byte of frame / accumulation-buffer data moves inside libyart_b200.so (yc_comm_*: NCCL on its own stream)
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)
@@ -205,36 +290,14 @@ def run_ours(args):
     log(f"[bench r{rank}] scene {scene.n_tris} tris, host SAH build {scene.build_ms:.0f} ms (load {time.time() - t0:.1f}s)")
     cam = Y.make_camera(W, H, CAM["focal"], CAM["fnum"], CAM["pos"], CAM["target"], (0, 0, 0), CAM["exposure"])
     spp = args.spp
-
-    # ---- device-resident arm ---------------------------------------------------------------
     trav = {"auto": Y.TRAVERSAL_AUTO, "reference": Y.TRAVERSAL_REFERENCE_ORDER, "wide": Y.TRAVERSAL_WIDE}[args.traversal]
-    ctx = Y.Context(device=local, max_depth=MAX_DEPTH, traversal=trav)
-    ctx.upload_scene(scene)
-    ctx.set_camera(cam)
-    ctx.set_profiling(os.environ.get('YART_BENCH_NO_PROFILE') is None)
-    n_warm = max(args.warmup, 3)
-    waves_per_rank = n_warm + args.steps
-    total_spp = spp * world * waves_per_rank  # the job: every rank renders `waves_per_rank` waves of `spp` samples
-    ctx.begin_frame(W, H, total_spp, 64, (0, 0, 0), Y.TONEMAP_AGX)
-
-    frame_t = None
     buckets = world > 1 and args.sharding == "buckets"
-    bucket_t, ar_events = None, []
-    if buckets:
-        import torch
-        b_ptr, b_bytes, _, plane_pix = ctx.bucket_device_ptrs()
-        m_wave = ctx.wave_buckets(spp * world)
 
-        class _BAlias:  # zero-copy int32 view of the planes a wave of spp * world samples uses
-            __cuda_array_interface__ = {"shape": (m_wave * plane_pix * 4,), "typestr": "<i4", "data": (b_ptr, False), "version": 3}
-        bucket_t = torch.as_tensor(_BAlias(), device=f"cuda:{local}")
+    comm_id = None
     if dist:
-        import torch
-        hdr_ptr, _, nbytes = ctx.frame_device_ptrs()
-
-        class _Alias:  # zero-copy view of the context's HDR frame for NCCL
-            __cuda_array_interface__ = {"shape": (nbytes // 4,), "typestr": "<f4", "data": (hdr_ptr, False), "version": 3}
-        frame_t = torch.as_tensor(_Alias(), device=f"cuda:{local}")
+        box = [Y.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        comm_id = box[0]
 
     def sync_all():
         if dist:
@@ -243,136 +306,159 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    def step(k):
-        """One pass: wave (k * world + rank) of the job — `spp` samples of every pixel — blended into this
-        rank's HDR frame with finishTile's sample-count weights."""
-        k = min(k, waves_per_rank - 1)
-        if buckets:
-            # sample sharding inside a wave of spp * world samples by (estimator bucket, pixel class) units: every
-            # rank accumulates its units, the GMoN accumulation buffers are summed with NCCL (int32: disjoint
-            # slots, bitwise exact), every rank finalizes — bit-identical to one GPU rendering the wave
-            import torch
-            S = spp * world
-            ctx.accumulate_wave(k * S, S, bucket_shard=rank, bucket_shard_count=world)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            dist.all_reduce(bucket_t)
-            e1.record()
-            torch.cuda.synchronize()
-            ar_events.append((e0, e1))
-            ctx.finalize_wave(S, k * S)
-            return
-        ctx.render_wave((k * world + rank) * spp, spp, k * spp)
-
-    def combine(scratch=False):
-        """N > 1: the per-GPU HDR frames (equal sample counts) are averaged with one NCCL all-reduce over
-        NVLink and re-tonemapped — once per job, inside the timed region.  scratch=True (warm-up) runs the
-        same collective on a copy so the frames being accumulated are left alone."""
-        if not dist or buckets:
-            return 0.0
+    def max_over_ranks(*vals):
+        if not dist:
+            return list(vals)
         import torch
-        t = frame_t.clone() if scratch else frame_t
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        t.mul_(1.0 / world)
+        t = torch.tensor(vals, device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.tolist()
+
+    def sum_over_ranks(*vals):
+        if not dist:
+            return list(vals)
+        import torch
+        t = torch.tensor(vals, device=f"cuda:{local}", dtype=torch.float64)
         dist.all_reduce(t)
-        e1.record()
-        torch.cuda.synchronize()
-        if not scratch:
-            ctx.retonemap()
-        return e0.elapsed_time(e1)
+        return t.tolist()
+
+    # ---- device-resident arm ---------------------------------------------------------------
+    ctx = Y.Context(device=local, max_depth=MAX_DEPTH, traversal=trav)
+    ctx.upload_scene(scene)
+    ctx.set_camera(cam)
+    ctx.set_profiling(os.environ.get('YART_BENCH_NO_PROFILE') is None)
+    if dist:
+        ctx.comm_init_rank(rank, world, comm_id)
+    n_warm = max(args.warmup, 3)
+
+    def timed_waves(S, steps, warm):
+        """`warm` + `steps` waves of S samples of the frame, sharded over the ranks: tiles of the reference's tile
+        list (rank r renders tile k when k % N == r; the frames are reduced to rank 0 after every wave) or (GMoN bucket,
+        pixel class) units (the accumulation buffers are all-reduced as int32 inside every wave).  Returns the
+        device time of the timed steps (CUDA events around the wave and around its collective, max over ranks),
+        whole-job reference rays, traced rays, launches, collective ms, host wall ms."""
+        total = S * (warm + steps)
+        if buckets:
+            ctx.begin_frame(W, H, total, 64, (0, 0, 0), Y.TONEMAP_AGX)
+        else:
+            ctx.begin_frame(W, H, total, 64, (0, 0, 0), Y.TONEMAP_AGX, shard_index=rank, shard_count=world)
+
+        def step(k):
+            if buckets:
+                ctx.accumulate_wave(k * S, S, bucket_shard=rank, bucket_shard_count=world)
+                ctx.comm_allreduce_buckets(S)
+                ctx.finalize_wave(S, k * S)
+            else:
+                ctx.render_wave(k * S, S, k * S)
+                if dist:
+                    ctx.comm_reduce_frames(0)
+
+        for k in range(warm):
+            step(k)
+        sync_all()
+        s0 = ctx.stats()
+        w0 = time.time()
+        for k in range(warm, warm + steps):
+            step(k)
+        sync_all()
+        w1 = time.time()
+        s1 = ctx.stats()
+        dev = (s1.gpuMs - s0.gpuMs) + (s1.commMs - s0.commMs)
+        dev, comm, wall = max_over_ranks(dev, s1.commMs - s0.commMs, (w1 - w0) * 1e3)
+        rays, traced, launches = sum_over_ranks(s1.raysReference - s0.raysReference,
+                                                (s1.raysExtend - s0.raysExtend) + (s1.raysShadow - s0.raysShadow),
+                                                s1.kernelLaunches - s0.kernelLaunches)
+        return dict(dev_ms=dev, comm_ms=comm, wall_ms=wall, rays=rays, traced=traced, launches=launches, w0=w0, w1=w1, s0=s0, s1=s1,
+                    step=step, total_waves=warm + steps)
 
     # started before the warm-up: nvidia-smi needs ~0.3 s to print its first sample.  Rank 0 samples its own
     # GPU only: eight concurrent nvidia-smi pollers contend for the driver lock and perturb the step time.
     clocks = ClockSampler(local if rank == 0 else -1)
-    for k in range(n_warm):
-        step(k)
-    if dist:
-        combine(scratch=True)  # warms NCCL up (parity of this path: tests/test_multi_gpu_cpu.py)
-    sync_all()
-    s0 = ctx.stats()
-    ar_events.clear()
-    w0 = time.time()
-    for k in range(args.steps):
-        step(n_warm + k)
-    ar_total = combine() + sum(a.elapsed_time(b) for a, b in ar_events)
-    sync_all()
-    w1 = time.time()
-    s1 = ctx.stats()
+    S_weak = spp * world  # weak scaling: the wave grows with the GPU count, every GPU keeps W*H*spp camera paths per step
+    weak = timed_waves(S_weak, args.steps, n_warm)
     # keep the GPU under the same load until a few clock samples exist (not timed); the number of
     # extra steps is agreed across ranks so nothing can hang
-    n_extra = int((0.5 - (w1 - w0)) / max((w1 - w0) / args.steps, 1e-4)) + 1 if w1 - w0 < 0.5 else 0
-    if dist:
-        import torch
-        t = torch.tensor([n_extra], device=f"cuda:{local}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        n_extra = int(t.item())
+    el = weak["w1"] - weak["w0"]
+    n_extra = int((0.5 - el) / max(el / args.steps, 1e-4)) + 1 if el < 0.5 else 0
+    n_extra = int(max_over_ranks(float(n_extra))[0])
     for _ in range(min(n_extra, 200)):
-        step(waves_per_rank - 1)
+        weak["step"](weak["total_waves"] - 1)
     sync_all()
-    clk = clocks.stop(w0, time.time())
-    dev_ms = (s1.gpuMs - s0.gpuMs) + ar_total
-    rays = s1.raysReference - s0.raysReference
-    traced = (s1.raysExtend - s0.raysExtend) + (s1.raysShadow - s0.raysShadow)
-    launches = s1.kernelLaunches - s0.kernelLaunches
+    clk = clocks.stop(weak["w0"], time.time())
+    s0, s1 = weak["s0"], weak["s1"]
+
+    strong = None
+    if dist:
+        # the same job as one GPU's step (one wave of `spp` samples of the frame) split over the ranks
+        st = timed_waves(spp, args.steps, n_warm)
+        strong = {"value": st["rays"] / st["dev_ms"] / 1e3, "unit": "Mrays/s", "ms_per_step": st["dev_ms"] / args.steps,
+                  "collective_ms_per_step": st["comm_ms"] / args.steps,
+                  "job": f"one wave of {spp} spp of the {W}x{H} frame per step, split over {world} GPUs"}
 
     # ---- extend-kernel roofline: algorithmic bytes of the reference traversal on these rays ------
     rspp = min(spp, max(1, (1 << 23) // (W * H)))  # roofline launch: at most 8 Mi primary rays (4 spp at 1080p)
     n_rays = W * H * rspp
     rays_dev, hits_dev = ctx.device_alloc(n_rays * 32), ctx.device_alloc(n_rays * 20)
-    ctx.begin_frame(W, H, total_spp, 64, (0, 0, 0), Y.TONEMAP_AGX)
-    ctx.generate_primary_rays((n_warm * world + rank) * spp, rspp, rays_dev)  # the first timed wave's rays
+    ctx.begin_frame(W, H, spp * (n_warm + args.steps), 64, (0, 0, 0), Y.TONEMAP_AGX)
+    ctx.generate_primary_rays(n_warm * spp, rspp, rays_dev)  # the first timed wave's rays at N = 1
     one = np.array([[0, 0, 40, 0.001, 0.01, 0.02, -0.99975, np.inf]], np.float32)  # any ordinary ray
-    ctx.trace(one, Y.TRACE_CLOSEST | Y.TRACE_COUNT)  # zeroes the work counters
-    c0 = ctx.stats()
-    lib, h = Y.lib(), ctx._h
     import ctypes as C
-    ms_c = C.c_float()
-    rc = lib.yc_trace_device(h, rays_dev, n_rays, Y.TRACE_CLOSEST | Y.TRACE_COUNT, hits_dev, 1, C.byref(ms_c))
-    assert rc == 0
-    c1 = ctx.stats()
-    box, tri = c1.boxTests - c0.boxTests, c1.triTests - c0.triTests
+    lib, h = Y.lib(), ctx._h
+
+    def count_tests(flags):
+        ctx.trace(one, Y.TRACE_CLOSEST | Y.TRACE_COUNT | flags)  # zeroes the work counters
+        c0 = ctx.stats()
+        ms_c = C.c_float()
+        assert lib.yc_trace_device(h, rays_dev, n_rays, Y.TRACE_CLOSEST | Y.TRACE_COUNT | flags, hits_dev, 1, C.byref(ms_c)) == 0
+        c1 = ctx.stats()
+        return c1.boxTests - c0.boxTests, c1.triTests - c0.triTests
+
+    box, tri = count_tests(Y.TRACE_REFERENCE_ORDER)  # SURVEY 8d: the REFERENCE walk's box / triangle tests define the bytes
+    wide_on = trav != Y.TRAVERSAL_REFERENCE_ORDER and args.workload != "sponza"
+    wbox, wtri = count_tests(Y.TRACE_WIDE) if wide_on else (None, None)
     trace_ms = ctx.trace_device(rays_dev, n_rays, hits_dev, Y.TRACE_CLOSEST, repeat=3)
+    ref_walk_ms = ctx.trace_device(rays_dev, n_rays, hits_dev, Y.TRACE_CLOSEST | Y.TRACE_REFERENCE_ORDER, repeat=3) if wide_on else trace_ms
     ctx.device_free(rays_dev)
     ctx.device_free(hits_dev)
     algo_bytes = n_rays * (32 + 20) + 32 * box + 52 * tri
     peak, peak_src = peaks()
-    # The dominant kernel is the persistent closest-hit traversal (extendKernel / traceKernel: the same
-    # tracePersistent body).  Roofline launch = ONE launch over the step's W*H*spp primary rays, timed alone with
-    # CUDA events right here (trace_ms, mean of 3 after the step warm-up), against its algorithmic bytes.
-    # Inside a step the same rays are traced by `in_step_launches` launches (one per chunk; two chunks of a wave
-    # are in flight on two streams), whose event times overlap each other and the other lane's kernels: their
-    # aggregate is reported next to it (sum of bytes / (sum of launch times / lanes in flight)).
+    # The dominant kernel is the persistent closest-hit traversal (extendWideKernel / traceWideKernel: the same
+    # traceWidePersistent body; extendKernel / traceKernel for the reference-order walk).  Roofline launch = ONE launch
+    # over the step's W*H*spp primary rays, timed alone with CUDA events right here (trace_ms, mean of 3 after the step
+    # warm-up), against the algorithmic bytes of the REFERENCE's traversal of the same rays.
     n_ext = max(1, s1.extendLaunches - s0.extendLaunches)
     ext_rays = (s1.raysExtend - s0.raysExtend)
     ext_ms_sum = s1.extendMs - s0.extendMs
-    lanes = 2
     in_step = None
     if MAX_DEPTH == 1 and ext_ms_sum > 0:
-        # maxDepth 1: every extend ray of the timed steps is a primary ray with the bytes counted above per ray
         step_bytes = algo_bytes / n_rays * ext_rays
         in_step = {"launches": int(n_ext), "rays_per_launch": ext_rays / n_ext, "avg_launch_ms": ext_ms_sum / n_ext,
-                   "lanes_in_flight": lanes, "aggregate_gbs": step_bytes / (ext_ms_sum / lanes / 1e3) / 1e9}
-    roof_ms, roof_kernel = trace_ms, "tracePersistent<closest> (extendKernel / traceKernel body), one launch over the step's primary rays, timed alone"
-    achieved = algo_bytes / (roof_ms / 1e3) / 1e9 if roof_ms > 0 else 0.0
+                   "lanes_in_flight": 2, "aggregate_gbs": step_bytes / (ext_ms_sum / 2 / 1e3) / 1e9}
+    roof_kernel = ("traceWidePersistent<closest> (extendWideKernel / traceWideKernel body: 4-wide quantised BVH)" if wide_on else
+                   "tracePersistent<closest> (extendKernel / traceKernel body: reference-order BVH2 walk)") + \
+        ", one launch over the step's primary rays, timed alone"
+    achieved = algo_bytes / (trace_ms / 1e3) / 1e9 if trace_ms > 0 else 0.0
     traffic = None
     tp = os.path.join(ROOT, "profiles", "extend_traffic.json")
     if os.path.exists(tp):
         tj = json.load(open(tp))
-        # DRAM bytes of one ncu-captured launch, scaled to this launch's ray count
-        traffic = tj.get("dram_bytes_per_launch") * n_rays / tj.get("rays_per_launch", n_rays)
+        key = "wide" if wide_on else "reference"
+        if key in tj:  # DRAM bytes of one ncu-captured launch, scaled to this launch's ray count
+            traffic = tj[key]["dram_bytes_per_launch"] * n_rays / tj[key]["rays_per_launch"]
 
-    # ---- end-to-end arm: public Renderer API, host buffers ------------------------------------
-    r = Y.Renderer(W, H, cam, scene, samples=spp, first_wave_samples=spp, max_wave_samples=spp, max_depth=MAX_DEPTH,
-                   tonemap=Y.TONEMAP_AGX, device=local, traversal=trav)
+    # ---- end-to-end arm: public Renderer API, host buffers; at N > 1 ONE image: tile shards reduced to rank 0 inside
+    # the timed region, a single host read there ------------------------------------------------------------------
+    r = Y.Renderer(W, H, cam, scene, samples=S_weak, first_wave_samples=S_weak, max_wave_samples=S_weak, max_depth=MAX_DEPTH,
+                   tonemap=Y.TONEMAP_AGX, device=local, traversal=trav, dist=(rank, world, comm_id) if dist else None,
+                   sharding=Y.SHARD_BUCKETS if buckets else Y.SHARD_TILES)
     e2e_rays = 0
 
     def e2e_step():
         nonlocal e2e_rays
         d = r.render_sync()
-        hdr, ldr, _ = r.read(pinned=True)
-        e2e_rays = d["total_rays"]
-        return hdr
+        if rank == 0:
+            r.read(pinned=True)
+        e2e_rays = d["total_rays"]  # whole-job figure on every rank
 
     for _ in range(2):
         e2e_step()
@@ -382,20 +468,24 @@ def run_ours(args):
     for _ in range(n_e2e):
         e2e_step()
     sync_all()
-    e2e_s = (time.time() - e0)
+    e2e_s = max_over_ranks(time.time() - e0)[0]
     r.close()
 
-    # ---- max over ranks, aggregate ------------------------------------------------------------
-    if dist:
-        import torch
-        t = torch.tensor([dev_ms, (w1 - w0) * 1e3, e2e_s], device=f"cuda:{local}", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, wall_ms, e2e_s = t.tolist()
-        c = torch.tensor([rays, traced, e2e_rays * n_e2e, launches], device=f"cuda:{local}", dtype=torch.float64)
-        dist.all_reduce(c)
-        rays, traced, e2e_total, launches = c.tolist()
-    else:
-        wall_ms, e2e_total = (w1 - w0) * 1e3, e2e_rays * n_e2e
+    # ---- parity of THIS configuration against the reference run on this box (rank 0, N = 1) ----------------------
+    parity = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        ref = oracle_frame(path, 1)
+        if ref is not None:
+            rp = Y.Renderer(W, H, cam, scene, samples=1, first_wave_samples=1, max_wave_samples=1, max_depth=MAX_DEPTH,
+                            tonemap=Y.TONEMAP_AGX, device=local, traversal=trav)
+            dp = rp.render_sync()
+            hdr, ldr, _ = rp.read()
+            rp.close()
+            eq = (hdr.view(np.uint32) == ref[0].view(np.uint32)) | (np.isnan(hdr) & np.isnan(ref[0]))
+            parity = {"against": "oracle/_ref/oracle_ref (unmodified reference, -O2 -ffp-contract=off) rendering 1 spp of the same "
+                                 "frame on this box", "relmse_hdr": rel_mse(hdr, ref[0]), "relmse_ldr": rel_mse(ldr, ref[1]),
+                      "bits_equal_frac": float(eq.all(-1).mean()), "pixels_differing": int((~eq.all(-1)).sum()),
+                      "rays": int(dp["total_rays"]), "rays_reference": int(ref[2]), "rays_equal": int(dp["total_rays"]) == int(ref[2])}
 
     if rank == 0:
         cpu = None
@@ -407,37 +497,62 @@ def run_ours(args):
                                  f"({cr['exe']}); BVH build {cr['build_ms']:.0f} ms excluded"}
             except Exception as ex:  # noqa: BLE001
                 cpu = {"value": None, "unit": "Mrays/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {ex}"}
+        workloads = None
+        if world == 1 and args.workload == "soup" and not args.no_workloads:
+            workloads = {}
+            for name in ("sponza", "mclaren"):
+                try:
+                    workloads[name] = workload_record(Y, name, local, trav, spp, max(3, min(args.steps, 8)))
+                except Exception as ex:  # noqa: BLE001
+                    workloads[name] = {"error": str(ex)}
+        dev_ms = weak["dev_ms"]
         line = {
-            "metric": METRIC, "value": rays / dev_ms / 1e3, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "metric": METRIC, "value": weak["rays"] / dev_ms / 1e3, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": n_warm, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD_TEXT,
-                       "step": f"one wave of {spp} spp per GPU ({W * H * spp} camera paths)",
-                       "parallelism": (f"bucket sharding x{world}: every wave of {spp * world} samples is split into (GMoN bucket b, pixel "
-                                       "class c) units, rank r takes (b + c) % N == r; scene replicated; NCCL all-reduce(int32 sum) "
-                                       "of the accumulation buffers per wave, inside the timed region") if buckets else
-                                      (f"sample-wave sharding x{world}: rank r renders waves r, r+N, ... of the job; scene replicated; "
-                                       "one NCCL all-reduce of the HDR frames per job (inside the timed region)"),
+                       "step": f"one wave of {S_weak} spp of the frame = {spp} spp per GPU ({W * H * spp} camera paths per GPU)",
+                       "traversal": ("4-wide quantised BVH collapsed from the reference's SAH tree (YC_TRAVERSAL_AUTO; same triangles, "
+                                     "same triangle arithmetic; `parity` below)" if wide_on else "reference-order BVH2 walk (bit-identical frames)"),
+                       "parallelism": "single GPU" if world == 1 else
+                                      (f"bucket sharding x{world} inside libyart_b200.so: every wave is split into (GMoN bucket, pixel class) "
+                                       "units, rank r takes (b + c) % N == r; scene replicated; ncclAllReduce(int32 sum) of the "
+                                       "accumulation buffers per wave, inside the timed region") if buckets else
+                                      (f"tile sharding x{world} inside libyart_b200.so: rank r renders tile k of the reference's tile list when "
+                                       "k % N == r; scene replicated; ncclReduce of the HDR + LDR frames to rank 0 after every wave, "
+                                       "inside the timed region"),
                        "l2": "inputs larger than L2: BVH + 0.8 GB of path state streamed per step exceed the 126 MB L2; no flush"},
-            "wall_ms_per_step": wall_ms / args.steps,
-            "traced_mrays_per_s": traced / dev_ms / 1e3,
-            "samples_per_s": W * H * spp * world / (dev_ms / args.steps / 1e3),
-            "gpu_launches": int(launches),
+            "wall_ms_per_step": weak["wall_ms"] / args.steps,
+            "collective_ms_per_step": weak["comm_ms"] / args.steps,
+            "traced_mrays_per_s": weak["traced"] / dev_ms / 1e3,
+            "samples_per_s": W * H * S_weak / (dev_ms / args.steps / 1e3),
+            "gpu_launches": int(weak["launches"]),
             "clocks": clk,
-            "e2e": {"value": e2e_total / e2e_s / 1e6, "unit": "Mrays/s",
-                    "h2d_bytes_per_step": 256, "d2h_bytes_per_step": 2 * W * H * 16,
-                    "call": "Renderer.render_sync() + Renderer.read(pinned=True) (yr_render_sync + yr_read): camera/frame description in, HDR + LDR frames out to page-locked host memory"},
+            "e2e": {"value": e2e_rays * n_e2e / e2e_s / 1e6, "unit": "Mrays/s",
+                    "h2d_bytes_per_step": 256 * world, "d2h_bytes_per_step": 2 * W * H * 16,
+                    "call": "Renderer.render_sync() + Renderer.read(pinned=True) on rank 0 (yr_render_sync + yr_read): camera / frame "
+                            "description in, ONE image out — the HDR + LDR frames to page-locked host memory" +
+                            ("; the ranks' tile shards are reduced to rank 0 by the library inside the timed region" if dist else "")},
             "metric_note": "value counts rays as the reference does (path segments + unoccluded NEE rays); traced_mrays_per_s counts every ray traced",
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic if args.workload == "soup" else None, "kernel": roof_kernel, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": algo_bytes, "rays_per_launch": n_rays, "avg_launch_ms": roof_ms,
+                         "algorithmic_bytes_per_launch": algo_bytes, "rays_per_launch": n_rays, "avg_launch_ms": trace_ms,
                          "box_tests_per_ray": box / n_rays, "tri_tests_per_ray": tri / n_rays,
+                         "wide_box_tests_per_ray": wbox / n_rays if wbox is not None else None,
+                         "wide_tri_tests_per_ray": wtri / n_rays if wtri is not None else None,
+                         "reference_order_walk_launch_ms": ref_walk_ms,
                          "in_step_extend_launches": in_step,
-                         "note": "frac > 1 is possible: the algorithmic bytes (SURVEY 8d: the reference BVH2's node and triangle "
-                                 "bytes per test) are served by the L2, where the BVH is resident; DRAM moves only `traffic`. ncu: "
-                                 "issue slots 65 %, L1/TEX 77 %, 18.7 of 32 lanes active, top stall L2 latency (profiles/README.md)"},
+                         "note": "algorithmic bytes = SURVEY 8d: (32 B ray + 20 B hit) per ray + 32 B per box test + 52 B per triangle "
+                                 "test of the REFERENCE's BVH2 traversal of these rays (counting build of the reference-order walk); "
+                                 "frac > 1 is possible: those bytes are served by the L1 / L2, where the BVH is resident, and the "
+                                 "wide walk fetches 16 B per box — DRAM moves only `traffic` (profiles/README.md)"},
             "cpu_baseline": cpu,
+            "parity": parity,
         }
+        if strong:
+            line["strong"] = strong
+        if workloads:
+            line["workloads"] = workloads
         print(json.dumps(line), file=_REAL_STDOUT, flush=True)
     ctx.close()
     if dist:
@@ -460,8 +575,9 @@ def main():
     ap.add_argument("--workload", default="soup", choices=sorted(WORKLOADS))
     ap.add_argument("--tris", type=int, default=0, help="triangle count (default: the workload's BASELINE.json size)")
     ap.add_argument("--spp", type=int, default=4)
-    ap.add_argument("--sharding", default="waves", choices=["waves", "buckets"],
-                    help="N > 1: whole waves per rank (default) or the samples of one wave split by GMoN bucket")
+    ap.add_argument("--sharding", default="tiles", choices=["tiles", "buckets"],
+                    help="N > 1: tiles of the reference's tile list per rank (default) or the samples of one wave split by GMoN bucket")
+    ap.add_argument("--no-workloads", action="store_true", help="skip the sponza / mclaren sub-records of the default line")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--traversal", default="auto", choices=["auto", "reference", "wide"],
                     help="YcOptions::traversal: auto = the 4-wide BVH for scenes without alpha-tested materials (default), "

@@ -277,6 +277,10 @@ typedef struct YcStats {
                                   walk's tests unless YC_TRACE_WIDE is OR-ed in (then: wide child boxes tested) */
   double extendMs;          /* CUDA-event time of the extend (closest-hit) launches, when yc_set_profiling(1) */
   uint64_t extendLaunches;
+  double shadeMs;           /* CUDA-event time of the surface-shading launches, when yc_set_profiling(4) */
+  uint64_t shadeLaunches;
+  uint64_t hitsShaded;      /* queue entries those launches shaded */
+  double commMs;            /* CUDA-event time of the yc_comm_* data collectives since begin_frame */
 } YcStats;
 
 typedef struct YcRay { float o[3], tmin, d[3], tmax; } YcRay;
@@ -349,7 +353,8 @@ int yc_frame_device_ptrs(yc_ctx* ctx, void** hdr, void** ldr, size_t* bytes);
 int yc_retonemap(yc_ctx* ctx);
 /* Bit 0: record per-launch CUDA-event time of the extend kernel into YcStats (bench roofline).
  * Bit 1: run the counting builds of extend / shadow so YcStats.boxTests / triTests accumulate
- * (reference-traversal work; the counting builds do not park leaves speculatively). */
+ * (reference-traversal work; the counting builds do not park leaves speculatively).
+ * Bit 2: record per-launch CUDA-event time of the surface-shading kernel and the hits it shaded. */
 int yc_set_profiling(yc_ctx* ctx, int flags);
 /* Ray-level parity hook: RayIntegrator::testNode on caller rays (ray-integrator.cpp:20-54). */
 int yc_trace(yc_ctx* ctx, const YcRay* rays, size_t n, int mode, YcHit* hits, YcStats* stats);

@@ -246,7 +246,27 @@ class Context:
     def retonemap(self):
         self._ck(lib().yc_retonemap(self._h), "yc_retonemap")
 
+    # ---- collectives (yc_comm_*) ----
+    def comm_init_rank(self, rank: int, world: int, comm_id: bytes):
+        cid = (C.c_char * capi.COMM_ID_BYTES).from_buffer_copy(bytes(comm_id))
+        self._ck(lib().yc_comm_init_rank(self._h, rank, world, cid), "yc_comm_init_rank")
+
+    def comm_reduce_frames(self, root: int = 0):
+        self._ck(lib().yc_comm_reduce_frames(self._h, root), "yc_comm_reduce_frames")
+
+    def comm_allreduce_buckets(self, wave_samples: int):
+        self._ck(lib().yc_comm_allreduce_buckets(self._h, wave_samples), "yc_comm_allreduce_buckets")
+
+    def resolve_combined(self, want_hdr=True, want_ldr=True):
+        h, w = self.frame.height, self.frame.width
+        hdr = np.empty((h, w, 4), np.float32) if want_hdr else None
+        ldr = np.empty((h, w, 4), np.float32) if want_ldr else None
+        self._ck(lib().yc_resolve_combined(self._h, hdr.ctypes.data if want_hdr else None, ldr.ctypes.data if want_ldr else None),
+                 "yc_resolve_combined")
+        return hdr, ldr
+
     def set_profiling(self, on: bool):
+        """on: bool, or the bit mask of yc_set_profiling (1 extend timing, 2 counting builds, 4 shade timing)."""
         self._ck(lib().yc_set_profiling(self._h, int(on)), "yc_set_profiling")
 
     def trace(self, rays: np.ndarray, mode=TRACE_CLOSEST):

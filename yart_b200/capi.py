@@ -56,7 +56,8 @@ class YcFrameDesc(C.Structure):
 class YcStats(C.Structure):
     _fields_ = [("raysReference", u64), ("raysExtend", u64), ("raysShadow", u64), ("samples", u64),
                 ("kernelLaunches", u64), ("gpuMs", C.c_double), ("boxTests", u64), ("triTests", u64),
-                ("extendMs", C.c_double), ("extendLaunches", u64)]
+                ("extendMs", C.c_double), ("extendLaunches", u64), ("shadeMs", C.c_double), ("shadeLaunches", u64),
+                ("hitsShaded", u64), ("commMs", C.c_double)]
 
 
 class YcRay(C.Structure):

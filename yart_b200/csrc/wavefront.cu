@@ -98,6 +98,11 @@ struct yc_ctx {
   rt::Event ev0, ev1;
   std::vector<std::pair<rt::Event, rt::Event>> extendEvents;  // one pair per timed extend launch of the wave
   size_t extendEventsUsed = 0;
+  std::vector<std::pair<rt::Event, rt::Event>> shadeEvents;   // the same for the surface-shading launches
+  size_t shadeEventsUsed = 0;
+  double shadeMs = 0, commMs = 0;
+  uint64_t shadeLaunches = 0, hitsShaded = 0;
+  bool timeShade = false;
   uint64_t launches = 0;
   double gpuMs = 0, extendMs = 0;
   uint64_t extendLaunches = 0, raysExtend = 0;
@@ -651,10 +656,11 @@ extern "C" void yc_destroy(yc_ctx* ctx) {
   freeAll(ctx->waveAllocs);
   rt::eventDestroy(ctx->ev0);
   rt::eventDestroy(ctx->ev1);
-  for (auto& ev : ctx->extendEvents) {
-    rt::eventDestroy(ev.first);
-    rt::eventDestroy(ev.second);
-  }
+  for (auto* evs : {&ctx->extendEvents, &ctx->shadeEvents})
+    for (auto& ev : *evs) {
+      rt::eventDestroy(ev.first);
+      rt::eventDestroy(ev.second);
+    }
   for (int l = 0; l < kLanes; l++) {
     Lane& L = ctx->lanes[l];
     rt::sync(L.st);
@@ -921,8 +927,8 @@ extern "C" int yc_begin_frame(yc_ctx* ctx, const YcFrameDesc* f) {
   YC_TRY(rt::zero(ctx->st, ctx->dCounters, sizeof(Counters)));
   YC_TRY(rt::sync(ctx->st));
   ctx->launches = 0;
-  ctx->gpuMs = ctx->extendMs = 0;
-  ctx->extendLaunches = 0;
+  ctx->gpuMs = ctx->extendMs = ctx->shadeMs = ctx->commMs = 0;
+  ctx->extendLaunches = ctx->shadeLaunches = ctx->hitsShaded = 0;
   ctx->raysExtend = 0;
   ctx->inFrame = true;
   return YC_OK;
@@ -938,7 +944,18 @@ static int issueBounce(yc_ctx* ctx, Lane& L) {
   else runExtend<ALPHA, false>(ctx, L, n);
   rt::launchFor(L.st, n, SortK{L.ps, L.qA, L.qH, L.qM, L.ctr});
   rt::launchFor(L.st, n, ShadeMissK{ctx->ds, L.w, L.ps, L.qM, L.ctr, ctx->dCounters});
+  std::pair<rt::Event, rt::Event>* sev = nullptr;
+  if (ctx->timeShade) {
+    if (ctx->shadeEventsUsed == ctx->shadeEvents.size()) {
+      ctx->shadeEvents.emplace_back();
+      rt::eventCreate(ctx->shadeEvents.back().first);
+      rt::eventCreate(ctx->shadeEvents.back().second);
+    }
+    sev = &ctx->shadeEvents[ctx->shadeEventsUsed++];
+    rt::eventRecord(L.st, sev->first);
+  }
   rt::launchFor<YB_SHADE_MIN_BLOCKS>(L.st, n, ShadeSurfaceK<ALPHA>{ctx->ds, L.w, L.ps, L.ns, L.qH, L.qA, L.qN, L.ctr, ctx->dCounters});
+  if (sev) rt::eventRecord(L.st, sev->second);
   rt::launchFor<YB_SHADE_MIN_BLOCKS>(L.st, n, ShadeNeeK{ctx->ds, L.w, L.ns, L.sq, L.qN, L.ctr});
   if (ctx->countTraversal) runShadow<ALPHA, true>(ctx, L, n);
   else runShadow<ALPHA, false>(ctx, L, n);
@@ -1094,6 +1111,7 @@ static int renderChunks(yc_ctx* ctx, const uint32_t* dList, uint32_t nPixCall, u
     rt::eventSync(L.evCtr);
     if (abortRequested()) return abortNow();
     L.waiting = false;
+    ctx->hitsShaded += L.hCtr[kCtrHitCount];  // of the bounces whose counters come back (all but a path's last possible one)
     L.n = L.hCtr[kCtrNextCount];
     L.bounce++;
     if (L.n == 0 || L.bounce >= ctx->opts.maxDepth) {
@@ -1155,6 +1173,11 @@ static int endTimedRegion(yc_ctx* ctx) {
     ctx->extendLaunches++;
   }
   ctx->extendEventsUsed = 0;
+  for (size_t i = 0; i < ctx->shadeEventsUsed; i++) {
+    ctx->shadeMs += rt::eventElapsedMs(ctx->shadeEvents[i].first, ctx->shadeEvents[i].second);
+    ctx->shadeLaunches++;
+  }
+  ctx->shadeEventsUsed = 0;
   return YC_OK;
 }
 
@@ -1258,6 +1281,8 @@ static int readStats(yc_ctx* ctx, YcStats* stats) {
   stats->kernelLaunches = ctx->launches;
   stats->gpuMs = ctx->gpuMs;
   stats->extendMs = ctx->extendMs;
+  stats->shadeMs = ctx->shadeMs, stats->shadeLaunches = ctx->shadeLaunches, stats->hitsShaded = ctx->hitsShaded;
+  stats->commMs = ctx->commMs;
   stats->extendLaunches = ctx->extendLaunches;
   return YC_OK;
 }
@@ -1298,6 +1323,7 @@ extern "C" int yc_set_profiling(yc_ctx* ctx, int timeExtendKernel) {
   rt::useDevice(ctx->device);
   ctx->timeExtend = (timeExtendKernel & 1) != 0;
   ctx->countTraversal = (timeExtendKernel & 2) != 0;  // counting builds of extend / shadow (box / triangle tests)
+  ctx->timeShade = (timeExtendKernel & 4) != 0;
   return YC_OK;
 }
 
@@ -1809,13 +1835,16 @@ extern "C" int yc_comm_reduce_frames(yc_ctx* ctx, int root) {
     c.frameTexels = texels;
   }
   // out of place: the context's own frames keep blending its tiles in later waves
+  rt::eventRecord(ctx->st, ctx->ev0);
   YC_TRY(rt::d2d(ctx->st, c.hdrAll, ctx->dHdr, texels * sizeof(float4)));
   YC_TRY(rt::d2d(ctx->st, c.ldrAll, ctx->dLdr, texels * sizeof(float4)));
   int rc = commSum(ctx, c.hdrAll, texels * 4, kCommF32, root);
   if (rc == YC_OK) rc = commSum(ctx, c.ldrAll, texels * 4, kCommF32, root);
   if (rc != YC_OK) return rc;
+  rt::eventRecord(ctx->st, ctx->ev1);
   YC_TRY(rt::sync(ctx->st));
   YC_TRY(rt::lastError());
+  ctx->commMs += rt::eventElapsedMs(ctx->ev0, ctx->ev1);
   return YC_OK;
 }
 
@@ -1835,10 +1864,13 @@ extern "C" int yc_comm_allreduce_buckets(yc_ctx* ctx, uint32_t waveSamples) {
   if (!ctx->comm) return fail(ctx, YC_ERR_STATE, "yc_comm_allreduce_buckets without a communicator");
   if (!ctx->inFrame) return fail(ctx, YC_ERR_STATE, "no frame");
   const size_t words = size_t(waveBuckets(ctx->frame, waveSamples)) * ctx->bucketCapacity * 4;
+  rt::eventRecord(ctx->st, ctx->ev0);
   const int rc = commSum(ctx, ctx->dBuckets, words, kCommI32, -1);
   if (rc != YC_OK) return rc;
+  rt::eventRecord(ctx->st, ctx->ev1);
   YC_TRY(rt::sync(ctx->st));
   YC_TRY(rt::lastError());
+  ctx->commMs += rt::eventElapsedMs(ctx->ev0, ctx->ev1);
   return YC_OK;
 }
 
