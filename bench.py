@@ -293,11 +293,13 @@ def run_ours(args):
     trav = {"auto": Y.TRAVERSAL_AUTO, "reference": Y.TRAVERSAL_REFERENCE_ORDER, "wide": Y.TRAVERSAL_WIDE}[args.traversal]
     buckets = world > 1 and args.sharding == "buckets"
 
-    comm_id = None
-    if dist:
+    def new_comm_id():
+        """One communicator id per communicator (ncclGetUniqueId on rank 0, handed to the others over the control plane)."""
+        if not dist:
+            return None
         box = [Y.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
-        comm_id = box[0]
+        return box[0]
 
     def sync_all():
         if dist:
@@ -328,7 +330,7 @@ def run_ours(args):
     ctx.set_camera(cam)
     ctx.set_profiling(os.environ.get('YART_BENCH_NO_PROFILE') is None)
     if dist:
-        ctx.comm_init_rank(rank, world, comm_id)
+        ctx.comm_init_rank(rank, world, new_comm_id())
     n_warm = max(args.warmup, 3)
 
     def timed_waves(S, steps, warm):
@@ -449,7 +451,7 @@ def run_ours(args):
     # ---- end-to-end arm: public Renderer API, host buffers; at N > 1 ONE image: tile shards reduced to rank 0 inside
     # the timed region, a single host read there ------------------------------------------------------------------
     r = Y.Renderer(W, H, cam, scene, samples=S_weak, first_wave_samples=S_weak, max_wave_samples=S_weak, max_depth=MAX_DEPTH,
-                   tonemap=Y.TONEMAP_AGX, device=local, traversal=trav, dist=(rank, world, comm_id) if dist else None,
+                   tonemap=Y.TONEMAP_AGX, device=local, traversal=trav, dist=(rank, world, new_comm_id()) if dist else None,
                    sharding=Y.SHARD_BUCKETS if buckets else Y.SHARD_TILES)
     e2e_rays = 0
 
