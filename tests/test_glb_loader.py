@@ -246,3 +246,47 @@ def test_glb_errors(tmp_path):
         Y.Scene(str(p))
     with pytest.raises(Y.YartError):
         Y.Scene(str(tmp_path / "missing.glb"))
+
+
+def test_hostile_sizes_are_rejected_not_trusted(tmp_path):
+    """counts / offsets in a .glb or .ysc are attacker-controlled.  Wrapping sums, negative or non-finite JSON
+    numbers, a short `matrix`, and counts larger than the file must produce an error code — not a heap overrun, not an
+    exception escaping the C ABI."""
+    import json
+    import struct
+
+    def glb(doc, bin_bytes=b"\0" * 64):
+        js = json.dumps(doc).encode()
+        js += b" " * (-len(js) % 4)
+        body = struct.pack("<II", len(js), 0x4E4F534A) + js + struct.pack("<II", len(bin_bytes), 0x004E4942) + bin_bytes
+        return struct.pack("<III", 0x46546C67, 2, 12 + len(body)) + body
+
+    def base(acc_pos, acc_idx=None, node=None):
+        return {"asset": {"version": "2.0"}, "buffers": [{"byteLength": 64}],
+                "bufferViews": [{"buffer": 0, "byteOffset": 0, "byteLength": 64}],
+                "accessors": [acc_pos, acc_idx or {"bufferView": 0, "componentType": 5125, "count": 3, "type": "SCALAR"}],
+                "meshes": [{"primitives": [{"attributes": {"POSITION": 0}, "indices": 1}]}],
+                "nodes": [node or {"mesh": 0}], "scenes": [{"nodes": [0]}], "scene": 0}
+
+    pos = {"bufferView": 0, "componentType": 5126, "type": "VEC3"}
+    cases = {
+        "wrapping_count": base(dict(pos, count=2 ** 63)),
+        "huge_count": base(dict(pos, count=1e30)),
+        "negative_count": base(dict(pos, count=-4)),
+        "wrapping_offset": base(dict(pos, count=1, byteOffset=2 ** 64 - 8)),
+        "index_count_beyond_view": base(dict(pos, count=3), {"bufferView": 0, "componentType": 5125, "count": 2 ** 62, "type": "SCALAR"}),
+        "short_matrix": base(dict(pos, count=3), node={"mesh": 0, "matrix": [1, 0, 0]}),
+        "view_beyond_bin": dict(base(dict(pos, count=3)), bufferViews=[{"buffer": 0, "byteOffset": 60, "byteLength": 2 ** 40}]),
+    }
+    for name, doc in cases.items():
+        p = tmp_path / f"{name}.glb"
+        p.write_bytes(glb(doc))
+        with pytest.raises(Y.YartError):
+            Y.Scene(str(p))
+    # .ysc: a texture count / mesh size far beyond the file
+    for name, payload in (("ysc_textures", b"YSC1" + struct.pack("<I", 0xFFFFFFF0)),
+                          ("ysc_mesh", b"YSC1" + struct.pack("<III", 0, 0, 1) + struct.pack("<II", 0xFFFFFFFF, 0xFFFFFFFF))):
+        p = tmp_path / f"{name}.ysc"
+        p.write_bytes(payload + b"\0" * 32)
+        with pytest.raises(Y.YartError, match="exceeds the file"):
+            Y.Scene(str(p))

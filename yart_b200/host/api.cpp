@@ -32,30 +32,50 @@ struct ys_scene {
 
 static thread_local std::string g_ysError;
 
+// Nothing may throw across the C ABI: allocation failures and container errors raised while loading a (possibly
+// hostile) file become error codes.
+template <class F>
+static int guarded(F&& body) {
+  try {
+    return body();
+  } catch (const std::bad_alloc&) {
+    g_ysError = "out of memory";
+    return YC_ERR_IO;
+  } catch (const std::exception& e) {
+    g_ysError = std::string("internal error: ") + e.what();
+    return YC_ERR_INVALID;
+  } catch (...) {
+    g_ysError = "internal error";
+    return YC_ERR_INVALID;
+  }
+}
+
 extern "C" const char* ys_last_error(void) { return g_ysError.c_str(); }
 
 extern "C" int ys_scene_load_bvh(const char* path, uint32_t bvhKind, ys_scene** out);
 extern "C" int ys_scene_load(const char* path, ys_scene** out) { return ys_scene_load_bvh(path, YS_BVH_SAH, out); }
 
 extern "C" int ys_scene_load_bvh(const char* path, uint32_t bvhKind, ys_scene** out) {
-  if (!path || !out || bvhKind > YS_BVH_MEDIAN_SPLIT) return YC_ERR_INVALID;
-  *out = nullptr;
-  ysc::SceneDesc d;
-  std::string err;
-  if (!ysc::load(path, d, &err)) {
-    g_ysError = err;
-    return YC_ERR_IO;
-  }
-  ys_scene* s = new (std::nothrow) ys_scene();
-  if (!s) return YC_ERR_INVALID;
-  s->host.bvhKind = bvhKind;
-  if (!s->host.build(d, &err)) {
-    g_ysError = err;
-    delete s;
-    return YC_ERR_INVALID;
-  }
-  *out = s;
-  return YC_OK;
+  return guarded([&]() -> int {
+    if (!path || !out || bvhKind > YS_BVH_MEDIAN_SPLIT) return YC_ERR_INVALID;
+    *out = nullptr;
+    ysc::SceneDesc d;
+    std::string err;
+    if (!ysc::load(path, d, &err)) {
+      g_ysError = err;
+      return YC_ERR_IO;
+    }
+    ys_scene* s = new (std::nothrow) ys_scene();
+    if (!s) return YC_ERR_INVALID;
+    s->host.bvhKind = bvhKind;
+    if (!s->host.build(d, &err)) {
+      g_ysError = err;
+      delete s;
+      return YC_ERR_INVALID;
+    }
+    *out = s;
+    return YC_OK;
+  });
 }
 
 // main.cpp:81-84: `ImageInfiniteLight(radius, &hdri); scene->addLight(...)` after gltf::load
@@ -75,60 +95,66 @@ static void appendEnv(ysc::SceneDesc& d, const YsEnvLight* env) {
 }
 
 extern "C" int ys_glb_convert(const char* glbPath, const char* yscPath, const YsEnvLight* env) {
-  if (!glbPath || !yscPath) return YC_ERR_INVALID;
-  ysc::SceneDesc d;
-  std::string err;
-  if (!loadGlb(glbPath, d, &err)) {
-    g_ysError = err;
-    return YC_ERR_IO;
-  }
-  appendEnv(d, env);
-  if (!ysc::save(yscPath, d)) {
-    g_ysError = std::string("cannot write ") + yscPath;
-    return YC_ERR_IO;
-  }
-  return YC_OK;
+  return guarded([&]() -> int {
+    if (!glbPath || !yscPath) return YC_ERR_INVALID;
+    ysc::SceneDesc d;
+    std::string err;
+    if (!loadGlb(glbPath, d, &err)) {
+      g_ysError = err;
+      return YC_ERR_IO;
+    }
+    appendEnv(d, env);
+    if (!ysc::save(yscPath, d)) {
+      g_ysError = std::string("cannot write ") + yscPath;
+      return YC_ERR_IO;
+    }
+    return YC_OK;
+  });
 }
 
 extern "C" int ys_scene_load_glb(const char* path, const YsEnvLight* env, ys_scene** out) {
-  if (!path || !out) return YC_ERR_INVALID;
-  *out = nullptr;
-  ysc::SceneDesc d;
-  std::string err;
-  if (!loadGlb(path, d, &err)) {
-    g_ysError = err;
-    return YC_ERR_IO;
-  }
-  appendEnv(d, env);
-  ys_scene* s = new (std::nothrow) ys_scene();
-  if (!s) return YC_ERR_INVALID;
-  if (!s->host.build(d, &err)) {
-    g_ysError = err;
-    delete s;
-    return YC_ERR_INVALID;
-  }
-  *out = s;
-  return YC_OK;
+  return guarded([&]() -> int {
+    if (!path || !out) return YC_ERR_INVALID;
+    *out = nullptr;
+    ysc::SceneDesc d;
+    std::string err;
+    if (!loadGlb(path, d, &err)) {
+      g_ysError = err;
+      return YC_ERR_IO;
+    }
+    appendEnv(d, env);
+    ys_scene* s = new (std::nothrow) ys_scene();
+    if (!s) return YC_ERR_INVALID;
+    if (!s->host.build(d, &err)) {
+      g_ysError = err;
+      delete s;
+      return YC_ERR_INVALID;
+    }
+    *out = s;
+    return YC_OK;
+  });
 }
 
 extern "C" int ys_decode_texture(const void* png, size_t len, uint32_t type, uint32_t nChannels, const int32_t* channels,
                                  uint8_t* out, size_t outBytes, uint32_t* width, uint32_t* height) {
-  if (!png || !channels || nChannels < 1 || nChannels > 4) return YC_ERR_INVALID;
-  ysc::TextureDesc t;
-  std::string err;
-  int ch[4] = {0, 1, 2, 3};
-  for (uint32_t i = 0; i < nChannels; i++) ch[i] = channels[i];
-  if (!decodeTextureForTest(static_cast<const uint8_t*>(png), len, type, int(nChannels), ch, t, err)) {
-    g_ysError = err;
-    return YC_ERR_IO;
-  }
-  if (width) *width = t.width;
-  if (height) *height = t.height;
-  if (out) {
-    if (outBytes < t.u8.size()) return YC_ERR_INVALID;
-    memcpy(out, t.u8.data(), t.u8.size());
-  }
-  return YC_OK;
+  return guarded([&]() -> int {
+    if (!png || !channels || nChannels < 1 || nChannels > 4) return YC_ERR_INVALID;
+    ysc::TextureDesc t;
+    std::string err;
+    int ch[4] = {0, 1, 2, 3};
+    for (uint32_t i = 0; i < nChannels; i++) ch[i] = channels[i];
+    if (!decodeTextureForTest(static_cast<const uint8_t*>(png), len, type, int(nChannels), ch, t, err)) {
+      g_ysError = err;
+      return YC_ERR_IO;
+    }
+    if (width) *width = t.width;
+    if (height) *height = t.height;
+    if (out) {
+      if (outBytes < t.u8.size()) return YC_ERR_INVALID;
+      memcpy(out, t.u8.data(), t.u8.size());
+    }
+    return YC_OK;
+  });
 }
 
 extern "C" int ys_write_ppm(const char* path, const float* rgba, uint32_t width, uint32_t height) {

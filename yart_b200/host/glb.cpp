@@ -57,7 +57,7 @@ struct Json {
   }
   long index(const char* key) const {  // -1 when absent
     const Json* j = get(key);
-    return j && j->type == Num ? long(j->num) : -1;
+    return j && j->type == Num && j->num >= 0.0 && j->num < 2147483648.0 ? long(j->num) : -1;  // NaN / negative / huge: absent
   }
   size_t size() const { return type == Arr ? arr.size() : 0; }
 };
@@ -303,20 +303,36 @@ static void convertTexture(const std::vector<uint8_t>& rgba, int w, int h, uint3
 // ---------------------------------------------------------------------------------------
 namespace {
 
+// A JSON number used as a size / offset: finite, non-negative, integral enough, and small enough that products with
+// strides cannot wrap (files are < 2^40 bytes).
+static bool toSize(double v, size_t& out) {
+  if (!(v >= 0.0) || !(v < 1099511627776.0)) return false;  // also rejects NaN
+  out = size_t(v);
+  return true;
+}
+
 struct Glb {
   Json root;
   std::vector<uint8_t> bin;
   std::string err;
+
+  // `count` elements of `elem` bytes, `stride` apart, starting at `off`, inside a view of `n` bytes — written so that
+  // nothing can wrap: off + (count - 1) * stride + elem <= n
+  static bool spanFits(size_t off, size_t count, size_t stride, size_t elem, size_t n) {
+    if (count == 0) return true;
+    if (off > n || elem > n - off) return false;
+    return stride == 0 ? count == 1 : (count - 1) <= (n - off - elem) / stride;
+  }
 
   bool view(long bv, const uint8_t*& p, size_t& n, size_t& stride) {
     const Json* views = root.get("bufferViews");
     if (bv < 0 || !views || size_t(bv) >= views->size()) return err = "bufferView index out of range", false;
     const Json& v = views->arr[bv];
     if (v.index("buffer") != 0) return err = "only the GLB-embedded buffer 0 is supported", false;
-    const size_t off = size_t(v.number("byteOffset", 0));
-    n = size_t(v.number("byteLength", 0));
-    stride = size_t(v.number("byteStride", 0));
-    if (off + n > bin.size()) return err = "bufferView exceeds the BIN chunk", false;
+    size_t off;
+    if (!toSize(v.number("byteOffset", 0), off) || !toSize(v.number("byteLength", 0), n) || !toSize(v.number("byteStride", 0), stride))
+      return err = "bufferView with a negative, non-finite or absurd offset / length / stride", false;
+    if (off > bin.size() || n > bin.size() - off) return err = "bufferView exceeds the BIN chunk", false;
     p = bin.data() + off;
     return true;
   }
@@ -331,13 +347,13 @@ struct Glb {
     const Json* ty = a.get("type");
     const int have = !ty ? 0 : ty->str == "SCALAR" ? 1 : ty->str == "VEC2" ? 2 : ty->str == "VEC3" ? 3 : ty->str == "VEC4" ? 4 : 0;
     if (have < comps) return err = "accessor has too few components", false;
-    const size_t count = size_t(a.number("count", 0));
+    size_t count, off;
+    if (!toSize(a.number("count", 0), count) || !toSize(a.number("byteOffset", 0), off)) return err = "accessor with a bad count / offset", false;
     const uint8_t* p;
     size_t n, stride;
     if (!view(a.index("bufferView"), p, n, stride)) return false;
-    const size_t off = size_t(a.number("byteOffset", 0));
     if (!stride) stride = size_t(have) * 4;
-    if (count && off + (count - 1) * stride + size_t(comps) * 4 > n) return err = "accessor exceeds its bufferView", false;
+    if (!spanFits(off, count, stride, size_t(comps) * 4, n)) return err = "accessor exceeds its bufferView", false;
     out.resize(count * comps);
     for (size_t i = 0; i < count; i++) memcpy(&out[i * comps], p + off + i * stride, size_t(comps) * 4);
     return true;
@@ -350,13 +366,13 @@ struct Glb {
     const long ct = long(a.number("componentType", 0));
     const size_t sz = ct == 5121 ? 1 : ct == 5123 ? 2 : ct == 5125 ? 4 : 0;
     if (!sz) return err = "index accessor must be u8/u16/u32", false;
-    const size_t count = size_t(a.number("count", 0));
+    size_t count, off;
+    if (!toSize(a.number("count", 0), count) || !toSize(a.number("byteOffset", 0), off)) return err = "index accessor with a bad count / offset", false;
     const uint8_t* p;
     size_t n, stride;
     if (!view(a.index("bufferView"), p, n, stride)) return false;
-    const size_t off = size_t(a.number("byteOffset", 0));
     if (!stride) stride = sz;
-    if (count && off + (count - 1) * stride + sz > n) return err = "index accessor exceeds its bufferView", false;
+    if (!spanFits(off, count, stride, sz, n)) return err = "index accessor exceeds its bufferView", false;
     out.resize(count);
     for (size_t i = 0; i < count; i++) {
       const uint8_t* q = p + off + i * stride;
@@ -523,6 +539,7 @@ struct Loader {
     const Json* ns = g.root.get("nodes");
     if (idx < 0 || !ns || size_t(idx) >= ns->size()) return g.err = "node index out of range", false;
     if (depth > 14) return g.err = "node hierarchy too deep", false;
+    if (d.nodes.size() > (1u << 20)) return g.err = "more than 2^20 node instances (a node graph that is not a tree?)", false;
     const Json& n = ns->arr[idx];
     ysc::NodeDesc nd;
     nd.parent = parentOut;
@@ -530,6 +547,7 @@ struct Loader {
     if (nd.mesh >= int32_t(d.meshes.size())) return g.err = "node references a missing mesh", false;
     Mat4 m;
     if (const Json* mj = n.get("matrix")) {
+      if (mj->size() != 16) return g.err = "node matrix must have 16 elements", false;
       // column-major in glTF.  (fastgltf would decompose this into TRS first; used as given here.)
       for (int r = 0; r < 4; r++)
         for (int c = 0; c < 4; c++) m(r, c) = float(mj->arr[size_t(c) * 4 + r].num);
@@ -551,7 +569,7 @@ struct Loader {
     const Transform local(mul(own.fwd, global.fwd), mul(global.inv, own.inv));
     if (const Json* ch = n.get("children"))
       for (const Json& c : ch->arr)
-        if (!node(long(c.num), self, local, depth + 1)) return false;
+        if (!node(c.type == Json::Num && c.num >= 0.0 && c.num < 2147483648.0 ? long(c.num) : -1, self, local, depth + 1)) return false;
     if (nd.mesh >= 0) {
       ysc::MeshDesc& mesh = d.meshes[nd.mesh];
       int32_t li = 0;
@@ -620,7 +638,7 @@ bool loadGlb(const std::string& path, ysc::SceneDesc& out, std::string* err) {
   if (scenes && size_t(sceneIdx) < scenes->size())
     if (const Json* roots = scenes->arr[sceneIdx].get("nodes"))
       for (const Json& r : roots->arr)
-        if (!L.node(long(r.num), 0, Transform(), 1)) return fail(L.g.err);
+        if (!L.node(r.type == Json::Num && r.num >= 0.0 && r.num < 2147483648.0 ? long(r.num) : -1, 0, Transform(), 1)) return fail(L.g.err);
   return true;
 }
 

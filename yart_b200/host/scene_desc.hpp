@@ -104,16 +104,29 @@ inline bool load(const std::string& path, SceneDesc& s, std::string* err = nullp
     fclose(f);
     return false;
   };
+  // every count read from the file is checked against the bytes the file still holds before anything is sized by it
+  fseek(f, 0, SEEK_END);
+  const long fileSize = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  auto holds = [&](uint64_t count, uint64_t elemBytes) {
+    const long at = ftell(f);
+    if (fileSize < 0 || at < 0 || at > fileSize) return false;
+    const uint64_t left = uint64_t(fileSize - at);
+    return elemBytes == 0 || count <= left / elemBytes;
+  };
   char magic[4];
   if (!rd(f, magic, 4) || memcmp(magic, "YSC1", 4) != 0) return fail("bad magic");
   uint32_t n;
   if (!rd(f, &n)) return fail("truncated");
+  if (!holds(n, 20)) return fail("texture count exceeds the file");
   s.textures.resize(n);
   for (auto& t : s.textures) {
     uint32_t hdr[5];
     if (!rd(f, hdr, 5)) return fail("truncated texture header");
     t.channels = hdr[0], t.isFloat = hdr[1], t.type = hdr[2], t.width = hdr[3], t.height = hdr[4];
+    if (t.channels == 0 || t.channels > 4 || t.width > (1u << 20) || t.height > (1u << 20)) return fail("bad texture header");
     size_t cnt = size_t(t.width) * t.height * t.channels;
+    if (!holds(cnt, t.isFloat ? 4 : 1)) return fail("texture size exceeds the file");
     if (t.isFloat) {
       t.f32.resize(cnt);
       if (!rd(f, t.f32.data(), cnt)) return fail("truncated texture data");
@@ -123,14 +136,17 @@ inline bool load(const std::string& path, SceneDesc& s, std::string* err = nullp
     }
   }
   if (!rd(f, &n)) return fail("truncated");
+  if (!holds(n, sizeof(MaterialDesc))) return fail("material count exceeds the file");
   s.materials.resize(n);
   static_assert(sizeof(MaterialDesc) == 26 * 4, "MaterialDesc must be packed 4-byte fields");
   if (n && !rd(f, s.materials.data(), n)) return fail("truncated materials");
   if (!rd(f, &n)) return fail("truncated");
+  if (!holds(n, 8)) return fail("mesh count exceeds the file");
   s.meshes.resize(n);
   for (auto& m : s.meshes) {
     uint32_t nv, nf;
     if (!rd(f, &nv) || !rd(f, &nf)) return fail("truncated mesh header");
+    if (!holds(uint64_t(nv) * 12 + uint64_t(nf) * 5, 4)) return fail("mesh size exceeds the file");
     m.positions.resize(size_t(nv) * 3);
     m.vertexData.resize(size_t(nv) * 9);
     m.faces.resize(size_t(nf) * 4);
@@ -140,10 +156,12 @@ inline bool load(const std::string& path, SceneDesc& s, std::string* err = nullp
       return fail("truncated mesh data");
   }
   if (!rd(f, &n)) return fail("truncated");
+  if (!holds(n, sizeof(NodeDesc))) return fail("node count exceeds the file");
   s.nodes.resize(n);
   static_assert(sizeof(NodeDesc) == 19 * 4, "NodeDesc must be packed");
   if (n && !rd(f, s.nodes.data(), n)) return fail("truncated nodes");
   if (!rd(f, &n)) return fail("truncated");
+  if (!holds(n, sizeof(LightDesc))) return fail("light count exceeds the file");
   s.lights.resize(n);
   static_assert(sizeof(LightDesc) == 26 * 4, "LightDesc must be packed");
   if (n && !rd(f, s.lights.data(), n)) return fail("truncated lights");
