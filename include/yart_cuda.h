@@ -437,10 +437,13 @@ typedef struct YsEnvLight {
 int ys_scene_load_glb(const char* path, const YsEnvLight* env, ys_scene** out);
 /* Same, written out as a .ysc description (so the identical scene can be fed to the oracle driver). */
 int ys_glb_convert(const char* glbPath, const char* yscPath, const YsEnvLight* env);
-/* loadTexture<C> (src/core/texture.hpp:62-90) on an in-memory PNG: decode to RGBA8, pick `channels`, sRGB →
- * gamma-2 8-bit.  out may be NULL to query the size. */
+/* loadTexture<C> (src/core/texture.hpp:62-90) on an in-memory PNG or JPEG (what stbi_load_from_memory decodes there;
+ * host/images.cpp): decode to RGBA8, pick `channels`, sRGB → gamma-2 8-bit.  out may be NULL to query the size. */
 int ys_decode_texture(const void* png, size_t len, uint32_t type, uint32_t nChannels, const int32_t* channels,
                       uint8_t* out, size_t outBytes, uint32_t* width, uint32_t* height);
+/* loadTextureHDR (src/core/texture.cpp:21-35 = stbi_loadf on a Radiance .hdr): width*height*3 floats.  rgb may be NULL
+ * to query the size.  The result is what YsEnvLight::rgb takes (main.cpp:81-84). */
+int ys_load_hdr(const char* path, uint32_t* width, uint32_t* height, float* rgb, size_t rgbFloats);
 /* output::writePPM (src/output/ppm.cpp:6-21) on an RGBA float frame. */
 int ys_write_ppm(const char* path, const float* rgba, uint32_t width, uint32_t height);
 void ys_scene_destroy(ys_scene* s);

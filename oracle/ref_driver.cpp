@@ -761,6 +761,17 @@ static int cmdTexload(int argc, char** argv) {
   return 1;
 }
 
+// hdrload in.hdr out.bin: loadTextureHDR (src/core/texture.cpp:21-35) → u32 w, h; f32 rgb[w*h*3]
+static int cmdHdrload(int argc, char** argv) {
+  if (argc < 4) return 1;
+  HDRTexture t = loadTextureHDR(argv[2]);
+  Writer out(argv[3]);
+  out.put(uint32_t(t.width()));
+  out.put(uint32_t(t.height()));
+  out.putn(t.data.data(), t.data.size());
+  return 0;
+}
+
 int main(int argc, char** argv) {
   if (argc < 2) {
     fprintf(stderr,
@@ -769,7 +780,8 @@ int main(int argc, char** argv) {
             "       oracle_ref bvh scene.ysc out.bin\n"
             "       oracle_ref tables out.bin\n"
             "       oracle_ref kat <kind> in.bin out.bin [scene.ysc]\n"
-            "       oracle_ref texload in.png type C ch0,ch1,.. out.bin\n");
+            "       oracle_ref texload in.png type C ch0,ch1,.. out.bin\n"
+            "       oracle_ref hdrload in.hdr out.bin\n");
     return 1;
   }
   std::string cmd = argv[1];
@@ -779,6 +791,7 @@ int main(int argc, char** argv) {
   if (cmd == "tables") return cmdTables(argc, argv);
   if (cmd == "kat") return cmdKat(argc, argv);
   if (cmd == "texload") return cmdTexload(argc, argv);
+  if (cmd == "hdrload") return cmdHdrload(argc, argv);
   fprintf(stderr, "unknown command %s\n", cmd.c_str());
   return 1;
 }

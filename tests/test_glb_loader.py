@@ -62,7 +62,7 @@ def test_png_decode_and_conversion_match_reference_loadTexture(name, tmp_path):
 def test_png_errors():
     with pytest.raises(Y.YartError, match="JPEG"):
         Y.decode_texture(b"\xff\xd8\xff\xe0" + b"\0" * 64, S.SRGB, [0, 1, 2, 3])
-    with pytest.raises(Y.YartError, match="PNG only"):
+    with pytest.raises(Y.YartError, match="unsupported image format"):
         Y.decode_texture(b"GIF89a" + b"\0" * 64, S.SRGB, [0])
     good = png_encode(sample_images()["rgb"])
     with pytest.raises(Y.YartError, match="inflate"):

@@ -95,6 +95,16 @@ def decode_texture(png: bytes, tex_type: int, channels) -> np.ndarray:
     return out
 
 
+def load_hdr(path: str) -> np.ndarray:
+    """loadTextureHDR (texture.cpp:21-35): a Radiance .hdr file as an (h, w, 3) float32 array."""
+    w, h = C.c_uint32(), C.c_uint32()
+    _check(lib().ys_load_hdr(path.encode(), C.byref(w), C.byref(h), None, 0), f"ys_load_hdr({path})", lib().ys_last_error() or b"")
+    out = np.empty((h.value, w.value, 3), np.float32)
+    _check(lib().ys_load_hdr(path.encode(), C.byref(w), C.byref(h), out.ctypes.data, out.size), f"ys_load_hdr({path})",
+           lib().ys_last_error() or b"")
+    return out
+
+
 def write_ppm(path: str, rgba: np.ndarray):
     rgba = np.ascontiguousarray(rgba, np.float32)
     _check(lib().ys_write_ppm(path.encode(), rgba.ctypes.data, rgba.shape[1], rgba.shape[0]), "ys_write_ppm")

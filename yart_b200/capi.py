@@ -167,6 +167,7 @@ PROTOTYPES = {
     "ys_scene_load_glb": (C.c_int, [C.c_char_p, C.POINTER(YsEnvLight), C.POINTER(P)]),
     "ys_glb_convert": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(YsEnvLight)]),
     "ys_decode_texture": (C.c_int, [P, C.c_size_t, u32, u32, C.POINTER(i32), P, C.c_size_t, C.POINTER(u32), C.POINTER(u32)]),
+    "ys_load_hdr": (C.c_int, [C.c_char_p, C.POINTER(u32), C.POINTER(u32), P, C.c_size_t]),
     "ys_write_ppm": (C.c_int, [C.c_char_p, P, u32, u32]),
     "ys_scene_destroy": (None, [P]),
     "ys_last_error": (C.c_char_p, []),

@@ -24,6 +24,7 @@ bool loadGlb(const std::string& path, ysc::SceneDesc& out, std::string* err);
 bool writePpm(const std::string& path, const float* rgba, uint32_t w, uint32_t h);
 bool decodeTextureForTest(const uint8_t* png, size_t len, uint32_t type, int C, const int* channels, ysc::TextureDesc& out,
                           std::string& err);
+bool decodeRadianceHdr(const uint8_t* data, size_t len, int& w, int& h, std::vector<float>& rgb, std::string& err);
 }  // namespace yartb
 
 struct ys_scene {
@@ -152,6 +153,35 @@ extern "C" int ys_decode_texture(const void* png, size_t len, uint32_t type, uin
     if (out) {
       if (outBytes < t.u8.size()) return YC_ERR_INVALID;
       memcpy(out, t.u8.data(), t.u8.size());
+    }
+    return YC_OK;
+  });
+}
+
+// loadTextureHDR(filename) (src/core/texture.cpp:21-35): the environment map main.cpp:81 hands to ImageInfiniteLight
+extern "C" int ys_load_hdr(const char* path, uint32_t* width, uint32_t* height, float* rgb, size_t rgbFloats) {
+  if (!path || !width || !height) return YC_ERR_INVALID;
+  return guarded([&]() -> int {
+    FILE* f = fopen(path, "rb");
+    if (!f) {
+      g_ysError = std::string("cannot open ") + path;
+      return YC_ERR_IO;
+    }
+    std::vector<uint8_t> buf;
+    uint8_t chunk[65536];
+    for (size_t n; (n = fread(chunk, 1, sizeof chunk, f)) > 0;) buf.insert(buf.end(), chunk, chunk + n);
+    fclose(f);
+    int w = 0, h = 0;
+    std::vector<float> px;
+    std::string err;
+    if (!decodeRadianceHdr(buf.data(), buf.size(), w, h, px, err)) {
+      g_ysError = err + " in " + path;
+      return YC_ERR_IO;
+    }
+    *width = uint32_t(w), *height = uint32_t(h);
+    if (rgb) {
+      if (rgbFloats < px.size()) return YC_ERR_INVALID;
+      memcpy(rgb, px.data(), px.size() * sizeof(float));
     }
     return YC_OK;
   });

@@ -183,97 +183,8 @@ class JsonParser {
 // ---------------------------------------------------------------------------------------
 // minimal PNG → RGBA8 (what stbi_load_from_memory(..., 4) returns for the supported subset)
 // ---------------------------------------------------------------------------------------
-static uint32_t be32(const uint8_t* p) { return (uint32_t(p[0]) << 24) | (uint32_t(p[1]) << 16) | (uint32_t(p[2]) << 8) | p[3]; }
-
-static bool decodePng(const uint8_t* data, size_t len, int& w, int& h, std::vector<uint8_t>& rgba, std::string& err) {
-  static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
-  if (len < 8 || memcmp(data, sig, 8) != 0) {
-    err = (len >= 2 && data[0] == 0xff && data[1] == 0xd8) ? "JPEG images are not supported by this loader (PNG only)"
-                                                           : "unsupported image format (PNG only)";
-    return false;
-  }
-  size_t pos = 8;
-  int depth = 0, ctype = 0, interlace = 0;
-  std::vector<uint8_t> idat, plte, trns;
-  bool gotHdr = false;
-  while (pos + 12 <= len) {
-    uint32_t n = be32(data + pos);
-    const uint8_t* tag = data + pos + 4;
-    const uint8_t* body = data + pos + 8;
-    if (pos + 12 + n > len) break;
-    if (!memcmp(tag, "IHDR", 4) && n >= 13) {
-      w = int(be32(body)), h = int(be32(body + 4));
-      depth = body[8], ctype = body[9], interlace = body[12];
-      gotHdr = true;
-    } else if (!memcmp(tag, "PLTE", 4)) {
-      plte.assign(body, body + n);
-    } else if (!memcmp(tag, "tRNS", 4)) {
-      trns.assign(body, body + n);
-    } else if (!memcmp(tag, "IDAT", 4)) {
-      idat.insert(idat.end(), body, body + n);
-    } else if (!memcmp(tag, "IEND", 4)) {
-      break;
-    }
-    pos += 12 + n;
-  }
-  if (!gotHdr || w <= 0 || h <= 0) return err = "PNG without IHDR", false;
-  if (interlace) return err = "interlaced PNG images are not supported", false;
-  if (!(depth == 8 || (depth == 16 && ctype != 3))) return err = "PNG bit depth must be 8 (or 16 for non-palette images)", false;
-  int ch = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
-  if (!ch) return err = "bad PNG colour type", false;
-  const size_t bpp = size_t(ch) * (depth / 8), stride = size_t(w) * bpp;
-  std::vector<uint8_t> raw((stride + 1) * size_t(h));
-  uLongf outLen = uLongf(raw.size());
-  if (uncompress(raw.data(), &outLen, idat.data(), uLong(idat.size())) != Z_OK || outLen != raw.size())
-    return err = "PNG inflate failed", false;
-  // unfilter in place (PNG spec §9)
-  std::vector<uint8_t> img(stride * size_t(h));
-  for (int y = 0; y < h; y++) {
-    const uint8_t ft = raw[(stride + 1) * y];
-    const uint8_t* in = &raw[(stride + 1) * y + 1];
-    uint8_t* out = &img[stride * y];
-    const uint8_t* up = y ? &img[stride * (y - 1)] : nullptr;
-    for (size_t i = 0; i < stride; i++) {
-      const int a = i >= bpp ? out[i - bpp] : 0, b = up ? up[i] : 0, c = (up && i >= bpp) ? up[i - bpp] : 0;
-      int pred = 0;
-      switch (ft) {
-        case 0: pred = 0; break;
-        case 1: pred = a; break;
-        case 2: pred = b; break;
-        case 3: pred = (a + b) >> 1; break;
-        case 4: {
-          const int p = a + b - c, pa = abs(p - a), pb = abs(p - b), pc = abs(p - c);
-          pred = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
-          break;
-        }
-        default: return err = "bad PNG filter type", false;
-      }
-      out[i] = uint8_t(in[i] + pred);
-    }
-  }
-  rgba.resize(size_t(w) * h * 4);
-  const size_t step = depth / 8;  // 16-bit samples: keep the high byte, as stb_image does
-  for (size_t i = 0; i < size_t(w) * h; i++) {
-    const uint8_t* px = &img[i * bpp];
-    uint8_t r, g, b, a = 255;
-    if (ctype == 3) {
-      const size_t k = px[0];
-      if (k * 3 + 2 >= plte.size()) return err = "PNG palette index out of range", false;
-      r = plte[k * 3], g = plte[k * 3 + 1], b = plte[k * 3 + 2];
-      if (k < trns.size()) a = trns[k];
-    } else if (ctype == 0) {
-      r = g = b = px[0];
-    } else if (ctype == 4) {
-      r = g = b = px[0], a = px[step];
-    } else {
-      r = px[0], g = px[step], b = px[2 * step];
-      if (ctype == 6) a = px[3 * step];
-    }
-    rgba[i * 4] = r, rgba[i * 4 + 1] = g, rgba[i * 4 + 2] = b, rgba[i * 4 + 3] = a;
-  }
-  // tRNS colour keys of grey / RGB images are ignored (stb_image applies them; rare in glTF assets)
-  return true;
-}
+// image decoding (stb_image's results restated): images.cpp
+bool decodeImageRGBA8(const uint8_t* data, size_t len, int& w, int& h, std::vector<uint8_t>& rgba, std::string& err);
 
 // core/color-utils.hpp:12-15
 static float sRGBDecode(float val) {
@@ -418,7 +329,7 @@ struct Loader {
     if (!g.view(bv, p, n, stride)) return -2;
     int w, h;
     std::vector<uint8_t> rgba;
-    if (!decodePng(p, n, w, h, rgba, g.err)) return -2;
+    if (!decodeImageRGBA8(p, n, w, h, rgba, g.err)) return -2;
     if (w < 2 || h < 2) return g.err = "textures must be at least 2x2", -2;
     ysc::TextureDesc t;
     convertTexture(rgba, w, h, type, C, channels, t);
@@ -646,7 +557,7 @@ bool decodeTextureForTest(const uint8_t* png, size_t len, uint32_t type, int C, 
                           std::string& err) {
   int w, h;
   std::vector<uint8_t> rgba;
-  if (!decodePng(png, len, w, h, rgba, err)) return false;
+  if (!decodeImageRGBA8(png, len, w, h, rgba, err)) return false;
   convertTexture(rgba, w, h, type, C, channels, out);
   return true;
 }
