@@ -229,7 +229,7 @@ def test_glb_scene_renders_bit_exactly_like_the_reference(tmp_path):
 def test_glb_errors(tmp_path):
     p = tmp_path / "x.glb"
     p.write_bytes(b"nope" + b"\0" * 32)
-    with pytest.raises(Y.YartError, match="bad magic"):
+    with pytest.raises(Y.YartError, match="not a glTF file"):
         Y.Scene(str(p))
     glb, _ = build_case(tmp_path, with_oracle_textures=False)
     raw = open(glb, "rb").read()
@@ -290,3 +290,43 @@ def test_hostile_sizes_are_rejected_not_trusted(tmp_path):
         p.write_bytes(payload + b"\0" * 32)
         with pytest.raises(Y.YartError, match="exceeds the file"):
             Y.Scene(str(p))
+
+
+def test_gltf_json_with_external_and_data_uri_buffers_equals_the_glb(tmp_path):
+    """.gltf (JSON) with its geometry in a .bin next to it, or in a base64 data URI, loads to the same scene as the
+    equivalent .glb (fastgltf Options::LoadExternalBuffers, gltf.cpp:335); images inside such buffers are dropped, as in
+    the reference (gltf.cpp:33-41 accepts ByteView buffers only)."""
+    import base64
+    import json
+    import struct
+    g = GlbBuilder()
+    g.material({"pbrMetallicRoughness": {"baseColorFactor": [0.2, 0.4, 0.6, 1.0], "roughnessFactor": 0.5}})
+    b0 = S.MeshBuilder()
+    b0.box((-1, 0, -1), (1, 2, 1), 0)
+    m = b0.build()
+    g.mesh([{"attributes": {"POSITION": g.accessor(m.positions.astype(f32), "VEC3"), "NORMAL": g.accessor(m.normals.astype(f32), "VEC3"),
+                            "TEXCOORD_0": g.accessor(m.uvs.astype(f32), "VEC2")},
+             "indices": g.accessor(m.faces[:, :3].astype(np.uint32).reshape(-1), "SCALAR"), "material": 0}])
+    g.node({"mesh": 0, "translation": [0.5, 0.0, -2.0]}, root=True)
+    glb = g.tobytes()
+    (tmp_path / "a.glb").write_bytes(glb)
+    jlen, = struct.unpack_from("<I", glb, 12)
+    doc = json.loads(glb[20:20 + jlen])
+    blen, = struct.unpack_from("<I", glb, 20 + jlen)
+    bin_bytes = glb[28 + jlen: 28 + jlen + blen]
+    ext = dict(doc, buffers=[{"byteLength": len(bin_bytes), "uri": "geometry.bin"}])
+    (tmp_path / "geometry.bin").write_bytes(bin_bytes)
+    (tmp_path / "ext.gltf").write_text(json.dumps(ext))
+    emb = dict(doc, buffers=[{"byteLength": len(bin_bytes), "uri": "data:application/octet-stream;base64," + base64.b64encode(bin_bytes).decode()}])
+    (tmp_path / "emb.gltf").write_text(json.dumps(emb))
+    out = {}
+    for name in ("a.glb", "ext.gltf", "emb.gltf"):
+        Y.glb_to_ysc(str(tmp_path / name), str(tmp_path / (name + ".ysc")))
+        out[name] = (tmp_path / (name + ".ysc")).read_bytes()
+    assert out["a.glb"] == out["ext.gltf"] == out["emb.gltf"]
+    with pytest.raises(Y.YartError, match="next to the asset"):
+        (tmp_path / "bad.gltf").write_text(json.dumps(dict(doc, buffers=[{"byteLength": 4, "uri": "../secret.bin"}])))
+        Y.Scene(str(tmp_path / "bad.gltf"))
+    with pytest.raises(Y.YartError, match="cannot open external buffer"):
+        (tmp_path / "missing.gltf").write_text(json.dumps(dict(doc, buffers=[{"byteLength": 4, "uri": "nope.bin"}])))
+        Y.Scene(str(tmp_path / "missing.gltf"))

@@ -115,7 +115,7 @@ class Scene:
 
     def __init__(self, path: str, env=None, env_radius=100.0, env_transform=None, bvh_kind: int = capi.BVH_SAH):
         self._h = C.c_void_p()
-        if path.lower().endswith(".glb"):
+        if path.lower().endswith((".glb", ".gltf")):
             e, keep = _env_struct(env, env_radius, env_transform)
             rc = lib().ys_scene_load_glb(path.encode(), C.byref(e) if e is not None else None, C.byref(self._h))
             _check(rc, f"ys_scene_load_glb({path})", lib().ys_last_error() or b"")

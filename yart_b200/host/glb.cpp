@@ -16,9 +16,11 @@
 //                                      transform `node.transform * globalTransform`; lightIdx restarts at
 //                                      0 for every node while lights are appended globally (:301,309)
 //   load             gltf.cpp:319-358  materials → meshes → scene nodes under an identity root
-// Not covered (an error, or noted): external .bin/.png URIs, sparse accessors, JPEG and interlaced or
-// 16-bit-palette PNG images (stb_image decodes those in the reference), `matrix` nodes are used as
-// given (fastgltf would decompose them to TRS first), cameras / skins / animations are ignored.
+// Containers: binary .glb, and .gltf JSON whose buffers are files next to the asset or base64 data URIs
+// (Options::LoadExternalBuffers, gltf.cpp:335).  Images: PNG and JPEG in bufferViews of the GLB's BIN chunk
+// (images.cpp); `uri` images and images inside external buffers are dropped, as the reference drops them.
+// Not covered (an error, or noted): sparse accessors, `matrix` nodes are used as given (fastgltf would decompose them
+// to TRS first), cameras / skins / animations are ignored.
 #include <zlib.h>
 
 #include <cmath>
@@ -224,7 +226,53 @@ static bool toSize(double v, size_t& out) {
 
 struct Glb {
   Json root;
-  std::vector<uint8_t> bin;
+  std::vector<uint8_t> bin;                      // the GLB's BIN chunk = buffer 0 of a .glb
+  std::vector<std::vector<uint8_t>> external;    // buffers loaded from `uri` (fastgltf Options::LoadExternalBuffers, gltf.cpp:335)
+  std::vector<bool> isExternal;                  // per buffer
+  std::string baseDir;
+
+  static bool base64(const std::string& in, std::vector<uint8_t>& out) {
+    uint32_t acc = 0;
+    int bits = 0;
+    for (char ch : in) {
+      int v;
+      if (ch >= 'A' && ch <= 'Z') v = ch - 'A';
+      else if (ch >= 'a' && ch <= 'z') v = ch - 'a' + 26;
+      else if (ch >= '0' && ch <= '9') v = ch - '0' + 52;
+      else if (ch == '+' || ch == '-') v = 62;
+      else if (ch == '/' || ch == '_') v = 63;
+      else if (ch == '=' || ch == '\n' || ch == '\r') continue;
+      else return false;
+      acc = (acc << 6) | uint32_t(v), bits += 6;
+      if (bits >= 8) out.push_back(uint8_t(acc >> (bits -= 8)));
+    }
+    return true;
+  }
+  // `buffers[i].uri`: a file next to the asset or a base64 data URI.  Buffer 0 without a uri is the BIN chunk.
+  bool loadBuffers() {
+    const Json* bufs = root.get("buffers");
+    const size_t n = bufs ? bufs->size() : 0;
+    external.resize(n), isExternal.assign(n, false);
+    for (size_t i = 0; i < n; i++) {
+      const Json* uri = bufs->arr[i].get("uri");
+      if (!uri || uri->type != Json::Str) continue;
+      isExternal[i] = true;
+      const std::string& u = uri->str;
+      if (u.compare(0, 5, "data:") == 0) {
+        const size_t comma = u.find(',');
+        if (comma == std::string::npos || u.find(";base64") == std::string::npos || !base64(u.substr(comma + 1), external[i]))
+          return err = "bad data URI in buffers", false;
+      } else {
+        if (u.find("..") != std::string::npos || (!u.empty() && u[0] == '/')) return err = "buffer uri must stay next to the asset", false;
+        FILE* f = fopen((baseDir + u).c_str(), "rb");
+        if (!f) return err = "cannot open external buffer " + u, false;
+        uint8_t chunk[65536];
+        for (size_t k; (k = fread(chunk, 1, sizeof chunk, f)) > 0;) external[i].insert(external[i].end(), chunk, chunk + k);
+        fclose(f);
+      }
+    }
+    return true;
+  }
   std::string err;
 
   // `count` elements of `elem` bytes, `stride` apart, starting at `off`, inside a view of `n` bytes — written so that
@@ -239,13 +287,25 @@ struct Glb {
     const Json* views = root.get("bufferViews");
     if (bv < 0 || !views || size_t(bv) >= views->size()) return err = "bufferView index out of range", false;
     const Json& v = views->arr[bv];
-    if (v.index("buffer") != 0) return err = "only the GLB-embedded buffer 0 is supported", false;
+    const long bi = std::max<long>(0, v.index("buffer"));
+    if (size_t(bi) >= isExternal.size() && bi != 0) return err = "bufferView names a missing buffer", false;
+    const std::vector<uint8_t>& data = (size_t(bi) < isExternal.size() && isExternal[bi]) ? external[bi] : bin;
+    if (&data == &bin && bi != 0) return err = "buffer without a uri that is not the GLB's BIN chunk", false;
     size_t off;
     if (!toSize(v.number("byteOffset", 0), off) || !toSize(v.number("byteLength", 0), n) || !toSize(v.number("byteStride", 0), stride))
       return err = "bufferView with a negative, non-finite or absurd offset / length / stride", false;
-    if (off > bin.size() || n > bin.size() - off) return err = "bufferView exceeds the BIN chunk", false;
-    p = bin.data() + off;
+    if (off > data.size() || n > data.size() - off) return err = "bufferView exceeds its buffer", false;
+    p = data.data() + off;
     return true;
+  }
+  // An image is decoded only when it sits in a bufferView of the GLB's own BIN chunk: the reference takes
+  // `sources::BufferView` images whose buffer is a `sources::ByteView` and returns nullptr otherwise (gltf.cpp:33-41) —
+  // external or data-URI buffers arrive as owned arrays there, and `uri` images are never opened.
+  bool viewIsEmbedded(long bv) const {
+    const Json* views = root.get("bufferViews");
+    if (bv < 0 || !views || size_t(bv) >= views->size()) return false;
+    const long bi = std::max<long>(0, views->arr[bv].index("buffer"));
+    return !(size_t(bi) < isExternal.size() && isExternal[bi]);
   }
 
   // reads accessor `idx` as `comps` floats per element
@@ -324,6 +384,7 @@ struct Loader {
     if (src < 0 || !imgs || size_t(src) >= imgs->size()) return -1;  // `if (!gltfTex.imageIndex) return nullptr`
     const long bv = imgs->arr[src].index("bufferView");
     if (bv < 0) return -1;  // external URI: the reference returns nullptr too (gltf.cpp:33-34)
+    if (!g.viewIsEmbedded(bv)) return -1;  // image inside an external / data-URI buffer: nullptr in the reference as well
     const uint8_t* p;
     size_t n, stride;
     if (!g.view(bv, p, n, stride)) return -2;
@@ -515,27 +576,39 @@ bool loadGlb(const std::string& path, ysc::SceneDesc& out, std::string* err) {
   std::vector<uint8_t> buf(sz > 0 ? size_t(sz) : 0);
   const bool readOk = buf.empty() || fread(buf.data(), 1, buf.size(), f) == buf.size();
   fclose(f);
-  if (!readOk || buf.size() < 20) return fail("truncated GLB");
+  if (!readOk || buf.size() < 2) return fail("truncated file");
   auto le32 = [&](size_t o) { return uint32_t(buf[o] | (buf[o + 1] << 8) | (buf[o + 2] << 16) | (uint32_t(buf[o + 3]) << 24)); };
-  if (le32(0) != 0x46546c67u) return fail("not a GLB file (bad magic)");
-  if (le32(4) != 2) return fail("unsupported glTF version");
   Loader L(out);
-  size_t pos = 12;
+  const size_t slash = path.find_last_of('/');
+  L.g.baseDir = slash == std::string::npos ? "" : path.substr(0, slash + 1);
   bool haveJson = false;
-  while (pos + 8 <= buf.size()) {
-    const uint32_t n = le32(pos), type = le32(pos + 4);
-    if (pos + 8 + n > buf.size()) return fail("truncated GLB chunk");
-    if (type == 0x4e4f534au) {  // JSON
-      JsonParser jp(reinterpret_cast<const char*>(&buf[pos + 8]), n);
-      std::string e;
-      if (!jp.parse(L.g.root, e)) return fail(e);
-      haveJson = true;
-    } else if (type == 0x004e4942u && L.g.bin.empty()) {  // BIN
-      L.g.bin.assign(buf.begin() + long(pos) + 8, buf.begin() + long(pos) + 8 + n);
+  if (buf.size() >= 20 && le32(0) == 0x46546c67u) {  // binary container
+    if (le32(4) != 2) return fail("unsupported glTF version");
+    size_t pos = 12;
+    while (pos + 8 <= buf.size()) {
+      const uint32_t n = le32(pos), type = le32(pos + 4);
+      if (n > buf.size() || pos + 8 + n > buf.size()) return fail("truncated GLB chunk");
+      if (type == 0x4e4f534au) {  // JSON
+        JsonParser jp(reinterpret_cast<const char*>(&buf[pos + 8]), n);
+        std::string e;
+        if (!jp.parse(L.g.root, e)) return fail(e);
+        haveJson = true;
+      } else if (type == 0x004e4942u && L.g.bin.empty()) {  // BIN
+        L.g.bin.assign(buf.begin() + long(pos) + 8, buf.begin() + long(pos) + 8 + n);
+      }
+      pos += 8 + size_t(n);
     }
-    pos += 8 + size_t(n);
+  } else {  // a .gltf: the JSON document itself, geometry in external / data-URI buffers
+    size_t k = 0;
+    while (k < buf.size() && (buf[k] == ' ' || buf[k] == '\n' || buf[k] == '\r' || buf[k] == '\t' || buf[k] == 0xef || buf[k] == 0xbb || buf[k] == 0xbf)) k++;
+    if (k >= buf.size() || buf[k] != '{') return fail("not a glTF file (neither the GLB magic nor a JSON document)");
+    JsonParser jp(reinterpret_cast<const char*>(&buf[k]), buf.size() - k);
+    std::string e;
+    if (!jp.parse(L.g.root, e)) return fail(e);
+    haveJson = true;
   }
   if (!haveJson) return fail("GLB without a JSON chunk");
+  if (!L.g.loadBuffers()) return fail(L.g.err);
   if (!L.materials() || !L.meshes()) return fail(L.g.err);
   if (out.materials.empty()) {  // the reference would index material 0 out of range; give it a default one
     ysc::MaterialDesc def;
