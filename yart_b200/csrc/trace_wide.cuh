@@ -56,10 +56,6 @@ __device__ __forceinline__ void traceWidePersistent(const DScene& sc, IO& io, ui
   constexpr uint32_t kPopRef = 0xfffffffeu;  // "pop at the top of the next inner step"
   uint32_t pend = 0u;                        // parked leaf (0 = none)
   float pendD = 0.0f;
-#ifdef YB_WIDE_PARK2
-  uint32_t pend2 = 0u;                       // second parked leaf (the order of triangle tests is free in this walk)
-  float pend2D = 0.0f;
-#endif
   // bits of 1.0f in a register ptxas cannot fold (shEntries <= 25), so that planeUnit's PRMT carries its selector as the
   // immediate instead of fetching four selectors into registers on every visit
   const uint32_t one = 0x3f800000u | (uint32_t(tune.shEntries) >> 30);
@@ -134,9 +130,6 @@ __device__ __forceinline__ void traceWidePersistent(const DScene& sc, IO& io, ui
         stack.put(stack.base, kNoRef, 0.0f);  // sentinel
         sp = stack.base + kPsStride;
         pend = 0u;
-#ifdef YB_WIDE_PARK2
-        pend2 = 0u;
-#endif
         meshHit = false;
         entered = true;
         break;
@@ -153,18 +146,10 @@ __device__ __forceinline__ void traceWidePersistent(const DScene& sc, IO& io, ui
     for (;;) {
       const bool trav = state == kLaneTrav;
       bool doPop = trav && cur == kPopRef;
-#ifdef YB_WIDE_PARK2
-      if (trav && pend2 == 0u && int32_t(cur) < -3) {  // a leaf: park it (two slots), keep walking
-        pend2 = pend, pend2D = pendD;
-        pend = cur, pendD = dcur;
-        doPop = true;
-      }
-#else
       if (trav && pend == 0u && int32_t(cur) < -3) {  // a leaf (bit 31) other than kNoRef / kPopRef / kWideEmpty: park it
         pend = cur, pendD = dcur;
         doPop = true;
       }
-#endif
       stack.popIf(doPop, sp, cur, dcur);  // the sentinel ends the mesh: cur = kNoRef
       const bool inner = trav && int32_t(cur) >= 0;
       const unsigned im = __ballot_sync(FULL, inner);
@@ -209,15 +194,9 @@ __device__ __forceinline__ void traceWidePersistent(const DScene& sc, IO& io, ui
 
     // ---- leaf step ---------------------------------------------------------------------------------
     if (state == kLaneTrav && (int32_t(cur) < 0 || pend != 0u)) {
-#ifdef YB_WIDE_PARK2
-      for (int slot = 0; slot < 2; slot++) {
-        const uint32_t leaf = slot == 0 ? pend2 : pend;  // the older one first
-        const float leafD = slot == 0 ? pend2D : pendD;
-#else
       {
         const uint32_t leaf = pend;
         const float leafD = pendD;
-#endif
         if (int32_t(leaf) < -3 && leafD < st.hit.t && !(NEE && didHit)) {
           const YcMesh& mesh = sc.meshes[meshIdx];
           uint32_t ti = leaf & ~YC_REF_LEAF;
@@ -233,9 +212,6 @@ __device__ __forceinline__ void traceWidePersistent(const DScene& sc, IO& io, ui
         }
       }
       pend = 0u;
-#ifdef YB_WIDE_PARK2
-      pend2 = 0u;
-#endif
       if (NEE && didHit) {  // no alpha-tested materials: the first occluder decides (shadowStage, integrator.cuh)
         io.store(item, st, true, smp);
         state = kLaneIdle;
