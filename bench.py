@@ -225,7 +225,10 @@ def rel_mse(img, ref, eps=1e-2):
 
 def workload_record(Y, name: str, local: int, trav: int, spp: int, steps: int) -> dict:
     """A BASELINE.json configs[2] / configs[3] shape on one GPU: full MIS+NEE paths, `steps` waves of `spp` samples of the
-    1080p frame after 3 warm-up waves, device-timed, with the surface-shading kernel's share and roofline."""
+    1080p frame after 3 warm-up waves, device-timed, with the surface-shading kernel's share and roofline.  `wave32`: the
+    same with 32-sample waves — the size class at which the configuration's 1024-spp render schedules its waves
+    (TileRenderer: 64 first, 128 max): 8 chunks per lane instead of 1, so the per-path tails that end every chunk of deep
+    paths overlap the other lane's next chunk instead of ending the wave."""
     global CAM, MAX_DEPTH, WORKLOAD_TEXT
     saved = (CAM, MAX_DEPTH, WORKLOAD_TEXT)
     tris = DEFAULT_TRIS[name]
@@ -244,6 +247,16 @@ def workload_record(Y, name: str, local: int, trav: int, spp: int, steps: int) -
         for k in range(3, 3 + steps):
             ctx.render_wave(k * spp, spp, k * spp)
         s1 = ctx.stats()
+        big, nbig = 32, 3
+        ctx.begin_frame(W, H, big * (nbig + 1), 64, (0, 0, 0), Y.TONEMAP_AGX)
+        ctx.render_wave(0, big, 0)
+        b0 = ctx.stats()
+        for k in range(1, 1 + nbig):
+            ctx.render_wave(k * big, big, k * big)
+        b1 = ctx.stats()
+        wave32 = {"spp_per_step": big, "steps": nbig, "ms_per_step": (b1.gpuMs - b0.gpuMs) / nbig,
+                  "value": (b1.raysReference - b0.raysReference) / (b1.gpuMs - b0.gpuMs) / 1e3, "unit": "Mrays/s",
+                  "samples_per_s": W * H * big / ((b1.gpuMs - b0.gpuMs) / nbig / 1e3)}
         ctx.close()
         ms = (s1.gpuMs - s0.gpuMs) / steps
         rays = s1.raysReference - s0.raysReference
@@ -255,6 +268,7 @@ def workload_record(Y, name: str, local: int, trav: int, spp: int, steps: int) -
                 "samples_per_s": W * H * spp / (ms / 1e3), "steps": steps, "spp_per_step": spp,
                 "traversal": "wide" if (trav != Y.TRAVERSAL_REFERENCE_ORDER and name != "sponza") else "reference order (alpha-tested materials)" if name == "sponza" else "reference order",
                 "extend_ms_per_step": (s1.extendMs - s0.extendMs) / steps, "shade_surface_ms_per_step": shade_ms / steps,
+                "wave32": wave32,
                 "shade_roofline": {"bound": "hbm", "kernel": "ShadeSurfaceK", "achieved": achieved, "peak": peak, "unit": "GB/s",
                                    "frac": achieved / peak, "bytes_per_hit": per_hit, "hits_per_step": hits / steps,
                                    "launches_per_step": n_shade / steps, "traffic": None, "peak_source": peak_src}}

@@ -50,20 +50,32 @@ enum { kCtrExtendHead = 0, kCtrNextCount = 1, kCtrShadowCount = 2, kCtrShadowHea
 constexpr int kLanes = 2;
 struct Lane {
   rt::Stream st;       // lane 0 shares the context's main stream
-  PathState ps{};
+  PathState ps{};      // ps.L points at Lbuf[lSel] while a chunk is in flight
   ShadowQueue sq{};
   NeeState ns{};
   uint32_t *qA = nullptr, *qH = nullptr, *qM = nullptr, *qN = nullptr, *ctr = nullptr;  // cur/next, hit, miss, NEE queues; counters
   uint32_t* hCtr = nullptr;  // page-locked copy of the counters
   void* spill = nullptr;     // traversal-stack spill area of the persistent kernels
-  rt::Event evCtr, evAcc;
+  rt::Event evCtr;
   uint32_t capacity = 0;
+  // A finished chunk leaves the lane at once: its per-path tail (the few paths that survive many bounces) and its
+  // accumulate run on the lane's SIDE stream, on copies of the surviving paths' state (`ts`, same indexing as `ps`) and
+  // on the chunk's own radiance buffer (two per lane), while the lane's stream starts the next chunk.
+  rt::Stream side;
+  PathState ts{};
+  ShadowQueue tsq{};
+  uint32_t* tq = nullptr;
+  float4* Lbuf[2] = {nullptr, nullptr};
+  int lSel = 0;
+  bool accPending[2] = {false, false};  // Lbuf[b] holds a finished chunk whose accumulate is not launched yet
+  rt::Event evChunk, evTail, evSide[2];  // end of the chunk's lane-stream work; tail buffers free; accumulate of Lbuf[b] done
   // chunk in flight
   bool active = false, waiting = false, done = false;
   uint32_t chunk = 0, n = 0, bounce = 0;
   WaveParams w{};
   uint32_t K = 0, sDone = 0;
 };
+constexpr uint32_t kTailCapacity = 65536;  // most paths a tail kernel takes over (YcOptions::tailThreshold is clamped to it)
 
 struct yc_ctx {
   rt::Stream st;
@@ -472,10 +484,23 @@ __global__ void __launch_bounds__(kTraceBlock, YB_WIDE_MIN_BLOCKS) shadowWideKer
 // order and with the same stage functions as the wavefront, so results are unchanged — and all the
 // slow rays overlap instead of adding up.
 constexpr int kTailBlock = 128;
+// The surviving paths' state copied out of the lane's arrays (same index), so that the lane can start its next chunk.
+struct TailGatherK {
+  PathState ps, ts;
+  const uint32_t* queue;
+  uint32_t* tq;
+  YB_DEV void operator()(uint32_t j) const {
+    const uint32_t i = queue[j];
+    tq[j] = i;
+    ts.rayO[i] = ps.rayO[i], ts.rayD[i] = ps.rayD[i], ts.L[i] = ps.L[i], ts.att[i] = ps.att[i];
+    ts.dim[i] = ps.dim[i], ts.flags[i] = ps.flags[i];
+  }
+};
+
 template <bool ALPHA, bool WIDE>
 __global__ void __launch_bounds__(kTailBlock) tailKernel(DScene sc, WaveParams w, PathState ps, ShadowQueue sq,
                                                          const uint32_t* queue, uint32_t n, uint32_t firstBounce,
-                                                         Counters* counters) {
+                                                         Counters* counters, float4* Lout) {
   __shared__ uint32_t shRef[kShStack * kTailBlock];
   __shared__ float shD[kShStack * kTailBlock];
   TravStack stack;
@@ -503,6 +528,7 @@ __global__ void __launch_bounds__(kTailBlock) tailKernel(DScene sc, WaveParams w
       }
       if (!(r & kShadeContinue)) break;
     }
+    Lout[i] = ps.L[i];  // back into the chunk's radiance buffer, where the accumulate reads it
   }
   __syncwarp();
   aggregatedCount(&counters->raysReference, raysRef);
@@ -626,9 +652,18 @@ extern "C" int yc_create(int device, const YcOptions* opts, yc_ctx** out) {
       delete ctx;
       return YC_ERR_CUDA;
     }
+    if (const char* le = rt::streamCreate(L.side)) {
+      fprintf(stderr, "yart_b200: cannot create a stream: %s\n", le);
+      delete ctx;
+      return YC_ERR_CUDA;
+    }
     rt::eventCreate(L.evCtr);
-    rt::eventCreate(L.evAcc);
+    rt::eventCreate(L.evChunk);
+    rt::eventCreate(L.evTail);
+    rt::eventCreate(L.evSide[0]);
+    rt::eventCreate(L.evSide[1]);
   }
+  if (ctx->tailThreshold > kTailCapacity) ctx->tailThreshold = kTailCapacity;
   *out = ctx;
   return YC_OK;
 }
@@ -664,9 +699,14 @@ extern "C" void yc_destroy(yc_ctx* ctx) {
   for (int l = 0; l < kLanes; l++) {
     Lane& L = ctx->lanes[l];
     rt::sync(L.st);
+    rt::sync(L.side);
     rt::hostRelease(L.hCtr);
     rt::eventDestroy(L.evCtr);
-    rt::eventDestroy(L.evAcc);
+    rt::eventDestroy(L.evChunk);
+    rt::eventDestroy(L.evTail);
+    rt::eventDestroy(L.evSide[0]);
+    rt::eventDestroy(L.evSide[1]);
+    rt::destroy(L.side);
     if (l > 0) rt::destroy(L.st);
   }
   rt::destroy(ctx->st);
@@ -801,7 +841,9 @@ static int ensureWaveStorage(yc_ctx* ctx) {
     const size_t P = L.capacity;
     YC_TRY(devAlloc(own, &L.ps.rayO, P));
     YC_TRY(devAlloc(own, &L.ps.rayD, P));
-    YC_TRY(devAlloc(own, &L.ps.L, P));
+    YC_TRY(devAlloc(own, &L.Lbuf[0], P));
+    YC_TRY(devAlloc(own, &L.Lbuf[1], P));
+    L.ps.L = L.Lbuf[0];
     YC_TRY(devAlloc(own, &L.ps.att, P));
     YC_TRY(devAlloc(own, &L.ps.dim, P));
     YC_TRY(devAlloc(own, &L.ps.flags, P));
@@ -831,6 +873,20 @@ static int ensureWaveStorage(yc_ctx* ctx) {
     uint2* sp = nullptr;
     YC_TRY(devAlloc(own, &sp, size_t(traceGridMax(ctx)) * kTraceBlock * kSpillEntries));
     L.spill = sp;
+    // the tail kernel's copies (index-compatible with the lane's own arrays) and private queues
+    YC_TRY(devAlloc(own, &L.ts.rayO, P));
+    YC_TRY(devAlloc(own, &L.ts.rayD, P));
+    YC_TRY(devAlloc(own, &L.ts.L, P));
+    YC_TRY(devAlloc(own, &L.ts.att, P));
+    YC_TRY(devAlloc(own, &L.ts.dim, P));
+    YC_TRY(devAlloc(own, &L.ts.flags, P));
+    YC_TRY(devAlloc(own, &L.ts.hitA, P));
+    YC_TRY(devAlloc(own, &L.ts.hitB, P));
+    YC_TRY(devAlloc(own, &L.tsq.o, size_t(kTailCapacity)));
+    YC_TRY(devAlloc(own, &L.tsq.d, size_t(kTailCapacity)));
+    YC_TRY(devAlloc(own, &L.tsq.lif, size_t(kTailCapacity)));
+    YC_TRY(devAlloc(own, &L.tsq.att, size_t(kTailCapacity)));
+    YC_TRY(devAlloc(own, &L.tq, size_t(kTailCapacity)));
 #endif
   }
   ctx->dCtr = ctx->lanes[0].ctr;
@@ -1033,23 +1089,69 @@ static int renderChunks(yc_ctx* ctx, const uint32_t* dList, uint32_t nPixCall, u
   }
   if (chunks.empty()) return YC_OK;
 
-  // the other lanes' streams start after everything already queued on the main stream (ev0)
-  for (int l = 1; l < kLanes; l++) rt::streamWaitEvent(ctx->lanes[l].st, ctx->ev0);
-  for (int l = 0; l < kLanes; l++) ctx->lanes[l].active = false;
-  size_t next = 0, nextAcc = 0;
-  rt::Event* lastAcc = nullptr;
+  // every stream of the wave starts after what is already queued on the main stream (ev0)
+  for (int l = 0; l < kLanes; l++) {
+    Lane& L = ctx->lanes[l];
+    if (l > 0) rt::streamWaitEvent(L.st, ctx->ev0);
+    rt::streamWaitEvent(L.side, ctx->ev0);
+    L.active = false;
+    L.accPending[0] = L.accPending[1] = false;
+  }
+  // A chunk that has left its lane and waits for its turn to be accumulated (chunk order).
+  struct Finished {
+    bool valid = false;
+    int lane = 0, buf = 0;
+    uint32_t pixBase = 0, nPix = 0, K = 0, sDone = 0, stride = 1;
+  };
+  std::vector<Finished> finished(chunks.size());
+  auto allStreams = [&](auto&& fn) {
+    for (int l = 0; l < kLanes; l++) fn(ctx->lanes[l].st), fn(ctx->lanes[l].side);
+  };
   auto abortRequested = [&] { return ctx->abortFlag && *ctx->abortFlag != 0; };
   auto abortNow = [&] {
     // stop issuing, let what is in flight drain (the lanes' buffers are reused by the next call)
-    for (int l = 0; l < kLanes; l++) rt::sync(ctx->lanes[l].st);
+    allStreams([](rt::Stream& st) { rt::sync(st); });
     return fail(ctx, YC_ERR_ABORTED, "aborted");
   };
+  // The chunk on lane L is complete as far as the lane's stream is concerned (`tail`: up to a per-path tail that the
+  // side stream runs on copies): hand it to the side stream and free the lane.
+  auto retire = [&](Lane& L, int l, bool tail) {
+#ifndef YB_HOSTSIM
+    if (tail) {
+      rt::streamWaitEvent(L.st, L.evTail);  // the previous tail of this lane has let go of `ts` / `tq`
+      rt::launchFor(L.st, L.n, TailGatherK{L.ps, L.ts, L.qA, L.tq});
+      ctx->launches++;
+    }
+#endif
+    rt::eventRecord(L.st, L.evChunk);
+    rt::streamWaitEvent(L.side, L.evChunk);
+#ifndef YB_HOSTSIM
+    if (tail) {
+      const dim3 tg((L.n + kTailBlock - 1) / kTailBlock);
+      if (!ALPHA && ctx->wide)
+        tailKernel<false, true><<<tg, kTailBlock, 0, L.side.s>>>(ctx->ds, L.w, L.ts, L.tsq, L.tq, L.n, L.bounce, ctx->dCounters, L.ps.L);
+      else
+        tailKernel<ALPHA, false><<<tg, kTailBlock, 0, L.side.s>>>(ctx->ds, L.w, L.ts, L.tsq, L.tq, L.n, L.bounce, ctx->dCounters, L.ps.L);
+      rt::eventRecord(L.side, L.evTail);
+      ctx->launches++;
+    }
+#endif
+    Finished& f = finished[L.chunk];
+    f.valid = true, f.lane = l, f.buf = L.lSel;
+    f.pixBase = L.w.pixBase, f.nPix = L.w.nPix, f.K = L.K, f.sDone = L.sDone, f.stride = L.w.sStrideM1 + 1u;
+    L.accPending[L.lSel] = true;
+    L.lSel ^= 1;
+    L.active = false, L.done = false, L.waiting = false;
+  };
+
+  size_t next = 0, nextAcc = 0;
+  rt::Event* lastAcc = nullptr;
   while (nextAcc < chunks.size()) {
     if (abortRequested()) return abortNow();
-    // start chunks on idle lanes
+    // start chunks on idle lanes whose next radiance buffer is free (its previous chunk's accumulate is at least launched)
     for (int l = 0; l < kLanes && next < chunks.size(); l++) {
       Lane& L = ctx->lanes[l];
-      if (L.active) continue;
+      if (L.active || L.accPending[L.lSel]) continue;
       const Chunk& c = chunks[next];
       L.active = true, L.done = false, L.waiting = false;
       L.chunk = uint32_t(next++);
@@ -1059,52 +1161,58 @@ static int renderChunks(yc_ctx* ctx, const uint32_t* dList, uint32_t nPixCall, u
       L.K = c.K, L.sDone = c.sDone;
       L.n = c.K * c.nPix;
       L.bounce = 0;
+      L.ps.L = L.Lbuf[L.lSel];
+      rt::streamWaitEvent(L.st, L.evSide[L.lSel]);  // the accumulate that read this buffer last
       rt::launchFor(L.st, L.n, RaygenK{L.w, L.ps, L.qA});
       ctx->launches++;
       if (ctx->opts.integrator == YC_INTEGRATOR_NAIVE) {
         runNaive<ALPHA>(ctx, L);  // the whole path in one launch: nothing to wait for
         ctx->launches++;
-        L.done = true;
+        retire(L, l, false);
         continue;
       }
       const int rc = issueBounce<ALPHA>(ctx, L);
       if (rc != YC_OK) return rc;
+      if (L.done) retire(L, l, false);
     }
-    // accumulate finished chunks in chunk order: Integrator::render adds a pixel's samples in sample order
+    // accumulate retired chunks in chunk order: Integrator::render adds a pixel's samples in sample order
     // (integrator.cpp:19-24), and the buckets' rounding sequence depends on it
-    bool progressed = true;
-    while (progressed) {
-      progressed = false;
-      for (int l = 0; l < kLanes; l++) {
-        Lane& L = ctx->lanes[l];
-        if (!(L.active && L.done && L.chunk == nextAcc)) continue;
-        if (lastAcc && lastAcc != &L.evAcc) rt::streamWaitEvent(L.st, *lastAcc);
-        rt::launchFor(L.st, L.w.nPix,
-                      AccumulateK{L.ps, ctx->dBuckets, ctx->bucketCapacity, L.w.pixBase, L.w.nPix, L.K, L.sDone,
-                                  L.w.sStrideM1 + 1u, m, f.estimator, exposureScale});
-        rt::eventRecord(L.st, L.evAcc);
-        lastAcc = &L.evAcc;
-        ctx->launches++;
-        L.active = false;
-        nextAcc++;
-        progressed = true;
-      }
+    bool progressed = false;
+    while (nextAcc < chunks.size() && finished[nextAcc].valid) {
+      const Finished& f = finished[nextAcc];
+      Lane& L = ctx->lanes[f.lane];
+      if (lastAcc) rt::streamWaitEvent(L.side, *lastAcc);
+      PathState acc = L.ps;
+      acc.L = L.Lbuf[f.buf];
+      rt::launchFor(L.side, f.nPix,
+                    AccumulateK{acc, ctx->dBuckets, ctx->bucketCapacity, f.pixBase, f.nPix, f.K, f.sDone, f.stride, m, ctx->frame.estimator,
+                                exposureScale});
+      rt::eventRecord(L.side, L.evSide[f.buf]);
+      lastAcc = &L.evSide[f.buf];
+      L.accPending[f.buf] = false;
+      ctx->launches++;
+      nextAcc++;
+      progressed = true;
     }
     if (nextAcc >= chunks.size()) break;
     if (next < chunks.size()) {
-      bool idle = false;
-      for (int l = 0; l < kLanes; l++) idle |= !ctx->lanes[l].active;
-      if (idle) continue;  // a lane was freed: give it the next chunk before blocking
+      bool canStart = false;
+      for (int l = 0; l < kLanes; l++) canStart |= !ctx->lanes[l].active && !ctx->lanes[l].accPending[ctx->lanes[l].lSel];
+      if (canStart) continue;  // a lane (or its buffer) was freed: give it the next chunk before blocking
     }
     // service whichever waiting lane's counters arrive first: they size its next bounce
     Lane* W = nullptr;
     int waiting = 0;
     for (int l = 0; l < kLanes; l++) waiting += ctx->lanes[l].active && ctx->lanes[l].waiting;
-    if (!waiting) return fail(ctx, YC_ERR_STATE, "wavefront scheduler stalled");
+    if (!waiting) {
+      if (progressed) continue;
+      return fail(ctx, YC_ERR_STATE, "wavefront scheduler stalled");
+    }
+    int wl = 0;
     for (int spin = 0; !W; spin++) {
       for (int l = 0; l < kLanes && !W; l++) {
         Lane& L = ctx->lanes[l];
-        if (L.active && L.waiting && (waiting == 1 || rt::eventReady(L.evCtr))) W = &L;
+        if (L.active && L.waiting && (waiting == 1 || rt::eventReady(L.evCtr))) W = &L, wl = l;
       }
     }
     Lane& L = *W;
@@ -1115,26 +1223,21 @@ static int renderChunks(yc_ctx* ctx, const uint32_t* dList, uint32_t nPixCall, u
     L.n = L.hCtr[kCtrNextCount];
     L.bounce++;
     if (L.n == 0 || L.bounce >= ctx->opts.maxDepth) {
-      L.done = true;
+      retire(L, wl, false);
       continue;
     }
 #ifndef YB_HOSTSIM
     if (L.n <= ctx->tailThreshold) {
-      const dim3 tg((L.n + kTailBlock - 1) / kTailBlock);
-      if (!ALPHA && ctx->wide)
-        tailKernel<false, true><<<tg, kTailBlock, 0, L.st.s>>>(ctx->ds, L.w, L.ps, L.sq, L.qA, L.n, L.bounce, ctx->dCounters);
-      else
-        tailKernel<ALPHA, false><<<tg, kTailBlock, 0, L.st.s>>>(ctx->ds, L.w, L.ps, L.sq, L.qA, L.n, L.bounce, ctx->dCounters);
-      ctx->launches++;
-      L.done = true;
+      retire(L, wl, true);
       continue;
     }
 #endif
     const int rc = issueBounce<ALPHA>(ctx, L);
     if (rc != YC_OK) return rc;
+    if (L.done) retire(L, wl, false);
   }
   // the main stream continues (finalize) after the last accumulate, which waited for all earlier ones
-  if (lastAcc && lastAcc != &ctx->lanes[0].evAcc) rt::streamWaitEvent(ctx->st, *lastAcc);
+  if (lastAcc) rt::streamWaitEvent(ctx->st, *lastAcc);
   YC_TRY(rt::lastError());
   return YC_OK;
 }
