@@ -19,11 +19,15 @@ def reference_order_by_default():
     delivers; contexts created without an explicit `traversal` use it.  The wide walk (the library's default for
     scenes without alpha-tested materials) is tested by name in test_wide_bvh.py / test_gpu_parity.py with the
     north-star tolerances (ids exact bar ties, t <= 1e-5, relMSE < 1e-3)."""
+    import gc
     import yart_b200
     old = yart_b200.default_traversal
     yart_b200.default_traversal = yart_b200.TRAVERSAL_REFERENCE_ORDER
     yield
     yart_b200.default_traversal = old
+    # contexts a test did not close hold 3-4 GB of wavefront storage each on the GPU: release them now rather than
+    # whenever the collector gets to them (a full `-m gpu` run in one process would otherwise pile them up)
+    gc.collect()
 
 
 @pytest.fixture

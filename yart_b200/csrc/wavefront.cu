@@ -873,20 +873,6 @@ static int ensureWaveStorage(yc_ctx* ctx) {
     uint2* sp = nullptr;
     YC_TRY(devAlloc(own, &sp, size_t(traceGridMax(ctx)) * kTraceBlock * kSpillEntries));
     L.spill = sp;
-    // the tail kernel's copies (index-compatible with the lane's own arrays) and private queues
-    YC_TRY(devAlloc(own, &L.ts.rayO, P));
-    YC_TRY(devAlloc(own, &L.ts.rayD, P));
-    YC_TRY(devAlloc(own, &L.ts.L, P));
-    YC_TRY(devAlloc(own, &L.ts.att, P));
-    YC_TRY(devAlloc(own, &L.ts.dim, P));
-    YC_TRY(devAlloc(own, &L.ts.flags, P));
-    YC_TRY(devAlloc(own, &L.ts.hitA, P));
-    YC_TRY(devAlloc(own, &L.ts.hitB, P));
-    YC_TRY(devAlloc(own, &L.tsq.o, size_t(kTailCapacity)));
-    YC_TRY(devAlloc(own, &L.tsq.d, size_t(kTailCapacity)));
-    YC_TRY(devAlloc(own, &L.tsq.lif, size_t(kTailCapacity)));
-    YC_TRY(devAlloc(own, &L.tsq.att, size_t(kTailCapacity)));
-    YC_TRY(devAlloc(own, &L.tq, size_t(kTailCapacity)));
 #endif
   }
   ctx->dCtr = ctx->lanes[0].ctr;
@@ -896,6 +882,30 @@ static int ensureWaveStorage(yc_ctx* ctx) {
   YC_TRY(rt::sync(ctx->st));
   return YC_OK;
 }
+
+#ifndef YB_HOSTSIM
+// The tail kernel's copies of the surviving paths' state (index-compatible with the lane's own arrays) and its private
+// queues: allocated when a chunk first leaves paths to a tail (renders of depth 1 never do).
+static int ensureTailStorage(yc_ctx* ctx, Lane& L) {
+  if (L.tq) return YC_OK;
+  auto& own = ctx->waveAllocs;
+  const size_t P = L.capacity;
+  YC_TRY(devAlloc(own, &L.ts.rayO, P));
+  YC_TRY(devAlloc(own, &L.ts.rayD, P));
+  YC_TRY(devAlloc(own, &L.ts.L, P));
+  YC_TRY(devAlloc(own, &L.ts.att, P));
+  YC_TRY(devAlloc(own, &L.ts.dim, P));
+  YC_TRY(devAlloc(own, &L.ts.flags, P));
+  YC_TRY(devAlloc(own, &L.ts.hitA, P));
+  YC_TRY(devAlloc(own, &L.ts.hitB, P));
+  YC_TRY(devAlloc(own, &L.tsq.o, size_t(kTailCapacity)));
+  YC_TRY(devAlloc(own, &L.tsq.d, size_t(kTailCapacity)));
+  YC_TRY(devAlloc(own, &L.tsq.lif, size_t(kTailCapacity)));
+  YC_TRY(devAlloc(own, &L.tsq.att, size_t(kTailCapacity)));
+  YC_TRY(devAlloc(own, &L.tq, size_t(kTailCapacity)));
+  return YC_OK;
+}
+#endif
 
 // ---------------------------------------------------------------------------------------
 // frame + waves
@@ -1228,6 +1238,7 @@ static int renderChunks(yc_ctx* ctx, const uint32_t* dList, uint32_t nPixCall, u
     }
 #ifndef YB_HOSTSIM
     if (L.n <= ctx->tailThreshold) {
+      if (const int trc = ensureTailStorage(ctx, L)) return trc;
       retire(L, wl, true);
       continue;
     }
