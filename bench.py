@@ -186,9 +186,11 @@ def run_reference(args):
     print(json.dumps(line), file=_REAL_STDOUT, flush=True)
 
 
-SHADE_BYTES_PER_HIT = 592  # surface shading, algorithmic bytes per hit: path state 92 B read + 92 B written,
-# vertex data of the hit triangle 120 B (3 indices + 3 x (normal, tangent, uv)), material record 176 B, NEE record 112 B;
-# + 36 B of texel taps (base colour, metallic-roughness, normal map: 4 taps each) on textured materials
+SHADE_BYTES_PER_HIT = 544  # surface shading (ResolveK + SampleK + ShadeNeeK), algorithmic bytes per hit:
+# path state 92 B read + 92 B written, vertex data of the hit triangle 120 B (3 indices + 3 x (normal, tangent, uv)),
+# material record 176 B, shadow request 64 B written; the 112 B surface record the three kernels hand each other is the
+# implementation's own traffic and is not counted; + 36 B of texel taps (base colour, metallic-roughness, normal map:
+# 4 taps each) on textured materials
 SHADE_TEXTURE_BYTES = 36
 
 
@@ -239,14 +241,22 @@ def workload_record(Y, name: str, local: int, trav: int, spp: int, steps: int) -
         ctx = Y.Context(device=local, max_depth=MAX_DEPTH, traversal=trav)
         ctx.upload_scene(scene)
         ctx.set_camera(cam)
-        ctx.set_profiling(1 | 4)
-        ctx.begin_frame(W, H, spp * (steps + 3), 64, (0, 0, 0), Y.TONEMAP_AGX)
+        ctx.set_profiling(1)
+        ctx.begin_frame(W, H, spp * (steps + 3 + 2), 64, (0, 0, 0), Y.TONEMAP_AGX)
         for k in range(3):
             ctx.render_wave(k * spp, spp, k * spp)
         s0 = ctx.stats()
         for k in range(3, 3 + steps):
             ctx.render_wave(k * spp, spp, k * spp)
         s1 = ctx.stats()
+        # the shading kernels' own duration: two more waves with one chunk in flight instead of two (profiling bit 3), so
+        # that the CUDA events around ResolveK + SampleK + ShadeNeeK do not also span the other lane's traversal kernels
+        ctx.set_profiling(1 | 4 | 8)
+        p0 = ctx.stats()
+        for k in range(3 + steps, 3 + steps + 2):
+            ctx.render_wave(k * spp, spp, k * spp)
+        p1 = ctx.stats()
+        ctx.set_profiling(1)
         big, nbig = 32, 3
         ctx.begin_frame(W, H, big * (nbig + 1), 64, (0, 0, 0), Y.TONEMAP_AGX)
         ctx.render_wave(0, big, 0)
@@ -260,18 +270,18 @@ def workload_record(Y, name: str, local: int, trav: int, spp: int, steps: int) -
         ctx.close()
         ms = (s1.gpuMs - s0.gpuMs) / steps
         rays = s1.raysReference - s0.raysReference
-        hits, shade_ms, n_shade = s1.hitsShaded - s0.hitsShaded, s1.shadeMs - s0.shadeMs, s1.shadeLaunches - s0.shadeLaunches
+        hits, shade_ms, n_shade = p1.hitsShaded - p0.hitsShaded, p1.shadeMs - p0.shadeMs, p1.shadeLaunches - p0.shadeLaunches
         per_hit = SHADE_BYTES_PER_HIT + (SHADE_TEXTURE_BYTES if name == "sponza" else 0)
         peak, peak_src = peaks()
         achieved = per_hit * hits / (shade_ms / 1e3) / 1e9 if shade_ms > 0 else 0.0
         return {"workload": WORKLOAD_TEXT, "value": rays / (ms * steps) / 1e3, "unit": "Mrays/s", "ms_per_step": ms,
                 "samples_per_s": W * H * spp / (ms / 1e3), "steps": steps, "spp_per_step": spp,
                 "traversal": "wide" if (trav != Y.TRAVERSAL_REFERENCE_ORDER and name != "sponza") else "reference order (alpha-tested materials)" if name == "sponza" else "reference order",
-                "extend_ms_per_step": (s1.extendMs - s0.extendMs) / steps, "shade_surface_ms_per_step": shade_ms / steps,
+                "extend_ms_per_step": (s1.extendMs - s0.extendMs) / steps, "shade_surface_ms_per_step": shade_ms / 2,
                 "wave32": wave32,
-                "shade_roofline": {"bound": "hbm", "kernel": "ShadeSurfaceK", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                                   "frac": achieved / peak, "bytes_per_hit": per_hit, "hits_per_step": hits / steps,
-                                   "launches_per_step": n_shade / steps, "traffic": None, "peak_source": peak_src}}
+                "shade_roofline": {"bound": "hbm", "kernel": "ResolveK + SampleK + ShadeNeeK", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                                   "frac": achieved / peak, "bytes_per_hit": per_hit, "hits_per_step": hits / 2,
+                                   "launches_per_step": n_shade / 2, "timed": "2 waves with one chunk in flight (CUDA events around the three launches of every bounce)", "traffic": None, "peak_source": peak_src}}
     finally:
         CAM, MAX_DEPTH, WORKLOAD_TEXT = saved
 
@@ -403,6 +413,7 @@ def run_ours(args):
     clk = clocks.stop(weak["w0"], time.time())
     s0, s1 = weak["s0"], weak["s1"]
 
+    frames_direct = bool(dist and not buckets and ctx.comm_frames_direct())
     strong = None
     if dist:
         # the same job as one GPU's step (one wave of `spp` samples of the frame) split over the ranks
@@ -554,11 +565,15 @@ def run_ours(args):
                                        "units, rank r takes (b + c) % N == r; scene replicated; ncclAllReduce(int32 sum) of the "
                                        "accumulation buffers per wave, inside the timed region") if buckets else
                                       (f"tile sharding x{world} inside libyart_b200.so: rank r renders tile k of the reference's tile list when "
-                                       "k % N == r; scene replicated; ncclReduce of the HDR + LDR frames to rank 0 after every wave, "
-                                       "inside the timed region"),
+                                       "k % N == r; scene replicated; " +
+                                       ("every rank's finalize kernel stores its finished pixels straight into rank 0's HDR + LDR "
+                                        "frames over NVLink (rank 0's allocation mapped into the other processes), one small NCCL "
+                                        "all-reduce per wave as the barrier, inside the timed region" if frames_direct else
+                                        "ncclReduce of the HDR + LDR frames to rank 0 after every wave, inside the timed region")),
                        "l2": "inputs larger than L2: BVH + 0.8 GB of path state streamed per step exceed the 126 MB L2; no flush"},
             "wall_ms_per_step": weak["wall_ms"] / args.steps,
             "collective_ms_per_step": weak["comm_ms"] / args.steps,
+            "frame_delivery": None if not dist or buckets else ("direct peer stores + barrier" if frames_direct else "reduce to rank 0"),
             "traced_mrays_per_s": weak["traced"] / dev_ms / 1e3,
             "samples_per_s": W * H * S_weak / (dev_ms / args.steps / 1e3),
             "gpu_launches": int(weak["launches"]),

@@ -354,7 +354,9 @@ int yc_retonemap(yc_ctx* ctx);
 /* Bit 0: record per-launch CUDA-event time of the extend kernel into YcStats (bench roofline).
  * Bit 1: run the counting builds of extend / shadow so YcStats.boxTests / triTests accumulate
  * (reference-traversal work; the counting builds do not park leaves speculatively).
- * Bit 2: record per-launch CUDA-event time of the surface-shading kernel and the hits it shaded. */
+ * Bit 2: record per-bounce CUDA-event time of the surface-shading kernels and the hits they shaded.
+ * Bit 3: issue a wave's chunks one after the other on one stream instead of two chunks in flight, so that the event
+ * times of bits 0 and 2 are the launches' own durations (slower waves; results unchanged). */
 int yc_set_profiling(yc_ctx* ctx, int flags);
 /* Ray-level parity hook: RayIntegrator::testNode on caller rays (ray-integrator.cpp:20-54). */
 int yc_trace(yc_ctx* ctx, const YcRay* rays, size_t n, int mode, YcHit* hits, YcStats* stats);
@@ -399,9 +401,15 @@ int yc_comm_init_all(yc_ctx** ctxs, int n);
 int yc_comm_init_custom(yc_ctx* ctx, int rank, int world, yc_collective_fn fn, void* user);
 int yc_comm_destroy(yc_ctx* ctx);
 /* Tile sharding (YcFrameDesc.shardIndex / shardCount): every participant's HDR and LDR frames hold its own tiles and
- * zeros elsewhere; their sum — bit-identical to one GPU's frame — lands in `root`'s combined frames (ncclReduce,
- * out of place: the participants' own frames keep blending their tiles wave after wave). */
+ * zeros elsewhere; their combination — bit-identical to one GPU's frame — lands in `root`'s combined frames, which
+ * yc_resolve_combined copies out on the root (the participants' own frames keep blending their tiles wave after wave).
+ * Collective: every participant calls it after the wave.  Where all participants can address the root GPU's memory
+ * (NVLink peer access — the devices of one process, or one process per GPU through an exported allocation) the
+ * finalize kernel has already stored each finished pixel into the root's frame, and this call is a barrier at most
+ * (none if yc_comm_sum_u64 ran since the wave); otherwise the frames are summed into the root (ncclReduce / the
+ * caller's collective).  yc_comm_frames_direct reports which (after the first yc_comm_reduce_frames of a frame size). */
 int yc_comm_reduce_frames(yc_ctx* ctx, int root);
+int yc_comm_frames_direct(yc_ctx* ctx, int* direct);
 int yc_resolve_combined(yc_ctx* ctx, float* hdrRGBA, float* ldrRGBA);
 /* Bucket sharding (yc_accumulate_wave): all-reduce(sum, int32) of the planes a wave of `waveSamples` samples uses. */
 int yc_comm_allreduce_buckets(yc_ctx* ctx, uint32_t waveSamples);

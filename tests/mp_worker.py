@@ -20,6 +20,8 @@ def run(rank: int, world: int, port: int, mode: str, out_dir: str):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
+    if mode.startswith("nccl_"):
+        return run_nccl(rank, world, mode, out_dir)
     Y.use_library(H.hostsim())
     cam = H.scene_camera("cornell")
     sc = Y.Scene(H.scene_file("cornell"))
@@ -106,6 +108,41 @@ def run(rank: int, world: int, port: int, mode: str, out_dir: str):
         if t_ldr is not None:
             np.save(os.path.join(out_dir, f"{mode}_ldr.npy"), t_ldr.numpy())
         np.save(os.path.join(out_dir, f"{mode}_rays.npy"), rays.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def run_nccl(rank: int, world: int, mode: str, out_dir: str):
+    """`-m gpu`, one process per GPU on the real library: yr_create_dist with NCCL inside libyart_b200.so; gloo only
+    carries the communicator id.  nccl_tiles: the finalize kernels store into rank 0's frame through the mapped
+    allocation (direct); nccl_tiles_reduce: the same with YART_B200_FRAMES_REDUCE=1 (ncclReduce of the frames)."""
+    import torch.distributed as dist
+    import harness as H
+    import yart_b200 as Y
+    if mode == "nccl_tiles_reduce":
+        os.environ["YART_B200_FRAMES_REDUCE"] = "1"
+    box = [Y.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    cam = H.scene_camera("material_zoo")
+    sc = Y.Scene(H.scene_file("material_zoo"))
+    w, h = 160, 90
+    c = Y.make_camera(w, h, cam["focal"], cam["fnum"], cam["pos"], cam["target"], (0, 0, 0), cam["exposure"])
+    r = Y.Renderer(w, h, c, sc, tile_size=16, tonemap=Y.TONEMAP_AGX, samples=56, first_wave_samples=8, max_wave_samples=16,
+                   max_depth=6, traversal=Y.TRAVERSAL_REFERENCE_ORDER, device=rank, dist=(rank, world, box[0]))
+    per_wave = []
+    target = np.zeros((h, w, 4), np.float32)
+    r.set_frame_target(target)
+    r.on_wave_complete(lambda rd, wd: per_wave.append(target.copy()))
+    for k in range(2):  # the second render reuses the mapped frames
+        data = r.render_sync()
+        hdr, ldr, _ = r.read()
+        if rank == 0:
+            np.save(os.path.join(out_dir, f"{mode}_hdr{k}.npy"), hdr)
+            np.save(os.path.join(out_dir, f"{mode}_ldr{k}.npy"), ldr)
+    if rank == 0:
+        np.save(os.path.join(out_dir, f"{mode}_waves.npy"), np.stack(per_wave))
+        np.save(os.path.join(out_dir, f"{mode}_info.npy"), np.array([data["total_rays"], int(r.frames_direct())], np.int64))
+    r.close()
     dist.barrier()
     dist.destroy_process_group()
 

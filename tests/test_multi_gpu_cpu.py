@@ -150,3 +150,58 @@ def test_abort_stops_a_long_render_between_chunks():
     assert r.wait() is False
     assert time.time() - t0 < 90 and done == [(True, 0)]  # one bounce of the chunks in flight at most
     r.close()
+
+
+def test_direct_frame_delivery_in_process_group_with_partial_and_repeated_waves():
+    """Tile sharding where every participant reaches the root's memory (here: one process, the in-process group): the
+    finalize kernel stores finished pixels into the root's combined frame and yc_comm_reduce_frames is a barrier.  The
+    root's frame equals one context's after every wave — also after a wave that finalized part of the frame only (the
+    stale path pushes the shard), after two waves without a reduce in between, and over a second frame (the two
+    alternating copies of the combined frame are reused)."""
+    import threading
+    n, size, tile = 3, 48, 16
+    cam = H.scene_camera("cornell")
+    sc = Y.Scene(H.scene_file("cornell"))
+    c = Y.make_camera(size, size, cam["focal"], cam["fnum"], cam["pos"], cam["target"])
+    # (sample offset, samples, rectangle or None, reduce after it?)
+    plan = [(0, 2, None, True), (2, 1, (0, 0, 20, size), True), (2, 1, (20, 0, size - 20, size), True), (3, 2, None, False),
+            (5, 1, None, True), (6, 2, None, True)]
+
+    def run(ctx, rank, world, out):
+        for frame in range(2):
+            ctx.begin_frame(size, size, 8, tile, (0, 0, 0), Y.TONEMAP_AGX, shard_index=rank, shard_count=world)
+            for (s0, k, rect, reduce) in plan:
+                ctx.render_wave(s0, k, s0, rect=rect)
+                if world > 1 and reduce:
+                    ctx.comm_reduce_frames(0)
+                if reduce and rank == 0:
+                    out.append(ctx.resolve_combined() if world > 1 else ctx.resolve()[:2])
+
+    one = Y.Context()
+    one.upload_scene(sc)
+    one.set_camera(c)
+    want = []
+    run(one, 0, 1, want)
+    ctxs = [Y.Context() for _ in range(n)]
+    for x in ctxs:
+        x.upload_scene(sc)
+        x.set_camera(c)
+    Y.comm_init_all(ctxs)
+    got, errs = [], []
+
+    def worker(r):
+        try:
+            run(ctxs[r], r, n, got)
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    ts = [threading.Thread(target=worker, args=(r,)) for r in range(n)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(120)
+    assert not errs, errs
+    assert all(x.comm_frames_direct() for x in ctxs)
+    assert len(got) == len(want) == 10
+    for k, ((hdr, ldr), (hdr1, ldr1)) in enumerate(zip(got, want)):
+        assert H.bits_equal(hdr, hdr1).all() and H.bits_equal(ldr, ldr1).all(), k

@@ -83,3 +83,46 @@ def test_abort_returns_quickly_mid_wave():
     assert time.time() - t0 < 1.0 and done == [(True, 0)]  # polled per chunk and per bounce, not per wave
     # and the renderer is reusable: a short render afterwards matches a fresh renderer's
     r.close()
+
+
+@pytest.mark.parametrize("mode", ["nccl_tiles", "nccl_tiles_reduce"])
+def test_one_process_per_gpu_direct_frame_delivery_equals_one_gpu_bitwise(tmp_path, mode):
+    """Two processes, one GPU each, NCCL inside the library (yr_create_dist).  nccl_tiles: rank 0's combined frames are
+    mapped into rank 1 and both finalize kernels store their tiles there (peer memory; the per-wave collective is a
+    barrier); nccl_tiles_reduce: the ncclReduce path.  Every wave's frame as the callback sees it, the final frames of
+    two consecutive renders and the ray count equal one GPU's."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (NCCL refuses two ranks on one device)")
+    import test_multi_gpu_cpu as M
+    port = M.free_port()
+    H.scene_file("material_zoo")
+    procs = [subprocess.Popen([sys.executable, M.WORKER, str(r), "2", str(port), mode, str(tmp_path)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    for p in procs:
+        out, _ = p.communicate(timeout=600)
+        assert p.returncode == 0, out[-3000:]
+    cam = H.scene_camera("material_zoo")
+    sc = Y.Scene(H.scene_file("material_zoo"))
+    c = Y.make_camera(160, 90, cam["focal"], cam["fnum"], cam["pos"], cam["target"], (0, 0, 0), cam["exposure"])
+    r1 = Y.Renderer(160, 90, c, sc, tile_size=16, tonemap=Y.TONEMAP_AGX, samples=56, first_wave_samples=8, max_wave_samples=16,
+                    max_depth=6, traversal=Y.TRAVERSAL_REFERENCE_ORDER)
+    waves = []
+    target = np.zeros((90, 160, 4), np.float32)
+    r1.set_frame_target(target)
+    r1.on_wave_complete(lambda rd, wd: waves.append(target.copy()))
+    d1 = r1.render_sync()
+    hdr1, ldr1, _ = r1.read()
+    r1.close()
+    rays, direct = (int(v) for v in np.load(tmp_path / f"{mode}_info.npy"))
+    assert rays == d1["total_rays"] and direct == (1 if mode == "nccl_tiles" else 0)
+    for k in range(2):
+        assert H.bits_equal(np.load(tmp_path / f"{mode}_hdr{k}.npy"), hdr1).all()
+        assert H.bits_equal(np.load(tmp_path / f"{mode}_ldr{k}.npy"), ldr1).all()
+    got = np.load(tmp_path / f"{mode}_waves.npy")
+    assert len(waves) == 4 and got.shape[0] == 8  # waves of 8, 16, 16, 16 samples, two renders
+    for k in range(8):
+        assert H.bits_equal(got[k], waves[k % 4]).all(), k

@@ -67,6 +67,12 @@ def _env_struct(env, radius, transform):
     return e, rgb  # keep rgb alive
 
 
+def comm_init_all(contexts):
+    """yc_comm_init_all: the contexts of ONE process become one communicator (each is then driven by its own thread)."""
+    arr = (C.c_void_p * len(contexts))(*[c._h for c in contexts])
+    _check(lib().yc_comm_init_all(C.cast(arr, C.POINTER(C.c_void_p)), len(contexts)), "yc_comm_init_all")
+
+
 def comm_unique_id() -> bytes:
     """ncclGetUniqueId through the library (rank 0 calls it and hands the bytes to the other ranks)."""
     buf = (C.c_char * capi.COMM_ID_BYTES)()
@@ -264,6 +270,13 @@ class Context:
     def comm_reduce_frames(self, root: int = 0):
         self._ck(lib().yc_comm_reduce_frames(self._h, root), "yc_comm_reduce_frames")
 
+    def comm_frames_direct(self) -> bool:
+        """True when the participants store finished pixels straight into the root's frame (peer memory) and
+        comm_reduce_frames is only a barrier; False when the frames are summed into the root."""
+        d = C.c_int()
+        self._ck(lib().yc_comm_frames_direct(self._h, C.byref(d)), "yc_comm_frames_direct")
+        return bool(d.value)
+
     def comm_allreduce_buckets(self, wave_samples: int):
         self._ck(lib().yc_comm_allreduce_buckets(self._h, wave_samples), "yc_comm_allreduce_buckets")
 
@@ -411,6 +424,14 @@ class Renderer:
     def set_camera(self, camera: capi.YcCamera):
         self._ck(lib().yr_set_camera(self._h, C.byref(camera)), "yr_set_camera")
 
+    def set_frame_target(self, ldr: np.ndarray):
+        """(height, width, 4) float32, C-contiguous: receives the tonemapped frame after every wave, before the callbacks
+        (Renderer::m_buffer; yr_set_frame_target).  None detaches."""
+        if ldr is not None:
+            assert ldr.dtype == np.float32 and ldr.flags.c_contiguous and ldr.size == self.settings.width * self.settings.height * 4
+        self._target = ldr
+        self._ck(lib().yr_set_frame_target(self._h, ldr.ctypes.data if ldr is not None else None), "yr_set_frame_target")
+
     def render(self):
         self._ck(lib().yr_render(self._h), "yr_render")
 
@@ -461,3 +482,10 @@ class Renderer:
 
     def context_handle(self):
         return lib().yr_context(self._h)
+
+    def frames_direct(self) -> bool:
+        """Several GPUs, tile sharding: True when finished pixels are stored straight into the root GPU's frame (peer
+        memory) instead of being reduced there (yc_comm_frames_direct; known after the first wave)."""
+        d = C.c_int()
+        _check(lib().yc_comm_frames_direct(C.c_void_p(lib().yr_context(self._h)), C.byref(d)), "yc_comm_frames_direct")
+        return bool(d.value)

@@ -158,6 +158,7 @@ PROTOTYPES = {
     "yc_comm_init_custom": (C.c_int, [P, C.c_int, C.c_int, COLLECTIVE_FN, P]),
     "yc_comm_destroy": (C.c_int, [P]),
     "yc_comm_reduce_frames": (C.c_int, [P, C.c_int]),
+    "yc_comm_frames_direct": (C.c_int, [P, C.POINTER(C.c_int)]),
     "yc_resolve_combined": (C.c_int, [P, P, P]),
     "yc_comm_allreduce_buckets": (C.c_int, [P, u32]),
     "yc_comm_sum_u64": (C.c_int, [P, C.POINTER(u64), u32]),

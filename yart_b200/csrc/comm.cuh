@@ -14,6 +14,11 @@
 //     buffers (a plain loop in the CPU build of the product sources, one kernel over the participants' device
 //     pointers in the CUDA build).  Used when two contexts of a communicator share a GPU — NCCL refuses that — so the
 //     multi-GPU renderer logic runs in the CPU test-suite and on a one-GPU box.
+// Tile sharding needs no reduction at all where every participant can address the root GPU's memory (NVLink peer
+// access: the other devices of the process, or other processes through an exported allocation): the finalize kernel
+// stores every finished pixel into the root's combined frame as it produces it, and the per-wave collective shrinks to
+// a barrier (yc_comm_reduce_frames, "direct").  Summing the frames is what remains where that is impossible (the
+// caller's own collective across processes).
 // Every data collective is a SUM over buffers in which each element is non-zero on at most one participant (disjoint
 // tiles; disjoint (bucket, pixel) slots, summed as int32), so x + 0 + ... + 0 is exact and the result is bit-identical
 // to one GPU whatever order the transport adds in.
@@ -21,6 +26,7 @@
 #include <condition_variable>
 #include <memory>
 #include <mutex>
+#include <unistd.h>
 
 #ifndef YB_HOSTSIM
 #include <dlfcn.h>
@@ -130,9 +136,20 @@ struct Comm {
   yc_collective_fn custom = nullptr;
   void* customUser = nullptr;
   std::shared_ptr<HostGroup> group;
-  float4 *hdrAll = nullptr, *ldrAll = nullptr;  // root's combined frames (tile sharding)
+  // Tile sharding: the root's combined frames.  One block holding {hdr, ldr} x 2: the two copies alternate by reduce
+  // (`epoch`), so that the root may still be copying wave k's frame out while wave k + 1 is stored into the other.
+  float4* block = nullptr;       // root only: the allocation
+  float4 *hdrAll[2] = {nullptr, nullptr}, *ldrAll[2] = {nullptr, nullptr};  // as THIS context addresses them (root: its
+                                 // own block; others in direct mode: the root's block through peer access)
+  void* imported = nullptr;      // cross-process mapping of the root's block (closed with the communicator)
   size_t frameTexels = 0;
-  uint64_t* scratch = nullptr;                  // device staging for yc_comm_sum_u64
+  int root = -1;
+  bool direct = false;           // every participant reaches the root's block: finished pixels are stored there directly
+  bool stale = true;             // direct: this context's pixels in the next copy are not all current (push them)
+  bool barrierSinceFinalize = false;  // a collective ran on the stream after the last finalize
+  uint32_t epoch = 0;            // reduces completed since the frames were mapped; the next one publishes copy epoch & 1
+  int cur = 0;                   // copy the last reduce completed into (yc_resolve_combined reads it)
+  uint64_t* scratch = nullptr;   // device staging for small host-value collectives
 };
 
 }  // namespace yb

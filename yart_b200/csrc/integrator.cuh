@@ -205,56 +205,88 @@ YB_DEV void shadeMissStage(const DScene& sc, const WaveParams& w, const PathStat
   ps.L[i] = make_float4(L.x, L.y, L.z, 0.0f);
 }
 
-// Surface shading is cut in two so that each kernel's instruction footprint stays near the instruction cache
-// (one fused kernel touched 134 KB of SASS per launch and stalled on instruction fetch more than on anything else):
-//   shadeSurface  hit resolution, textures, the BSDF sample, emission MIS, throughput, next ray, Russian roulette
-//                 (mis-integrator.cpp:46-73, 83-102) — and, when the bounce takes a NEE sample, a NeeRecord;
-//   shadeNee      Ld up to the shadow ray (mis-integrator.cpp:79-80 → :111-124, 135-148) from that record.
-// The sampler dimensions of the NEE draws are reserved by shadeSurface (they precede the roulette draw), so both
-// halves draw exactly what the fused loop drew; L is only touched by shadeSurface (emission) and later by the shadow
+// Surface shading is cut in three so that each kernel's instruction footprint stays near the instruction cache and its
+// register need matches what it does (one fused kernel touched 134 KB of SASS per launch and stalled on instruction
+// fetch more than on anything else; surface + NEE in two kernels still spilled 1-2 KB per thread at any occupancy that
+// hid the gather chain's latency):
+//   resolveSurface  the gather chain: hit → node → mesh → indices → vertices → material → texels, the shading frame
+//                   (ray-integrator.cpp:56-82, 205-227; core/bsdf.cpp:43-58; parametric.cpp's texture preambles) —
+//                   memory latency, few registers, runs at full occupancy — into a SurfRecord;
+//   sampleSurface   the BSDF sample, emission MIS, throughput, next ray, Russian roulette (mis-integrator.cpp:46-73,
+//                   83-102) from that record — arithmetic only;
+//   shadeNee        Ld up to the shadow ray (mis-integrator.cpp:79-80 → :111-124, 135-148) from the same record.
+// The sampler dimensions of the NEE draws are reserved by sampleSurface (they precede the roulette draw), so the three
+// pieces draw exactly what the fused loop drew; L is only touched by sampleSurface (emission) and later by the shadow
 // stage, in the reference's order.
-struct NeeRecord {
+struct SurfRecord {
   V3 p, n, fx, fy;  // hit point, shading normal (= frame z), frame x / y
-  V3 woLocal, att;  // outgoing direction in the frame; path throughput before this bounce's update
+  V3 woLocal;       // outgoing direction in the frame
   MatEval me;       // material parameters with their textures applied
-  int32_t material;
-  uint32_t dim;     // sampler dimension of the first NEE draw
+  V2 uv;
+  float t;          // hit distance (volume attenuation, parametric.cpp:834-838)
+  int32_t material, lightIdx;
+  uint32_t backSide;
 };
 
-// SoA storage of NeeRecords, one slot per path slot (7 x float4 = 112 B).
-struct NeeState {
-  float4 *r0, *r1, *r2, *r3, *r4, *r5, *r6;
+// SoA storage of SurfRecords, one slot per entry of the bounce's hit queue (7 x float4 = 112 B), plus what
+// sampleSurface hands to shadeNee for the hits that take a NEE sample: the throughput before this bounce's update and
+// the sampler dimension of the first NEE draw (r7).
+struct SurfState {
+  float4 *r0, *r1, *r2, *r3, *r4, *r5, *r6, *r7;
 };
-YB_DEV void storeNee(const NeeState& ns, uint32_t i, const NeeRecord& r) {
-  ns.r0[i] = make_float4(r.p.x, r.p.y, r.p.z, __uint_as_float(uint32_t(r.material)));
-  ns.r1[i] = make_float4(r.n.x, r.n.y, r.n.z, __uint_as_float(r.dim));
-  ns.r2[i] = make_float4(r.fx.x, r.fx.y, r.fx.z, r.me.r);
-  ns.r3[i] = make_float4(r.fy.x, r.fy.y, r.fy.z, r.me.m);
-  ns.r4[i] = make_float4(r.woLocal.x, r.woLocal.y, r.woLocal.z, r.me.t);
-  ns.r5[i] = make_float4(r.me.base.x, r.me.base.y, r.me.base.z, r.me.c);
-  ns.r6[i] = make_float4(r.att.x, r.att.y, r.att.z, r.me.cr);
+YB_DEV void storeSurf(const SurfState& ss, uint32_t j, const SurfRecord& r) {
+  ss.r0[j] = make_float4(r.p.x, r.p.y, r.p.z, __uint_as_float(uint32_t(r.material) | (r.backSide << 31)));
+  ss.r1[j] = make_float4(r.n.x, r.n.y, r.n.z, r.t);
+  ss.r2[j] = make_float4(r.fx.x, r.fx.y, r.fx.z, r.me.r);
+  ss.r3[j] = make_float4(r.fy.x, r.fy.y, r.fy.z, r.me.m);
+  ss.r4[j] = make_float4(r.woLocal.x, r.woLocal.y, r.woLocal.z, r.me.t);
+  ss.r5[j] = make_float4(r.me.base.x, r.me.base.y, r.me.base.z, r.me.c);
+  ss.r6[j] = make_float4(r.uv.x, r.uv.y, r.me.cr, __uint_as_float(uint32_t(r.lightIdx)));
 }
-YB_DEV NeeRecord loadNee(const NeeState& ns, uint32_t i) {
-  const float4 a = ns.r0[i], b = ns.r1[i], c = ns.r2[i], d = ns.r3[i], e = ns.r4[i], f = ns.r5[i], g = ns.r6[i];
-  NeeRecord r;
-  r.p = V3(a.x, a.y, a.z), r.material = int32_t(__float_as_uint(a.w));
-  r.n = V3(b.x, b.y, b.z), r.dim = __float_as_uint(b.w);
+YB_DEV SurfRecord loadSurf(const SurfState& ss, uint32_t j) {
+  const float4 a = ss.r0[j], b = ss.r1[j], c = ss.r2[j], d = ss.r3[j], e = ss.r4[j], f = ss.r5[j], g = ss.r6[j];
+  SurfRecord r;
+  const uint32_t mb = __float_as_uint(a.w);
+  r.p = V3(a.x, a.y, a.z), r.material = int32_t(mb & 0x7fffffffu), r.backSide = mb >> 31;
+  r.n = V3(b.x, b.y, b.z), r.t = b.w;
   r.fx = V3(c.x, c.y, c.z), r.me.r = c.w;
   r.fy = V3(d.x, d.y, d.z), r.me.m = d.w;
   r.woLocal = V3(e.x, e.y, e.z), r.me.t = e.w;
   r.me.base = V3(f.x, f.y, f.z), r.me.c = f.w;
-  r.att = V3(g.x, g.y, g.z), r.me.cr = g.w;
+  r.uv = V2(g.x, g.y), r.me.cr = g.z, r.lightIdx = int32_t(__float_as_uint(g.w));
   return r;
 }
 
-enum : uint32_t { kShadeNee = 4u };  // shadeSurface: `nee` was filled, run shadeNee on it
+enum : uint32_t { kShadeNee = 4u };  // sampleSurface: the bounce takes a NEE sample, run shadeNee on its record
 
-// Returns kShadeContinue / kShadeNee bits.  DEFER_RR ⇔ scene has alpha.
-template <bool DEFER_RR>
-YB_DEV uint32_t shadeSurface(const DScene& sc, const WaveParams& w, const PathState& ps, uint32_t i, NeeRecord& nee,
-                             uint32_t& raysReference) {
-  raysReference += 1;  // mis-integrator.cpp:22
+YB_DEV SurfRecord resolveSurface(const DScene& sc, const PathState& ps, uint32_t i) {
   const int32_t hb = ps.hitB[i];
+  const float4 ro4 = ps.rayO[i], rd4 = ps.rayD[i];
+  const V3 rayO(ro4.x, ro4.y, ro4.z), rayD(rd4.x, rd4.y, rd4.z);
+  HitRec h;
+  const float4 ha = ps.hitA[i];
+  h.t = ha.x, h.u = ha.y, h.v = ha.z, h.prim = __float_as_uint(ha.w);
+  h.node = int32_t(uint32_t(hb) & ~kBackSideBit);
+  h.backSide = (uint32_t(hb) & kBackSideBit) ? 1u : 0u;
+  const SurfaceHit hit = resolveHit(sc, h, rayO, rayD);
+  // BSDF::sample / f / pdf (core/bsdf.cpp:5-41) each rebuild the same local frame and re-read the same
+  // texels; here they are evaluated once per hit and shared (identical values, see bsdf.cuh).
+  const Frame fr = Bsdf::localFrame(hit.n, hit.tg);
+  SurfRecord s;
+  s.me = evalMaterialTextures(sc, sc.materials[hit.material], hit.uv);
+  s.p = hit.p, s.n = hit.n, s.fx = fr.x, s.fy = fr.y;
+  s.woLocal = fr.wtl(-rayD);
+  s.uv = hit.uv, s.t = h.t;
+  s.material = hit.material, s.lightIdx = hit.lightIdx, s.backSide = h.backSide;
+  return s;
+}
+
+// Returns kShadeContinue / kShadeNee bits; with kShadeNee, `neeAtt` / `neeDim` are what shadeNee needs besides the
+// record.  DEFER_RR ⇔ scene has alpha.
+template <bool DEFER_RR>
+YB_DEV uint32_t sampleSurface(const DScene& sc, const WaveParams& w, const PathState& ps, uint32_t i, const SurfRecord& s,
+                              V3& neeAtt, uint32_t& neeDim, uint32_t& raysReference) {
+  raysReference += 1;  // mis-integrator.cpp:22
   const float4 ro4 = ps.rayO[i], rd4 = ps.rayD[i], L4 = ps.L[i], a4 = ps.att[i];
   const V3 rayO(ro4.x, ro4.y, ro4.z), rayD(rd4.x, rd4.y, rd4.z);
   float lastPdf = ro4.w, accRoughness = rd4.w;
@@ -262,38 +294,28 @@ YB_DEV uint32_t shadeSurface(const DScene& sc, const WaveParams& w, const PathSt
   uint32_t fl = ps.flags[i];
   uint32_t depth = fl & kFlagDepthMask;
   const bool specularBounce = (fl & kFlagSpecular) != 0, regularized = (fl & kFlagRegularized) != 0;
-
-  HitRec h;
-  const float4 ha = ps.hitA[i];
-  h.t = ha.x, h.u = ha.y, h.v = ha.z, h.prim = __float_as_uint(ha.w);
-  h.node = int32_t(uint32_t(hb) & ~kBackSideBit);
-  h.backSide = (uint32_t(hb) & kBackSideBit) ? 1u : 0u;
-  const SurfaceHit hit = resolveHit(sc, h, rayO, rayD);
-  const YcMaterial& mat = sc.materials[hit.material];
+  const YcMaterial& mat = sc.materials[s.material];
   const Bsdf bsdf(sc, mat);
   Sampler smp = pathSampler(w, i, ps.dim[i]);
   const V3 wo = -rayD;
+  Frame fr;
+  fr.x = s.fx, fr.y = s.fy, fr.z = s.n;
 
   // mis-integrator.cpp:46-58
   const V2 u = smp.get2D();
   const float uc = smp.get1D();
   const float uc2 = smp.get1D();
-  // BSDF::sample / f / pdf (core/bsdf.cpp:5-41) each rebuild the same local frame and re-read the same
-  // texels; here they are evaluated once per hit and shared (identical values, see bsdf.cuh).
-  const Frame fr = Bsdf::localFrame(hit.n, hit.tg);
-  const MatEval me = evalMaterialTextures(sc, mat, hit.uv);
-  const V3 woLocal = fr.wtl(wo);
-  BSDFSample res = bsdf.sampleImpl(woLocal, hit.uv, me, u, uc, uc2, regularized);
+  BSDFSample res = bsdf.sampleImpl(s.woLocal, s.uv, s.me, u, uc, uc2, regularized);
   res.wi = fr.ltw(res.wi);
 
   // mis-integrator.cpp:61-73 (lastHit.p is this ray's origin: ray = Ray(hit.p, wi), lastHit = hit)
   if (res.is(Emitted)) {
     if (depth == 0 || specularBounce) {
       L += att * res.Le;
-    } else if (hit.lightIdx != -1) {
-      const YcLight& light = sc.lights[hit.lightIdx];
-      const float pdfLight = lightPdf(sc, light, wo) * length2(rayO - hit.p) *
-                             lightPickProbability(sc, uint32_t(hit.lightIdx)) / absDot(wo, hit.n);
+    } else if (s.lightIdx != -1) {
+      const YcLight& light = sc.lights[s.lightIdx];
+      const float pdfLight = lightPdf(sc, light, wo) * length2(rayO - s.p) *
+                             lightPickProbability(sc, uint32_t(s.lightIdx)) / absDot(wo, s.n);
       const float wBSDF = lastPdf / (lastPdf + pdfLight);
       L += att * wBSDF * res.Le;
     }
@@ -303,17 +325,15 @@ YB_DEV uint32_t shadeSurface(const DScene& sc, const WaveParams& w, const PathSt
   if (res.is(Reflected | Transmitted)) {
     // mis-integrator.cpp:79-80 → Ld: its three draws (get1D, get2D) come next in the sampler's order
     if (!res.is(Emitted | Specular) && sc.nLights != 0) {
-      nee.p = hit.p, nee.n = hit.n, nee.fx = fr.x, nee.fy = fr.y;
-      nee.woLocal = woLocal, nee.att = att, nee.me = me;
-      nee.material = hit.material;
-      nee.dim = smp.dim;
+      neeAtt = att;
+      neeDim = smp.dim;
       smp.dim += 3;
       result |= kShadeNee;
     }
     // mis-integrator.cpp:83-95
-    const V3 fcos = res.f * absDot(res.wi, hit.n);
+    const V3 fcos = res.f * absDot(res.wi, s.n);
     att *= fcos / res.pdf;
-    if (h.backSide) att *= bsdf.attenuation(h.t);
+    if (s.backSide) att *= bsdf.attenuation(s.t);
     fl = 0u;
     if (res.is(Specular)) fl |= kFlagSpecular;
     accRoughness += res.roughness;
@@ -329,7 +349,7 @@ YB_DEV uint32_t shadeSurface(const DScene& sc, const WaveParams& w, const PathSt
       alive = russianRoulette(smp, depth, att) && depth < w.maxDepth;
     }
     if (alive) {
-      ps.rayO[i] = make_float4(hit.p.x, hit.p.y, hit.p.z, lastPdf);
+      ps.rayO[i] = make_float4(s.p.x, s.p.y, s.p.z, lastPdf);
       ps.rayD[i] = make_float4(res.wi.x, res.wi.y, res.wi.z, accRoughness);
       ps.att[i] = make_float4(att.x, att.y, att.z, 0.0f);
       ps.flags[i] = fl | (depth & kFlagDepthMask);
@@ -342,35 +362,36 @@ YB_DEV uint32_t shadeSurface(const DScene& sc, const WaveParams& w, const PathSt
 }
 
 // Ld (mis-integrator.cpp:111-133) up to the shadow ray.  Returns true when `rq` holds a request.
-YB_DEV bool shadeNee(const DScene& sc, const WaveParams& w, uint32_t i, const NeeRecord& nee, ShadowRequest& rq) {
-  const Bsdf bsdf(sc, sc.materials[nee.material]);
+YB_DEV bool shadeNee(const DScene& sc, const WaveParams& w, uint32_t i, const SurfRecord& s, V3 att, uint32_t dim,
+                     ShadowRequest& rq) {
+  const Bsdf bsdf(sc, sc.materials[s.material]);
   Frame fr;
-  fr.x = nee.fx, fr.y = nee.fy, fr.z = nee.n;
-  Sampler smp = pathSampler(w, i, nee.dim);
+  fr.x = s.fx, fr.y = s.fy, fr.z = s.n;
+  Sampler smp = pathSampler(w, i, dim);
   const float ucl = smp.get1D();
   const V2 ul = smp.get2D();
   const PickedLight pick = pickLight(sc, ucl);
   const YcLight& light = sc.lights[pick.index];
-  const LightSample ls = lightSample(sc, light, nee.p, ul);
+  const LightSample ls = lightSample(sc, light, s.p, ul);
   const V3 wiLocal = fr.wtl(ls.wi);
-  const V3 f = bsdf.fImpl(nee.woLocal, wiLocal, nee.me);
+  const V3 f = bsdf.fImpl(s.woLocal, wiLocal, s.me);
   if (length2(f) == 0.0f) return false;
   // unoccluded(), :135-148
-  const V3 to = ls.p - nee.p;
-  rq.o = nee.p;
+  const V3 to = ls.p - s.p;
+  rq.o = s.p;
   rq.d = normalized(to);
   rq.tMax = length(to) - 0.001f;
-  const float pdfBSDF = bsdf.pdfImpl(nee.woLocal, wiLocal, nee.me);
+  const float pdfBSDF = bsdf.pdfImpl(s.woLocal, wiLocal, s.me);
   float pdfLight = pick.p * ls.pdf / absDot(ls.n, ls.wi);
-  if (light.type == YC_LIGHT_AREA) pdfLight *= length2(nee.p - ls.p);
+  if (light.type == YC_LIGHT_AREA) pdfLight *= length2(s.p - ls.p);
   rq.lif = ls.Li * f;
-  rq.absDotN = absDot(ls.wi, nee.n);
+  rq.absDotN = absDot(ls.wi, s.n);
   rq.denom = pdfBSDF + pdfLight;
-  rq.att = nee.att;
+  rq.att = att;
   return true;
 }
 
-// Both halves back to back (the per-path tail kernel).  Returns kShade* bits; `rq` is filled when kShadeShadow is set.
+// The three pieces back to back (the per-path tail kernel).  Returns kShade* bits; `rq` is filled when kShadeShadow is set.
 template <bool DEFER_RR>
 YB_DEV uint32_t shadeStage(const DScene& sc, const WaveParams& w, const PathState& ps, uint32_t i, ShadowRequest& rq,
                            uint32_t& raysReference) {
@@ -380,9 +401,11 @@ YB_DEV uint32_t shadeStage(const DScene& sc, const WaveParams& w, const PathStat
     shadeMissStage(sc, w, ps, i, raysReference);
     return 0u;
   }
-  NeeRecord nee;
-  uint32_t result = shadeSurface<DEFER_RR>(sc, w, ps, i, nee, raysReference);
-  if ((result & kShadeNee) && shadeNee(sc, w, i, nee, rq)) result |= kShadeShadow;
+  const SurfRecord s = resolveSurface(sc, ps, i);
+  V3 neeAtt;
+  uint32_t neeDim = 0;
+  uint32_t result = sampleSurface<DEFER_RR>(sc, w, ps, i, s, neeAtt, neeDim, raysReference);
+  if ((result & kShadeNee) && shadeNee(sc, w, i, s, neeAtt, neeDim, rq)) result |= kShadeShadow;
   return result & (kShadeContinue | kShadeShadow);
 }
 

@@ -60,6 +60,15 @@ inline const char* d2hAsync(Stream&, void* d, const void* s, size_t n) {
 }
 inline float eventElapsedMs(Event& a, Event& b) { return std::chrono::duration<float, std::milli>(b.t - a.t).count(); }
 inline const char* lastError() { return nullptr; }
+// peer memory: the CPU build's "devices" are one address space, and there is nothing to map across processes
+constexpr size_t kIpcHandleBytes = 64;
+inline const char* ipcExport(void*, void* handle) {
+  memset(handle, 0, kIpcHandleBytes);
+  return nullptr;
+}
+inline const char* ipcImport(void**, const void*) { return "no cross-process device memory in the CPU build"; }
+inline void ipcClose(void*) {}
+inline const char* enablePeer(int, int) { return nullptr; }
 
 template <int MIN_BLOCKS = 1, class F>
 inline void launchFor(Stream&, uint32_t n, const F& f) {
@@ -137,6 +146,34 @@ inline float eventElapsedMs(Event& a, Event& b) {
   return ms;
 }
 inline const char* lastError() { return errstr(cudaGetLastError()); }
+// Peer memory (comm.cuh: finished pixels are stored straight into the root GPU's frame over NVLink).  A cudaMalloc
+// block is exported as an opaque handle, imported by another PROCESS (mapping enables peer access), or — for another
+// device of the same process — reached through plain peer access.
+constexpr size_t kIpcHandleBytes = sizeof(cudaIpcMemHandle_t);
+inline const char* ipcExport(void* p, void* handle) {
+  return errstr(cudaIpcGetMemHandle(static_cast<cudaIpcMemHandle_t*>(handle), p));
+}
+inline const char* ipcImport(void** p, const void* handle) {
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof h);
+  return errstr(cudaIpcOpenMemHandle(p, h, cudaIpcMemLazyEnablePeerAccess));
+}
+inline void ipcClose(void* p) {
+  if (p) cudaIpcCloseMemHandle(p);
+}
+inline const char* enablePeer(int device, int peer) {
+  if (device == peer) return nullptr;
+  int can = 0;
+  cudaError_t e = cudaDeviceCanAccessPeer(&can, device, peer);
+  if (e != cudaSuccess) return cudaGetErrorString(e);
+  if (!can) return "no peer access between the two devices";
+  e = cudaDeviceEnablePeerAccess(peer, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return errstr(e);
+}
 
 // MIN_BLOCKS: resident CTAs per SM the register allocation must allow (occupancy vs registers)
 template <class F, int MIN_BLOCKS>

@@ -34,8 +34,15 @@ using namespace yb;
 #ifndef YB_SHADOW_MIN_BLOCKS
 #define YB_SHADOW_MIN_BLOCKS 7  // 72 registers, no spills (uncapped: 96 registers, 5 CTAs — C2 step 11.5 ms; 7: 10.9; 8 spills: 11.9)
 #endif
-#ifndef YB_SHADE_MIN_BLOCKS
-#define YB_SHADE_MIN_BLOCKS 8  // 8 x 256 threads per SM (32 registers + local-memory spills): shading is latency-bound, resident warps beat registers (CTAs/SM 2: 35.6, 4: 33.7, 6: 32.4-34.5, 8: 32.3-34.0 ms on the Sponza-shaped step)
+// Resident CTAs (x 256 threads) per SM the three shading kernels are compiled for (registers = 65536 / 256 / CTAs)
+#ifndef YB_RESOLVE_MIN_BLOCKS
+#define YB_RESOLVE_MIN_BLOCKS 4
+#endif
+#ifndef YB_SAMPLE_MIN_BLOCKS
+#define YB_SAMPLE_MIN_BLOCKS 4
+#endif
+#ifndef YB_NEE_MIN_BLOCKS
+#define YB_NEE_MIN_BLOCKS 4
 #endif
 
 // ---------------------------------------------------------------------------------------
@@ -52,7 +59,7 @@ struct Lane {
   rt::Stream st;       // lane 0 shares the context's main stream
   PathState ps{};      // ps.L points at Lbuf[lSel] while a chunk is in flight
   ShadowQueue sq{};
-  NeeState ns{};
+  SurfState ss{};
   uint32_t *qA = nullptr, *qH = nullptr, *qM = nullptr, *qN = nullptr, *ctr = nullptr;  // cur/next, hit, miss, NEE queues; counters
   uint32_t* hCtr = nullptr;  // page-locked copy of the counters
   void* spill = nullptr;     // traversal-stack spill area of the persistent kernels
@@ -115,6 +122,7 @@ struct yc_ctx {
   double shadeMs = 0, commMs = 0;
   uint64_t shadeLaunches = 0, hitsShaded = 0;
   bool timeShade = false;
+  bool oneLane = false;  // profiling: chunks one after the other on lane 0, so that a launch's event time is its own
   uint64_t launches = 0;
   double gpuMs = 0, extendMs = 0;
   uint64_t extendLaunches = 0, raysExtend = 0;
@@ -182,17 +190,29 @@ struct RaygenK {
   }
 };
 
-// Surface shading over the HIT queue extend produced (count on the device: the launch is sized for the
-// upper bound and surplus threads leave at once), in two kernels (integrator.cuh: shadeSurface / shadeNee) so
-// that neither outgrows the instruction cache: the first appends the surviving paths to the next queue and the
-// paths that take a NEE sample, with their NeeRecord, to the NEE queue; the second turns NEE records into shadow
-// requests.
+// Surface shading over the HIT queue extend produced (count on the device: the launches are sized for the upper
+// bound and surplus threads leave at once), in three kernels (integrator.cuh: resolveSurface / sampleSurface /
+// shadeNee): the first gathers each hit's surface into a SurfRecord at the hit's queue position, the second samples
+// the BSDF from it and appends the surviving paths to the next queue and the hits that take a NEE sample to the NEE
+// queue, the third turns those into shadow requests.
+struct ResolveK {
+  DScene sc;
+  PathState ps;
+  SurfState ss;
+  const uint32_t* queue;
+  const uint32_t* ctr;
+  YB_DEV void operator()(uint32_t j) const {
+    if (j >= ctr[kCtrHitCount]) return;
+    storeSurf(ss, j, resolveSurface(sc, ps, queue[j]));
+  }
+};
+
 template <bool DEFER_RR>
-struct ShadeSurfaceK {
+struct SampleK {
   DScene sc;
   WaveParams w;
   PathState ps;
-  NeeState ns;
+  SurfState ss;
   const uint32_t* queue;
   uint32_t *nextQueue, *neeQueue;
   uint32_t* ctr;
@@ -200,14 +220,14 @@ struct ShadeSurfaceK {
   YB_DEV void operator()(uint32_t j) const {
     if (j >= ctr[kCtrHitCount]) return;
     const uint32_t i = queue[j];
-    NeeRecord nee;
-    uint32_t rays = 0;
-    const uint32_t r = shadeSurface<DEFER_RR>(sc, w, ps, i, nee, rays);
+    V3 neeAtt;
+    uint32_t neeDim = 0, rays = 0;
+    const uint32_t r = sampleSurface<DEFER_RR>(sc, w, ps, i, loadSurf(ss, j), neeAtt, neeDim, rays);
     aggregatedCount(&counters->raysReference, rays);
     if (r & kShadeContinue) nextQueue[aggregatedAppend(ctr + kCtrNextCount)] = i;
     if (r & kShadeNee) {
-      storeNee(ns, i, nee);
-      neeQueue[aggregatedAppend(ctr + kCtrNeeCount)] = i;
+      ss.r7[j] = make_float4(neeAtt.x, neeAtt.y, neeAtt.z, __uint_as_float(neeDim));
+      neeQueue[aggregatedAppend(ctr + kCtrNeeCount)] = j;
     }
   }
 };
@@ -215,20 +235,22 @@ struct ShadeSurfaceK {
 struct ShadeNeeK {
   DScene sc;
   WaveParams w;
-  NeeState ns;
+  SurfState ss;
   ShadowQueue sq;
-  const uint32_t* neeQueue;
+  const uint32_t *queue, *neeQueue;  // hit queue (position → path), NEE queue (positions in the hit queue)
   uint32_t* ctr;
-  YB_DEV void operator()(uint32_t j) const {
-    if (j >= ctr[kCtrNeeCount]) return;
-    const uint32_t i = neeQueue[j];
+  YB_DEV void operator()(uint32_t k) const {
+    if (k >= ctr[kCtrNeeCount]) return;
+    const uint32_t j = neeQueue[k];
+    const uint32_t i = queue[j];
+    const float4 x = ss.r7[j];
     ShadowRequest rq;
-    if (shadeNee(sc, w, i, loadNee(ns, i), rq)) {
-      const uint32_t k = aggregatedAppend(ctr + kCtrShadowCount);
-      sq.o[k] = make_float4(rq.o.x, rq.o.y, rq.o.z, rq.tMax);
-      sq.d[k] = make_float4(rq.d.x, rq.d.y, rq.d.z, rq.absDotN);
-      sq.lif[k] = make_float4(rq.lif.x, rq.lif.y, rq.lif.z, rq.denom);
-      sq.att[k] = make_float4(rq.att.x, rq.att.y, rq.att.z, __uint_as_float(i));
+    if (shadeNee(sc, w, i, loadSurf(ss, j), V3(x.x, x.y, x.z), __float_as_uint(x.w), rq)) {
+      const uint32_t q = aggregatedAppend(ctr + kCtrShadowCount);
+      sq.o[q] = make_float4(rq.o.x, rq.o.y, rq.o.z, rq.tMax);
+      sq.d[q] = make_float4(rq.d.x, rq.d.y, rq.d.z, rq.absDotN);
+      sq.lif[q] = make_float4(rq.lif.x, rq.lif.y, rq.lif.z, rq.denom);
+      sq.att[q] = make_float4(rq.att.x, rq.att.y, rq.att.z, __uint_as_float(i));
     }
   }
 };
@@ -294,6 +316,7 @@ struct FinalizeK {
   float4* buckets;
   size_t planeStride;
   float4 *hdr, *ldr;
+  float4 *hdrRoot, *ldrRoot;  // tile sharding over GPUs that reach the root's memory (comm.cuh): the combined frames, else null
   uint32_t width, m, estimator, waveSamples, tonemap;
   float wCurrent, wWave;
   YB_DEV void operator()(uint32_t p) const {
@@ -316,12 +339,27 @@ struct FinalizeK {
     h.z = cur.z * wCurrent + wave.z * wWave;
     h.w = cur.w * wCurrent + 1.0f * wWave;
     hdr[idx] = h;
-    if (tonemap == YC_TONEMAP_NONE) {
-      ldr[idx] = h;
-    } else {
+    float4 l = h;
+    if (tonemap != YC_TONEMAP_NONE) {
       const V3 t = agx(V3(h.x, h.y, h.z), agxLook(tonemap));
-      ldr[idx] = make_float4(t.x, t.y, t.z, 1.0f);
+      l = make_float4(t.x, t.y, t.z, 1.0f);
     }
+    ldr[idx] = l;
+    if (hdrRoot) hdrRoot[idx] = h, ldrRoot[idx] = l;  // stores over NVLink when the root is another GPU
+  }
+};
+
+// Tile sharding, direct delivery: this shard's pixels of the own frames into the root's combined frames (the first
+// wave after the frames were mapped, or after a wave that finalized only part of the shard).
+struct PushFramesK {
+  const uint32_t* pixelList;
+  const float4 *hdr, *ldr;
+  float4 *hdrRoot, *ldrRoot;
+  uint32_t width;
+  YB_DEV void operator()(uint32_t p) const {
+    const uint32_t pix = pixelList[p];
+    const size_t idx = size_t(pix >> 16) * width + (pix & 0xffffu);
+    hdrRoot[idx] = hdr[idx], ldrRoot[idx] = ldr[idx];
   }
 };
 
@@ -857,13 +895,7 @@ static int ensureWaveStorage(yc_ctx* ctx) {
     YC_TRY(devAlloc(own, &L.qH, P));
     YC_TRY(devAlloc(own, &L.qM, P));
     YC_TRY(devAlloc(own, &L.qN, P));
-    YC_TRY(devAlloc(own, &L.ns.r0, P));
-    YC_TRY(devAlloc(own, &L.ns.r1, P));
-    YC_TRY(devAlloc(own, &L.ns.r2, P));
-    YC_TRY(devAlloc(own, &L.ns.r3, P));
-    YC_TRY(devAlloc(own, &L.ns.r4, P));
-    YC_TRY(devAlloc(own, &L.ns.r5, P));
-    YC_TRY(devAlloc(own, &L.ns.r6, P));
+    for (float4** r : {&L.ss.r0, &L.ss.r1, &L.ss.r2, &L.ss.r3, &L.ss.r4, &L.ss.r5, &L.ss.r6, &L.ss.r7}) YC_TRY(devAlloc(own, r, P));
     YC_TRY(devAlloc(own, &L.ctr, size_t(kCtrCount)));
     YC_TRY(rt::zero(ctx->st, L.ctr, kCtrCount * sizeof(uint32_t)));
     void* hp = nullptr;
@@ -1020,12 +1052,13 @@ static int issueBounce(yc_ctx* ctx, Lane& L) {
     sev = &ctx->shadeEvents[ctx->shadeEventsUsed++];
     rt::eventRecord(L.st, sev->first);
   }
-  rt::launchFor<YB_SHADE_MIN_BLOCKS>(L.st, n, ShadeSurfaceK<ALPHA>{ctx->ds, L.w, L.ps, L.ns, L.qH, L.qA, L.qN, L.ctr, ctx->dCounters});
+  rt::launchFor<YB_RESOLVE_MIN_BLOCKS>(L.st, n, ResolveK{ctx->ds, L.ps, L.ss, L.qH, L.ctr});
+  rt::launchFor<YB_SAMPLE_MIN_BLOCKS>(L.st, n, SampleK<ALPHA>{ctx->ds, L.w, L.ps, L.ss, L.qH, L.qA, L.qN, L.ctr, ctx->dCounters});
+  rt::launchFor<YB_NEE_MIN_BLOCKS>(L.st, n, ShadeNeeK{ctx->ds, L.w, L.ss, L.sq, L.qH, L.qN, L.ctr});
   if (sev) rt::eventRecord(L.st, sev->second);
-  rt::launchFor<YB_SHADE_MIN_BLOCKS>(L.st, n, ShadeNeeK{ctx->ds, L.w, L.ns, L.sq, L.qN, L.ctr});
   if (ctx->countTraversal) runShadow<ALPHA, true>(ctx, L, n);
   else runShadow<ALPHA, false>(ctx, L, n);
-  ctx->launches += 6;
+  ctx->launches += 7;
   ctx->raysExtend += n;  // every queue entry is one closest-hit ray
   if (L.bounce + 1 < ctx->opts.maxDepth) {
     YC_TRY(rt::d2hAsync(L.st, L.hCtr, L.ctr, kCtrCount * sizeof(uint32_t)));
@@ -1155,11 +1188,12 @@ static int renderChunks(yc_ctx* ctx, const uint32_t* dList, uint32_t nPixCall, u
   };
 
   size_t next = 0, nextAcc = 0;
+  const int lanesUsed = ctx->oneLane ? 1 : kLanes;
   rt::Event* lastAcc = nullptr;
   while (nextAcc < chunks.size()) {
     if (abortRequested()) return abortNow();
     // start chunks on idle lanes whose next radiance buffer is free (its previous chunk's accumulate is at least launched)
-    for (int l = 0; l < kLanes && next < chunks.size(); l++) {
+    for (int l = 0; l < lanesUsed && next < chunks.size(); l++) {
       Lane& L = ctx->lanes[l];
       if (L.active || L.accPending[L.lSel]) continue;
       const Chunk& c = chunks[next];
@@ -1207,7 +1241,7 @@ static int renderChunks(yc_ctx* ctx, const uint32_t* dList, uint32_t nPixCall, u
     if (nextAcc >= chunks.size()) break;
     if (next < chunks.size()) {
       bool canStart = false;
-      for (int l = 0; l < kLanes; l++) canStart |= !ctx->lanes[l].active && !ctx->lanes[l].accPending[ctx->lanes[l].lSel];
+      for (int l = 0; l < lanesUsed; l++) canStart |= !ctx->lanes[l].active && !ctx->lanes[l].accPending[ctx->lanes[l].lSel];
       if (canStart) continue;  // a lane (or its buffer) was freed: give it the next chunk before blocking
     }
     // service whichever waiting lane's counters arrive first: they size its next bounce
@@ -1309,17 +1343,35 @@ static void finalizeWave(yc_ctx* ctx, const uint32_t* dList, uint32_t nPixCall, 
   const YcFrameDesc& f = ctx->frame;
   const uint32_t takenAfter = takenBefore + waveSamples;
   const float wCurrent = float(takenBefore) / float(takenAfter), wWave = float(waveSamples) / float(takenAfter);
+  float4 *hdrRoot = nullptr, *ldrRoot = nullptr;
+  if (ctx->comm && ctx->comm->direct) {
+    Comm& c = *ctx->comm;
+    // the copy the next yc_comm_reduce_frames publishes (noteWave has marked it stale if this wave is a partial one)
+    if (dList == ctx->dPixels && !c.stale && c.frameTexels == size_t(f.width) * f.height) hdrRoot = c.hdrAll[c.epoch & 1u], ldrRoot = c.ldrAll[c.epoch & 1u];
+  }
   rt::launchFor(ctx->st, nPixCall,
-                FinalizeK{dList, ctx->dBuckets, ctx->bucketCapacity, ctx->dHdr, ctx->dLdr, f.width, waveBuckets(f, waveSamples),
-                          f.estimator, waveSamples, f.tonemap, wCurrent, wWave});
+                FinalizeK{dList, ctx->dBuckets, ctx->bucketCapacity, ctx->dHdr, ctx->dLdr, hdrRoot, ldrRoot, f.width,
+                          waveBuckets(f, waveSamples), f.estimator, waveSamples, f.tonemap, wCurrent, wWave});
   ctx->launches++;
   if (dList == ctx->dPixels) ctx->bucketsDirty = false;  // every plane this shard touches was read and zeroed
+}
+
+// Bookkeeping for the direct frame delivery of comm.cuh, from the ARGUMENTS of a finalizing call only — every
+// participant makes the same calls, whether or not its shard has pixels in the rectangle, so all of them take the same
+// decisions in the next yc_comm_reduce_frames (a collective must be entered by all or none).
+static void noteWave(yc_ctx* ctx, YcRect px) {
+  if (!ctx->comm) return;
+  Comm& c = *ctx->comm;
+  c.barrierSinceFinalize = false;
+  const YcFrameDesc& f = ctx->frame;
+  if (!(px.x == 0 && px.y == 0 && px.w == f.width && px.h == f.height) || c.frameTexels != size_t(f.width) * f.height) c.stale = true;
 }
 
 extern "C" int yc_render_wave(yc_ctx* ctx, YcRect px, uint32_t sampleOffset, uint32_t waveSamples, uint32_t takenBefore) {
   if (!ctx) return YC_ERR_INVALID;
   rt::useDevice(ctx->device);
   if (!ctx->inFrame) return fail(ctx, YC_ERR_STATE, "yc_render_wave before yc_begin_frame");
+  noteWave(ctx, px);
   if (waveSamples == 0 || px.w == 0 || px.h == 0) return YC_OK;
   const uint32_t* dList;
   uint32_t nPixCall;
@@ -1353,6 +1405,7 @@ extern "C" int yc_finalize_wave(yc_ctx* ctx, YcRect px, uint32_t waveSamples, ui
   if (!ctx) return YC_ERR_INVALID;
   rt::useDevice(ctx->device);
   if (!ctx->inFrame) return fail(ctx, YC_ERR_STATE, "yc_finalize_wave before yc_begin_frame");
+  noteWave(ctx, px);
   if (waveSamples == 0 || px.w == 0 || px.h == 0) return YC_OK;
   const uint32_t* dList;
   uint32_t nPixCall;
@@ -1438,6 +1491,7 @@ extern "C" int yc_set_profiling(yc_ctx* ctx, int timeExtendKernel) {
   ctx->timeExtend = (timeExtendKernel & 1) != 0;
   ctx->countTraversal = (timeExtendKernel & 2) != 0;  // counting builds of extend / shadow (box / triangle tests)
   ctx->timeShade = (timeExtendKernel & 4) != 0;
+  ctx->oneLane = (timeExtendKernel & 8) != 0;
   return YC_OK;
 }
 
@@ -1782,8 +1836,8 @@ static void destroyComm(yc_ctx* ctx) {
 #ifndef YB_HOSTSIM
   if (c.nccl) nccl().CommDestroy(c.nccl);
 #endif
-  rt::release(c.hdrAll);
-  rt::release(c.ldrAll);
+  rt::ipcClose(c.imported);
+  rt::release(c.block);
   rt::release(c.scratch);
   ctx->comm.reset();
 }
@@ -1842,6 +1896,13 @@ extern "C" int yc_comm_init_all(yc_ctx** ctxs, int n) {
 #endif
     if (shared) {
       if (n > kGroupMax) return fail(ctxs[0], YC_ERR_INVALID, "at most %d contexts in an in-process group", kGroupMax);
+      // the group's sums read every participant's buffer from one device: distinct devices need peer access
+      for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++) {
+          rt::useDevice(ctxs[i]->device);
+          if (const char* e = rt::enablePeer(ctxs[i]->device, ctxs[j]->device))
+            return fail(ctxs[0], YC_ERR_UNSUPPORTED, "in-process group over devices %d and %d: %s", ctxs[i]->device, ctxs[j]->device, e);
+        }
       auto group = std::make_shared<HostGroup>();
       group->n = n;
       for (int i = 0; i < n; i++) {
@@ -1929,6 +1990,81 @@ static int commSum(yc_ctx* ctx, void* buf, size_t count, int dtype, int root) {
 #endif
 }
 
+// Sum of n (<= 64) host values over all participants, in place.
+static int commSumHost(yc_ctx* ctx, uint64_t* values, uint32_t n) {
+  Comm& c = *ctx->comm;
+  if (!c.scratch) {
+    void* p = nullptr;
+    YC_TRY(rt::alloc(&p, 64 * sizeof(uint64_t)));
+    c.scratch = static_cast<uint64_t*>(p);
+  }
+  YC_TRY(rt::h2d(ctx->st, c.scratch, values, n * sizeof(uint64_t)));
+  const int rc = commSum(ctx, c.scratch, n, kCommU64, -1);
+  if (rc != YC_OK) return rc;
+  YC_TRY(rt::d2h(ctx->st, values, c.scratch, n * sizeof(uint64_t)));
+  c.barrierSinceFinalize = true;
+  return YC_OK;
+}
+
+// (Re)creates the root's combined frames for the current frame size and finds out — collectively — whether every
+// participant can address them (Comm::direct).  The root hands out {process id, device, address, exported handle} as a
+// sum in which everybody else contributes zeros.
+static int mapCombinedFrames(yc_ctx* ctx, int root, size_t texels) {
+  Comm& c = *ctx->comm;
+  rt::ipcClose(c.imported);
+  c.imported = nullptr;
+  rt::release(c.block);
+  c.block = nullptr;
+  for (int k = 0; k < 2; k++) c.hdrAll[k] = c.ldrAll[k] = nullptr;
+  c.frameTexels = texels, c.root = root, c.direct = false, c.stale = true, c.epoch = 0, c.cur = 0;
+  const bool isRoot = c.rank == root;
+  if (isRoot) {
+    void* p = nullptr;
+    YC_TRY(rt::alloc(&p, 4 * texels * sizeof(float4)));
+    c.block = static_cast<float4*>(p);
+    YC_TRY(rt::zero(ctx->st, c.block, 4 * texels * sizeof(float4)));
+    YC_TRY(rt::sync(ctx->st));
+  }
+  auto carve = [&](float4* base) {
+    for (int k = 0; k < 2; k++) c.hdrAll[k] = base + size_t(2 * k) * texels, c.ldrAll[k] = base + size_t(2 * k + 1) * texels;
+  };
+  if (isRoot) carve(c.block);
+  if (c.world == 1 || c.custom) return YC_OK;  // the caller's collective: nothing is known about the other side's memory
+
+  constexpr uint32_t kWords = 3 + uint32_t((rt::kIpcHandleBytes + 7) / 8);
+  static_assert(kWords <= 64, "payload must fit the staging buffer");
+  uint64_t msg[kWords] = {};
+  if (isRoot) {
+    msg[0] = uint64_t(getpid()), msg[1] = uint64_t(ctx->device), msg[2] = uint64_t(reinterpret_cast<uintptr_t>(c.block));
+    if (rt::ipcExport(c.block, &msg[3])) memset(&msg[3], 0, rt::kIpcHandleBytes), rt::lastError();
+  }
+  if (const int rc = commSumHost(ctx, msg, kWords)) return rc;
+  uint64_t failed = 0;
+  if (!isRoot) {
+    float4* base = nullptr;
+    if (msg[0] == uint64_t(getpid())) {  // another context of this process: plain peer access
+      if (rt::enablePeer(ctx->device, int(msg[1]))) failed = 1, rt::lastError();
+      else base = reinterpret_cast<float4*>(uintptr_t(msg[2]));
+    } else {
+      void* p = nullptr;
+      if (rt::ipcImport(&p, &msg[3])) failed = 1, rt::lastError();
+      else c.imported = p, base = static_cast<float4*>(p);
+    }
+    if (base) carve(base);
+  }
+  // YART_B200_FRAMES_REDUCE=1 (set for every participant) forces the summing path: for A/B measurements
+  if (const char* e = getenv("YART_B200_FRAMES_REDUCE"))
+    if (*e && *e != '0') failed = 1;
+  if (const int rc = commSumHost(ctx, &failed, 1)) return rc;
+  c.direct = failed == 0;
+  if (!c.direct && !isRoot) {
+    rt::ipcClose(c.imported);
+    c.imported = nullptr;
+    for (int k = 0; k < 2; k++) c.hdrAll[k] = c.ldrAll[k] = nullptr;
+  }
+  return YC_OK;
+}
+
 extern "C" int yc_comm_reduce_frames(yc_ctx* ctx, int root) {
   if (!ctx) return YC_ERR_INVALID;
   rt::useDevice(ctx->device);
@@ -1937,24 +2073,49 @@ extern "C" int yc_comm_reduce_frames(yc_ctx* ctx, int root) {
   Comm& c = *ctx->comm;
   if (root < 0 || root >= c.world) return fail(ctx, YC_ERR_INVALID, "bad root");
   const size_t texels = size_t(ctx->frame.width) * ctx->frame.height;
-  if (c.frameTexels != texels) {
-    rt::release(c.hdrAll);
-    rt::release(c.ldrAll);
-    c.hdrAll = c.ldrAll = nullptr;
-    void* p = nullptr;
-    YC_TRY(rt::alloc(&p, texels * sizeof(float4)));
-    c.hdrAll = static_cast<float4*>(p);
-    YC_TRY(rt::alloc(&p, texels * sizeof(float4)));
-    c.ldrAll = static_cast<float4*>(p);
-    c.frameTexels = texels;
+  if (c.frameTexels != texels || c.root != root) {
+    if (const int rc = mapCombinedFrames(ctx, root, texels)) return rc;
   }
-  // out of place: the context's own frames keep blending its tiles in later waves
   rt::eventRecord(ctx->st, ctx->ev0);
-  YC_TRY(rt::d2d(ctx->st, c.hdrAll, ctx->dHdr, texels * sizeof(float4)));
-  YC_TRY(rt::d2d(ctx->st, c.ldrAll, ctx->dLdr, texels * sizeof(float4)));
-  int rc = commSum(ctx, c.hdrAll, texels * 4, kCommF32, root);
-  if (rc == YC_OK) rc = commSum(ctx, c.ldrAll, texels * 4, kCommF32, root);
-  if (rc != YC_OK) return rc;
+  if (c.direct) {
+    // Every finished pixel is already in the root's copy `epoch & 1` (FinalizeK stored it there), unless this context
+    // has to catch up.  What is left is the guarantee that everybody's stores have landed: one small collective on
+    // the streams that ran the finalize kernels — or none, if the caller has run one since (yc_comm_sum_u64).
+    const int k = int(c.epoch & 1u);
+    bool barrier = !c.barrierSinceFinalize;
+    if (c.stale) {
+      rt::launchFor(ctx->st, uint32_t(ctx->pixels.size()),
+                    PushFramesK{ctx->dPixels, ctx->dHdr, ctx->dLdr, c.hdrAll[k], c.ldrAll[k], ctx->frame.width});
+      ctx->launches++;
+      c.stale = false;
+      barrier = true;
+    }
+    if (barrier) {
+      uint64_t one = 1;
+      if (const int rc = commSumHost(ctx, &one, 1)) return rc;
+    }
+    c.barrierSinceFinalize = false;
+    c.cur = k;
+    c.epoch++;
+  } else {
+    // out of place: the context's own frames keep blending its tiles in later waves
+    float4 *hdr = c.hdrAll[0], *ldr = c.ldrAll[0];
+    if (c.rank != root) {
+      // a non-root participant of a summing transport needs a send buffer of its own
+      if (!c.block) {
+        void* p = nullptr;
+        YC_TRY(rt::alloc(&p, 2 * texels * sizeof(float4)));
+        c.block = static_cast<float4*>(p);
+      }
+      hdr = c.block, ldr = c.block + texels;
+    }
+    YC_TRY(rt::d2d(ctx->st, hdr, ctx->dHdr, texels * sizeof(float4)));
+    YC_TRY(rt::d2d(ctx->st, ldr, ctx->dLdr, texels * sizeof(float4)));
+    int rc = commSum(ctx, hdr, texels * 4, kCommF32, root);
+    if (rc == YC_OK) rc = commSum(ctx, ldr, texels * 4, kCommF32, root);
+    if (rc != YC_OK) return rc;
+    c.cur = 0;
+  }
   rt::eventRecord(ctx->st, ctx->ev1);
   YC_TRY(rt::sync(ctx->st));
   YC_TRY(rt::lastError());
@@ -1962,13 +2123,22 @@ extern "C" int yc_comm_reduce_frames(yc_ctx* ctx, int root) {
   return YC_OK;
 }
 
+extern "C" int yc_comm_frames_direct(yc_ctx* ctx, int* direct) {
+  if (!ctx || !direct) return YC_ERR_INVALID;
+  if (!ctx->comm) return fail(ctx, YC_ERR_STATE, "yc_comm_frames_direct without a communicator");
+  *direct = ctx->comm->direct ? 1 : 0;
+  return YC_OK;
+}
+
 extern "C" int yc_resolve_combined(yc_ctx* ctx, float* hdrRGBA, float* ldrRGBA) {
   if (!ctx) return YC_ERR_INVALID;
   rt::useDevice(ctx->device);
-  if (!ctx->comm || !ctx->comm->hdrAll) return fail(ctx, YC_ERR_STATE, "yc_resolve_combined before yc_comm_reduce_frames");
-  const size_t bytes = ctx->comm->frameTexels * sizeof(float4);
-  if (hdrRGBA) YC_TRY(rt::d2h(ctx->st, hdrRGBA, ctx->comm->hdrAll, bytes));
-  if (ldrRGBA) YC_TRY(rt::d2h(ctx->st, ldrRGBA, ctx->comm->ldrAll, bytes));
+  if (!ctx->comm || ctx->comm->root != ctx->comm->rank || !ctx->comm->hdrAll[0])
+    return fail(ctx, YC_ERR_STATE, "yc_resolve_combined: not the root of a completed yc_comm_reduce_frames");
+  const Comm& c = *ctx->comm;
+  const size_t bytes = c.frameTexels * sizeof(float4);
+  if (hdrRGBA) YC_TRY(rt::d2h(ctx->st, hdrRGBA, c.hdrAll[c.cur], bytes));
+  if (ldrRGBA) YC_TRY(rt::d2h(ctx->st, ldrRGBA, c.ldrAll[c.cur], bytes));
   return YC_OK;
 }
 
@@ -1992,17 +2162,7 @@ extern "C" int yc_comm_sum_u64(yc_ctx* ctx, uint64_t* values, uint32_t n) {
   if (!ctx || !values || n == 0 || n > 64) return YC_ERR_INVALID;
   rt::useDevice(ctx->device);
   if (!ctx->comm) return fail(ctx, YC_ERR_STATE, "yc_comm_sum_u64 without a communicator");
-  Comm& c = *ctx->comm;
-  if (!c.scratch) {
-    void* p = nullptr;
-    YC_TRY(rt::alloc(&p, 64 * sizeof(uint64_t)));
-    c.scratch = static_cast<uint64_t*>(p);
-  }
-  YC_TRY(rt::h2d(ctx->st, c.scratch, values, n * sizeof(uint64_t)));
-  const int rc = commSum(ctx, c.scratch, n, kCommU64, -1);
-  if (rc != YC_OK) return rc;
-  YC_TRY(rt::d2h(ctx->st, values, c.scratch, n * sizeof(uint64_t)));
-  return YC_OK;
+  return commSumHost(ctx, values, n);
 }
 
 #include "kat.cuh"
