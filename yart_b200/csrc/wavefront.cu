@@ -2091,8 +2091,14 @@ extern "C" int yc_comm_reduce_frames(yc_ctx* ctx, int root) {
       barrier = true;
     }
     if (barrier) {
-      uint64_t one = 1;
-      if (const int rc = commSumHost(ctx, &one, 1)) return rc;
+      // the smallest collective there is, on the stream, no host values involved (the staging word's content is irrelevant)
+      if (!c.scratch) {
+        void* p = nullptr;
+        YC_TRY(rt::alloc(&p, 64 * sizeof(uint64_t)));
+        c.scratch = static_cast<uint64_t*>(p);
+        YC_TRY(rt::zero(ctx->st, c.scratch, 64 * sizeof(uint64_t)));
+      }
+      if (const int rc = commSum(ctx, c.scratch, 1, kCommU64, -1)) return rc;
     }
     c.barrierSinceFinalize = false;
     c.cur = k;
