@@ -244,10 +244,10 @@ def workload_record(Y, name: str, local: int, trav: int, spp: int, steps: int) -
         ctx.set_profiling(1)
         ctx.begin_frame(W, H, spp * (steps + 3 + 2), 64, (0, 0, 0), Y.TONEMAP_AGX)
         for k in range(3):
-            ctx.render_wave(k * spp, spp, k * spp)
-        s0 = ctx.stats()
+            ctx.render_wave_async(k * spp, spp, k * spp)
+        s0 = ctx.stats()  # (waits for the waves in flight)
         for k in range(3, 3 + steps):
-            ctx.render_wave(k * spp, spp, k * spp)
+            ctx.render_wave_async(k * spp, spp, k * spp)
         s1 = ctx.stats()
         # the shading kernels' own duration: two more waves with one chunk in flight instead of two (profiling bit 3), so
         # that the CUDA events around ResolveK + SampleK + ShadeNeeK do not also span the other lane's traversal kernels
@@ -262,7 +262,7 @@ def workload_record(Y, name: str, local: int, trav: int, spp: int, steps: int) -
         ctx.render_wave(0, big, 0)
         b0 = ctx.stats()
         for k in range(1, 1 + nbig):
-            ctx.render_wave(k * big, big, k * big)
+            ctx.render_wave_async(k * big, big, k * big)
         b1 = ctx.stats()
         wave32 = {"spp_per_step": big, "steps": nbig, "ms_per_step": (b1.gpuMs - b0.gpuMs) / nbig,
                   "value": (b1.raysReference - b0.raysReference) / (b1.gpuMs - b0.gpuMs) / 1e3, "unit": "Mrays/s",
@@ -326,6 +326,7 @@ def run_ours(args):
         return box[0]
 
     def sync_all():
+        ctx.wave_sync()  # waves left in flight by yc_render_wave_async
         if dist:
             import torch
             torch.cuda.synchronize()
@@ -375,9 +376,12 @@ def run_ours(args):
                 ctx.comm_allreduce_buckets(S)
                 ctx.finalize_wave(S, k * S)
             else:
-                ctx.render_wave(k * S, S, k * S)
+                # consecutive waves of one progressive frame are left in flight (yc_render_wave_async): the next wave's
+                # chunks start while this wave's tails, bucket sums, finalize kernel and — with several GPUs — its
+                # barrier still run; sync_all() below waits for all of them inside the timed region
+                ctx.render_wave_async(k * S, S, k * S)
                 if dist:
-                    ctx.comm_reduce_frames(0)
+                    ctx.comm_reduce_frames_async(0)
 
         for k in range(warm):
             step(k)

@@ -324,6 +324,14 @@ int yc_begin_frame(yc_ctx* ctx, const YcFrameDesc* frame);
  * (takenBefore = samples already blended) and tonemaps. */
 int yc_render_wave(yc_ctx* ctx, YcRect pixels, uint32_t sampleOffset, uint32_t waveSamples,
                    uint32_t takenBefore);
+/* The same wave, left in flight: the call returns once the wave's last chunk has been handed to the GPU, and the next
+ * yc_render_wave_async starts its chunks while this wave's per-path tails, bucket sums and finalize kernel still run
+ * (the results are the same bits: accumulation stays in sample order and a wave's finalize precedes the next wave's
+ * first bucket sum).  yc_wave_sync — or any other entry point — waits for the waves in flight; the frames, statistics
+ * and device times (YcStats.gpuMs: first unsettled wave's start → last one's end) are complete after that. */
+int yc_render_wave_async(yc_ctx* ctx, YcRect pixels, uint32_t sampleOffset, uint32_t waveSamples,
+                         uint32_t takenBefore);
+int yc_wave_sync(yc_ctx* ctx);
 /* The same wave in two steps, for sample sharding across GPUs (SURVEY §8e alternative B; north_star:
  * "per-GPU ... median-of-means and GMoN accumulation buffers are combined with NCCL"):
  *   yc_accumulate_wave  Integrator::render's sample loop (integrator.cpp:19-24) for this GPU's share of the wave:
@@ -409,6 +417,9 @@ int yc_comm_destroy(yc_ctx* ctx);
  * (none if yc_comm_sum_u64 ran since the wave); otherwise the frames are summed into the root (ncclReduce / the
  * caller's collective).  yc_comm_frames_direct reports which (after the first yc_comm_reduce_frames of a frame size). */
 int yc_comm_reduce_frames(yc_ctx* ctx, int root);
+/* Behind yc_render_wave_async: with direct delivery over NCCL the wave's barrier is enqueued after its finalize kernel
+ * and not waited for (otherwise the same as yc_comm_reduce_frames, waiting included). */
+int yc_comm_reduce_frames_async(yc_ctx* ctx, int root);
 int yc_comm_frames_direct(yc_ctx* ctx, int* direct);
 int yc_resolve_combined(yc_ctx* ctx, float* hdrRGBA, float* ldrRGBA);
 /* Bucket sharding (yc_accumulate_wave): all-reduce(sum, int32) of the planes a wave of `waveSamples` samples uses. */

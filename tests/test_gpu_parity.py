@@ -458,3 +458,41 @@ def test_traversal_stack_spill_path_gives_identical_hits_and_frames(soup_100k):
     cx.render_wave(0, spp, 0)
     hdr, _, st = cx.resolve()
     assert H.bits_equal(hdr, g["hdr"]).all() and st.raysReference == int(g["rays"])
+
+
+@pytest.mark.parametrize("scene,depth,cap", [("material_zoo", 12, 0), ("material_zoo", 12, 20_000), ("cornell", 8, 6_000)])
+def test_waves_left_in_flight_equal_waves_waited_for(scene, depth, cap):
+    """yc_render_wave_async: the next wave's chunks start while the previous wave's tails, bucket sums and finalize
+    still run.  Progressive GMoN waves (deep paths → tail kernels on the side streams; small capacities → many chunks
+    per wave) issued back to back must give the bits of the same waves rendered one at a time, also when a synchronous
+    call (a sub-rectangle wave) is mixed in, and the statistics must agree."""
+    cam = H.scene_camera(scene)
+    sc = Y.Scene(H.scene_file(scene))
+    w, h = 320, 180
+    c = Y.make_camera(w, h, cam["focal"], cam["fnum"], cam["pos"], cam["target"], (0, 0, 0), cam["exposure"])
+    waves = [2, 4, 8, 8, 2, 8]
+    out = []
+    for mode in ("sync", "async"):
+        ctx = Y.Context(max_depth=depth, max_paths=cap, tail_threshold=2048)
+        ctx.upload_scene(sc)
+        ctx.set_camera(c)
+        frames = []
+        for rep in range(2):
+            ctx.begin_frame(w, h, sum(waves) + 2, 32, (0, 0, 0), Y.TONEMAP_AGX)
+            taken = 0
+            for k, wv in enumerate(waves):
+                (ctx.render_wave_async if mode == "async" else ctx.render_wave)(taken, wv, taken)
+                taken += wv
+                if k == 3:  # a synchronous partial wave in the middle: left and right halves, one sample more each
+                    ctx.render_wave(taken, 1, taken, rect=(0, 0, 100, h))
+                    ctx.render_wave(taken, 1, taken, rect=(100, 0, w - 100, h))
+                    taken += 1
+            if mode == "async":
+                ctx.wave_sync()
+            hdr, ldr, st = ctx.resolve()
+            frames.append((hdr, ldr, st.raysReference, st.raysExtend, st.raysShadow))
+        out.append(frames)
+        ctx.close()
+    for (a, b) in zip(out[0], out[1]):
+        assert H.bits_equal(a[0], b[0]).all() and H.bits_equal(a[1], b[1]).all()
+        assert a[2:] == b[2:]

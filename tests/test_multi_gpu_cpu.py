@@ -205,3 +205,30 @@ def test_direct_frame_delivery_in_process_group_with_partial_and_repeated_waves(
     assert len(got) == len(want) == 10
     for k, ((hdr, ldr), (hdr1, ldr1)) in enumerate(zip(got, want)):
         assert H.bits_equal(hdr, hdr1).all() and H.bits_equal(ldr, ldr1).all(), k
+
+
+def test_waves_left_in_flight_state_machine_on_the_cpu_build():
+    """yc_render_wave_async / yc_wave_sync in the CPU build (nothing overlaps there, but the bookkeeping is the same):
+    waves issued without waiting, a synchronous call in the middle, statistics read while waves are pending."""
+    size = 48
+    cam = H.scene_camera("cornell")
+    sc = Y.Scene(H.scene_file("cornell"))
+    c = Y.make_camera(size, size, cam["focal"], cam["fnum"], cam["pos"], cam["target"])
+    res = []
+    for mode in ("sync", "async"):
+        ctx = Y.Context()
+        ctx.upload_scene(sc)
+        ctx.set_camera(c)
+        ctx.begin_frame(size, size, 8, 16, (0, 0, 0), Y.TONEMAP_AGX)
+        f = ctx.render_wave_async if mode == "async" else ctx.render_wave
+        f(0, 2, 0)
+        f(2, 2, 2)
+        mid = ctx.stats().raysReference  # settles what is pending
+        f(4, 1, 4, rect=(0, 0, 20, size))
+        f(4, 1, 4, rect=(20, 0, size - 20, size))
+        f(5, 3, 5)
+        hdr, ldr, st = ctx.resolve()
+        res.append((hdr, ldr, mid, st.raysReference, st.gpuMs))
+        ctx.close()
+    assert H.bits_equal(res[0][0], res[1][0]).all() and H.bits_equal(res[0][1], res[1][1]).all()
+    assert res[0][2:4] == res[1][2:4] and res[1][4] > 0

@@ -216,6 +216,13 @@ class Context:
         r = capi.YcRect(0, 0, self.frame.width, self.frame.height) if rect is None else capi.YcRect(*rect)
         self._ck(lib().yc_render_wave(self._h, r, sample_offset, wave_samples, taken_before), "yc_render_wave")
 
+    def render_wave_async(self, sample_offset, wave_samples, taken_before, rect=None):
+        """yc_render_wave_async: the wave stays in flight; wave_sync() (or any other call) waits for it."""
+        self._ck(lib().yc_render_wave_async(self._h, self._rect(rect), sample_offset, wave_samples, taken_before), "yc_render_wave_async")
+
+    def wave_sync(self):
+        self._ck(lib().yc_wave_sync(self._h), "yc_wave_sync")
+
     def _rect(self, rect):
         return capi.YcRect(0, 0, self.frame.width, self.frame.height) if rect is None else capi.YcRect(*rect)
 
@@ -269,6 +276,9 @@ class Context:
 
     def comm_reduce_frames(self, root: int = 0):
         self._ck(lib().yc_comm_reduce_frames(self._h, root), "yc_comm_reduce_frames")
+
+    def comm_reduce_frames_async(self, root: int = 0):
+        self._ck(lib().yc_comm_reduce_frames_async(self._h, root), "yc_comm_reduce_frames_async")
 
     def comm_frames_direct(self) -> bool:
         """True when the participants store finished pixels straight into the root's frame (peer memory) and

@@ -133,6 +133,8 @@ PROTOTYPES = {
     "yc_set_camera": (C.c_int, [P, C.POINTER(YcCamera)]),
     "yc_begin_frame": (C.c_int, [P, C.POINTER(YcFrameDesc)]),
     "yc_render_wave": (C.c_int, [P, YcRect, u32, u32, u32]),
+    "yc_render_wave_async": (C.c_int, [P, YcRect, u32, u32, u32]),
+    "yc_wave_sync": (C.c_int, [P]),
     "yc_accumulate_wave": (C.c_int, [P, YcRect, u32, u32, u32, u32]),
     "yc_bucket_device_ptrs": (C.c_int, [P, C.POINTER(P), C.POINTER(C.c_size_t), C.POINTER(u32), C.POINTER(C.c_size_t)]),
     "yc_finalize_wave": (C.c_int, [P, YcRect, u32, u32]),
@@ -158,6 +160,7 @@ PROTOTYPES = {
     "yc_comm_init_custom": (C.c_int, [P, C.c_int, C.c_int, COLLECTIVE_FN, P]),
     "yc_comm_destroy": (C.c_int, [P]),
     "yc_comm_reduce_frames": (C.c_int, [P, C.c_int]),
+    "yc_comm_reduce_frames_async": (C.c_int, [P, C.c_int]),
     "yc_comm_frames_direct": (C.c_int, [P, C.POINTER(C.c_int)]),
     "yc_resolve_combined": (C.c_int, [P, P, P]),
     "yc_comm_allreduce_buckets": (C.c_int, [P, u32]),

@@ -56,7 +56,7 @@ enum { kCtrExtendHead = 0, kCtrNextCount = 1, kCtrShadowCount = 2, kCtrShadowHea
 // 14 K boxes alone, see profiles/README.md) or for its bounce-count read-back, the other keeps the GPU busy.
 constexpr int kLanes = 2;
 struct Lane {
-  rt::Stream st;       // lane 0 shares the context's main stream
+  rt::Stream st;       // the lane's own stream (the context's main stream runs finalize, copies, ray hooks, collectives)
   PathState ps{};      // ps.L points at Lbuf[lSel] while a chunk is in flight
   ShadowQueue sq{};
   SurfState ss{};
@@ -115,6 +115,10 @@ struct yc_ctx {
   std::vector<void*> waveAllocs;
 
   rt::Event ev0, ev1;
+  // Waves issued by yc_render_wave_async and not yet waited for (every other entry point settles them first): the next
+  // wave's chunks start while the previous wave's per-path tails, accumulates and finalize are still running.
+  bool wavesPending = false;
+  rt::Event evFinal;  // after the last finalize kernel: the bucket planes are zeroed, the next wave may accumulate
   std::vector<std::pair<rt::Event, rt::Event>> extendEvents;  // one pair per timed extend launch of the wave
   size_t extendEventsUsed = 0;
   std::vector<std::pair<rt::Event, rt::Event>> shadeEvents;   // the same for the surface-shading launches
@@ -135,6 +139,8 @@ struct yc_ctx {
   uint64_t nWideNodes = 0;
 };
 
+static int settleWaves(yc_ctx* ctx);
+
 static int fail(yc_ctx* c, int code, const char* fmt, ...) {
   if (c) {
     char buf[512];
@@ -150,6 +156,17 @@ static int fail(yc_ctx* c, int code, const char* fmt, ...) {
   do {                                                                      \
     const char* e_ = (expr);                                                \
     if (e_) return fail(ctx, YC_ERR_CUDA, "%s: %s", #expr, e_);             \
+  } while (0)
+
+// Start of every entry point that touches the device: select it (the current device is per-thread state) and wait for
+// waves still in flight from yc_render_wave_async — only that call and yc_comm_reduce_frames_async chain behind them.
+static int enter(yc_ctx* ctx) {
+  rt::useDevice(ctx->device);
+  return ctx->wavesPending ? settleWaves(ctx) : YC_OK;
+}
+#define YC_ENTER(ctx)                        \
+  do {                                       \
+    if (const int e_ = enter(ctx)) return e_; \
   } while (0)
 
 template <typename T>
@@ -682,10 +699,10 @@ extern "C" int yc_create(int device, const YcOptions* opts, yc_ctx** out) {
   }
   rt::eventCreate(ctx->ev0);
   rt::eventCreate(ctx->ev1);
+  rt::eventCreate(ctx->evFinal);
   for (int l = 0; l < kLanes; l++) {
     Lane& L = ctx->lanes[l];
-    if (l == 0) L.st = ctx->st;
-    else if (const char* le = rt::streamCreate(L.st)) {
+    if (const char* le = rt::streamCreate(L.st)) {
       fprintf(stderr, "yart_b200: cannot create a stream: %s\n", le);
       delete ctx;
       return YC_ERR_CUDA;
@@ -721,7 +738,7 @@ static void destroyComm(yc_ctx* ctx);
 
 extern "C" void yc_destroy(yc_ctx* ctx) {
   if (!ctx) return;
-  rt::useDevice(ctx->device);
+  enter(ctx);
   rt::sync(ctx->st);
   destroyComm(ctx);
   freeFrame(ctx);
@@ -729,6 +746,7 @@ extern "C" void yc_destroy(yc_ctx* ctx) {
   freeAll(ctx->waveAllocs);
   rt::eventDestroy(ctx->ev0);
   rt::eventDestroy(ctx->ev1);
+  rt::eventDestroy(ctx->evFinal);
   for (auto* evs : {&ctx->extendEvents, &ctx->shadeEvents})
     for (auto& ev : *evs) {
       rt::eventDestroy(ev.first);
@@ -745,7 +763,7 @@ extern "C" void yc_destroy(yc_ctx* ctx) {
     rt::eventDestroy(L.evSide[0]);
     rt::eventDestroy(L.evSide[1]);
     rt::destroy(L.side);
-    if (l > 0) rt::destroy(L.st);
+    rt::destroy(L.st);
   }
   rt::destroy(ctx->st);
   delete ctx;
@@ -755,14 +773,14 @@ extern "C" const char* yc_last_error(const yc_ctx* ctx) { return ctx ? ctx->err.
 
 extern "C" int yc_synchronize(yc_ctx* ctx) {
   if (!ctx) return YC_ERR_INVALID;
-  rt::useDevice(ctx->device);
+  YC_ENTER(ctx);
   YC_TRY(rt::sync(ctx->st));
   return YC_OK;
 }
 
 extern "C" int yc_upload_scene(yc_ctx* ctx, const YcScene* s) {
   if (!ctx || !s) return YC_ERR_INVALID;
-  rt::useDevice(ctx->device);
+  YC_ENTER(ctx);
   if (!s->nodes || s->nNodes == 0 || !s->lutTables) return fail(ctx, YC_ERR_INVALID, "scene has no nodes or no LUT tables");
   for (uint32_t i = 0; i < s->nNodes; i++) {
     const YcNode& n = s->nodes[i];
@@ -864,7 +882,7 @@ extern "C" int yc_upload_scene(yc_ctx* ctx, const YcScene* s) {
 
 extern "C" int yc_set_camera(yc_ctx* ctx, const YcCamera* cam) {
   if (!ctx || !cam) return YC_ERR_INVALID;
-  rt::useDevice(ctx->device);
+  YC_ENTER(ctx);
   ctx->cam = *cam;
   ctx->hasCamera = true;
   return YC_OK;
@@ -961,7 +979,7 @@ static uint32_t roundUpPow2(uint32_t v) {  // math_base.hpp:164-170
 
 extern "C" int yc_begin_frame(yc_ctx* ctx, const YcFrameDesc* f) {
   if (!ctx || !f) return YC_ERR_INVALID;
-  rt::useDevice(ctx->device);
+  YC_ENTER(ctx);
   if (!ctx->hasScene) return fail(ctx, YC_ERR_NO_SCENE, "yc_begin_frame before yc_upload_scene");
   if (!ctx->hasCamera) return fail(ctx, YC_ERR_STATE, "yc_begin_frame before yc_set_camera");
   if (f->width == 0 || f->height == 0 || f->width > 65535 || f->height > 65535 || f->tileSize == 0 ||
@@ -1132,11 +1150,13 @@ static int renderChunks(yc_ctx* ctx, const uint32_t* dList, uint32_t nPixCall, u
   }
   if (chunks.empty()) return YC_OK;
 
-  // every stream of the wave starts after what is already queued on the main stream (ev0)
+  // A wave that follows a settled context starts after what is queued on the main stream (ev0).  A wave chained behind
+  // a pending one (yc_render_wave_async) starts its chunks at once — their buffers are guarded by the lanes' own events
+  // — and only its accumulates wait: for the previous wave's finalize, which reads and zeroes the bucket planes.
   for (int l = 0; l < kLanes; l++) {
     Lane& L = ctx->lanes[l];
-    if (l > 0) rt::streamWaitEvent(L.st, ctx->ev0);
-    rt::streamWaitEvent(L.side, ctx->ev0);
+    if (!ctx->wavesPending) rt::streamWaitEvent(L.st, ctx->ev0);
+    rt::streamWaitEvent(L.side, ctx->wavesPending ? ctx->evFinal : ctx->ev0);
     L.active = false;
     L.accPending[0] = L.accPending[1] = false;
   }
@@ -1313,7 +1333,19 @@ static uint32_t waveBuckets(const YcFrameDesc& f, uint32_t waveSamples) {
 
 static int endTimedRegion(yc_ctx* ctx) {
   rt::eventRecord(ctx->st, ctx->ev1);
+  return settleWaves(ctx);
+}
+
+// Waits for everything the context has issued (the main stream's last operation — a finalize, or the wait for the
+// last accumulate — is ordered after all of a wave's work) and books the device time from the first unsettled wave's
+// start to here.
+static int settleWaves(yc_ctx* ctx) {
+  ctx->wavesPending = false;
   YC_TRY(rt::sync(ctx->st));
+  for (int l = 0; l < kLanes; l++) {  // idle already unless a wave was cut short (error, abort)
+    YC_TRY(rt::sync(ctx->lanes[l].st));
+    YC_TRY(rt::sync(ctx->lanes[l].side));
+  }
   YC_TRY(rt::lastError());
   ctx->gpuMs += rt::eventElapsedMs(ctx->ev0, ctx->ev1);
   for (size_t i = 0; i < ctx->extendEventsUsed; i++) {
@@ -1352,6 +1384,7 @@ static void finalizeWave(yc_ctx* ctx, const uint32_t* dList, uint32_t nPixCall, 
   rt::launchFor(ctx->st, nPixCall,
                 FinalizeK{dList, ctx->dBuckets, ctx->bucketCapacity, ctx->dHdr, ctx->dLdr, hdrRoot, ldrRoot, f.width,
                           waveBuckets(f, waveSamples), f.estimator, waveSamples, f.tonemap, wCurrent, wWave});
+  rt::eventRecord(ctx->st, ctx->evFinal);
   ctx->launches++;
   if (dList == ctx->dPixels) ctx->bucketsDirty = false;  // every plane this shard touches was read and zeroed
 }
@@ -1367,9 +1400,9 @@ static void noteWave(yc_ctx* ctx, YcRect px) {
   if (!(px.x == 0 && px.y == 0 && px.w == f.width && px.h == f.height) || c.frameTexels != size_t(f.width) * f.height) c.stale = true;
 }
 
-extern "C" int yc_render_wave(yc_ctx* ctx, YcRect px, uint32_t sampleOffset, uint32_t waveSamples, uint32_t takenBefore) {
-  if (!ctx) return YC_ERR_INVALID;
-  rt::useDevice(ctx->device);
+// One wave: the sample loop into the buckets, then estimator + blend + tonemap.  Chains behind waves that are still in
+// flight (ctx->wavesPending) and leaves this one in flight.
+static int issueWave(yc_ctx* ctx, YcRect px, uint32_t sampleOffset, uint32_t waveSamples, uint32_t takenBefore) {
   if (!ctx->inFrame) return fail(ctx, YC_ERR_STATE, "yc_render_wave before yc_begin_frame");
   noteWave(ctx, px);
   if (waveSamples == 0 || px.w == 0 || px.h == 0) return YC_OK;
@@ -1377,17 +1410,42 @@ extern "C" int yc_render_wave(yc_ctx* ctx, YcRect px, uint32_t sampleOffset, uin
   uint32_t nPixCall;
   if (const int prc = wavePixels(ctx, px, &dList, &nPixCall)) return prc;
   if (nPixCall == 0) return YC_OK;
-  rt::eventRecord(ctx->st, ctx->ev0);
+  if (!ctx->wavesPending) rt::eventRecord(ctx->st, ctx->ev0);
   const int rc = accumulateWave(ctx, dList, nPixCall, sampleOffset, waveSamples, 0, 1);
-  if (rc != YC_OK) return rc;
+  if (rc != YC_OK) {
+    ctx->wavesPending = true;  // whatever was issued is waited for by the next entry point
+    return rc;
+  }
   finalizeWave(ctx, dList, nPixCall, waveSamples, takenBefore);
-  return endTimedRegion(ctx);
+  rt::eventRecord(ctx->st, ctx->ev1);
+  ctx->wavesPending = true;
+  return YC_OK;
+}
+
+extern "C" int yc_render_wave(yc_ctx* ctx, YcRect px, uint32_t sampleOffset, uint32_t waveSamples, uint32_t takenBefore) {
+  if (!ctx) return YC_ERR_INVALID;
+  YC_ENTER(ctx);
+  const int rc = issueWave(ctx, px, sampleOffset, waveSamples, takenBefore);
+  const int src = ctx->wavesPending ? settleWaves(ctx) : YC_OK;
+  return rc != YC_OK ? rc : src;
+}
+
+extern "C" int yc_render_wave_async(yc_ctx* ctx, YcRect px, uint32_t sampleOffset, uint32_t waveSamples, uint32_t takenBefore) {
+  if (!ctx) return YC_ERR_INVALID;
+  rt::useDevice(ctx->device);
+  return issueWave(ctx, px, sampleOffset, waveSamples, takenBefore);
+}
+
+extern "C" int yc_wave_sync(yc_ctx* ctx) {
+  if (!ctx) return YC_ERR_INVALID;
+  YC_ENTER(ctx);
+  return YC_OK;
 }
 
 extern "C" int yc_accumulate_wave(yc_ctx* ctx, YcRect px, uint32_t sampleOffset, uint32_t waveSamples, uint32_t bucketShard,
                                   uint32_t bucketShardCount) {
   if (!ctx) return YC_ERR_INVALID;
-  rt::useDevice(ctx->device);
+  YC_ENTER(ctx);
   if (!ctx->inFrame) return fail(ctx, YC_ERR_STATE, "yc_accumulate_wave before yc_begin_frame");
   if (bucketShardCount == 0 || bucketShard >= bucketShardCount) return fail(ctx, YC_ERR_INVALID, "bucket shard out of range");
   if (waveSamples == 0 || px.w == 0 || px.h == 0) return YC_OK;
@@ -1403,7 +1461,7 @@ extern "C" int yc_accumulate_wave(yc_ctx* ctx, YcRect px, uint32_t sampleOffset,
 
 extern "C" int yc_finalize_wave(yc_ctx* ctx, YcRect px, uint32_t waveSamples, uint32_t takenBefore) {
   if (!ctx) return YC_ERR_INVALID;
-  rt::useDevice(ctx->device);
+  YC_ENTER(ctx);
   if (!ctx->inFrame) return fail(ctx, YC_ERR_STATE, "yc_finalize_wave before yc_begin_frame");
   noteWave(ctx, px);
   if (waveSamples == 0 || px.w == 0 || px.h == 0) return YC_OK;
@@ -1418,7 +1476,7 @@ extern "C" int yc_finalize_wave(yc_ctx* ctx, YcRect px, uint32_t waveSamples, ui
 
 extern "C" int yc_wave_buckets(yc_ctx* ctx, uint32_t waveSamples, uint32_t* m) {
   if (!ctx || !m) return YC_ERR_INVALID;
-  rt::useDevice(ctx->device);
+  YC_ENTER(ctx);
   if (!ctx->inFrame) return fail(ctx, YC_ERR_STATE, "no frame");
   *m = waveBuckets(ctx->frame, waveSamples);
   return YC_OK;
@@ -1426,7 +1484,7 @@ extern "C" int yc_wave_buckets(yc_ctx* ctx, uint32_t waveSamples, uint32_t* m) {
 
 extern "C" int yc_bucket_device_ptrs(yc_ctx* ctx, void** buckets, size_t* bytes, uint32_t* planes, size_t* planePixels) {
   if (!ctx) return YC_ERR_INVALID;
-  rt::useDevice(ctx->device);
+  YC_ENTER(ctx);
   if (!ctx->inFrame) return fail(ctx, YC_ERR_STATE, "no frame");
   if (buckets) *buckets = ctx->dBuckets;
   if (bytes) *bytes = ctx->bucketCapacity * kMaxBuckets * sizeof(float4);
@@ -1456,7 +1514,7 @@ static int readStats(yc_ctx* ctx, YcStats* stats) {
 
 extern "C" int yc_resolve(yc_ctx* ctx, float* hdrRGBA, float* ldrRGBA, YcStats* stats) {
   if (!ctx) return YC_ERR_INVALID;
-  rt::useDevice(ctx->device);
+  YC_ENTER(ctx);
   if (!ctx->inFrame) return fail(ctx, YC_ERR_STATE, "yc_resolve before yc_begin_frame");
   const size_t bytes = size_t(ctx->frame.width) * ctx->frame.height * sizeof(float4);
   if (hdrRGBA) YC_TRY(rt::d2h(ctx->st, hdrRGBA, ctx->dHdr, bytes));
@@ -1466,7 +1524,7 @@ extern "C" int yc_resolve(yc_ctx* ctx, float* hdrRGBA, float* ldrRGBA, YcStats* 
 
 extern "C" int yc_frame_device_ptrs(yc_ctx* ctx, void** hdr, void** ldr, size_t* bytes) {
   if (!ctx) return YC_ERR_INVALID;
-  rt::useDevice(ctx->device);
+  YC_ENTER(ctx);
   if (!ctx->inFrame) return fail(ctx, YC_ERR_STATE, "no frame");
   if (hdr) *hdr = ctx->dHdr;
   if (ldr) *ldr = ctx->dLdr;
@@ -1476,7 +1534,7 @@ extern "C" int yc_frame_device_ptrs(yc_ctx* ctx, void** hdr, void** ldr, size_t*
 
 extern "C" int yc_retonemap(yc_ctx* ctx) {
   if (!ctx) return YC_ERR_INVALID;
-  rt::useDevice(ctx->device);
+  YC_ENTER(ctx);
   if (!ctx->inFrame) return fail(ctx, YC_ERR_STATE, "no frame");
   rt::launchFor(ctx->st, ctx->frame.width * ctx->frame.height, RetonemapK{ctx->dHdr, ctx->dLdr, ctx->frame.tonemap});
   ctx->launches++;
@@ -1487,7 +1545,7 @@ extern "C" int yc_retonemap(yc_ctx* ctx) {
 
 extern "C" int yc_set_profiling(yc_ctx* ctx, int timeExtendKernel) {
   if (!ctx) return YC_ERR_INVALID;
-  rt::useDevice(ctx->device);
+  YC_ENTER(ctx);
   ctx->timeExtend = (timeExtendKernel & 1) != 0;
   ctx->countTraversal = (timeExtendKernel & 2) != 0;  // counting builds of extend / shadow (box / triangle tests)
   ctx->timeShade = (timeExtendKernel & 4) != 0;
@@ -1688,7 +1746,7 @@ static void dispatchTrace(yc_ctx* ctx, int mode, bool wide, const YcRay* rays, u
 
 extern "C" int yc_trace_device(yc_ctx* ctx, const void* raysDev, size_t n, int mode, void* hitsDev, int repeat, float* ms) {
   if (!ctx || !raysDev || !hitsDev || n > 0xffffffffull) return YC_ERR_INVALID;
-  rt::useDevice(ctx->device);
+  YC_ENTER(ctx);
   if (!ctx->hasScene) return fail(ctx, YC_ERR_NO_SCENE, "yc_trace_device before yc_upload_scene");
   int rc = ensureWaveStorage(ctx);
   if (rc != YC_OK) return rc;
@@ -1712,7 +1770,7 @@ extern "C" int yc_trace_device(yc_ctx* ctx, const void* raysDev, size_t n, int m
 
 extern "C" int yc_trace(yc_ctx* ctx, const YcRay* rays, size_t n, int mode, YcHit* hits, YcStats* stats) {
   if (!ctx || (n && (!rays || !hits)) || n > 0xffffffffull) return YC_ERR_INVALID;
-  rt::useDevice(ctx->device);
+  YC_ENTER(ctx);
   if (!ctx->hasScene) return fail(ctx, YC_ERR_NO_SCENE, "yc_trace before yc_upload_scene");
   int rc = ensureWaveStorage(ctx);
   if (rc != YC_OK) return rc;
@@ -1744,38 +1802,38 @@ extern "C" int yc_trace(yc_ctx* ctx, const YcRay* rays, size_t n, int mode, YcHi
 
 extern "C" int yc_device_alloc(yc_ctx* ctx, size_t bytes, void** out) {
   if (!ctx || !out) return YC_ERR_INVALID;
-  rt::useDevice(ctx->device);
+  YC_ENTER(ctx);
   YC_TRY(rt::alloc(out, bytes));
   return YC_OK;
 }
 extern "C" int yc_device_free(yc_ctx* ctx, void* p) {
   if (!ctx) return YC_ERR_INVALID;
-  rt::useDevice(ctx->device);
+  YC_ENTER(ctx);
   rt::sync(ctx->st);
   rt::release(p);
   return YC_OK;
 }
 extern "C" int yc_host_alloc(yc_ctx* ctx, size_t bytes, void** out) {
   if (!ctx || !out) return YC_ERR_INVALID;
-  rt::useDevice(ctx->device);
+  YC_ENTER(ctx);
   YC_TRY(rt::hostAlloc(out, bytes));
   return YC_OK;
 }
 extern "C" int yc_host_free(yc_ctx* ctx, void* p) {
   if (!ctx) return YC_ERR_INVALID;
-  rt::useDevice(ctx->device);
+  YC_ENTER(ctx);
   rt::hostRelease(p);
   return YC_OK;
 }
 extern "C" int yc_memcpy_h2d(yc_ctx* ctx, void* dst, const void* src, size_t bytes) {
   if (!ctx || !dst || !src) return YC_ERR_INVALID;
-  rt::useDevice(ctx->device);
+  YC_ENTER(ctx);
   YC_TRY(rt::h2d(ctx->st, dst, src, bytes));
   return YC_OK;
 }
 extern "C" int yc_memcpy_d2h(yc_ctx* ctx, void* dst, const void* src, size_t bytes) {
   if (!ctx || !dst || !src) return YC_ERR_INVALID;
-  rt::useDevice(ctx->device);
+  YC_ENTER(ctx);
   YC_TRY(rt::d2h(ctx->st, dst, src, bytes));
   return YC_OK;
 }
@@ -1800,7 +1858,7 @@ struct PrimaryRayK {
 
 extern "C" int yc_generate_primary_rays(yc_ctx* ctx, uint32_t sampleOffset, uint32_t spp, void* raysDev) {
   if (!ctx || !raysDev) return YC_ERR_INVALID;
-  rt::useDevice(ctx->device);
+  YC_ENTER(ctx);
   if (!ctx->inFrame) return fail(ctx, YC_ERR_STATE, "yc_generate_primary_rays before yc_begin_frame");
   const YcFrameDesc& f = ctx->frame;
   WaveParams w{};
@@ -1868,7 +1926,7 @@ extern "C" int yc_comm_unique_id(void* id128) {
 
 extern "C" int yc_comm_init_rank(yc_ctx* ctx, int rank, int world, const void* id128) {
   if (!ctx || !id128 || world < 1 || rank < 0 || rank >= world) return YC_ERR_INVALID;
-  rt::useDevice(ctx->device);
+  YC_ENTER(ctx);
 #ifdef YB_HOSTSIM
   return fail(ctx, YC_ERR_UNSUPPORTED, "the CPU build has no NCCL: use yc_comm_init_custom or yc_comm_init_all");
 #else
@@ -1943,7 +2001,7 @@ extern "C" int yc_comm_init_custom(yc_ctx* ctx, int rank, int world, yc_collecti
 
 extern "C" int yc_comm_destroy(yc_ctx* ctx) {
   if (!ctx) return YC_ERR_INVALID;
-  rt::useDevice(ctx->device);
+  YC_ENTER(ctx);
   rt::sync(ctx->st);
   destroyComm(ctx);
   return YC_OK;
@@ -2065,7 +2123,7 @@ static int mapCombinedFrames(yc_ctx* ctx, int root, size_t texels) {
   return YC_OK;
 }
 
-extern "C" int yc_comm_reduce_frames(yc_ctx* ctx, int root) {
+static int reduceFrames(yc_ctx* ctx, int root, bool async) {
   if (!ctx) return YC_ERR_INVALID;
   rt::useDevice(ctx->device);
   if (!ctx->comm) return fail(ctx, YC_ERR_STATE, "yc_comm_reduce_frames without a communicator");
@@ -2073,6 +2131,25 @@ extern "C" int yc_comm_reduce_frames(yc_ctx* ctx, int root) {
   Comm& c = *ctx->comm;
   if (root < 0 || root >= c.world) return fail(ctx, YC_ERR_INVALID, "bad root");
   const size_t texels = size_t(ctx->frame.width) * ctx->frame.height;
+#ifndef YB_HOSTSIM
+  if (async && ctx->wavesPending && c.direct && !c.stale && c.nccl && c.frameTexels == texels && c.root == root) {
+    // Chained behind waves in flight: the barrier is enqueued on the main stream after the wave's finalize kernel and
+    // nobody waits for it here.  (The stores of wave k + 2 into this copy are issued after barrier k + 1, which the
+    // root enters only once it has read what it wanted of wave k.)
+    if (!c.barrierSinceFinalize) {
+      if (!c.scratch) return fail(ctx, YC_ERR_STATE, "no staging buffer");
+      if (const int rc = commSum(ctx, c.scratch, 1, kCommU64, -1)) return rc;
+    }
+    rt::eventRecord(ctx->st, ctx->ev1);
+    c.barrierSinceFinalize = false;
+    c.cur = int(c.epoch & 1u);
+    c.epoch++;
+    return YC_OK;
+  }
+#endif
+  (void)async;
+  if (ctx->wavesPending)
+    if (const int rc = settleWaves(ctx)) return rc;
   if (c.frameTexels != texels || c.root != root) {
     if (const int rc = mapCombinedFrames(ctx, root, texels)) return rc;
   }
@@ -2129,6 +2206,9 @@ extern "C" int yc_comm_reduce_frames(yc_ctx* ctx, int root) {
   return YC_OK;
 }
 
+extern "C" int yc_comm_reduce_frames(yc_ctx* ctx, int root) { return reduceFrames(ctx, root, false); }
+extern "C" int yc_comm_reduce_frames_async(yc_ctx* ctx, int root) { return reduceFrames(ctx, root, true); }
+
 extern "C" int yc_comm_frames_direct(yc_ctx* ctx, int* direct) {
   if (!ctx || !direct) return YC_ERR_INVALID;
   if (!ctx->comm) return fail(ctx, YC_ERR_STATE, "yc_comm_frames_direct without a communicator");
@@ -2138,7 +2218,7 @@ extern "C" int yc_comm_frames_direct(yc_ctx* ctx, int* direct) {
 
 extern "C" int yc_resolve_combined(yc_ctx* ctx, float* hdrRGBA, float* ldrRGBA) {
   if (!ctx) return YC_ERR_INVALID;
-  rt::useDevice(ctx->device);
+  YC_ENTER(ctx);
   if (!ctx->comm || ctx->comm->root != ctx->comm->rank || !ctx->comm->hdrAll[0])
     return fail(ctx, YC_ERR_STATE, "yc_resolve_combined: not the root of a completed yc_comm_reduce_frames");
   const Comm& c = *ctx->comm;
@@ -2150,7 +2230,7 @@ extern "C" int yc_resolve_combined(yc_ctx* ctx, float* hdrRGBA, float* ldrRGBA) 
 
 extern "C" int yc_comm_allreduce_buckets(yc_ctx* ctx, uint32_t waveSamples) {
   if (!ctx) return YC_ERR_INVALID;
-  rt::useDevice(ctx->device);
+  YC_ENTER(ctx);
   if (!ctx->comm) return fail(ctx, YC_ERR_STATE, "yc_comm_allreduce_buckets without a communicator");
   if (!ctx->inFrame) return fail(ctx, YC_ERR_STATE, "no frame");
   const size_t words = size_t(waveBuckets(ctx->frame, waveSamples)) * ctx->bucketCapacity * 4;
@@ -2166,7 +2246,7 @@ extern "C" int yc_comm_allreduce_buckets(yc_ctx* ctx, uint32_t waveSamples) {
 
 extern "C" int yc_comm_sum_u64(yc_ctx* ctx, uint64_t* values, uint32_t n) {
   if (!ctx || !values || n == 0 || n > 64) return YC_ERR_INVALID;
-  rt::useDevice(ctx->device);
+  YC_ENTER(ctx);
   if (!ctx->comm) return fail(ctx, YC_ERR_STATE, "yc_comm_sum_u64 without a communicator");
   return commSumHost(ctx, values, n);
 }
