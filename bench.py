@@ -364,7 +364,7 @@ def run_ours(args):
         pixel class) units (the accumulation buffers are all-reduced as int32 inside every wave).  Returns the
         device time of the timed steps (CUDA events around the wave and around its collective, max over ranks),
         whole-job reference rays, traced rays, launches, collective ms, host wall ms."""
-        total = S * (warm + steps)
+        total = S * (warm + steps + 3)
         if buckets:
             ctx.begin_frame(W, H, total, 64, (0, 0, 0), Y.TONEMAP_AGX)
         else:
@@ -394,7 +394,15 @@ def run_ours(args):
         w1 = time.time()
         s1 = ctx.stats()
         dev = (s1.gpuMs - s0.gpuMs) + (s1.commMs - s0.commMs)
-        dev, comm, wall = max_over_ranks(dev, s1.commMs - s0.commMs, (w1 - w0) * 1e3)
+        comm_ms = s1.commMs - s0.commMs
+        if dist and not buckets:
+            # the waves in flight do not time their barrier separately (it is inside gpuMs): three more waves, waited for
+            # one at a time, give the collective's own duration (not part of the timed region)
+            for k in range(warm + steps, warm + steps + 3):
+                ctx.render_wave(k * S, S, k * S)
+                ctx.comm_reduce_frames(0)
+            comm_ms = (ctx.stats().commMs - s1.commMs) / 3 * steps
+        dev, comm, wall = max_over_ranks(dev, comm_ms, (w1 - w0) * 1e3)
         rays, traced, launches = sum_over_ranks(s1.raysReference - s0.raysReference,
                                                 (s1.raysExtend - s0.raysExtend) + (s1.raysShadow - s0.raysShadow),
                                                 s1.kernelLaunches - s0.kernelLaunches)

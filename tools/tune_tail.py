@@ -15,11 +15,11 @@ for tail in [int(x) for x in (sys.argv[2] if len(sys.argv) > 2 else "-1,4096,163
     ctx.upload_scene(sc)
     ctx.set_camera(cam)
     ctx.begin_frame(bench.W, bench.H, 4, 64, (0, 0, 0), Y.TONEMAP_AGX)
-    for _ in range(2):
-        ctx.render_wave(0, 4, 0)
-    s0 = ctx.stats()
     for _ in range(3):
-        ctx.render_wave(0, 4, 0)
+        ctx.render_wave_async(0, 4, 0)
+    s0 = ctx.stats()
+    for _ in range(6):
+        ctx.render_wave_async(0, 4, 0)  # waves left in flight, as bench.py times them
     s1 = ctx.stats()
-    print(f"{workload} tail={tail:8d}: {(s1.gpuMs - s0.gpuMs) / 3:.2f} ms/step, launches/step {(s1.kernelLaunches - s0.kernelLaunches) / 3:.0f}, rays {s1.raysReference - s0.raysReference}")
+    print(f"{workload} tail={tail:8d}: {(s1.gpuMs - s0.gpuMs) / 6:.2f} ms/step, launches/step {(s1.kernelLaunches - s0.kernelLaunches) / 6:.0f}, rays {s1.raysReference - s0.raysReference}")
     ctx.close()
