@@ -26,6 +26,7 @@
 #include <condition_variable>
 #include <memory>
 #include <mutex>
+#include <thread>
 #include <unistd.h>
 
 #ifndef YB_HOSTSIM
@@ -142,6 +143,9 @@ struct Comm {
   float4 *hdrAll[2] = {nullptr, nullptr}, *ldrAll[2] = {nullptr, nullptr};  // as THIS context addresses them (root: its
                                  // own block; others in direct mode: the root's block through peer access)
   void* imported = nullptr;      // cross-process mapping of the root's block (closed with the communicator)
+  uint32_t* detached = nullptr;  // kGroupMax words behind the frames in the block: participant r sets word r before it
+                                 // closes its mapping, and the root frees the block only when every importer has
+  uint32_t importers = 0;        // root: participants that mapped the block from another process
   size_t frameTexels = 0;
   int root = -1;
   bool direct = false;           // every participant reaches the root's block: finished pixels are stored there directly

@@ -735,6 +735,7 @@ static void freeFrame(yc_ctx* ctx) {
 }
 
 static void destroyComm(yc_ctx* ctx);
+static void detachCombinedFrames(yc_ctx* ctx);
 
 extern "C" void yc_destroy(yc_ctx* ctx) {
   if (!ctx) return;
@@ -1894,8 +1895,7 @@ static void destroyComm(yc_ctx* ctx) {
 #ifndef YB_HOSTSIM
   if (c.nccl) nccl().CommDestroy(c.nccl);
 #endif
-  rt::ipcClose(c.imported);
-  rt::release(c.block);
+  detachCombinedFrames(ctx);
   rt::release(c.scratch);
   ctx->comm.reset();
 }
@@ -2064,27 +2064,59 @@ static int commSumHost(yc_ctx* ctx, uint64_t* values, uint32_t n) {
   return YC_OK;
 }
 
+// Letting go of the root's combined frames.  An importer says so in the block itself before it closes its mapping; the
+// root frees the block once every importer has (freeing memory that another process still maps is undefined), waits
+// two seconds for that at most — a peer may have died — and then rather leaks the block than frees it.
+static void detachCombinedFrames(yc_ctx* ctx) {
+  Comm& c = *ctx->comm;
+  if (c.imported) {
+    const uint32_t one = 1;
+    if (c.detached && c.rank >= 0 && c.rank < kGroupMax) rt::h2d(ctx->st, c.detached + c.rank, &one, sizeof one);
+    rt::ipcClose(c.imported);
+    rt::lastError();
+    c.imported = nullptr;
+  }
+  if (c.block) {
+    bool free_ = true;
+    if (c.importers && c.detached) {
+      free_ = false;
+      for (int spin = 0; spin < 2000 && !free_; spin++) {
+        uint32_t flags[kGroupMax] = {};
+        if (rt::d2h(ctx->st, flags, c.detached, sizeof flags)) break;
+        uint32_t n = 0;
+        for (uint32_t f : flags) n += f != 0;
+        free_ = n >= c.importers;
+        if (!free_) std::this_thread::sleep_for(std::chrono::milliseconds(1));
+      }
+      if (!free_) fprintf(stderr, "yart_b200: a participant still maps the combined frames; leaving them allocated\n");
+    }
+    if (free_) rt::release(c.block);
+    c.block = nullptr;
+  }
+  c.detached = nullptr;
+  c.importers = 0;
+  for (int k = 0; k < 2; k++) c.hdrAll[k] = c.ldrAll[k] = nullptr;
+}
+
 // (Re)creates the root's combined frames for the current frame size and finds out — collectively — whether every
 // participant can address them (Comm::direct).  The root hands out {process id, device, address, exported handle} as a
 // sum in which everybody else contributes zeros.
 static int mapCombinedFrames(yc_ctx* ctx, int root, size_t texels) {
   Comm& c = *ctx->comm;
-  rt::ipcClose(c.imported);
-  c.imported = nullptr;
-  rt::release(c.block);
-  c.block = nullptr;
-  for (int k = 0; k < 2; k++) c.hdrAll[k] = c.ldrAll[k] = nullptr;
+  detachCombinedFrames(ctx);
   c.frameTexels = texels, c.root = root, c.direct = false, c.stale = true, c.epoch = 0, c.cur = 0;
   const bool isRoot = c.rank == root;
+  const size_t blockBytes = 4 * texels * sizeof(float4) + kGroupMax * sizeof(uint32_t);
   if (isRoot) {
     void* p = nullptr;
-    YC_TRY(rt::alloc(&p, 4 * texels * sizeof(float4)));
+    YC_TRY(rt::alloc(&p, blockBytes));
     c.block = static_cast<float4*>(p);
-    YC_TRY(rt::zero(ctx->st, c.block, 4 * texels * sizeof(float4)));
+    YC_TRY(rt::zero(ctx->st, c.block, blockBytes));
     YC_TRY(rt::sync(ctx->st));
   }
   auto carve = [&](float4* base) {
     for (int k = 0; k < 2; k++) c.hdrAll[k] = base + size_t(2 * k) * texels, c.ldrAll[k] = base + size_t(2 * k + 1) * texels;
+    c.detached = reinterpret_cast<uint32_t*>(base + 4 * texels);
   };
   if (isRoot) carve(c.block);
   if (c.world == 1 || c.custom) return YC_OK;  // the caller's collective: nothing is known about the other side's memory
@@ -2113,13 +2145,11 @@ static int mapCombinedFrames(yc_ctx* ctx, int root, size_t texels) {
   // YART_B200_FRAMES_REDUCE=1 (set for every participant) forces the summing path: for A/B measurements
   if (const char* e = getenv("YART_B200_FRAMES_REDUCE"))
     if (*e && *e != '0') failed = 1;
-  if (const int rc = commSumHost(ctx, &failed, 1)) return rc;
-  c.direct = failed == 0;
-  if (!c.direct && !isRoot) {
-    rt::ipcClose(c.imported);
-    c.imported = nullptr;
-    for (int k = 0; k < 2; k++) c.hdrAll[k] = c.ldrAll[k] = nullptr;
-  }
+  uint64_t votes[2] = {failed, uint64_t(c.imported != nullptr)};
+  if (const int rc = commSumHost(ctx, votes, 2)) return rc;
+  c.direct = votes[0] == 0;
+  if (isRoot) c.importers = uint32_t(votes[1]);
+  if (!c.direct && !isRoot) detachCombinedFrames(ctx);  // (the root keeps its block: the summing path's destination)
   return YC_OK;
 }
 
