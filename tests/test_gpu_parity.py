@@ -496,3 +496,13 @@ def test_waves_left_in_flight_equal_waves_waited_for(scene, depth, cap):
     for (a, b) in zip(out[0], out[1]):
         assert H.bits_equal(a[0], b[0]).all() and H.bits_equal(a[1], b[1]).all()
         assert a[2:] == b[2:]
+
+
+def test_graft_entry_smoke_in_a_fresh_process():
+    """__graft_entry__.smoke() as the driver runs it: its own process, the library's defaults (wide walk)."""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], cwd=H.ROOT, capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+    assert "smoke: ok" in r.stdout
