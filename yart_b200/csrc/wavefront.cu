@@ -29,7 +29,7 @@
 using namespace yb;
 
 #ifndef YB_TRACE_MIN_BLOCKS
-#define YB_TRACE_MIN_BLOCKS 8  // 8 CTAs x 4 warps per SM: caps the traversal kernels at 64 registers
+#define YB_TRACE_MIN_BLOCKS 7  // CTAs x 4 warps per SM of the reference-order closest-hit kernels: 72 registers, no spills in the alpha build (8 CTAs = 64 registers: Sponza-shaped step 28.4-28.9 ms, 7: 27.2, 6: 27.8 on one box)
 #endif
 #ifndef YB_SHADOW_MIN_BLOCKS
 #define YB_SHADOW_MIN_BLOCKS 7  // 72 registers, no spills (uncapped: 96 registers, 5 CTAs — C2 step 11.5 ms; 7: 10.9; 8 spills: 11.9)
