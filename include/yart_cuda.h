@@ -426,6 +426,18 @@ int yc_resolve_combined(yc_ctx* ctx, float* hdrRGBA, float* ldrRGBA);
 int yc_comm_allreduce_buckets(yc_ctx* ctx, uint32_t waveSamples);
 /* Control values (ray counts, abort votes): in-place sum over all participants. */
 int yc_comm_sum_u64(yc_ctx* ctx, uint64_t* values, uint32_t n);
+/* The reference's binned-SAH BVH (src/core/bvh.hpp:140-184, 273-347) built on the device, level by level: the same
+ * tree and the same triangle order as the host builder — and the reference — produce.  `pool` receives at most
+ * 2 * nTris + 2 nodes in creation order (node 0 is the root; children of an inner node are left and left + 1;
+ * left == 0 marks a leaf over indices[first .. first + span)); the host layer renumbers them in the reference's
+ * allocation order.  `faces4`: 4 words per triangle (3 vertex indices, 1 ignored).  Vertex positions must be finite. */
+typedef struct YcBuildNode {
+  float mn[3], mx[3];
+  uint32_t first, span, left, reserved;
+} YcBuildNode;
+int yc_build_bvh_sah(int device, const float* positions, size_t nVerts, const uint32_t* faces4, size_t nTris,
+                     YcBuildNode* pool, uint32_t* nNodes, uint32_t* indices, uint32_t* levels);
+const char* yc_build_last_error(void);
 /* Function-level hooks used by the parity tests (device evaluations of the restated math). */
 int yc_kat(yc_ctx* ctx, const char* kind, const void* in, size_t inBytes, void* out, size_t outBytes);
 
@@ -440,6 +452,11 @@ int ys_scene_load(const char* path, ys_scene** out);
  * bvh.hpp:266-347), YS_BVH_MEDIAN_SPLIT = MedianSplitBVH (bvh.hpp:237-264, its baseline builder). */
 #define YS_BVH_SAH 0
 #define YS_BVH_MEDIAN_SPLIT 1
+/* Where SahBVH is built.  YS_BVH_SAH picks by itself: meshes of at least 32768 triangles on the GPU
+ * (yc_build_bvh_sah, device ys_set_build_device chose; finite vertex data) when there is one, everything else — and
+ * everything after a failure of the device build — on the host cores (host/bvh_build.hpp).  Same tree either way. */
+#define YS_BVH_SAH_DEVICE 2 /* always through yc_build_bvh_sah (an error if that fails) */
+#define YS_BVH_SAH_HOST 3   /* always on the host cores */
 int ys_scene_load_bvh(const char* path, uint32_t bvhKind, ys_scene** out);
 /* Environment map handed to the GLB entry points: main.cpp:81-84 adds an ImageInfiniteLight(sceneRadius,
  * &hdri) after gltf::load.  rgb = width*height*3 floats in octahedral layout; transform row-major 4x4. */
@@ -472,8 +489,11 @@ const YcScene* ys_scene_flat(const ys_scene* s);
 /* The library's data tables for YcScene::lutTables (the values of the reference's src/bsdf/luts.hpp, 14112 floats). */
 const float* ys_lut_tables(size_t* count);
 double ys_scene_build_ms(const ys_scene* s);
+uint32_t ys_scene_device_builds(const ys_scene* s); /* meshes whose SAH BVH was built on the GPU */
 /* BVH of mesh `mesh` in the REFERENCE's node numbering/layout (for builder parity tests):
  * nodes = nNodes × {min[3] max[3] leftFirst span} (32 B), indices = nTris × u32. */
+/* Device the SAH builds of later scene loads run on (default 0; -1: host builds only). */
+int ys_set_build_device(int device);
 int ys_scene_bvh(const ys_scene* s, uint32_t mesh, const void** nodes, uint32_t* nNodes,
                  const uint32_t** indices, uint32_t* nTris);
 

@@ -13,7 +13,7 @@ import ctypes as C
 import numpy as np
 
 from . import capi
-from .capi import (LIGHT_SAMPLER_POWER, LIGHT_SAMPLER_UNIFORM, SAMPLER_SOBOL, SAMPLER_NAIVE, SAMPLER_STRATIFIED, BVH_SAH, BVH_MEDIAN_SPLIT, SCRAMBLER_FAST_OWEN, SCRAMBLER_OWEN, SCRAMBLER_BINARY_PERMUTE, INTEGRATOR_MIS, INTEGRATOR_NAIVE, ESTIMATOR_GMONB, ESTIMATOR_GMON, ESTIMATOR_MEAN, ESTIMATOR_MON, TONEMAP_AGX, TONEMAP_AGX_GOLDEN, TONEMAP_AGX_PUNCHY,
+from .capi import (LIGHT_SAMPLER_POWER, LIGHT_SAMPLER_UNIFORM, SAMPLER_SOBOL, SAMPLER_NAIVE, SAMPLER_STRATIFIED, BVH_SAH, BVH_MEDIAN_SPLIT, BVH_SAH_DEVICE, BVH_SAH_HOST, SCRAMBLER_FAST_OWEN, SCRAMBLER_OWEN, SCRAMBLER_BINARY_PERMUTE, INTEGRATOR_MIS, INTEGRATOR_NAIVE, ESTIMATOR_GMONB, ESTIMATOR_GMON, ESTIMATOR_MEAN, ESTIMATOR_MON, TONEMAP_AGX, TONEMAP_AGX_GOLDEN, TONEMAP_AGX_PUNCHY,
                    TONEMAP_NONE, TRACE_ANY, TRACE_CLOSEST, TRACE_COUNT, TRACE_USE_TMAX, TRACE_REFERENCE_ORDER, TRACE_WIDE,
                    TRAVERSAL_AUTO, TRAVERSAL_REFERENCE_ORDER, TRAVERSAL_WIDE, SHARD_TILES, SHARD_BUCKETS)
 
@@ -65,6 +65,11 @@ def _env_struct(env, radius, transform):
     if transform is not None:
         e.transform = (C.c_float * 16)(*np.asarray(transform, np.float32).reshape(-1))
     return e, rgb  # keep rgb alive
+
+
+def set_build_device(device: int):
+    """Device the SAH BVH builds of later scene loads run on (-1: host builds only)."""
+    lib().ys_set_build_device(int(device))
 
 
 def comm_init_all(contexts):
@@ -130,6 +135,7 @@ class Scene:
             _check(rc, f"ys_scene_load_bvh({path})", lib().ys_last_error() or b"")
         self.flat = lib().ys_scene_flat(self._h).contents
         self.build_ms = lib().ys_scene_build_ms(self._h)
+        self.device_builds = lib().ys_scene_device_builds(self._h)  # meshes whose SAH BVH was built on the GPU
 
     def close(self):
         if self._h:

@@ -30,7 +30,7 @@ class YcCamera(C.Structure):
                 ("apertureSides", u32), ("exposure", f32)]
 
 
-BVH_SAH, BVH_MEDIAN_SPLIT = 0, 1
+BVH_SAH, BVH_MEDIAN_SPLIT, BVH_SAH_DEVICE, BVH_SAH_HOST = 0, 1, 2, 3
 INTEGRATOR_MIS, INTEGRATOR_NAIVE = 0, 1
 SCRAMBLER_FAST_OWEN, SCRAMBLER_OWEN, SCRAMBLER_BINARY_PERMUTE = 0, 1, 2
 SAMPLER_SOBOL, SAMPLER_NAIVE, SAMPLER_STRATIFIED = 0, 1, 2
@@ -168,6 +168,8 @@ PROTOTYPES = {
     "yc_kat": (C.c_int, [P, C.c_char_p, P, C.c_size_t, P, C.c_size_t]),
     "ys_scene_load": (C.c_int, [C.c_char_p, C.POINTER(P)]),
     "ys_scene_load_bvh": (C.c_int, [C.c_char_p, u32, C.POINTER(P)]),
+    "ys_set_build_device": (C.c_int, [C.c_int]),
+    "ys_scene_device_builds": (u32, [P]),
     "ys_scene_load_glb": (C.c_int, [C.c_char_p, C.POINTER(YsEnvLight), C.POINTER(P)]),
     "ys_glb_convert": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(YsEnvLight)]),
     "ys_decode_texture": (C.c_int, [P, C.c_size_t, u32, u32, C.POINTER(i32), P, C.c_size_t, C.POINTER(u32), C.POINTER(u32)]),

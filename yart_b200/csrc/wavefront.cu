@@ -22,6 +22,7 @@
 #include "integrator.cuh"
 #include "rt.cuh"
 #include "comm.cuh"
+#include "bvh_build.cuh"
 #ifndef YB_HOSTSIM
 #include "trace_wide.cuh"
 #endif
@@ -2279,6 +2280,29 @@ extern "C" int yc_comm_sum_u64(yc_ctx* ctx, uint64_t* values, uint32_t n) {
   YC_ENTER(ctx);
   if (!ctx->comm) return fail(ctx, YC_ERR_STATE, "yc_comm_sum_u64 without a communicator");
   return commSumHost(ctx, values, n);
+}
+
+// ---- the reference's SAH BVH built on the device (bvh_build.cuh) -----------------------------------------------------
+static thread_local std::string gBuildError;
+extern "C" const char* yc_build_last_error() { return gBuildError.c_str(); }
+static_assert(sizeof(YcBuildNode) == sizeof(yb::bvhb::GNode), "YcBuildNode mirrors bvhb::GNode");
+
+extern "C" int yc_build_bvh_sah(int device, const float* positions, size_t nVerts, const uint32_t* faces4, size_t nTris,
+                                YcBuildNode* pool, uint32_t* nNodes, uint32_t* indices, uint32_t* levels) {
+  if (!positions || !faces4 || !pool || !nNodes || !indices || nTris == 0) return YC_ERR_INVALID;
+  rt::Stream st;
+  int sms = 0;
+  if (const char* e = rt::init(device, st, sms)) {
+    gBuildError = e;
+    return YC_ERR_NO_DEVICE;
+  }
+  const char* e = bvhb::build(st, positions, nVerts, faces4, nTris, reinterpret_cast<bvhb::GNode*>(pool), nNodes, indices, levels);
+  rt::destroy(st);
+  if (e) {
+    gBuildError = e;
+    return YC_ERR_CUDA;
+  }
+  return YC_OK;
 }
 
 #include "kat.cuh"

@@ -58,7 +58,7 @@ extern "C" int ys_scene_load(const char* path, ys_scene** out) { return ys_scene
 
 extern "C" int ys_scene_load_bvh(const char* path, uint32_t bvhKind, ys_scene** out) {
   return guarded([&]() -> int {
-    if (!path || !out || bvhKind > YS_BVH_MEDIAN_SPLIT) return YC_ERR_INVALID;
+    if (!path || !out || bvhKind > YS_BVH_SAH_HOST) return YC_ERR_INVALID;
     *out = nullptr;
     ysc::SceneDesc d;
     std::string err;
@@ -195,6 +195,8 @@ extern "C" int ys_write_ppm(const char* path, const float* rgba, uint32_t width,
 extern "C" void ys_scene_destroy(ys_scene* s) { delete s; }
 extern "C" const YcScene* ys_scene_flat(const ys_scene* s) { return s ? &s->host.flat : nullptr; }
 extern "C" double ys_scene_build_ms(const ys_scene* s) { return s ? s->host.buildMs : 0.0; }
+extern "C" uint32_t ys_scene_device_builds(const ys_scene* s) { return s ? s->host.deviceBuilds : 0u; }
+extern "C" int ys_set_build_device(int device) { return yartb::setBuildDevice(device); }
 
 extern "C" int ys_scene_bvh(const ys_scene* s, uint32_t mesh, const void** nodes, uint32_t* nNodes,
                             const uint32_t** indices, uint32_t* nTris) {

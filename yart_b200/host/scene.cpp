@@ -1,7 +1,10 @@
 // scene.cpp — SceneDesc → HostScene (derived constants + flat GPU layout).  See scene.hpp.
 #include "scene.hpp"
 
+#include <atomic>
 #include <chrono>
+#include <cmath>
+#include <limits>
 #include <cstring>
 #include <functional>
 
@@ -46,6 +49,70 @@ static float buildDistribution1D(const float* f, size_t n, float mn, float mx, f
     for (size_t i = 1; i < n + 1; i++) cdf[i] /= integral;
   }
   return integral;
+}
+
+// ---- SAH build on the device (csrc/bvh_build.cuh through the C ABI) ---------------------------------------------------
+static std::atomic<int> gBuildDevice{0};
+int setBuildDevice(int device) {
+  gBuildDevice.store(device);
+  return 0;
+}
+
+// YS_BVH_SAH: the GPU for meshes worth the round trip, if there is one and the vertex data is finite (the device
+// build's min / max atomics assume an ordered set; the host builder folds NaNs the way the reference does).
+static bool autoDeviceBuild(const std::vector<float>& positions, size_t nTris) {
+#ifdef YB_HOSTSIM
+  (void)positions, (void)nTris;
+  return false;  // the CPU build of the device layer runs the stages as plain loops: the host builder is faster there
+#else
+  if (gBuildDevice.load() < 0 || nTris < 32768) return false;
+  for (float v : positions)
+    if (!(std::fabs(v) <= std::numeric_limits<float>::max())) return false;
+  return true;
+#endif
+}
+
+// Pool of nodes in creation order → the reference's numbering (children adjacent, allocated when the parent is visited,
+// left subtree first: bvh.hpp:165-166, 180-183), exactly what SahBvhBuilder::number produces.
+static bool buildOnDevice(const float* positions, size_t nVerts, const uint32_t* faces4, size_t nTris, BvhBuildResult& out,
+                          std::string* err) {
+  std::vector<YcBuildNode> pool(2 * nTris + 2);
+  uint32_t nNodes = 0, levels = 0;
+  out.indices.resize(nTris);
+  const int dev = std::max(0, gBuildDevice.load());
+  const int rc = yc_build_bvh_sah(dev, positions, nVerts, faces4, nTris, pool.data(), &nNodes, out.indices.data(), &levels);
+  if (rc != YC_OK) {
+    if (err) *err = yc_build_last_error();
+    return false;
+  }
+  out.nodes.clear();
+  out.nodes.reserve(nNodes);
+  out.nodes.resize(1);
+  std::vector<std::pair<uint32_t, uint32_t>> stack;  // (pool node, its number)
+  stack.push_back({0u, 0u});
+  while (!stack.empty()) {
+    const auto [pn, self] = stack.back();
+    stack.pop_back();
+    const YcBuildNode& g = pool[pn];
+    RefBvhNode n{};
+    for (int k = 0; k < 3; k++) n.mn[k] = g.mn[k], n.mx[k] = g.mx[k];
+    if (g.left == 0) {
+      n.leftFirst = g.first, n.span = g.span;
+      out.nodes[self] = n;
+      continue;
+    }
+    if (g.left + 1 >= nNodes) {
+      if (err) *err = "device BVH build returned a broken node pool";
+      return false;
+    }
+    const uint32_t l = uint32_t(out.nodes.size());
+    out.nodes.resize(out.nodes.size() + 2);
+    n.leftFirst = l, n.span = 0;
+    out.nodes[self] = n;
+    stack.push_back({g.left + 1, l + 1});  // popped after the whole left subtree has been numbered
+    stack.push_back({g.left, l});
+  }
+  return true;
 }
 
 bool HostScene::build(const ysc::SceneDesc& d, std::string* err) {
@@ -144,9 +211,19 @@ bool HostScene::build(const ysc::SceneDesc& d, std::string* err) {
     for (size_t i = 0; i < nv; i++) vb.expandToInclude(f3(&m.positions[3 * i]));
     meshVertexBounds.push_back(vb);
 
-    SahBvhBuilder builder;
-    builder.kind = bvhKind == 1 ? SahBvhBuilder::kMedianSplit : SahBvhBuilder::kSah;
-    BvhBuildResult ref = builder.build(m.positions.data(), nv, m.faces.data(), nf);
+    BvhBuildResult ref;
+    bool onDevice = false;
+    if (bvhKind == YS_BVH_SAH_DEVICE || (bvhKind == YS_BVH_SAH && autoDeviceBuild(m.positions, nf))) {
+      std::string berr;
+      onDevice = buildOnDevice(m.positions.data(), nv, m.faces.data(), nf, ref, &berr);
+      if (!onDevice && bvhKind == YS_BVH_SAH_DEVICE) return fail(("device BVH build: " + berr).c_str());
+    }
+    if (!onDevice) {
+      SahBvhBuilder builder;
+      builder.kind = bvhKind == YS_BVH_MEDIAN_SPLIT ? SahBvhBuilder::kMedianSplit : SahBvhBuilder::kSah;
+      ref = builder.build(m.positions.data(), nv, m.faces.data(), nf);
+    }
+    deviceBuilds += onDevice ? 1u : 0u;
 
     // reference nodes → inner-node records with both children inlined; leaves → contiguous tri runs
     std::vector<uint32_t> innerRank(ref.nodes.size(), 0);

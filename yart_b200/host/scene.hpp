@@ -42,11 +42,14 @@ struct HostScene {
   // reference-layout BVHs kept for parity tests
   std::vector<BvhBuildResult> refBvh;
   double buildMs = 0;
+  uint32_t deviceBuilds = 0;  // meshes whose SAH BVH was built on the GPU (yc_build_bvh_sah)
   YcScene flat{};
 
   uint32_t bvhKind = 0;  // YS_BVH_* (Mesh::BVHType, mesh.hpp:17)
   bool build(const ysc::SceneDesc& d, std::string* err);
   bool loadLuts(std::string* err);
 };
+
+int setBuildDevice(int device);  // ys_set_build_device
 
 }  // namespace yartb

@@ -295,6 +295,43 @@ def soup(n_tris=1_000_000, seed=1234, with_light=True) -> Scene:
     return s
 
 
+def degenerate_soup(n_tris=6000, seed=7) -> Scene:
+    """Builder stress: clusters of identical triangles (zero centroid extent in nodes of more than a leaf's size),
+    centroids on a coarse grid (many elements exactly on split planes), zero-area triangles, extents from 1e-4 to 1e3,
+    signed zeros in the vertex data."""
+    rng = np.random.default_rng(seed)
+    s = Scene()
+    s.materials = [Material(base=(0.7, 0.7, 0.7), roughness=1.0),
+                   Material(base=(1.0, 1.0, 1.0), roughness=1.0, emission=(10.0, 10.0, 10.0))]
+    kinds = rng.integers(0, 5, n_tris)
+    centres = np.round(rng.uniform(-8.0, 8.0, (n_tris, 1, 3)) * 2.0) / 2.0  # half-unit grid
+    ext = np.where(kinds == 3, 1e-4, np.where(kinds == 4, 50.0, 0.3))[:, None, None]
+    verts = centres + rng.uniform(-1.0, 1.0, (n_tris, 3, 3)) * ext
+    dup = np.nonzero(kinds == 1)[0]
+    if len(dup) > 1:  # runs of copies of one triangle: 120 copies at most, so some runs exceed kSmallSpan and kMaxLeaf
+        for start in range(0, len(dup), 120):
+            verts[dup[start:start + 120]] = verts[dup[start]]
+    flat = np.nonzero(kinds == 2)[0]
+    verts[flat, 2] = verts[flat, 1]  # zero-area triangles
+    verts[rng.integers(0, n_tris, n_tris // 50), rng.integers(0, 3, n_tris // 50), rng.integers(0, 3, n_tris // 50)] = -0.0
+    verts = verts.astype(np.float32)
+    nrm = np.zeros((n_tris * 3, 3), np.float32)
+    nrm[:, 1] = 1.0
+    faces = np.zeros((n_tris, 4), np.uint32)
+    faces[:, 0] = np.arange(n_tris) * 3
+    faces[:, 1] = faces[:, 0] + 1
+    faces[:, 2] = faces[:, 0] + 2
+    s.meshes = [Mesh(verts.reshape(-1, 3), nrm, None, None, faces)]
+    s.nodes = [Node(-1, -1), Node(0, 0)]
+    lb = MeshBuilder()
+    lb.quad((-30, 25, -30), (30, 25, -30), (30, 25, 30), (-30, 25, 30), 1)
+    s.meshes.append(lb.build())
+    s.nodes.append(Node(0, 1))
+    s.add_area_lights(1, None)
+    s.camera = dict(pos=(0.0, 0.0, 40.0), target=(0.0, 0.0, 0.0), focal=35.0, fnum=0.0, exposure=0.0, w=64, h=64, spp=1, maxdepth=1)
+    return s
+
+
 # ------------------------------------------------------------------------------------------
 # tiny two-quad scene (smoke tests / SURVEY Appendix C style)
 # ------------------------------------------------------------------------------------------
