@@ -452,9 +452,10 @@ int ys_scene_load(const char* path, ys_scene** out);
  * bvh.hpp:266-347), YS_BVH_MEDIAN_SPLIT = MedianSplitBVH (bvh.hpp:237-264, its baseline builder). */
 #define YS_BVH_SAH 0
 #define YS_BVH_MEDIAN_SPLIT 1
-/* Where SahBVH is built.  YS_BVH_SAH picks by itself: meshes of at least 32768 triangles on the GPU
- * (yc_build_bvh_sah, device ys_set_build_device chose; finite vertex data) when there is one, everything else — and
- * everything after a failure of the device build — on the host cores (host/bvh_build.hpp).  Same tree either way. */
+/* Where SahBVH is built: YS_BVH_SAH on the host cores (host/bvh_build.hpp, multithreaded) — or, with
+ * YART_B200_BVH_DEVICE=1 in the environment, meshes of at least 32768 triangles with finite vertex data on the GPU
+ * (yc_build_bvh_sah on the device ys_set_build_device chose), falling back to the host if that fails.  Same tree either
+ * way, node for node. */
 #define YS_BVH_SAH_DEVICE 2 /* always through yc_build_bvh_sah (an error if that fails) */
 #define YS_BVH_SAH_HOST 3   /* always on the host cores */
 int ys_scene_load_bvh(const char* path, uint32_t bvhKind, ys_scene** out);

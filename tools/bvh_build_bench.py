@@ -12,8 +12,6 @@ n = len(faces)
 pool = np.zeros((2*n+2, 10), np.uint32); idx = np.zeros(n, np.uint32)
 nn = C.c_uint32(); lv = C.c_uint32()
 f = lib.yc_build_bvh_sah
-f.restype = C.c_int
-f.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p, C.POINTER(C.c_uint32)]
 for rep in range(4):
     t0 = time.time()
     rc = f(0, pos.ctypes.data, len(pos), faces.ctypes.data, n, pool.ctypes.data, C.byref(nn), idx.ctypes.data, C.byref(lv))

@@ -159,6 +159,8 @@ PROTOTYPES = {
     "yc_comm_init_all": (C.c_int, [C.POINTER(P), C.c_int]),
     "yc_comm_init_custom": (C.c_int, [P, C.c_int, C.c_int, COLLECTIVE_FN, P]),
     "yc_comm_destroy": (C.c_int, [P]),
+    "yc_build_bvh_sah": (C.c_int, [C.c_int, P, C.c_size_t, P, C.c_size_t, P, C.POINTER(u32), P, C.POINTER(u32)]),
+    "yc_build_last_error": (C.c_char_p, []),
     "yc_comm_reduce_frames": (C.c_int, [P, C.c_int]),
     "yc_comm_reduce_frames_async": (C.c_int, [P, C.c_int]),
     "yc_comm_frames_direct": (C.c_int, [P, C.POINTER(C.c_int)]),

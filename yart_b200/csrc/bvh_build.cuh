@@ -513,6 +513,20 @@ inline void inclusiveScan(rt::Stream& st, unsigned long long* v, unsigned long l
 }
 #endif
 
+// One device allocation, handed out in 256-byte-aligned pieces (pass 1: sizes only, base == nullptr).
+struct Arena {
+  char* base = nullptr;
+  size_t used = 0;
+  ~Arena() { rt::release(base); }
+  template <class T>
+  T* take(size_t count) {
+    used = (used + 255) & ~size_t(255);
+    T* p = base ? reinterpret_cast<T*>(base + used) : nullptr;
+    used += count * sizeof(T);
+    return p;
+  }
+};
+
 // ---- the build ------------------------------------------------------------------------------
 // Returns nullptr or an error string.  `poolOut` receives up to 2 n nodes in creation order (node 0 = root), `indicesOut`
 // the reference's m_indices.
@@ -520,20 +534,9 @@ inline const char* build(rt::Stream& st, const float* positions, size_t nVerts, 
                          GNode* poolOut, uint32_t* nNodesOut, uint32_t* indicesOut, uint32_t* levelsOut) {
   if (nTris == 0 || nTris > 0x7ffffff0u) return "triangle count out of range";
   const uint32_t n = uint32_t(nTris);
-  std::vector<void*> own;
-  auto dev = [&](auto** p, size_t count) -> const char* {
-    void* v = nullptr;
-    if (const char* e = rt::alloc(&v, count * sizeof(**p))) return e;
-    own.push_back(v);
-    *p = static_cast<std::remove_reference_t<decltype(*p)>>(v);
-    return nullptr;
-  };
-  struct Release {
-    std::vector<void*>& v;
-    ~Release() {
-      for (void* p : v) rt::release(p);
-    }
-  } release{own};
+  // one device allocation for everything (18 cudaMalloc / cudaFree pairs cost more than the build itself)
+  const size_t maxActive = size_t(n) / (kSmallSpan + 1) + 2;  // active nodes are disjoint runs of more than kSmallSpan
+  Arena arena;
 #define YB_B(expr)                       \
   do {                                   \
     if (const char* e_ = (expr)) return e_; \
@@ -545,25 +548,23 @@ inline const char* build(rt::Stream& st, const float* positions, size_t nVerts, 
   NodeWork* work = nullptr;
   Bin* bins = nullptr;
   unsigned long long *scan = nullptr, *sums = nullptr;
-  const size_t maxActive = size_t(n) / (kSmallSpan + 1) + 2;  // active nodes are disjoint runs of more than kSmallSpan
-  YB_B(dev(&dPos, 3 * nVerts));
-  YB_B(dev(&dFaces, 4 * size_t(n)));
-  YB_B(dev(&triB, 6 * size_t(n)));
-  YB_B(dev(&cen, 3 * size_t(n)));
-  YB_B(dev(&idxA, n));
-  YB_B(dev(&idxB, n));
-  YB_B(dev(&nodeOf, n));
-  YB_B(dev(&tabR, n));
-  YB_B(dev(&tabL, n));
-  YB_B(dev(&scan, n));
-  YB_B(dev(&sums, size_t(n) / 1024 + 64));
-  YB_B(dev(&pool, 2 * size_t(n) + 2));
-  YB_B(dev(&work, maxActive));
-  YB_B(dev(&bins, maxActive * 3 * kBins));
-  YB_B(dev(&listA, maxActive));
-  YB_B(dev(&listB, maxActive));
-  YB_B(dev(&small, size_t(n) + 2));
-  YB_B(dev(&counters, 4));  // pool count, next count, small count
+  for (int pass = 0; pass < 2; pass++) {  // pass 0 sizes the arena, pass 1 hands out the pieces
+    arena.used = 0;
+    dPos = arena.take<float>(3 * nVerts), dFaces = arena.take<uint32_t>(4 * size_t(n));
+    triB = arena.take<float>(6 * size_t(n)), cen = arena.take<float>(3 * size_t(n));
+    idxA = arena.take<uint32_t>(n), idxB = arena.take<uint32_t>(n), nodeOf = arena.take<uint32_t>(n);
+    tabR = arena.take<uint32_t>(n), tabL = arena.take<uint32_t>(n);
+    scan = arena.take<unsigned long long>(n), sums = arena.take<unsigned long long>(size_t(n) / 1024 + 64);
+    pool = arena.take<GNode>(2 * size_t(n) + 2);
+    work = arena.take<NodeWork>(maxActive), bins = arena.take<Bin>(maxActive * 3 * kBins);
+    listA = arena.take<uint32_t>(maxActive), listB = arena.take<uint32_t>(maxActive);
+    small = arena.take<uint32_t>(size_t(n) + 2), counters = arena.take<uint32_t>(4);
+    if (pass == 0) {
+      void* v = nullptr;
+      YB_B(rt::alloc(&v, arena.used + 256));
+      arena.base = static_cast<char*>(v);
+    }
+  }
   // YART_B200_BUILD_TRACE=1: stage times on stderr
   const char* traceEnv = getenv("YART_B200_BUILD_TRACE");
   const bool trace = traceEnv && *traceEnv && *traceEnv != '0';

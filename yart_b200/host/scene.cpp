@@ -5,6 +5,7 @@
 #include <chrono>
 #include <cmath>
 #include <limits>
+#include <memory>
 #include <cstring>
 #include <functional>
 
@@ -58,13 +59,19 @@ int setBuildDevice(int device) {
   return 0;
 }
 
-// YS_BVH_SAH: the GPU for meshes worth the round trip, if there is one and the vertex data is finite (the device
-// build's min / max atomics assume an ordered set; the host builder folds NaNs the way the reference does).
+// YS_BVH_SAH builds on the host cores unless YART_B200_BVH_DEVICE=1 asks for the GPU builder, and then for meshes
+// worth the round trip with finite vertex data (the device build's min / max atomics assume an ordered set; the host
+// builder folds NaNs the way the reference does).  The device build itself is 5 x faster than the 16-thread host build
+// (1 M triangles: 72 ms of kernels + copies against 300-360 ms), but the 230 MB of device memory it needs and the 84 MB it
+// copies back into fresh host memory cost, on the boxes measured, anything between 40 and 700 ms on top — see
+// profiles/README.md — so it is not the default.
 static bool autoDeviceBuild(const std::vector<float>& positions, size_t nTris) {
 #ifdef YB_HOSTSIM
   (void)positions, (void)nTris;
   return false;  // the CPU build of the device layer runs the stages as plain loops: the host builder is faster there
 #else
+  const char* e = getenv("YART_B200_BVH_DEVICE");
+  if (!e || !*e || *e == '0') return false;
   if (gBuildDevice.load() < 0 || nTris < 32768) return false;
   for (float v : positions)
     if (!(std::fabs(v) <= std::numeric_limits<float>::max())) return false;
@@ -76,42 +83,57 @@ static bool autoDeviceBuild(const std::vector<float>& positions, size_t nTris) {
 // left subtree first: bvh.hpp:165-166, 180-183), exactly what SahBvhBuilder::number produces.
 static bool buildOnDevice(const float* positions, size_t nVerts, const uint32_t* faces4, size_t nTris, BvhBuildResult& out,
                           std::string* err) {
-  std::vector<YcBuildNode> pool(2 * nTris + 2);
+  const char* traceEnv = getenv("YART_B200_BUILD_TRACE");
+  const bool trace = traceEnv && *traceEnv && *traceEnv != '0';
+  auto tick = [] { return std::chrono::high_resolution_clock::now(); };
+  auto since = [&](std::chrono::high_resolution_clock::time_point t) { return std::chrono::duration<double, std::milli>(tick() - t).count(); };
+  const auto tb0 = tick();
+  std::unique_ptr<YcBuildNode[]> pool(new YcBuildNode[2 * nTris + 2]);  // (not zeroed: 80 MB for a million triangles)
   uint32_t nNodes = 0, levels = 0;
   out.indices.resize(nTris);
   const int dev = std::max(0, gBuildDevice.load());
-  const int rc = yc_build_bvh_sah(dev, positions, nVerts, faces4, nTris, pool.data(), &nNodes, out.indices.data(), &levels);
+  const int rc = yc_build_bvh_sah(dev, positions, nVerts, faces4, nTris, pool.get(), &nNodes, out.indices.data(), &levels);
   if (rc != YC_OK) {
     if (err) *err = yc_build_last_error();
     return false;
   }
-  out.nodes.clear();
-  out.nodes.reserve(nNodes);
-  out.nodes.resize(1);
+  const double msCall = since(tb0);
+  out.nodes.resize(nNodes);
+  const double msResize = since(tb0) - msCall;
+  uint32_t used = 1;
   std::vector<std::pair<uint32_t, uint32_t>> stack;  // (pool node, its number)
+  stack.reserve(256);
   stack.push_back({0u, 0u});
   while (!stack.empty()) {
     const auto [pn, self] = stack.back();
     stack.pop_back();
     const YcBuildNode& g = pool[pn];
-    RefBvhNode n{};
+    RefBvhNode& n = out.nodes[self];
     for (int k = 0; k < 3; k++) n.mn[k] = g.mn[k], n.mx[k] = g.mx[k];
     if (g.left == 0) {
       n.leftFirst = g.first, n.span = g.span;
-      out.nodes[self] = n;
       continue;
     }
-    if (g.left + 1 >= nNodes) {
+    if (g.left + 1 >= nNodes || used + 2 > nNodes) {
       if (err) *err = "device BVH build returned a broken node pool";
       return false;
     }
-    const uint32_t l = uint32_t(out.nodes.size());
-    out.nodes.resize(out.nodes.size() + 2);
+    // the walk is depth-first over a pool in creation order: fetch the grandchildren's records while the left subtree
+    // is being numbered
+    const YcBuildNode &c0 = pool[g.left], &c1 = pool[g.left + 1];
+    if (c0.left) __builtin_prefetch(&pool[c0.left]);
+    if (c1.left) __builtin_prefetch(&pool[c1.left]);
+    const uint32_t l = used;
+    used += 2;
     n.leftFirst = l, n.span = 0;
-    out.nodes[self] = n;
     stack.push_back({g.left + 1, l + 1});  // popped after the whole left subtree has been numbered
     stack.push_back({g.left, l});
   }
+  if (used != nNodes) {
+    if (err) *err = "device BVH build returned unreachable nodes";
+    return false;
+  }
+  if (trace) fprintf(stderr, "yart_b200 scene build: device call %.1f ms, node array %.1f ms, renumbering %.1f ms\n", msCall, msResize, since(tb0) - msCall - msResize);
   return true;
 }
 
@@ -188,6 +210,11 @@ bool HostScene::build(const ysc::SceneDesc& d, std::string* err) {
       if (m.faces[4 * i + 3] >= d.materials.size()) return fail("material index out of range");
       if (m.lightIdx[i] >= int32_t(d.lights.size())) return fail("light index out of range");
     }
+    const char* traceEnv = getenv("YART_B200_BUILD_TRACE");
+    const bool trace = traceEnv && *traceEnv && *traceEnv != '0';
+    auto tick = [] { return std::chrono::high_resolution_clock::now(); };
+    auto since = [&](std::chrono::high_resolution_clock::time_point t) { return std::chrono::duration<double, std::milli>(tick() - t).count(); };
+    const auto tm0 = tick();
     YcMesh ym{};
     ym.vertOffset = uint32_t(positions.size() / 3);
     ym.primOffset = uint32_t(primMaterial.size());
@@ -196,21 +223,30 @@ bool HostScene::build(const ysc::SceneDesc& d, std::string* err) {
     ym.nTris = uint32_t(nf), ym.nVerts = uint32_t(nv);
 
     positions.insert(positions.end(), m.positions.begin(), m.positions.end());
-    for (size_t i = 0; i < nv; i++) {
-      const float* v = &m.vertexData[9 * i];
-      normals.insert(normals.end(), v, v + 3);
-      tangents.insert(tangents.end(), v + 3, v + 7);
-      uvs.insert(uvs.end(), v + 7, v + 9);
-    }
-    for (size_t i = 0; i < nf; i++) {
-      primIndices.insert(primIndices.end(), &m.faces[4 * i], &m.faces[4 * i] + 3);
-      primMaterial.push_back(m.faces[4 * i + 3]);
-      primLight.push_back(m.lightIdx[i]);
+    {
+      // interleaved (normal, tangent, uv) per vertex → the three SoA arrays; (i0, i1, i2, material) per face → two
+      const size_t n0 = normals.size(), t0 = tangents.size(), u0 = uvs.size();
+      normals.resize(n0 + 3 * nv), tangents.resize(t0 + 4 * nv), uvs.resize(u0 + 2 * nv);
+      float *pn = normals.data() + n0, *pt = tangents.data() + t0, *pu = uvs.data() + u0;
+      const float* v = m.vertexData.data();
+      for (size_t i = 0; i < nv; i++, v += 9, pn += 3, pt += 4, pu += 2) {
+        pn[0] = v[0], pn[1] = v[1], pn[2] = v[2];
+        pt[0] = v[3], pt[1] = v[4], pt[2] = v[5], pt[3] = v[6];
+        pu[0] = v[7], pu[1] = v[8];
+      }
+      const size_t i0 = primIndices.size(), m0 = primMaterial.size();
+      primIndices.resize(i0 + 3 * nf), primMaterial.resize(m0 + nf);
+      uint32_t *pi = primIndices.data() + i0, *pm = primMaterial.data() + m0;
+      const uint32_t* f = m.faces.data();
+      for (size_t i = 0; i < nf; i++, f += 4, pi += 3) pi[0] = f[0], pi[1] = f[1], pi[2] = f[2], pm[i] = f[3];
+      primLight.insert(primLight.end(), m.lightIdx.begin(), m.lightIdx.end());
     }
     Bounds3 vb;  // Node(Mesh*) ctor: unpadded vertex bounds (scene.hpp:17-22)
     for (size_t i = 0; i < nv; i++) vb.expandToInclude(f3(&m.positions[3 * i]));
     meshVertexBounds.push_back(vb);
 
+    const double msAttr = since(tm0);
+    const auto tm1 = tick();
     BvhBuildResult ref;
     bool onDevice = false;
     if (bvhKind == YS_BVH_SAH_DEVICE || (bvhKind == YS_BVH_SAH && autoDeviceBuild(m.positions, nf))) {
@@ -224,6 +260,8 @@ bool HostScene::build(const ysc::SceneDesc& d, std::string* err) {
       ref = builder.build(m.positions.data(), nv, m.faces.data(), nf);
     }
     deviceBuilds += onDevice ? 1u : 0u;
+    const double msBvh = since(tm1);
+    const auto tm2 = tick();
 
     // reference nodes → inner-node records with both children inlined; leaves → contiguous tri runs
     std::vector<uint32_t> innerRank(ref.nodes.size(), 0);
@@ -270,6 +308,9 @@ bool HostScene::build(const ysc::SceneDesc& d, std::string* err) {
       if (n.span != 0) bvhTris[tbase + n.leftFirst + n.span - 1].flags |= YC_TRI_LAST;
     meshes.push_back(ym);
     refBvh.push_back(std::move(ref));
+    if (trace && nf >= 1000)
+      fprintf(stderr, "yart_b200 scene build: mesh of %zu tris: attributes %.1f ms, BVH (%s) %.1f ms, flatten %.1f ms\n", nf, msAttr,
+              onDevice ? "GPU" : "host", msBvh, since(tm2));
   }
   buildMs = std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - t0).count();
 
