@@ -427,16 +427,16 @@ int yc_comm_allreduce_buckets(yc_ctx* ctx, uint32_t waveSamples);
 /* Control values (ray counts, abort votes): in-place sum over all participants. */
 int yc_comm_sum_u64(yc_ctx* ctx, uint64_t* values, uint32_t n);
 /* The reference's binned-SAH BVH (src/core/bvh.hpp:140-184, 273-347) built on the device, level by level: the same
- * tree and the same triangle order as the host builder — and the reference — produce.  `pool` receives at most
- * 2 * nTris + 2 nodes in creation order (node 0 is the root; children of an inner node are left and left + 1;
- * left == 0 marks a leaf over indices[first .. first + span)); the host layer renumbers them in the reference's
- * allocation order.  `faces4`: 4 words per triangle (3 vertex indices, 1 ignored).  Vertex positions must be finite. */
+ * tree, the same node numbering and the same triangle order as the host builder — and the reference — produce.
+ * `nodes` (capacity 2 * nTris + 2) receives the reference's BVHNode array (bvh.hpp:21-33): span == 0 marks an inner node
+ * whose children are leftFirst and leftFirst + 1, otherwise a leaf over indices[leftFirst .. leftFirst + span).
+ * `faces4`: 4 words per triangle (3 vertex indices, 1 ignored).  Vertex positions must be finite. */
 typedef struct YcBuildNode {
   float mn[3], mx[3];
-  uint32_t first, span, left, reserved;
+  uint32_t leftFirst, span;
 } YcBuildNode;
 int yc_build_bvh_sah(int device, const float* positions, size_t nVerts, const uint32_t* faces4, size_t nTris,
-                     YcBuildNode* pool, uint32_t* nNodes, uint32_t* indices, uint32_t* levels);
+                     YcBuildNode* nodes, uint32_t* nNodes, uint32_t* indices, uint32_t* levels);
 const char* yc_build_last_error(void);
 /* Function-level hooks used by the parity tests (device evaluations of the restated math). */
 int yc_kat(yc_ctx* ctx, const char* kind, const void* in, size_t inBytes, void* out, size_t outBytes);
@@ -452,10 +452,10 @@ int ys_scene_load(const char* path, ys_scene** out);
  * bvh.hpp:266-347), YS_BVH_MEDIAN_SPLIT = MedianSplitBVH (bvh.hpp:237-264, its baseline builder). */
 #define YS_BVH_SAH 0
 #define YS_BVH_MEDIAN_SPLIT 1
-/* Where SahBVH is built: YS_BVH_SAH on the host cores (host/bvh_build.hpp, multithreaded) — or, with
- * YART_B200_BVH_DEVICE=1 in the environment, meshes of at least 32768 triangles with finite vertex data on the GPU
- * (yc_build_bvh_sah on the device ys_set_build_device chose), falling back to the host if that fails.  Same tree either
- * way, node for node. */
+/* Where SahBVH is built.  YS_BVH_SAH picks by itself: meshes of at least 32768 triangles with finite vertex data on
+ * the GPU (yc_build_bvh_sah, on the device ys_set_build_device chose) when there is one, everything else — and
+ * everything after a failure of the device build, or with YART_B200_BVH_DEVICE=0 in the environment — on the host cores
+ * (host/bvh_build.hpp, multithreaded).  Same tree either way, node for node. */
 #define YS_BVH_SAH_DEVICE 2 /* always through yc_build_bvh_sah (an error if that fails) */
 #define YS_BVH_SAH_HOST 3   /* always on the host cores */
 int ys_scene_load_bvh(const char* path, uint32_t bvhKind, ys_scene** out);

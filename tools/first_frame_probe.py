@@ -25,7 +25,7 @@ for rep in range(2):
     t4 = time.time()
     c2.close()
     print(f"context {1e3 * (t1 - t0):.0f} ms, upload + wide collapse {1e3 * (t2 - t1):.0f} ms, begin_frame {1e3 * (t3 - t2):.0f} ms, first wave {1e3 * (t4 - t3):.0f} ms", flush=True)
-for kind, name in ((Y.BVH_SAH_HOST, "host"), (Y.BVH_SAH, "auto"), (Y.BVH_SAH, "auto"), (Y.BVH_SAH_HOST, "host"), (Y.BVH_SAH, "auto")):
+for kind, name in ((Y.BVH_SAH_HOST, "host"), (Y.BVH_SAH, "gpu"), (Y.BVH_SAH, "gpu"), (Y.BVH_SAH_HOST, "host"), (Y.BVH_SAH, "gpu")):
     t0 = time.time()
     s = Y.Scene(path, bvh_kind=kind)
     print(f"{name}: load {1e3 * (time.time() - t0):.0f} ms, build_ms {s.build_ms:.0f}, on gpu {s.device_builds}", flush=True)

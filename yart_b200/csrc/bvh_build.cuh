@@ -16,7 +16,7 @@
 //     positions of the k-th right element from the front / k-th left element from the back — one scan and two
 //     scatters per level (partitionDest below).
 // Nodes of at most kSmallSpan triangles are finished by one thread each with the reference's sequential code.
-// The node pool is in creation order; the host renumbers it in the reference's allocation order afterwards.
+// The node pool is in creation order; three more passes per tree level put it into the reference's allocation order.
 // In the CPU build of the product sources (YB_HOSTSIM) the same stages run as plain loops.
 #pragma once
 #include <limits>
@@ -72,6 +72,36 @@ YB_DEV uint32_t atomAddU(uint32_t* a, uint32_t v) {
   return o;
 #else
   return atomicAdd(a, v);
+#endif
+}
+
+YB_DEV void atomMaxU(uint32_t* a, uint32_t v) {
+#ifdef YB_HOSTSIM
+  if (v > *a) *a = v;
+#else
+  atomicMax(a, v);
+#endif
+}
+
+// min / max of a box into the box at `mn` / `mx`, one set of atomics per group of lanes of the warp that share the
+// target (`key`): in the first levels a warp's 32 triangles all belong to one node, and a million lanes would queue
+// on six addresses.  The float order is carried through the warp reduction as an order-preserving unsigned key.
+YB_DEV uint32_t orderedKey(float v) {
+  const uint32_t u = __float_as_uint(v);
+  return (u >> 31) ? ~u : (u | 0x80000000u);
+}
+YB_DEV float fromOrderedKey(uint32_t k) { return __uint_as_float((k >> 31) ? (k & 0x7fffffffu) : ~k); }
+YB_DEV void foldBoxAtomic(float* mn, float* mx, const float* lo, const float* hi, const void* key) {
+#ifdef YB_HOSTSIM
+  (void)key;
+  for (int k = 0; k < 3; k++) atomMinF(&mn[k], lo[k]), atomMaxF(&mx[k], hi[k]);
+#else
+  const unsigned group = __match_any_sync(__activemask(), reinterpret_cast<unsigned long long>(key));
+  const bool leader = (threadIdx.x & 31) == __ffs(group) - 1;
+  for (int k = 0; k < 3; k++) {
+    const uint32_t a = __reduce_min_sync(group, orderedKey(lo[k])), b = __reduce_max_sync(group, orderedKey(hi[k]));
+    if (leader) atomMinF(&mn[k], fromOrderedKey(a)), atomMaxF(&mx[k], fromOrderedKey(b));
+  }
 #endif
 }
 
@@ -157,6 +187,8 @@ struct Arrays {
   uint32_t* nextCount;
   uint32_t* small;     // pool indices of small-subtree roots
   uint32_t* smallCount;
+  uint32_t* depth;     // per pool node
+  uint32_t* maxDepth;
 };
 
 // ---- stages --------------------------------------------------------------------------
@@ -191,7 +223,7 @@ struct RootBoundsK {  // per triangle: the root's box
   YB_DEV void operator()(uint32_t p) const {
     GNode& n = a.pool[0];
     const float* b = a.triB + 6 * size_t(a.idx[p]);
-    for (int k = 0; k < 3; k++) atomMinF(&n.mn[k], b[k]), atomMaxF(&n.mx[k], b[3 + k]);
+    foldBoxAtomic(n.mn, n.mx, b, b + 3, &n);
   }
 };
 
@@ -217,7 +249,7 @@ struct CentroidBoundsK {  // per position
     if (s == kNone) return;
     NodeWork& w = a.work[s];
     const float* c = a.cen + 3 * size_t(a.idx[p]);
-    for (int k = 0; k < 3; k++) atomMinF(&w.cmn[k], c[k]), atomMaxF(&w.cmx[k], c[k]);
+    foldBoxAtomic(w.cmn, w.cmx, c, c, &w);
   }
 };
 struct BinK {  // per position: the three axes' bins (bvh.hpp:288-298)
@@ -238,6 +270,49 @@ struct BinK {  // per position: the three axes' bins (bvh.hpp:288-298)
     }
   }
 };
+#ifndef YB_HOSTSIM
+// BinK with the bins of the block's first node in shared memory: in the first levels all 256 positions of a block
+// belong to one node, and its 60 bins take the block's 256 x 21 atomics in shared memory instead of in L2.
+constexpr int kBinBlock = 256;
+__global__ void __launch_bounds__(kBinBlock) binSharedK(Arrays a, uint32_t n) {
+  __shared__ uint32_t sCount[3 * kBins];
+  __shared__ float sMn[3 * kBins][3], sMx[3 * kBins][3];
+  const uint32_t p = blockIdx.x * kBinBlock + threadIdx.x;
+  const uint32_t blockSlot = a.nodeOf[blockIdx.x * kBinBlock];
+  if (threadIdx.x < 3 * kBins) {
+    sCount[threadIdx.x] = 0;
+    emptyBox(sMn[threadIdx.x], sMx[threadIdx.x]);
+  }
+  __syncthreads();
+  const uint32_t s = p < n ? a.nodeOf[p] : kNone;
+  if (s != kNone) {
+    const NodeWork& w = a.work[s];
+    const uint32_t t = a.idx[p];
+    const float* c = a.cen + 3 * size_t(t);
+    const float* tb = a.triB + 6 * size_t(t);
+    for (uint32_t ax = 0; ax < 3; ax++) {
+      const float bmin = w.cmn[ax], bsize = w.cmx[ax] - w.cmn[ax];
+      const float scale = float(kBins) / bsize;
+      const uint32_t bi = ax * kBins + binOf(c[ax], bmin, scale);
+      if (s == blockSlot) {
+        atomicAdd(&sCount[bi], 1u);
+        for (int k = 0; k < 3; k++) atomMinF(&sMn[bi][k], tb[k]), atomMaxF(&sMx[bi][k], tb[3 + k]);
+      } else {
+        Bin& b = a.bins[size_t(s) * 3 * kBins + bi];
+        atomicAdd(&b.count, 1u);
+        for (int k = 0; k < 3; k++) atomMinF(&b.mn[k], tb[k]), atomMaxF(&b.mx[k], tb[3 + k]);
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 3 * kBins && blockSlot != kNone && sCount[threadIdx.x] > 0) {
+    Bin& b = a.bins[size_t(blockSlot) * 3 * kBins + threadIdx.x];
+    atomicAdd(&b.count, sCount[threadIdx.x]);
+    for (int k = 0; k < 3; k++) atomMinF(&b.mn[k], sMn[threadIdx.x][k]), atomMaxF(&b.mx[k], sMx[threadIdx.x][k]);
+  }
+}
+#endif
+
 struct ChooseK {  // per active node: SahBVH::getSplit's decision
   Arrays a;
   YB_DEV void operator()(uint32_t s) const {
@@ -326,12 +401,14 @@ struct ChildrenK {  // per active node: bvh.hpp:160-183
     if (!w.split || w.nLeft == 0 || w.nLeft == n.span) return;  // stays a leaf (its indices keep the partition's order)
     const uint32_t l = atomAddU(a.poolCount, 2u);
     n.left = l;
+    atomMaxU(a.maxDepth, a.depth[w.node] + 1u);
     for (uint32_t c = 0; c < 2; c++) {
       GNode& ch = a.pool[l + c];
       emptyBox(ch.mn, ch.mx);
       ch.first = c == 0 ? n.first : n.first + w.nLeft;
       ch.span = c == 0 ? w.nLeft : n.span - w.nLeft;
       ch.left = 0, ch.slot = kNone;
+      a.depth[l + c] = a.depth[w.node] + 1u;
       if (ch.span > kSmallSpan) {
         ch.slot = atomAddU(a.nextCount, 1u);
         a.nextWork[ch.slot] = l + c;
@@ -355,7 +432,7 @@ struct ChildBoundsK {  // per position (new order): updateBounds of the two chil
     GNode& ch = a.pool[n.left + (p < n.first + w.nLeft ? 0u : 1u)];
     a.nodeOf[p] = ch.slot;
     const float* tb = a.triB + 6 * size_t(a.idxNext[p]);
-    for (int k = 0; k < 3; k++) atomMinF(&ch.mn[k], tb[k]), atomMaxF(&ch.mx[k], tb[3 + k]);
+    foldBoxAtomic(ch.mn, ch.mx, tb, tb + 3, &ch);
   }
 };
 // One thread finishes a small subtree with the reference's sequential code (bvh.hpp:140-184, 273-347).
@@ -366,7 +443,8 @@ struct SmallSubtreeK {
     int sp = 0;
     stack[sp++] = a.small[s];
     while (sp > 0) {
-      GNode& n = a.pool[stack[--sp]];
+      const uint32_t self = stack[--sp];
+      GNode& n = a.pool[self];
       const uint32_t first = n.first, span = n.span;
       // getSplit
       float cmn[3], cmx[3];
@@ -413,8 +491,10 @@ struct SmallSubtreeK {
       if (nLeft == 0 || nLeft == span) continue;
       const uint32_t l = atomAddU(a.poolCount, 2u);
       n.left = l;
+      atomMaxU(a.maxDepth, a.depth[self] + 1u);
       for (uint32_t c = 0; c < 2; c++) {
         GNode& ch = a.pool[l + c];
+        a.depth[l + c] = a.depth[self] + 1u;
         ch.first = c == 0 ? first : first + nLeft;
         ch.span = c == 0 ? nLeft : span - nLeft;
         ch.left = 0, ch.slot = kNone;
@@ -428,6 +508,52 @@ struct SmallSubtreeK {
   }
 };
 
+
+// ---- the reference's node numbering ----------------------------------------------------------------------------------
+// BVH::subdivide numbers a node's two children when the node is visited, depth first, left subtree first (bvh.hpp:165-166,
+// 180-183): the children of the inner node with pre-order rank p (among inner nodes) are 1 + 2 p and 2 + 2 p.  The pool is
+// in creation order with child links; inner-node counts per subtree come bottom-up, ranks top-down, one depth at a time.
+struct RefNode {  // = RefBvhNode of the host layer, the reference's BVHNode (bvh.hpp:21-33)
+  float mn[3], mx[3];
+  uint32_t leftFirst, span;
+};
+struct CountUpK {
+  Arrays a;
+  uint32_t* cnt;
+  uint32_t d;
+  YB_DEV void operator()(uint32_t i) const {
+    if (a.depth[i] != d) return;
+    const uint32_t l = a.pool[i].left;
+    cnt[i] = l ? 1u + cnt[l] + cnt[l + 1] : 0u;
+  }
+};
+struct NumberDownK {
+  Arrays a;
+  const uint32_t* cnt;
+  uint32_t *pre, *ref;
+  uint32_t d;
+  YB_DEV void operator()(uint32_t i) const {
+    if (a.depth[i] != d) return;
+    const uint32_t l = a.pool[i].left;
+    if (!l) return;
+    const uint32_t p = pre[i], r = 1u + 2u * p;
+    ref[l] = r, ref[l + 1] = r + 1u;
+    pre[l] = p + 1u, pre[l + 1] = p + 1u + cnt[l];
+  }
+};
+struct EmitK {
+  Arrays a;
+  const uint32_t *pre, *ref;
+  RefNode* out;
+  YB_DEV void operator()(uint32_t i) const {
+    const GNode& g = a.pool[i];
+    RefNode o;
+    for (int k = 0; k < 3; k++) o.mn[k] = g.mn[k], o.mx[k] = g.mx[k];
+    if (g.left) o.leftFirst = 1u + 2u * pre[i], o.span = 0u;
+    else o.leftFirst = g.first, o.span = g.span;
+    out[ref[i]] = o;
+  }
+};
 
 // ---- inclusive scan of the packed class counts over all positions ---------------------------
 #ifdef YB_HOSTSIM
@@ -528,10 +654,10 @@ struct Arena {
 };
 
 // ---- the build ------------------------------------------------------------------------------
-// Returns nullptr or an error string.  `poolOut` receives up to 2 n nodes in creation order (node 0 = root), `indicesOut`
-// the reference's m_indices.
+// Returns nullptr or an error string.  `nodesOut` receives up to 2 n nodes in the reference's numbering, `indicesOut` the
+// reference's m_indices.
 inline const char* build(rt::Stream& st, const float* positions, size_t nVerts, const uint32_t* faces4, size_t nTris,
-                         GNode* poolOut, uint32_t* nNodesOut, uint32_t* indicesOut, uint32_t* levelsOut) {
+                         RefNode* nodesOut, uint32_t* nNodesOut, uint32_t* indicesOut, uint32_t* levelsOut) {
   if (nTris == 0 || nTris > 0x7ffffff0u) return "triangle count out of range";
   const uint32_t n = uint32_t(nTris);
   // one device allocation for everything (18 cudaMalloc / cudaFree pairs cost more than the build itself)
@@ -548,6 +674,8 @@ inline const char* build(rt::Stream& st, const float* positions, size_t nVerts, 
   NodeWork* work = nullptr;
   Bin* bins = nullptr;
   unsigned long long *scan = nullptr, *sums = nullptr;
+  uint32_t *depth = nullptr, *cnt = nullptr, *pre = nullptr, *ref = nullptr;
+  RefNode* refNodes = nullptr;
   for (int pass = 0; pass < 2; pass++) {  // pass 0 sizes the arena, pass 1 hands out the pieces
     arena.used = 0;
     dPos = arena.take<float>(3 * nVerts), dFaces = arena.take<uint32_t>(4 * size_t(n));
@@ -559,6 +687,9 @@ inline const char* build(rt::Stream& st, const float* positions, size_t nVerts, 
     work = arena.take<NodeWork>(maxActive), bins = arena.take<Bin>(maxActive * 3 * kBins);
     listA = arena.take<uint32_t>(maxActive), listB = arena.take<uint32_t>(maxActive);
     small = arena.take<uint32_t>(size_t(n) + 2), counters = arena.take<uint32_t>(4);
+    depth = arena.take<uint32_t>(2 * size_t(n) + 2), cnt = arena.take<uint32_t>(2 * size_t(n) + 2);
+    pre = arena.take<uint32_t>(2 * size_t(n) + 2), ref = arena.take<uint32_t>(2 * size_t(n) + 2);
+    refNodes = arena.take<RefNode>(2 * size_t(n) + 2);
     if (pass == 0) {
       void* v = nullptr;
       YB_B(rt::alloc(&v, arena.used + 256));
@@ -576,6 +707,7 @@ inline const char* build(rt::Stream& st, const float* positions, size_t nVerts, 
   const auto t0 = now();
   double tAlloc = 0, tPrep = 0, tLevels = 0, tSmall = 0;
   if (trace) tAlloc = msSince(t0);
+  const auto tEnter = t0;
   YB_B(rt::h2d(st, dPos, positions, 3 * nVerts * sizeof(float)));
   YB_B(rt::h2d(st, dFaces, faces4, 4 * size_t(n) * sizeof(uint32_t)));
 
@@ -595,6 +727,8 @@ inline const char* build(rt::Stream& st, const float* positions, size_t nVerts, 
   a.triB = triB, a.cen = cen, a.idx = idxA, a.idxNext = idxB, a.nodeOf = nodeOf, a.pool = pool, a.poolCount = counters;
   a.work = work, a.bins = bins, a.scan = scan, a.tabR = tabR, a.tabL = tabL, a.nextWork = listB, a.nextCount = counters + 1;
   a.small = small, a.smallCount = counters + 2;
+  a.depth = depth, a.maxDepth = counters + 3;
+  YB_B(rt::zero(st, depth, sizeof(uint32_t)));  // the root
   rt::launchFor(st, n, RootBoundsK{a});
   if (trace) tPrep = msSince(t0);
   uint32_t* list = listA;
@@ -615,7 +749,11 @@ inline const char* build(rt::Stream& st, const float* positions, size_t nVerts, 
     a.nextWork = list == listA ? listB : listA;
     rt::launchFor(st, nActive, WorkInitK{a, list});
     rt::launchFor(st, n, CentroidBoundsK{a});
+#ifdef YB_HOSTSIM
     rt::launchFor(st, n, BinK{a});
+#else
+    binSharedK<<<(n + kBinBlock - 1) / kBinBlock, kBinBlock, 0, st.s>>>(a, n);
+#endif
     rt::launchFor(st, nActive, ChooseK{a});
     rt::launchFor(st, n, ClassK{a});
     inclusiveScan(st, scan, sums, n);
@@ -639,7 +777,16 @@ inline const char* build(rt::Stream& st, const float* positions, size_t nVerts, 
   if (const char* e = rt::lastError()) return e;
   if (trace) tSmall = msSince(t0);
   if (hc[0] > 2 * n + 2) return "BVH build: node pool overflow";
-  YB_B(rt::d2h(st, poolOut, pool, size_t(hc[0]) * sizeof(GNode)));
+  {
+    const uint32_t nNodes = hc[0], deepest = hc[3];
+    if (deepest > 4096) return "BVH build: tree too deep";
+    for (uint32_t d = deepest + 1; d-- > 0;) rt::launchFor(st, nNodes, CountUpK{a, cnt, d});
+    YB_B(rt::zero(st, pre, sizeof(uint32_t)));
+    YB_B(rt::zero(st, ref, sizeof(uint32_t)));
+    for (uint32_t d = 0; d <= deepest; d++) rt::launchFor(st, nNodes, NumberDownK{a, cnt, pre, ref, d});
+    rt::launchFor(st, nNodes, EmitK{a, pre, ref, refNodes});
+  }
+  YB_B(rt::d2h(st, nodesOut, refNodes, size_t(hc[0]) * sizeof(RefNode)));
   YB_B(rt::d2h(st, indicesOut, a.idx, size_t(n) * sizeof(uint32_t)));
   *nNodesOut = hc[0];
   if (levelsOut) *levelsOut = levels;

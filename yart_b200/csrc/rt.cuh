@@ -21,6 +21,7 @@ inline const char* init(int, Stream&, int& smCount) {
   smCount = 1;
   return nullptr;
 }
+inline const char* initStream(int, Stream&) { return nullptr; }
 inline void destroy(Stream&) {}
 inline void useDevice(int) {}
 inline const char* alloc(void** p, size_t bytes) {
@@ -91,6 +92,13 @@ inline const char* init(int device, Stream& st, int& smCount) {
   cudaDeviceProp prop;
   if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return cudaGetErrorString(e);
   smCount = prop.multiProcessorCount;
+  if ((e = cudaStreamCreateWithFlags(&st.s, cudaStreamNonBlocking)) != cudaSuccess) return cudaGetErrorString(e);
+  return nullptr;
+}
+// A stream on `device` without the device-property query of init() (which costs up to a quarter of a second per call).
+inline const char* initStream(int device, Stream& st) {
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return cudaGetErrorString(e);
   if ((e = cudaStreamCreateWithFlags(&st.s, cudaStreamNonBlocking)) != cudaSuccess) return cudaGetErrorString(e);
   return nullptr;
 }

@@ -2285,19 +2285,26 @@ extern "C" int yc_comm_sum_u64(yc_ctx* ctx, uint64_t* values, uint32_t n) {
 // ---- the reference's SAH BVH built on the device (bvh_build.cuh) -----------------------------------------------------
 static thread_local std::string gBuildError;
 extern "C" const char* yc_build_last_error() { return gBuildError.c_str(); }
-static_assert(sizeof(YcBuildNode) == sizeof(yb::bvhb::GNode), "YcBuildNode mirrors bvhb::GNode");
+static_assert(sizeof(YcBuildNode) == sizeof(yb::bvhb::RefNode), "YcBuildNode mirrors bvhb::RefNode");
 
 extern "C" int yc_build_bvh_sah(int device, const float* positions, size_t nVerts, const uint32_t* faces4, size_t nTris,
-                                YcBuildNode* pool, uint32_t* nNodes, uint32_t* indices, uint32_t* levels) {
-  if (!positions || !faces4 || !pool || !nNodes || !indices || nTris == 0) return YC_ERR_INVALID;
+                                YcBuildNode* nodes, uint32_t* nNodes, uint32_t* indices, uint32_t* levels) {
+  if (!positions || !faces4 || !nodes || !nNodes || !indices || nTris == 0) return YC_ERR_INVALID;
   rt::Stream st;
-  int sms = 0;
-  if (const char* e = rt::init(device, st, sms)) {
+  const char* traceEnv = getenv("YART_B200_BUILD_TRACE");
+  const auto tA = std::chrono::high_resolution_clock::now();
+  if (const char* e = rt::initStream(device, st)) {
     gBuildError = e;
     return YC_ERR_NO_DEVICE;
   }
-  const char* e = bvhb::build(st, positions, nVerts, faces4, nTris, reinterpret_cast<bvhb::GNode*>(pool), nNodes, indices, levels);
+  const auto tB = std::chrono::high_resolution_clock::now();
+  const char* e = bvhb::build(st, positions, nVerts, faces4, nTris, reinterpret_cast<bvhb::RefNode*>(nodes), nNodes, indices, levels);
+  const auto tC = std::chrono::high_resolution_clock::now();
   rt::destroy(st);
+  if (traceEnv && *traceEnv && *traceEnv != '0')
+    fprintf(stderr, "yart_b200 bvh build: device + stream %.1f ms, build incl. allocation %.1f ms, stream release %.1f ms\n",
+            std::chrono::duration<double, std::milli>(tB - tA).count(), std::chrono::duration<double, std::milli>(tC - tB).count(),
+            std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - tC).count());
   if (e) {
     gBuildError = e;
     return YC_ERR_CUDA;

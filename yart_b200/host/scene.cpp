@@ -59,19 +59,16 @@ int setBuildDevice(int device) {
   return 0;
 }
 
-// YS_BVH_SAH builds on the host cores unless YART_B200_BVH_DEVICE=1 asks for the GPU builder, and then for meshes
-// worth the round trip with finite vertex data (the device build's min / max atomics assume an ordered set; the host
-// builder folds NaNs the way the reference does).  The device build itself is 5 x faster than the 16-thread host build
-// (1 M triangles: 72 ms of kernels + copies against 300-360 ms), but the 230 MB of device memory it needs and the 84 MB it
-// copies back into fresh host memory cost, on the boxes measured, anything between 40 and 700 ms on top — see
-// profiles/README.md — so it is not the default.
+// YS_BVH_SAH: the GPU for meshes worth the round trip, if there is one and the vertex data is finite (the device
+// build's min / max atomics assume an ordered set; the host builder folds NaNs the way the reference does).
+// YART_B200_BVH_DEVICE=0 keeps every build on the host cores.
 static bool autoDeviceBuild(const std::vector<float>& positions, size_t nTris) {
 #ifdef YB_HOSTSIM
   (void)positions, (void)nTris;
   return false;  // the CPU build of the device layer runs the stages as plain loops: the host builder is faster there
 #else
   const char* e = getenv("YART_B200_BVH_DEVICE");
-  if (!e || !*e || *e == '0') return false;
+  if (e && *e == '0') return false;
   if (gBuildDevice.load() < 0 || nTris < 32768) return false;
   for (float v : positions)
     if (!(std::fabs(v) <= std::numeric_limits<float>::max())) return false;
@@ -79,61 +76,21 @@ static bool autoDeviceBuild(const std::vector<float>& positions, size_t nTris) {
 #endif
 }
 
-// Pool of nodes in creation order → the reference's numbering (children adjacent, allocated when the parent is visited,
-// left subtree first: bvh.hpp:165-166, 180-183), exactly what SahBvhBuilder::number produces.
+// yc_build_bvh_sah delivers the reference's node array and index order as they are.
+static_assert(sizeof(RefBvhNode) == sizeof(YcBuildNode), "RefBvhNode and YcBuildNode are the reference's BVHNode");
 static bool buildOnDevice(const float* positions, size_t nVerts, const uint32_t* faces4, size_t nTris, BvhBuildResult& out,
                           std::string* err) {
-  const char* traceEnv = getenv("YART_B200_BUILD_TRACE");
-  const bool trace = traceEnv && *traceEnv && *traceEnv != '0';
-  auto tick = [] { return std::chrono::high_resolution_clock::now(); };
-  auto since = [&](std::chrono::high_resolution_clock::time_point t) { return std::chrono::duration<double, std::milli>(tick() - t).count(); };
-  const auto tb0 = tick();
-  std::unique_ptr<YcBuildNode[]> pool(new YcBuildNode[2 * nTris + 2]);  // (not zeroed: 80 MB for a million triangles)
   uint32_t nNodes = 0, levels = 0;
   out.indices.resize(nTris);
+  out.nodes.resize(2 * nTris + 2);
   const int dev = std::max(0, gBuildDevice.load());
-  const int rc = yc_build_bvh_sah(dev, positions, nVerts, faces4, nTris, pool.get(), &nNodes, out.indices.data(), &levels);
+  const int rc = yc_build_bvh_sah(dev, positions, nVerts, faces4, nTris, reinterpret_cast<YcBuildNode*>(out.nodes.data()), &nNodes,
+                                  out.indices.data(), &levels);
   if (rc != YC_OK) {
     if (err) *err = yc_build_last_error();
     return false;
   }
-  const double msCall = since(tb0);
   out.nodes.resize(nNodes);
-  const double msResize = since(tb0) - msCall;
-  uint32_t used = 1;
-  std::vector<std::pair<uint32_t, uint32_t>> stack;  // (pool node, its number)
-  stack.reserve(256);
-  stack.push_back({0u, 0u});
-  while (!stack.empty()) {
-    const auto [pn, self] = stack.back();
-    stack.pop_back();
-    const YcBuildNode& g = pool[pn];
-    RefBvhNode& n = out.nodes[self];
-    for (int k = 0; k < 3; k++) n.mn[k] = g.mn[k], n.mx[k] = g.mx[k];
-    if (g.left == 0) {
-      n.leftFirst = g.first, n.span = g.span;
-      continue;
-    }
-    if (g.left + 1 >= nNodes || used + 2 > nNodes) {
-      if (err) *err = "device BVH build returned a broken node pool";
-      return false;
-    }
-    // the walk is depth-first over a pool in creation order: fetch the grandchildren's records while the left subtree
-    // is being numbered
-    const YcBuildNode &c0 = pool[g.left], &c1 = pool[g.left + 1];
-    if (c0.left) __builtin_prefetch(&pool[c0.left]);
-    if (c1.left) __builtin_prefetch(&pool[c1.left]);
-    const uint32_t l = used;
-    used += 2;
-    n.leftFirst = l, n.span = 0;
-    stack.push_back({g.left + 1, l + 1});  // popped after the whole left subtree has been numbered
-    stack.push_back({g.left, l});
-  }
-  if (used != nNodes) {
-    if (err) *err = "device BVH build returned unreachable nodes";
-    return false;
-  }
-  if (trace) fprintf(stderr, "yart_b200 scene build: device call %.1f ms, node array %.1f ms, renumbering %.1f ms\n", msCall, msResize, since(tb0) - msCall - msResize);
   return true;
 }
 
