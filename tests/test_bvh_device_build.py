@@ -74,3 +74,22 @@ def test_gpu_builder_one_million_triangles_and_the_automatic_choice(cuda_lib, mo
         assert Y.Scene(path).device_builds == 0
     finally:
         Y.set_build_device(0)
+
+
+def test_build_entry_point_rejects_bad_input(hostsim_lib):
+    import ctypes as C
+    from yart_b200 import lib
+    pos = np.zeros((3, 3), np.float32)
+    pos[1, 0] = pos[2, 1] = 1.0
+    faces = np.array([[0, 1, 2, 0]], np.uint32)
+    nodes = np.zeros((4, 8), np.uint32)
+    idx = np.zeros(1, np.uint32)
+    n, lv = C.c_uint32(), C.c_uint32()
+    f = lib().yc_build_bvh_sah
+    assert f(0, pos.ctypes.data, 3, faces.ctypes.data, 1, nodes.ctypes.data, C.byref(n), idx.ctypes.data, C.byref(lv)) == 0
+    assert n.value == 1 and nodes[0, 7] == 1 and nodes[0, 6] == 0 and idx[0] == 0  # one leaf over the one triangle
+    assert f(0, pos.ctypes.data, 3, faces.ctypes.data, 0, nodes.ctypes.data, C.byref(n), idx.ctypes.data, C.byref(lv)) == -1
+    bad = np.array([[0, 1, 3, 0]], np.uint32)
+    assert f(0, pos.ctypes.data, 3, bad.ctypes.data, 1, nodes.ctypes.data, C.byref(n), idx.ctypes.data, C.byref(lv)) == -1
+    assert b"out of range" in lib().yc_build_last_error()
+    assert f(0, None, 3, faces.ctypes.data, 1, nodes.ctypes.data, C.byref(n), idx.ctypes.data, C.byref(lv)) == -1

@@ -2289,7 +2289,13 @@ static_assert(sizeof(YcBuildNode) == sizeof(yb::bvhb::RefNode), "YcBuildNode mir
 
 extern "C" int yc_build_bvh_sah(int device, const float* positions, size_t nVerts, const uint32_t* faces4, size_t nTris,
                                 YcBuildNode* nodes, uint32_t* nNodes, uint32_t* indices, uint32_t* levels) {
-  if (!positions || !faces4 || !nodes || !nNodes || !indices || nTris == 0) return YC_ERR_INVALID;
+  if (!positions || !faces4 || !nodes || !nNodes || !indices || nTris == 0 || nVerts == 0) return YC_ERR_INVALID;
+  for (size_t i = 0; i < nTris; i++)
+    for (int k = 0; k < 3; k++)
+      if (faces4[4 * i + k] >= nVerts) {
+        gBuildError = "vertex index out of range";
+        return YC_ERR_INVALID;
+      }
   rt::Stream st;
   const char* traceEnv = getenv("YART_B200_BUILD_TRACE");
   const auto tA = std::chrono::high_resolution_clock::now();
