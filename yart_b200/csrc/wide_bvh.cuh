@@ -37,6 +37,8 @@
 
 #include "traverse.cuh"
 
+#include <thread>
+
 namespace yb {
 
 constexpr uint32_t kWideEmpty = 0xfffffffdu;  // unused child slot (has the leaf bit; never equals a real leaf ref)
@@ -52,20 +54,72 @@ static_assert(sizeof(WideNode) == 64, "WideNode is two 32-byte sectors");
 // ---- host: BVH2 → BVH4 collapse --------------------------------------------------------------------
 // Appends mesh `m`'s wide nodes to `out` (children of a node are allocated together, parents before children)
 // and returns the deepest level (root = 1; 0 for a single-leaf mesh).
+// Two passes: the walk that decides which BVH2 nodes open into which wide node (sequential: a node's children are
+// numbered when it is visited) and the quantisation of every wide node's child boxes (independent per node, double
+// arithmetic: spread over the host's cores).
+struct WideChildBox {
+  float lo[3], hi[3];
+  uint32_t ref;  // BVH2 ref while collapsing, then the wide ref
+};
+struct WideDraft {
+  WideChildBox c[4];
+  int n;
+};
+inline void quantiseWideNode(const WideDraft& d, WideNode& node) {
+  const WideChildBox* c = d.c;
+  const int n = d.n;
+  node = WideNode{};
+  // Quantisation grid per axis: quantum Q = 2^e, S = 2^15 Q, p' = the float at or below (low corner - S), grid
+  // origin P = p' + S (<= the low corner; P, q * Q and their sums are exact in double).  e is the smallest exponent
+  // for which the planes fit in a byte with the guard below.
+  for (int a = 0; a < 3; a++) {
+    double lo = INFINITY, hi = -INFINITY;
+    for (int k = 0; k < n; k++) lo = std::min(lo, double(c[k].lo[a])), hi = std::max(hi, double(c[k].hi[a]));
+    int e = -100;
+    if (hi - lo > 0.0 && std::isfinite(hi - lo)) std::frexp((hi - lo) / 254.0, &e);
+    e = std::max(-100, std::min(100, e));
+    for (;; e++) {
+      const double Q = std::ldexp(1.0, e), S = std::ldexp(1.0, e + 15);
+      float pS = float(lo - S - Q / 64);  // the origin sits 1/64 quantum below the low corner: a guard for q = 0 too
+      if (double(pS) > lo - S - Q / 64) pS = std::nextafterf(pS, -INFINITY);
+      const double P = double(pS) + S;
+      // outward rounding with a 1/128-quantum guard: the device forms t = v * (S / d) + (p' - o) / d in float, whose
+      // rounding (at the magnitude of S / d) is worth up to ~1/512 of a quantum
+      bool fits = e >= 100;
+      uint32_t ql[4], qh[4];
+      if (!fits) {
+        fits = true;
+        for (int k = 0; k < n && fits; k++) {
+          const double l = std::floor((double(c[k].lo[a]) - P) / Q - 1.0 / 128), h = std::ceil((double(c[k].hi[a]) - P) / Q + 1.0 / 128);
+          fits = l >= 0.0 && h <= 255.0;
+          ql[k] = uint32_t(std::max(0.0, l)), qh[k] = uint32_t(std::max(0.0, std::min(255.0, h)));
+        }
+      } else {
+        for (int k = 0; k < n; k++) ql[k] = 0u, qh[k] = 255u;
+      }
+      if (!fits) continue;
+      node.pS[a] = pS, node.S[a] = float(S);
+      for (int k = 0; k < 4; k++) {
+        // unused slots: lo = 255, hi = 0 — an empty interval on every axis
+        node.q[2 * a] |= (k < n ? ql[k] : 255u) << (8 * k);
+        node.q[2 * a + 1] |= (k < n ? qh[k] : 0u) << (8 * k);
+      }
+      break;
+    }
+  }
+  for (int k = 0; k < 4; k++) node.ref[k] = k < n ? c[k].ref : kWideEmpty;
+}
+
 inline int collapseToWide(const YcBvhNode* bvh2, const YcMesh& m, std::vector<WideNode>& out, WideMesh& wm) {
   wm.nodeOffset = uint32_t(out.size());
   wm.rootRef = m.rootRef;
   if (m.rootRef & YC_REF_LEAF) return 0;
-  struct Child {
-    float lo[3], hi[3];
-    uint32_t ref;
-  };
+  using Child = WideChildBox;
   struct Work {
     uint32_t ref2, wide;
     int depth;
   };
-  const size_t base = out.size();
-  out.emplace_back();
+  std::vector<WideDraft> drafts(1);
   std::vector<Work> todo{{m.rootRef, 0u, 1}};
   int maxDepth = 1;
   auto area = [](const Child& c) {
@@ -99,57 +153,30 @@ inline int collapseToWide(const YcBvhNode* bvh2, const YcMesh& m, std::vector<Wi
       put(c[best], nd.c0min, nd.c0max, nd.ref0), put(c[best + 1], nd.c1min, nd.c1max, nd.ref1);
       n++;
     }
-    WideNode node{};
-    // Quantisation grid per axis: quantum Q = 2^e, S = 2^15 Q, p' = the float at or below (low corner - S), grid
-    // origin P = p' + S (<= the low corner; P, q * Q and their sums are exact in double).  e is the smallest exponent
-    // for which the planes fit in a byte with the guard below.
-    for (int a = 0; a < 3; a++) {
-      double lo = INFINITY, hi = -INFINITY;
-      for (int k = 0; k < n; k++) lo = std::min(lo, double(c[k].lo[a])), hi = std::max(hi, double(c[k].hi[a]));
-      int e = -100;
-      if (hi - lo > 0.0 && std::isfinite(hi - lo)) std::frexp((hi - lo) / 254.0, &e);
-      e = std::max(-100, std::min(100, e));
-      for (;; e++) {
-        const double Q = std::ldexp(1.0, e), S = std::ldexp(1.0, e + 15);
-        float pS = float(lo - S - Q / 64);  // the origin sits 1/64 quantum below the low corner: a guard for q = 0 too
-        if (double(pS) > lo - S - Q / 64) pS = std::nextafterf(pS, -INFINITY);
-        const double P = double(pS) + S;
-        // outward rounding with a 1/128-quantum guard: the device forms t = v * (S / d) + (p' - o) / d in float, whose
-        // rounding (at the magnitude of S / d) is worth up to ~1/512 of a quantum
-        bool fits = e >= 100;
-        uint32_t ql[4], qh[4];
-        if (!fits) {
-          fits = true;
-          for (int k = 0; k < n && fits; k++) {
-            const double l = std::floor((double(c[k].lo[a]) - P) / Q - 1.0 / 128), h = std::ceil((double(c[k].hi[a]) - P) / Q + 1.0 / 128);
-            fits = l >= 0.0 && h <= 255.0;
-            ql[k] = uint32_t(std::max(0.0, l)), qh[k] = uint32_t(std::max(0.0, std::min(255.0, h)));
-          }
-        } else {
-          for (int k = 0; k < n; k++) ql[k] = 0u, qh[k] = 255u;
-        }
-        if (!fits) continue;
-        node.pS[a] = pS, node.S[a] = float(S);
-        for (int k = 0; k < 4; k++) {
-          // unused slots: lo = 255, hi = 0 — an empty interval on every axis
-          node.q[2 * a] |= (k < n ? ql[k] : 255u) << (8 * k);
-          node.q[2 * a + 1] |= (k < n ? qh[k] : 0u) << (8 * k);
-        }
-        break;
-      }
+    for (int k = 0; k < n; k++) {
+      if (c[k].ref & YC_REF_LEAF) continue;
+      const uint32_t wide = uint32_t(drafts.size());
+      todo.push_back({c[k].ref, wide, w.depth + 1});
+      c[k].ref = wide;
+      drafts.emplace_back();
     }
-    for (int k = 0; k < 4; k++) {
-      if (k >= n) {
-        node.ref[k] = kWideEmpty;
-      } else if (c[k].ref & YC_REF_LEAF) {
-        node.ref[k] = c[k].ref;
-      } else {
-        node.ref[k] = uint32_t(out.size() - base);
-        todo.push_back({c[k].ref, node.ref[k], w.depth + 1});
-        out.emplace_back();
-      }
-    }
-    out[base + w.wide] = node;
+    WideDraft& d = drafts[w.wide];
+    d.n = n;
+    for (int k = 0; k < n; k++) d.c[k] = c[k];
+  }
+  const size_t base = out.size(), count = drafts.size();
+  out.resize(base + count);
+  unsigned threads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  if (count < 20000) threads = 1;
+  auto run = [&](size_t lo, size_t hi) {
+    for (size_t i = lo; i < hi; i++) quantiseWideNode(drafts[i], out[base + i]);
+  };
+  if (threads == 1) {
+    run(0, count);
+  } else {
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < threads; t++) pool.emplace_back(run, count * t / threads, count * (t + 1) / threads);
+    for (auto& th : pool) th.join();
   }
   return maxDepth;
 }

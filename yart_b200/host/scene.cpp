@@ -6,6 +6,7 @@
 #include <cmath>
 #include <limits>
 #include <memory>
+#include <thread>
 #include <cstring>
 #include <functional>
 
@@ -50,6 +51,19 @@ static float buildDistribution1D(const float* f, size_t n, float mn, float mx, f
     for (size_t i = 1; i < n + 1; i++) cdf[i] /= integral;
   }
   return integral;
+}
+
+// fn(first, last) over [0, n) on the host's cores (big meshes only: the loops below are copies and gathers)
+template <class F>
+static void parallelRanges(size_t n, const F& fn) {
+  unsigned threads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  if (n < 100000 || threads == 1) {
+    fn(size_t(0), n);
+    return;
+  }
+  std::vector<std::thread> pool;
+  for (unsigned t = 0; t < threads; t++) pool.emplace_back([&, t] { fn(n * t / threads, n * (t + 1) / threads); });
+  for (auto& th : pool) th.join();
 }
 
 // ---- SAH build on the device (csrc/bvh_build.cuh through the C ABI) ---------------------------------------------------
@@ -185,17 +199,22 @@ bool HostScene::build(const ysc::SceneDesc& d, std::string* err) {
       const size_t n0 = normals.size(), t0 = tangents.size(), u0 = uvs.size();
       normals.resize(n0 + 3 * nv), tangents.resize(t0 + 4 * nv), uvs.resize(u0 + 2 * nv);
       float *pn = normals.data() + n0, *pt = tangents.data() + t0, *pu = uvs.data() + u0;
-      const float* v = m.vertexData.data();
-      for (size_t i = 0; i < nv; i++, v += 9, pn += 3, pt += 4, pu += 2) {
-        pn[0] = v[0], pn[1] = v[1], pn[2] = v[2];
-        pt[0] = v[3], pt[1] = v[4], pt[2] = v[5], pt[3] = v[6];
-        pu[0] = v[7], pu[1] = v[8];
-      }
+      const float* vd = m.vertexData.data();
+      parallelRanges(nv, [&](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; i++) {
+          const float* v = vd + 9 * i;
+          pn[3 * i] = v[0], pn[3 * i + 1] = v[1], pn[3 * i + 2] = v[2];
+          pt[4 * i] = v[3], pt[4 * i + 1] = v[4], pt[4 * i + 2] = v[5], pt[4 * i + 3] = v[6];
+          pu[2 * i] = v[7], pu[2 * i + 1] = v[8];
+        }
+      });
       const size_t i0 = primIndices.size(), m0 = primMaterial.size();
       primIndices.resize(i0 + 3 * nf), primMaterial.resize(m0 + nf);
       uint32_t *pi = primIndices.data() + i0, *pm = primMaterial.data() + m0;
-      const uint32_t* f = m.faces.data();
-      for (size_t i = 0; i < nf; i++, f += 4, pi += 3) pi[0] = f[0], pi[1] = f[1], pi[2] = f[2], pm[i] = f[3];
+      const uint32_t* fd = m.faces.data();
+      parallelRanges(nf, [&](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; i++) pi[3 * i] = fd[4 * i], pi[3 * i + 1] = fd[4 * i + 1], pi[3 * i + 2] = fd[4 * i + 2], pm[i] = fd[4 * i + 3];
+      });
       primLight.insert(primLight.end(), m.lightIdx.begin(), m.lightIdx.end());
     }
     Bounds3 vb;  // Node(Mesh*) ctor: unpadded vertex bounds (scene.hpp:17-22)
@@ -249,18 +268,20 @@ bool HostScene::build(const ysc::SceneDesc& d, std::string* err) {
     }
     size_t tbase = bvhTris.size();
     bvhTris.resize(tbase + nf);
-    for (size_t i = 0; i < nf; i++) {
-      uint32_t prim = ref.indices[i];
-      YcBvhTri& t = bvhTris[tbase + i];
-      memcpy(t.p0, &m.positions[3 * size_t(m.faces[4 * prim + 0])], 12);
-      memcpy(t.p1, &m.positions[3 * size_t(m.faces[4 * prim + 1])], 12);
-      memcpy(t.p2, &m.positions[3 * size_t(m.faces[4 * prim + 2])], 12);
-      t.prim = prim;
-      const YcMaterial& mat = materials[m.faces[4 * prim + 3]];
-      t.flags = (mat.hasAlpha ? YC_TRI_ALPHA : 0) |
-                ((mat.thinTransmission && mat.transmission > 0.0f) ? YC_TRI_TRANSPARENT : 0);
-      t.pad = 0;
-    }
+    parallelRanges(nf, [&](size_t lo, size_t hi) {
+      for (size_t i = lo; i < hi; i++) {
+        uint32_t prim = ref.indices[i];
+        YcBvhTri& t = bvhTris[tbase + i];
+        memcpy(t.p0, &m.positions[3 * size_t(m.faces[4 * prim + 0])], 12);
+        memcpy(t.p1, &m.positions[3 * size_t(m.faces[4 * prim + 1])], 12);
+        memcpy(t.p2, &m.positions[3 * size_t(m.faces[4 * prim + 2])], 12);
+        t.prim = prim;
+        const YcMaterial& mat = materials[m.faces[4 * prim + 3]];
+        t.flags = (mat.hasAlpha ? YC_TRI_ALPHA : 0) |
+                  ((mat.thinTransmission && mat.transmission > 0.0f) ? YC_TRI_TRANSPARENT : 0);
+        t.pad = 0;
+      }
+    });
     for (const RefBvhNode& n : ref.nodes)
       if (n.span != 0) bvhTris[tbase + n.leftFirst + n.span - 1].flags |= YC_TRI_LAST;
     meshes.push_back(ym);
