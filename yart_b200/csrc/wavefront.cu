@@ -61,7 +61,7 @@ struct Lane {
   PathState ps{};      // ps.L points at Lbuf[lSel] while a chunk is in flight
   ShadowQueue sq{};
   SurfState ss{};
-  uint32_t *qA = nullptr, *qH = nullptr, *qM = nullptr, *qN = nullptr, *ctr = nullptr;  // cur/next, hit, miss, NEE queues; counters
+  uint32_t *qA = nullptr, *qH = nullptr, *qN = nullptr, *ctr = nullptr;  // cur/next, hit, NEE queues; counters
   uint32_t* hCtr = nullptr;  // page-locked copy of the counters
   void* spill = nullptr;     // traversal-stack spill area of the persistent kernels
   rt::Event evCtr;
@@ -273,34 +273,24 @@ struct ShadeNeeK {
   }
 };
 
-// After extend: sorts the bounce's paths into a hit queue and a miss queue (paths killed by a deferred
-// roulette drop out), one warp-aggregated append per category and warp, so that the heavy surface shading
-// runs in full warps.  (Appending from inside the persistent extend kernel costs one atomic per ray.)
-struct SortK {
-  PathState ps;
-  const uint32_t* queue;
-  uint32_t *hitQueue, *missQueue, *ctr;
-  YB_DEV void operator()(uint32_t j) const {
-    const uint32_t i = queue[j];
-    const int32_t hb = ps.hitB[i];
-    if (hb >= 0) hitQueue[aggregatedAppend(ctr + kCtrHitCount)] = i;
-    else if (hb == kHitMiss) missQueue[aggregatedAppend(ctr + kCtrMissCount)] = i;
-  }
-};
-
-// Miss shading over the MISS queue (environment lights with MIS, background).
-struct ShadeMissK {
+// After extend: the bounce's hits go to the hit queue (one warp-aggregated append per warp, so that the heavy surface
+// shading runs in full warps; appending from inside the persistent extend kernel costs one atomic per ray), its misses
+// are shaded on the spot — environment lights with their MIS weight, background (mis-integrator.cpp:27-43): a few
+// texel taps, not worth a queue and a launch of their own — and paths killed by a deferred roulette drop out.
+struct SortMissK {
   DScene sc;
   WaveParams w;
   PathState ps;
   const uint32_t* queue;
-  uint32_t* ctr;
+  uint32_t *hitQueue, *ctr;
   Counters* counters;
   YB_DEV void operator()(uint32_t j) const {
-    if (j >= ctr[kCtrMissCount]) return;
+    const uint32_t i = queue[j];
+    const int32_t hb = ps.hitB[i];
     uint32_t rays = 0;
-    shadeMissStage(sc, w, ps, queue[j], rays);
-    aggregatedCount(&counters->raysReference, rays);
+    if (hb >= 0) hitQueue[aggregatedAppend(ctr + kCtrHitCount)] = i;
+    else if (hb == kHitMiss) shadeMissStage(sc, w, ps, i, rays);
+    aggregatedCount(&counters->raysReference, rays);  // (per group of lanes, if the branches above have not reconverged)
   }
 };
 
@@ -913,7 +903,6 @@ static int ensureWaveStorage(yc_ctx* ctx) {
     YC_TRY(devAlloc(own, &L.sq.att, P));
     YC_TRY(devAlloc(own, &L.qA, P));
     YC_TRY(devAlloc(own, &L.qH, P));
-    YC_TRY(devAlloc(own, &L.qM, P));
     YC_TRY(devAlloc(own, &L.qN, P));
     for (float4** r : {&L.ss.r0, &L.ss.r1, &L.ss.r2, &L.ss.r3, &L.ss.r4, &L.ss.r5, &L.ss.r6, &L.ss.r7}) YC_TRY(devAlloc(own, r, P));
     YC_TRY(devAlloc(own, &L.ctr, size_t(kCtrCount)));
@@ -1060,8 +1049,7 @@ static int issueBounce(yc_ctx* ctx, Lane& L) {
   YC_TRY(rt::zero(L.st, L.ctr, kCtrCount * sizeof(uint32_t)));
   if (ctx->countTraversal) runExtend<ALPHA, true>(ctx, L, n);
   else runExtend<ALPHA, false>(ctx, L, n);
-  rt::launchFor(L.st, n, SortK{L.ps, L.qA, L.qH, L.qM, L.ctr});
-  rt::launchFor(L.st, n, ShadeMissK{ctx->ds, L.w, L.ps, L.qM, L.ctr, ctx->dCounters});
+  rt::launchFor(L.st, n, SortMissK{ctx->ds, L.w, L.ps, L.qA, L.qH, L.ctr, ctx->dCounters});
   std::pair<rt::Event, rt::Event>* sev = nullptr;
   if (ctx->timeShade) {
     if (ctx->shadeEventsUsed == ctx->shadeEvents.size()) {
@@ -1078,7 +1066,7 @@ static int issueBounce(yc_ctx* ctx, Lane& L) {
   if (sev) rt::eventRecord(L.st, sev->second);
   if (ctx->countTraversal) runShadow<ALPHA, true>(ctx, L, n);
   else runShadow<ALPHA, false>(ctx, L, n);
-  ctx->launches += 7;
+  ctx->launches += 6;
   ctx->raysExtend += n;  // every queue entry is one closest-hit ray
   if (L.bounce + 1 < ctx->opts.maxDepth) {
     YC_TRY(rt::d2hAsync(L.st, L.hCtr, L.ctr, kCtrCount * sizeof(uint32_t)));
