@@ -14,7 +14,7 @@
 //     Left elements end up at first + (number of left elements examined before them), right elements at last - (number
 //     of right elements examined before them), and both counts follow from prefix counts of the classes and from the
 //     positions of the k-th right element from the front / k-th left element from the back — one scan and two
-//     scatters per level (partitionDest below).
+//     scatters per level (ClassK, TablesK, PartitionK below).
 // Nodes of at most kSmallSpan triangles are finished by one thread each with the reference's sequential code.
 // The node pool is in creation order; three more passes per tree level put it into the reference's allocation order.
 // In the CPU build of the product sources (YB_HOSTSIM) the same stages run as plain loops.
@@ -707,7 +707,6 @@ inline const char* build(rt::Stream& st, const float* positions, size_t nVerts, 
   const auto t0 = now();
   double tAlloc = 0, tPrep = 0, tLevels = 0, tSmall = 0;
   if (trace) tAlloc = msSince(t0);
-  const auto tEnter = t0;
   YB_B(rt::h2d(st, dPos, positions, 3 * nVerts * sizeof(float)));
   YB_B(rt::h2d(st, dFaces, faces4, 4 * size_t(n) * sizeof(uint32_t)));
 

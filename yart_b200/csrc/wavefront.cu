@@ -49,7 +49,7 @@ using namespace yb;
 // ---------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------
-enum { kCtrExtendHead = 0, kCtrNextCount = 1, kCtrShadowCount = 2, kCtrShadowHead = 3, kCtrHitCount = 4, kCtrMissCount = 5,
+enum { kCtrExtendHead = 0, kCtrNextCount = 1, kCtrShadowCount = 2, kCtrShadowHead = 3, kCtrHitCount = 4,
        kCtrNeeCount = 6, kCtrCount = 8 };
 
 // Two chunks of a wave are in flight at a time, each on its own stream with its own path state: while one
