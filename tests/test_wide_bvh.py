@@ -190,3 +190,28 @@ def test_wide_gpu_kernels_equal_the_cpu_build_of_the_same_sources(cuda_lib):
         ctx.close()
     Y.use_library(cuda_lib)
     assert recs[0][0] == recs[1][0] and recs[0][1] == recs[1][1] and recs[0][2] == recs[1][2]
+
+
+def test_wide_collapse_shared_out_over_threads_cpu_build(hostsim_lib):
+    """A mesh big enough (>= 50 000 inner nodes) for the collapse to hand subtrees to worker threads and stitch the
+    pieces: the wide walk finds what the reference-order walk finds (ids bar ties at the bit-identical t, t to 1e-5)."""
+    sc = Y.Scene(H.scene_file("soup", n_tris=120_000))
+    ctx = Y.Context(traversal=Y.TRAVERSAL_WIDE)
+    ctx.upload_scene(sc)
+    rng = np.random.default_rng(3)
+    n = 20000
+    o = rng.uniform(-12, 12, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([o, np.full((n, 1), 1e-4, np.float32), d, np.full((n, 1), np.inf, np.float32)], axis=1).astype(np.float32)
+    wide, _ = ctx.trace(rays, Y.TRACE_CLOSEST)
+    ref, _ = ctx.trace(rays, Y.TRACE_CLOSEST | Y.TRACE_REFERENCE_ORDER)
+    assert np.array_equal(wide["didHit"], ref["didHit"]) and ref["didHit"].sum() > n // 4
+    m = ref["didHit"] == 1
+    assert (np.abs(wide["t"][m] - ref["t"][m]) <= 1e-5 * np.abs(ref["t"][m])).all()
+    other = m & (wide["prim"] != ref["prim"])
+    assert np.array_equal(wide["t"][other].view(np.uint32), ref["t"][other].view(np.uint32)) and other.sum() <= 4
+    any_w, _ = ctx.trace(rays, Y.TRACE_ANY)
+    any_r, _ = ctx.trace(rays, Y.TRACE_ANY | Y.TRACE_REFERENCE_ORDER)
+    assert np.array_equal(any_w["didHit"], any_r["didHit"])
+    ctx.close()

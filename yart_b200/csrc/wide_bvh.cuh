@@ -37,6 +37,10 @@
 
 #include "traverse.cuh"
 
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <thread>
 
 namespace yb {
@@ -110,74 +114,154 @@ inline void quantiseWideNode(const WideDraft& d, WideNode& node) {
   for (int k = 0; k < 4; k++) node.ref[k] = k < n ? c[k].ref : kWideEmpty;
 }
 
+// One step of the collapse: the wide node that the BVH2 inner node `ref2` opens into (greedy by surface area, the
+// reference tree's left-to-right order kept).  Children that are BVH2 inner nodes keep their BVH2 ref in `d.c[k].ref`.
+inline void openWideNode(const YcBvhNode* bvh2, uint32_t ref2, WideDraft& d) {
+  WideChildBox* c = d.c;
+  int n = 0;
+  auto put = [&](WideChildBox& dst, const float* lo, const float* hi, uint32_t ref) {
+    memcpy(dst.lo, lo, 12), memcpy(dst.hi, hi, 12), dst.ref = ref;
+  };
+  auto area = [](const WideChildBox& b) {
+    const float dx = b.hi[0] - b.lo[0], dy = b.hi[1] - b.lo[1], dz = b.hi[2] - b.lo[2];
+    return dx * dy + dy * dz + dz * dx;
+  };
+  {
+    const YcBvhNode& nd = bvh2[ref2];
+    put(c[0], nd.c0min, nd.c0max, nd.ref0), put(c[1], nd.c1min, nd.c1max, nd.ref1);
+    n = 2;
+  }
+  while (n < 4) {
+    int best = -1;
+    float bestArea = -1.0f;
+    for (int k = 0; k < n; k++)
+      if (!(c[k].ref & YC_REF_LEAF) && area(c[k]) > bestArea) best = k, bestArea = area(c[k]);
+    if (best < 0) break;
+    // the opened child's slot receives its left child, its right child is inserted after it
+    const YcBvhNode& nd = bvh2[c[best].ref];
+    for (int k = n - 1; k > best; k--) c[k + 1] = c[k];
+    put(c[best], nd.c0min, nd.c0max, nd.ref0), put(c[best + 1], nd.c1min, nd.c1max, nd.ref1);
+    n++;
+  }
+  d.n = n;
+}
+
+// Collapses the subtree under BVH2 node `ref2` into `drafts` (index 0 = the subtree's root; children are numbered when
+// their parent is visited).  `limit` > 0: stop opening once that many subtrees are pending and report them in
+// `pending` as (BVH2 ref, draft index) — the caller finishes those elsewhere.  Returns the deepest level reached.
+struct WidePending {
+  uint32_t ref2, draft;
+  int depth;
+};
+inline int collapseSubtree(const YcBvhNode* bvh2, uint32_t ref2, int depth0, std::vector<WideDraft>& drafts, size_t limit,
+                           std::vector<WidePending>* pending) {
+  drafts.assign(1, WideDraft{});
+  std::vector<WidePending> todo{{ref2, 0u, depth0}};
+  int maxDepth = depth0;
+  size_t head = 0;  // breadth-first while a limit is set (an even split of the work), depth-first otherwise
+  while (head < todo.size()) {
+    if (limit && todo.size() - head >= limit) break;
+    WidePending w;
+    if (limit) {
+      w = todo[head++];
+    } else {
+      w = todo.back();
+      todo.pop_back();
+    }
+    maxDepth = std::max(maxDepth, w.depth);
+    WideDraft d;
+    openWideNode(bvh2, w.ref2, d);
+    for (int k = 0; k < d.n; k++) {
+      if (d.c[k].ref & YC_REF_LEAF) continue;
+      const uint32_t wide = uint32_t(drafts.size());
+      __builtin_prefetch(&bvh2[d.c[k].ref]);
+      todo.push_back({d.c[k].ref, wide, w.depth + 1});
+      d.c[k].ref = wide;
+      drafts.emplace_back();
+    }
+    drafts[w.draft] = d;
+  }
+  if (pending) pending->assign(todo.begin() + long(head), todo.end());
+  return maxDepth;
+}
+
 inline int collapseToWide(const YcBvhNode* bvh2, const YcMesh& m, std::vector<WideNode>& out, WideMesh& wm) {
   wm.nodeOffset = uint32_t(out.size());
   wm.rootRef = m.rootRef;
   if (m.rootRef & YC_REF_LEAF) return 0;
-  using Child = WideChildBox;
-  struct Work {
-    uint32_t ref2, wide;
-    int depth;
-  };
-  std::vector<WideDraft> drafts(1);
-  std::vector<Work> todo{{m.rootRef, 0u, 1}};
-  int maxDepth = 1;
-  auto area = [](const Child& c) {
-    const float dx = c.hi[0] - c.lo[0], dy = c.hi[1] - c.lo[1], dz = c.hi[2] - c.lo[2];
-    return dx * dy + dy * dz + dz * dx;
-  };
-  while (!todo.empty()) {
-    const Work w = todo.back();
-    todo.pop_back();
-    maxDepth = std::max(maxDepth, w.depth);
-    Child c[4];
-    int n = 0;
-    auto put = [&](Child& dst, const float* lo, const float* hi, uint32_t ref) {
-      memcpy(dst.lo, lo, 12), memcpy(dst.hi, hi, 12), dst.ref = ref;
-    };
-    {
-      const YcBvhNode& nd = bvh2[w.ref2];
-      put(c[0], nd.c0min, nd.c0max, nd.ref0), put(c[1], nd.c1min, nd.c1max, nd.ref1);
-      n = 2;
-    }
-    while (n < 4) {
-      int best = -1;
-      float bestArea = -1.0f;
-      for (int k = 0; k < n; k++)
-        if (!(c[k].ref & YC_REF_LEAF) && area(c[k]) > bestArea) best = k, bestArea = area(c[k]);
-      if (best < 0) break;
-      // the opened child's slot receives its left child, its right child is inserted after it (left-to-right
-      // order of the reference tree is kept)
-      const YcBvhNode& nd = bvh2[c[best].ref];
-      for (int k = n - 1; k > best; k--) c[k + 1] = c[k];
-      put(c[best], nd.c0min, nd.c0max, nd.ref0), put(c[best + 1], nd.c1min, nd.c1max, nd.ref1);
-      n++;
-    }
-    for (int k = 0; k < n; k++) {
-      if (c[k].ref & YC_REF_LEAF) continue;
-      const uint32_t wide = uint32_t(drafts.size());
-      todo.push_back({c[k].ref, wide, w.depth + 1});
-      c[k].ref = wide;
-      drafts.emplace_back();
-    }
-    WideDraft& d = drafts[w.wide];
-    d.n = n;
-    for (int k = 0; k < n; k++) d.c[k] = c[k];
-  }
-  const size_t base = out.size(), count = drafts.size();
-  out.resize(base + count);
+  const char* traceEnv = getenv("YART_B200_BUILD_TRACE");
+  const bool trace = traceEnv && *traceEnv && *traceEnv != '0';
+  const auto tw = std::chrono::high_resolution_clock::now();
   unsigned threads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-  if (count < 20000) threads = 1;
-  auto run = [&](size_t lo, size_t hi) {
-    for (size_t i = lo; i < hi; i++) quantiseWideNode(drafts[i], out[base + i]);
-  };
-  if (threads == 1) {
-    run(0, count);
-  } else {
+  if (m.nInner < 50000) threads = 1;
+  // the top of the tree on this thread until there are enough pending subtrees to share out, then one subtree at a
+  // time per worker into its own array; the pieces are appended and their references shifted afterwards
+  std::vector<WideDraft> top;
+  std::vector<WidePending> pending;
+  int maxDepth = collapseSubtree(bvh2, m.rootRef, 1, top, threads > 1 ? size_t(threads) * 8 : 0, &pending);
+  std::vector<std::vector<WideDraft>> parts(pending.size());
+  std::vector<int> depths(pending.size(), 0);
+  if (!pending.empty()) {
+    std::atomic<size_t> next{0};
+    auto work = [&] {
+      for (size_t i; (i = next.fetch_add(1)) < pending.size();)
+        depths[i] = collapseSubtree(bvh2, pending[i].ref2, pending[i].depth, parts[i], 0, nullptr);
+    };
     std::vector<std::thread> pool;
-    for (unsigned t = 0; t < threads; t++) pool.emplace_back(run, count * t / threads, count * (t + 1) / threads);
+    for (unsigned t = 0; t < threads; t++) pool.emplace_back(work);
     for (auto& th : pool) th.join();
   }
+  // layout: the top's drafts first (the pending subtrees' roots already have their slots there), then every part
+  // without its root
+  std::vector<size_t> partBase(parts.size());
+  size_t count = top.size();
+  for (size_t i = 0; i < parts.size(); i++) {
+    partBase[i] = count;
+    count += parts[i].size() - 1;
+    maxDepth = std::max(maxDepth, depths[i]);
+  }
+  const auto tq = std::chrono::high_resolution_clock::now();
+  const size_t base = out.size();
+  out.resize(base + count);
+  auto emitTop = [&](size_t lo, size_t hi) {
+    for (size_t i = lo; i < hi; i++) quantiseWideNode(top[i], out[base + i]);
+  };
+  auto emitPart = [&](size_t p) {
+    // local index 0 is the part's root, which lives in the top's slot; local index j >= 1 lives at partBase + j - 1
+    std::vector<WideDraft>& part = parts[p];
+    for (size_t j = 0; j < part.size(); j++) {
+      WideDraft d = part[j];
+      for (int k = 0; k < d.n; k++)
+        if (!(d.c[k].ref & YC_REF_LEAF)) d.c[k].ref = uint32_t(partBase[p] + d.c[k].ref - 1);
+      quantiseWideNode(d, out[base + (j == 0 ? size_t(pending[p].draft) : partBase[p] + j - 1)]);
+    }
+  };
+  if (threads == 1) {
+    emitTop(0, top.size());
+    for (size_t p = 0; p < parts.size(); p++) emitPart(p);
+  } else {
+    // the pending roots' slots in `top` are placeholders: their real content comes from the parts
+    std::vector<char> isPendingRoot(top.size(), 0);
+    for (const WidePending& w : pending) isPendingRoot[w.draft] = 1;
+    std::atomic<size_t> next{0};
+    auto work = [&] {
+      for (size_t i; (i = next.fetch_add(1)) < parts.size() + 1;) {
+        if (i == parts.size()) {
+          for (size_t t = 0; t < top.size(); t++)
+            if (!isPendingRoot[t]) quantiseWideNode(top[t], out[base + t]);
+        } else {
+          emitPart(i);
+        }
+      }
+    };
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < threads; t++) pool.emplace_back(work);
+    for (auto& th : pool) th.join();
+  }
+  if (trace && count > 10000)
+    fprintf(stderr, "yart_b200 wide collapse: %zu nodes, walk %.1f ms, quantisation %.1f ms\n", count,
+            std::chrono::duration<double, std::milli>(tq - tw).count(),
+            std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - tq).count());
   return maxDepth;
 }
 
