@@ -64,9 +64,13 @@ int main(int argc, char** argv) {
   ref.tonemapper = tonemapper;
   size_t refWaves = 0, refTiles = 0, refDone = 0;
   ref.onRenderWaveComplete = [&](Renderer::RenderData, Renderer::WaveData) { refWaves++; };
-  ref.onRenderTileComplete = [&](Renderer::RenderData, Renderer::TileData) { refTiles++; };
+  // (the reference adds tile ray counts into m_totalRays outside its mutex, tile-renderer.hpp:217-218: the sum of the
+  // per-tile counts, handed over under m_bufferMutex, is the exact figure — see ref_driver.cpp)
+  uint64_t refTileRays = 0;
+  ref.onRenderTileComplete = [&](Renderer::RenderData, Renderer::TileData t) { refTiles++, refTileRays += t.rays; };
   ref.onRenderComplete = [&](Renderer::RenderData) { refDone++; };
-  const auto ra = ref.renderSync();
+  auto ra = ref.renderSync();
+  ra.totalRays = refTileRays;
 
   // ---- the adapter, on the same yart::Scene and Camera objects ----------------------------------------
   cuda::WavefrontRenderer gpu(Buffer(w, h), cam);

@@ -284,6 +284,13 @@ static int cmdRenderWith(int argc, char** argv) {
   r.backgroundColor = a.vec3("bg", {0, 0, 0});
   r.tonemapper = nullptr;  // m_buffer then carries the HDR accumulation (tile-renderer.hpp:238)
 
+  // Ray count of a render: the reference's worker threads add their tiles' counts into m_totalRays OUTSIDE its mutex
+  // (tile-renderer.hpp:217-218), so RenderData::totalRays can lose an update when two tiles finish together (seen as a
+  // rare off-by-one-tile count on a loaded box).  The per-tile counts are exact, and the tile callback runs under
+  // m_bufferMutex (tile-renderer.hpp:225, 243-262): their sum is the render's ray count.
+  uint64_t tileRaySum = 0;
+  r.onRenderTileComplete = [&](Renderer::RenderData, Renderer::TileData t) { tileRaySum += t.rays; };
+
   // repeat=N: time N back-to-back renderSync() calls of the same frame (bench.py's reference arm);
   // the last one is written out.  Each line of "steps" is one call: rays and wall milliseconds.
   int repeat = int(a.num("repeat", 1));
@@ -292,13 +299,17 @@ static int cmdRenderWith(int argc, char** argv) {
   auto res = r.renderSync();
   auto t1 = std::chrono::high_resolution_clock::now();
   double ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
-  steps.push_back({uint64_t(res.totalRays), ms});
+  const uint64_t reportedRays = res.totalRays;  // what the reference itself reports (kept in the JSON line: "rays_reported")
+  res.totalRays = tileRaySum;
+  steps.push_back({tileRaySum, ms});
   for (int it = 1; it < repeat; it++) {
+    tileRaySum = 0;
     t0 = std::chrono::high_resolution_clock::now();
     auto again = r.renderSync();
     t1 = std::chrono::high_resolution_clock::now();
     ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
-    steps.push_back({uint64_t(again.totalRays), ms});
+    (void)again;
+    steps.push_back({tileRaySum, ms});
   }
 
   tonemap::AgX agx;
@@ -335,8 +346,8 @@ static int cmdRenderWith(int argc, char** argv) {
     std::ofstream os(a.str("ppm", "out.ppm"), std::ios::binary);
     output::writePPM(os, ldr);
   }
-  printf("{\"rays\": %llu, \"ms\": %.3f, \"threads\": %u, \"build_ms\": %.3f, \"w\": %u, \"h\": %u, \"spp\": %u, \"steps\": [",
-         (unsigned long long) res.totalRays, ms, r.threadCount, rs.buildMs, w, h, r.samples);
+  printf("{\"rays\": %llu, \"rays_reported\": %llu, \"ms\": %.3f, \"threads\": %u, \"build_ms\": %.3f, \"w\": %u, \"h\": %u, \"spp\": %u, \"steps\": [",
+         (unsigned long long) res.totalRays, (unsigned long long) reportedRays, ms, r.threadCount, rs.buildMs, w, h, r.samples);
   for (size_t i = 0; i < steps.size(); i++)
     printf("%s[%llu, %.3f]", i ? ", " : "", (unsigned long long) steps[i].first, steps[i].second);
   printf("]}\n");
