@@ -302,8 +302,7 @@ static int cmdRenderWith(int argc, char** argv) {
   const uint64_t reportedRays = res.totalRays;  // what the reference itself reports (kept in the JSON line: "rays_reported")
   res.totalRays = tileRaySum;
   steps.push_back({tileRaySum, ms});
-  for (int it = 1; it < repeat; it++) {
-    tileRaySum = 0;
+  for (int it = 1; it < repeat; it++) {  // (the sum keeps growing over the calls, like the reference's m_totalRays)
     t0 = std::chrono::high_resolution_clock::now();
     auto again = r.renderSync();
     t1 = std::chrono::high_resolution_clock::now();
