@@ -152,13 +152,16 @@ def test_abort_stops_a_long_render_between_chunks():
     r.close()
 
 
-def test_direct_frame_delivery_in_process_group_with_partial_and_repeated_waves():
+@pytest.mark.parametrize("force_reduce", [False, True])
+def test_direct_frame_delivery_in_process_group_with_partial_and_repeated_waves(force_reduce, monkeypatch):
     """Tile sharding where every participant reaches the root's memory (here: one process, the in-process group): the
     finalize kernel stores finished pixels into the root's combined frame and yc_comm_reduce_frames is a barrier.  The
     root's frame equals one context's after every wave — also after a wave that finalized part of the frame only (the
     stale path pushes the shard), after two waves without a reduce in between, and over a second frame (the two
     alternating copies of the combined frame are reused)."""
     import threading
+    if force_reduce:  # the summing path behind the same calls (what participants without peer access fall back to)
+        monkeypatch.setenv("YART_B200_FRAMES_REDUCE", "1")
     n, size, tile = 3, 48, 16
     cam = H.scene_camera("cornell")
     sc = Y.Scene(H.scene_file("cornell"))
@@ -201,7 +204,7 @@ def test_direct_frame_delivery_in_process_group_with_partial_and_repeated_waves(
     for t in ts:
         t.join(120)
     assert not errs, errs
-    assert all(x.comm_frames_direct() for x in ctxs)
+    assert all(x.comm_frames_direct() != force_reduce for x in ctxs)
     assert len(got) == len(want) == 10
     for k, ((hdr, ldr), (hdr1, ldr1)) in enumerate(zip(got, want)):
         assert H.bits_equal(hdr, hdr1).all() and H.bits_equal(ldr, ldr1).all(), k
